@@ -1,0 +1,667 @@
+// hrd_api.cu -- the C ABI of libhrd_b200.so (include/hrd.h): batch handles, per-stream
+// parameters with the reference's setter semantics, table construction, host<->device
+// staging and kernel dispatch.  No DSP happens on the host; without a CUDA device every
+// entry point fails (there is deliberately no CPU fallback).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/hrd.h"
+#include "hrd_tables.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define HRD_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) return fail(HRD_ECUDA, "%s: %s", #call, cudaGetErrorString(e_));     \
+    } while (0)
+
+// ---- the reference's filter designs (float literals as the reference spells them) -----
+const float k_fe1[3] = {0.2504357f, 0.5000000f, 0.2504357f};   // IqDataProcessor.cc:8-13
+const float k_fe2[3] = {0.2517491f, 0.4999998f, 0.2517491f};   // :15-20
+const float k_fe3[3] = {0.2570951f, 0.5000000f, 0.2570951f};   // :22-27
+const float k_am1[8] = {0.0242683f, 0.0766338f, 0.1457589f, 0.1959036f,
+                        0.1959036f, 0.1457589f, 0.0766338f, 0.0242683f};
+const float k_am2[12] = {0.0057496f, 0.0263853f, 0.0605301f, 0.1074406f, 0.1523486f, 0.1804951f,
+                         0.1804951f, 0.1523486f, 0.1074406f, 0.0605301f, 0.0263853f, 0.0057496f};
+const float k_am3[16] = {0.0116487f, 0.0152694f, -0.0109804f, -0.0611915f, -0.0736143f, 0.0187617f,
+                         0.1988190f, 0.3481364f, 0.3481364f,  0.1988190f,  0.0187617f,  -0.0736143f,
+                         -0.0611915f, -0.0109804f, 0.0152694f, 0.0116487f};
+const float k_fm_tuner[32] = {
+    0.0041331f, 0.0054174f, 0.0076016f, 0.0115481f, 0.0151685f, 0.0203192f, 0.0251608f, 0.0311322f,
+    0.0366372f, 0.0427168f, 0.0480527f, 0.0533425f, 0.0575831f, 0.0611914f, 0.0635413f, 0.0648239f,
+    0.0648239f, 0.0635413f, 0.0611914f, 0.0575831f, 0.0533425f, 0.0480527f, 0.0427168f, 0.0366372f,
+    0.0311322f, 0.0251608f, 0.0203192f, 0.0151685f, 0.0115481f, 0.0076016f, 0.0054174f, 0.0041331f};
+const float k_fm_post[12] = {0.0022977f, 0.0237042f, 0.0605386f, 0.1127073f, 0.1645167f, 0.1971107f,
+                             0.1971107f, 0.1645167f, 0.1127073f, 0.0605386f, 0.0237042f, 0.0022977f};
+const float k_audio40[40] = {
+    0.0015969f,  -0.0111080f, -0.0270501f, -0.0265610f, -0.0023190f, 0.0180618f,  0.0065495f,  -0.0183409f,
+    -0.0133345f, 0.0184489f,  0.0230891f,  -0.0161248f, -0.0363745f, 0.0091343f,  0.0550219f,  0.0070312f,
+    -0.0862280f, -0.0497761f, 0.1793543f,  0.4145808f,  0.4145808f,  0.1793543f,  -0.0497761f, -0.0862280f,
+    0.0070312f,  0.0550219f,  0.0091343f,  -0.0363745f, -0.0161248f, 0.0230891f,  0.0184489f,  -0.0133345f,
+    -0.0183409f, 0.0065495f,  0.0180618f,  -0.0023190f, -0.0265610f, -0.0270501f, -0.0111080f, 0.0015969f};
+const float k_wbfm_post1[8] = {0.0243699f, 0.0769537f, 0.1463572f, 0.1967096f,
+                               0.1967096f, 0.1463572f, 0.0769537f, 0.0243699f};
+const float k_delay16[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1};
+const float k_hilbert31[31] = {-0.0033953f, 0, -0.0058652f, 0, -0.0134385f, 0, -0.0281423f, 0,
+                               -0.0534836f, 0, -0.0980394f, 0, -0.1935638f, 0, -0.6302204f, 0,
+                               0.6302204f,  0, 0.1935638f,  0, 0.0980394f,  0, 0.0534836f,  0,
+                               0.0281423f,  0, 0.0134385f,  0, 0.0058652f,  0, 0.0033953f};
+const float k_tx_hb8[8] = {-0.0440934f, 0, 0.2913764f, 0.5000000f, 0.2913764f, 0, -0.0440934f, 0};
+
+struct TapSet {
+    const float *c;
+    int n;
+};
+// numbering shared with oracle/hrd_oracle.h HRO_TAPS_* so tests can compare table by table
+const TapSet k_tapsets[] = {{k_fe1, 3},      {k_fe2, 3},     {k_fe3, 3},       {k_am1, 8},      {k_am2, 12},
+                            {k_am3, 16},     {k_fm_tuner, 32}, {k_fm_post, 12}, {k_audio40, 40}, {k_wbfm_post1, 8},
+                            {k_delay16, 16}, {k_hilbert31, 31}, {k_tx_hb8, 8}};
+const int k_n_tapsets = (int)(sizeof k_tapsets / sizeof k_tapsets[0]);
+
+// (int16_t)round(c*32768) evaluated in float; the narrowing keeps the low 16 bits, so
+// 1.0 -> 32768 -> -32768 exactly as the reference build does
+int16_t quantise(float c)
+{
+    float scaled = c * 32768;
+    scaled = roundf(scaled);
+    int32_t v = (int32_t)scaled;
+    return (int16_t)(uint16_t)((uint32_t)v & 0xffffu);
+}
+
+uint32_t pair16(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+
+int build_tables(hrd::ConstTables &t)
+{
+    memset(&t, 0, sizeof t);
+    const float *fe[3] = {k_fe1, k_fe2, k_fe3};
+    for (int s = 0; s < 3; s++) {
+        int q0 = quantise(fe[s][0]), q1 = quantise(fe[s][1]), q2 = quantise(fe[s][2]);
+        // doubled taps must fit an unsigned 16-bit dp2a operand
+        if (q0 < 0 || q1 < 0 || q2 < 0 || 2 * q0 > 65535 || 2 * q1 > 65535 || 2 * q2 > 65535)
+            return fail(HRD_EINVAL, "front-end taps do not fit the dp2a encoding");
+        t.fe_a[s] = pair16(2 * q1, 2 * q0);
+        t.fe_b[s] = pair16(0, 2 * q2);
+    }
+    for (int i = 0; i < 16; i++) t.fm_tuner[i] = pair16(quantise(k_fm_tuner[31 - 2 * i]), quantise(k_fm_tuner[30 - 2 * i]));
+    for (int i = 0; i < 4; i++) t.am1[i] = pair16(quantise(k_am1[7 - 2 * i]), quantise(k_am1[6 - 2 * i]));
+    for (int i = 0; i < 12; i++) t.am2[i] = quantise(k_am2[i]);
+    for (int i = 0; i < 16; i++) t.am3[i] = quantise(k_am3[i]);
+    for (int i = 0; i < 12; i++) t.fm_post[i] = quantise(k_fm_post[i]);
+    for (int i = 0; i < 40; i++) t.audio40[i] = quantise(k_audio40[i]);
+    for (int i = 0; i < 8; i++) t.wbfm_post1[i] = quantise(k_wbfm_post1[i]);
+    for (int i = 0; i < 31; i++) t.hilbert[i] = quantise(k_hilbert31[i]);
+    for (int i = 0; i < 16; i++) t.delay[i] = quantise(k_delay16[i]);
+    for (int i = 0; i < 8; i++) t.tx_hb8[i] = quantise(k_tx_hb8[i]);
+    t.tx_c3 = quantise(k_fe3[0]);
+    t.tx_m3 = quantise(k_fe3[1]);
+    t.tx_c7 = quantise(k_fe2[0]);
+    t.tx_m7 = quantise(k_fe2[1]);
+    t.tx_c8 = quantise(k_fe1[0]);
+    t.tx_m8 = quantise(k_fe1[1]);
+    // structural facts the kernels rely on
+    for (int i = 1; i < 31; i += 2)
+        if (t.hilbert[i] != 0) return fail(HRD_EINVAL, "Hilbert odd taps expected to be zero");
+    for (int i = 0; i < 15; i++)
+        if (t.delay[i] != 0) return fail(HRD_EINVAL, "delay-line taps expected to be zero");
+    if (t.tx_hb8[7] != 0) return fail(HRD_EINVAL, "Tx half-band tap 7 expected to be zero");
+    return HRD_OK;
+}
+
+// per-device tables ---------------------------------------------------------------------
+struct DeviceTables {
+    bool ready = false;
+    float *atan2_lut = nullptr;
+    float *nco_sin = nullptr, *nco_cos = nullptr;
+};
+std::mutex g_tab_mutex;
+DeviceTables g_dev_tables[64];
+
+int ensure_tables(int device)
+{
+    std::lock_guard<std::mutex> lock(g_tab_mutex);
+    DeviceTables &d = g_dev_tables[device];
+    if (d.ready) return HRD_OK;
+    hrd::ConstTables t;
+    int rc = build_tables(t);
+    if (rc) return rc;
+    hrd::upload_tables(t);
+    hrd::upload_tables_tx(t);
+    HRD_CUDA(cudaGetLastError());
+    // atan2 table (FmDemodulator.cc:158-170): double atan2 narrowed to float, [q+128][i+128]
+    std::vector<float> lut(65536);
+    for (int x = 0; x < 256; x++)
+        for (int y = 0; y < 256; y++) lut[(size_t)y * 256 + x] = (float)atan2((double)y - 128, (double)x - 128);
+    // NCO tables (Nco.cc:45-61): the angle is accumulated in float, sinf/cosf of it
+    std::vector<float> s(16384), c(16384);
+    float inc = (float)(2 * M_PI / 16384);
+    volatile float ang = (float)(-M_PI);
+    for (int i = 0; i < 16384; i++) {
+        s[i] = sinf(ang);
+        c[i] = cosf(ang);
+        ang = ang + inc;
+    }
+    HRD_CUDA(cudaMalloc(&d.atan2_lut, 65536 * sizeof(float)));
+    HRD_CUDA(cudaMalloc(&d.nco_sin, 16384 * sizeof(float)));
+    HRD_CUDA(cudaMalloc(&d.nco_cos, 16384 * sizeof(float)));
+    HRD_CUDA(cudaMemcpy(d.atan2_lut, lut.data(), 65536 * sizeof(float), cudaMemcpyHostToDevice));
+    HRD_CUDA(cudaMemcpy(d.nco_sin, s.data(), 16384 * sizeof(float), cudaMemcpyHostToDevice));
+    HRD_CUDA(cudaMemcpy(d.nco_cos, c.data(), 16384 * sizeof(float), cudaMemcpyHostToDevice));
+    d.ready = true;
+    return HRD_OK;
+}
+
+int kernel_kind_of_mode(int mode)
+{
+    switch (mode) {
+    case HRD_MODE_AM: return hrd::K_AM;
+    case HRD_MODE_FM: return hrd::K_FM;
+    case HRD_MODE_WBFM: return hrd::K_WBFM;
+    case HRD_MODE_LSB:
+    case HRD_MODE_USB: return hrd::K_SSB;
+    default: return hrd::K_NONE;
+    }
+}
+
+} // namespace
+
+struct hrd_batch {
+    int device = 0, n = 0, kind = HRD_RX;
+    std::vector<int32_t> mode;
+    std::vector<uint8_t> lsb;
+    std::vector<float> param[HRD_PARAM_COUNT];
+    bool dirty = true;
+    void *d_state = nullptr;
+    int32_t *d_ids = nullptr; // streams grouped by kernel kind
+    int32_t *d_all = nullptr; // 0..n-1
+    uint8_t *d_lsb = nullptr;
+    float *d_param[HRD_PARAM_COUNT] = {};
+    int group_off[5] = {}, group_cnt[5] = {};
+    void *d_in = nullptr, *d_out = nullptr;
+    size_t d_in_cap = 0, d_out_cap = 0;
+    cudaStream_t own = nullptr;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+size_t state_size(int kind) { return kind == HRD_RX ? sizeof(hrd::RxState) : sizeof(hrd::TxState); }
+
+int regroup(hrd_batch *b)
+{
+    if (!b->dirty) return HRD_OK;
+    HRD_CUDA(cudaDeviceSynchronize()); // earlier launches may still be reading the old tables
+    std::vector<int32_t> ids;
+    ids.reserve((size_t)b->n);
+    for (int k = 0; k < 5; k++) {
+        b->group_off[k] = (int)ids.size();
+        for (int s = 0; s < b->n; s++)
+            if (kernel_kind_of_mode(b->mode[(size_t)s]) == k) ids.push_back(s);
+        b->group_cnt[k] = (int)ids.size() - b->group_off[k];
+    }
+    HRD_CUDA(cudaMemcpy(b->d_ids, ids.data(), (size_t)b->n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    HRD_CUDA(cudaMemcpy(b->d_lsb, b->lsb.data(), (size_t)b->n, cudaMemcpyHostToDevice));
+    for (int p = 0; p < HRD_PARAM_COUNT; p++)
+        HRD_CUDA(cudaMemcpy(b->d_param[p], b->param[p].data(), (size_t)b->n * sizeof(float), cudaMemcpyHostToDevice));
+    b->dirty = false;
+    return HRD_OK;
+}
+
+int ensure_cap(void **ptr, size_t *cap, size_t need)
+{
+    if (*cap >= need) return HRD_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    HRD_CUDA(cudaMalloc(ptr, need));
+    *cap = need;
+    return HRD_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int check_stream_arg(hrd_batch *b, int stream)
+{
+    if (!b) return fail(HRD_EINVAL, "null batch");
+    if (stream != HRD_ALL_STREAMS && (stream < 0 || stream >= b->n))
+        return fail(HRD_EINVAL, "stream %d out of range [0,%d)", stream, b->n);
+    return HRD_OK;
+}
+
+// zero [off, off+len) of every selected stream's state record
+int zero_state(hrd_batch *b, int stream, size_t off, size_t len)
+{
+    const size_t pitch = state_size(b->kind);
+    char *base = (char *)b->d_state + off;
+    if (stream == HRD_ALL_STREAMS)
+        HRD_CUDA(cudaMemset2DAsync(base, pitch, 0, len, (size_t)b->n, b->own));
+    else
+        HRD_CUDA(cudaMemsetAsync(base + (size_t)stream * pitch, 0, len, b->own));
+    return HRD_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int hrd_abi_version(void) { return HRD_ABI_VERSION; }
+
+const char *hrd_last_error(void) { return g_err; }
+
+size_t hrd_state_bytes_per_stream(int kind) { return state_size(kind); }
+
+int hrd_get_taps(int which, int16_t *out, int cap)
+{
+    if (which < 0 || which >= k_n_tapsets || !out) return fail(HRD_EINVAL, "bad tap set %d", which);
+    for (int i = 0; i < k_tapsets[which].n && i < cap; i++) out[i] = quantise(k_tapsets[which].c[i]);
+    return k_tapsets[which].n;
+}
+
+int hrd_create(int device, int n_streams, int kind, hrd_batch_t **out)
+{
+    if (!out) return fail(HRD_EINVAL, "out is null");
+    *out = nullptr;
+    if (n_streams <= 0) return fail(HRD_EINVAL, "n_streams must be positive");
+    if (kind != HRD_RX && kind != HRD_TX) return fail(HRD_EINVAL, "kind must be HRD_RX or HRD_TX");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return fail(HRD_ENODEV, "no CUDA device: libhrd_b200 has no CPU fallback");
+    if (device < 0 || device >= count || device >= 64) return fail(HRD_ENODEV, "device %d not present", device);
+    cudaDeviceProp prop;
+    HRD_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(HRD_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(HRD_ECUDA, "cudaSetDevice(%d) failed", device);
+    int rc = ensure_tables(device);
+    if (rc) return rc;
+    hrd_batch *b = new (std::nothrow) hrd_batch;
+    if (!b) return fail(HRD_ENOMEM, "out of host memory");
+    b->device = device;
+    b->n = n_streams;
+    b->kind = kind;
+    b->mode.assign((size_t)n_streams, HRD_MODE_NONE); // IqDataProcessor.cc:70, BasebandDataProcessor ctor
+    b->lsb.assign((size_t)n_streams, 1);              // SsbDemodulator.cc:143, SsbModulator.cc:278
+    const float defaults[HRD_PARAM_COUNT] = {300.f,                              // AmDemodulator.cc:102
+                                             (float)(64000 / (2 * M_PI)),        // FmDemodulator.cc:173
+                                             (float)(256000 / (2 * M_PI)),       // WbFmDemodulator.cc:151
+                                             300.f,                              // SsbDemodulator.cc:146
+                                             0.8f,                               // AmModulator.cc:218
+                                             3500.f,                             // FmModulator.cc:218
+                                             70000.f};                           // WbFmModulator.cc:204
+    for (int p = 0; p < HRD_PARAM_COUNT; p++) b->param[p].assign((size_t)n_streams, defaults[p]);
+    cudaError_t e = cudaSuccess;
+    const size_t ssz = state_size(kind) * (size_t)n_streams;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->own, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_state, ssz);
+    if (e == cudaSuccess) e = cudaMemset(b->d_state, 0, ssz);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_ids, (size_t)n_streams * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_all, (size_t)n_streams * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_lsb, (size_t)n_streams);
+    for (int p = 0; p < HRD_PARAM_COUNT && e == cudaSuccess; p++)
+        e = cudaMalloc(&b->d_param[p], (size_t)n_streams * sizeof(float));
+    if (e == cudaSuccess) {
+        std::vector<int32_t> all((size_t)n_streams);
+        for (int s = 0; s < n_streams; s++) all[(size_t)s] = s;
+        e = cudaMemcpy(b->d_all, all.data(), (size_t)n_streams * sizeof(int32_t), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        hrd_destroy(b);
+        return fail(HRD_ECUDA, "hrd_create: %s", cudaGetErrorString(e));
+    }
+    *out = b;
+    return HRD_OK;
+}
+
+int hrd_destroy(hrd_batch_t *b)
+{
+    if (!b) return HRD_OK;
+    DeviceGuard guard(b->device);
+    if (b->own) cudaStreamSynchronize(b->own);
+    cudaFree(b->d_state);
+    cudaFree(b->d_ids);
+    cudaFree(b->d_all);
+    cudaFree(b->d_lsb);
+    for (int p = 0; p < HRD_PARAM_COUNT; p++) cudaFree(b->d_param[p]);
+    cudaFree(b->d_in);
+    cudaFree(b->d_out);
+    if (b->own) cudaStreamDestroy(b->own);
+    delete b;
+    return HRD_OK;
+}
+
+int hrd_set_mode(hrd_batch_t *b, int stream, int mode)
+{
+    int rc = check_stream_arg(b, stream);
+    if (rc) return rc;
+    if (mode < HRD_MODE_NONE || mode > HRD_MODE_USB) return fail(HRD_EINVAL, "bad mode %d", mode);
+    const int lo = stream == HRD_ALL_STREAMS ? 0 : stream, hi = stream == HRD_ALL_STREAMS ? b->n : stream + 1;
+    for (int s = lo; s < hi; s++) {
+        b->mode[(size_t)s] = mode;
+        // the sideband flag lives in the SSB object and survives mode changes
+        if (mode == HRD_MODE_LSB) b->lsb[(size_t)s] = 1;
+        if (mode == HRD_MODE_USB) b->lsb[(size_t)s] = 0;
+    }
+    b->dirty = true;
+    return HRD_OK;
+}
+
+int hrd_get_mode(hrd_batch_t *b, int stream, int *mode)
+{
+    int rc = check_stream_arg(b, stream);
+    if (rc) return rc;
+    if (stream == HRD_ALL_STREAMS || !mode) return fail(HRD_EINVAL, "hrd_get_mode needs one stream");
+    *mode = b->mode[(size_t)stream];
+    return HRD_OK;
+}
+
+int hrd_set_param(hrd_batch_t *b, int stream, int param, float value)
+{
+    int rc = check_stream_arg(b, stream);
+    if (rc) return rc;
+    if (param < 0 || param >= HRD_PARAM_COUNT) return fail(HRD_EINVAL, "bad param %d", param);
+    const int lo = stream == HRD_ALL_STREAMS ? 0 : stream, hi = stream == HRD_ALL_STREAMS ? b->n : stream + 1;
+    for (int s = lo; s < hi; s++) {
+        float &cur = b->param[param][(size_t)s];
+        switch (param) {
+        case HRD_PARAM_AM_INDEX: // AmModulator.cc:329-339: silently ignored outside 0..1
+            if (value >= 0 && value <= 1) cur = value;
+            break;
+        case HRD_PARAM_FM_DEV: // FmModulator.cc:336-346: the guard reads the member, not the argument
+            if (cur >= 0 && cur <= 3500) cur = value;
+            break;
+        case HRD_PARAM_WBFM_DEV: // WbFmModulator.cc:318-328
+            if (cur >= 0 && cur <= 112000) cur = value;
+            break;
+        default:
+            cur = value;
+        }
+    }
+    b->dirty = true;
+    return HRD_OK;
+}
+
+int hrd_get_param(hrd_batch_t *b, int stream, int param, float *value)
+{
+    int rc = check_stream_arg(b, stream);
+    if (rc) return rc;
+    if (stream == HRD_ALL_STREAMS || !value || param < 0 || param >= HRD_PARAM_COUNT)
+        return fail(HRD_EINVAL, "hrd_get_param needs one stream and a valid param");
+    *value = b->param[param][(size_t)stream];
+    return HRD_OK;
+}
+
+int hrd_reset(hrd_batch_t *b, int stream, int unit)
+{
+    int rc = check_stream_arg(b, stream);
+    if (rc) return rc;
+    DeviceGuard guard(b->device);
+    HRD_CUDA(cudaDeviceSynchronize()); // calls on one batch are serialised; make that true on the device too
+    using hrd::RxState;
+    using hrd::TxState;
+#define RANGE(T, first, next) offsetof(T, first), offsetof(T, next) - offsetof(T, first)
+    if (b->kind == HRD_RX) {
+        switch (unit) {
+        case HRD_UNIT_AM: rc = zero_state(b, stream, RANGE(RxState, am_r256, fm_r256)); break;
+        case HRD_UNIT_FM: rc = zero_state(b, stream, RANGE(RxState, fm_r256, wb_prev_theta)); break;
+        case HRD_UNIT_WBFM: // WbFmDemodulator.cc:284-298: decimators and previousTheta, not the IIR
+            rc = zero_state(b, stream, RANGE(RxState, wb_prev_theta, wb_x1));
+            if (!rc) rc = zero_state(b, stream, RANGE(RxState, wb_d256, ssb_r256));
+            break;
+        case HRD_UNIT_SSB:
+            rc = zero_state(b, stream, offsetof(RxState, ssb_r256), sizeof(RxState) - offsetof(RxState, ssb_r256));
+            break;
+        case HRD_UNIT_FRONT_END: rc = zero_state(b, stream, RANGE(RxState, fe_t, am_r256)); break;
+        case HRD_UNIT_ALL: rc = zero_state(b, stream, 0, sizeof(RxState)); break;
+        default: return fail(HRD_EINVAL, "bad unit %d", unit);
+        }
+    } else {
+        switch (unit) {
+        case HRD_UNIT_AM: rc = zero_state(b, stream, RANGE(TxState, am, fm)); break;
+        case HRD_UNIT_FM: rc = zero_state(b, stream, RANGE(TxState, fm, ssb)); break; // phase kept
+        case HRD_UNIT_SSB:
+            rc = zero_state(b, stream, RANGE(TxState, ssb, wb));
+            if (!rc) rc = zero_state(b, stream, RANGE(TxState, ssb_h8, pad));
+            break;
+        case HRD_UNIT_WBFM: rc = zero_state(b, stream, RANGE(TxState, wb, fm_phase)); break; // phase kept
+        case HRD_UNIT_ALL: rc = zero_state(b, stream, 0, sizeof(TxState)); break;
+        default: return fail(HRD_EINVAL, "bad unit %d", unit);
+        }
+    }
+#undef RANGE
+    if (rc) return rc;
+    HRD_CUDA(cudaStreamSynchronize(b->own));
+    return HRD_OK;
+}
+
+int hrd_synchronize(hrd_batch_t *b)
+{
+    if (!b) return fail(HRD_EINVAL, "null batch");
+    DeviceGuard guard(b->device);
+    HRD_CUDA(cudaDeviceSynchronize());
+    return HRD_OK;
+}
+
+int hrd_launch_count(hrd_batch_t *b, uint64_t *count)
+{
+    if (!b || !count) return fail(HRD_EINVAL, "null argument");
+    *count = b->launches;
+    return HRD_OK;
+}
+
+int hrd_get_table(hrd_batch_t *b, int which, float *out, size_t n)
+{
+    if (!b || !out) return fail(HRD_EINVAL, "null argument");
+    DeviceGuard guard(b->device);
+    const DeviceTables &d = g_dev_tables[b->device];
+    const float *src = which == 0 ? d.atan2_lut : which == 1 ? d.nco_sin : which == 2 ? d.nco_cos : nullptr;
+    const size_t have = which == 0 ? 65536 : 16384;
+    if (!src || n > have) return fail(HRD_EINVAL, "bad table request");
+    HRD_CUDA(cudaMemcpy(out, src, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return HRD_OK;
+}
+
+static int rx_common(hrd_batch_t *b, const int8_t *iq, size_t bytes, size_t iq_stride, int entry, int16_t *pcm,
+                     size_t pcm_stride, int8_t *out256, size_t out_stride, uint32_t *pcm_counts, int mem,
+                     void *cuda_stream, bool front_end_only)
+{
+    if (!b || b->kind != HRD_RX) return fail(HRD_EINVAL, "not an Rx batch");
+    if (!iq) return fail(HRD_EINVAL, "iq is null");
+    if (entry != HRD_ENTRY_2048K && entry != HRD_ENTRY_256K) return fail(HRD_EINVAL, "bad entry %d", entry);
+    const size_t unit = entry == HRD_ENTRY_2048K ? 512 : 64;
+    if (bytes % unit) return fail(HRD_EINVAL, "bytes_per_stream %zu is not a multiple of %zu", bytes, unit);
+    if (mem != HRD_MEM_HOST && mem != HRD_MEM_DEVICE) return fail(HRD_EINVAL, "bad mem %d", mem);
+    const size_t n256 = entry == HRD_ENTRY_2048K ? bytes / 16 : bytes / 2;
+    const size_t npcm = n256 / 32;
+    if (n256 > 0xffffffffu) return fail(HRD_EINVAL, "call too long");
+    if (iq_stride < bytes) return fail(HRD_EINVAL, "iq_stride smaller than bytes_per_stream");
+    if (!front_end_only && !pcm) return fail(HRD_EINVAL, "pcm is null");
+    if (!front_end_only && pcm_stride < npcm) return fail(HRD_EINVAL, "pcm_stride too small");
+    DeviceGuard guard(b->device);
+    int rc = regroup(b);
+    if (rc) return rc;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : (mem == HRD_MEM_HOST ? b->own : (cudaStream_t) nullptr);
+    if (pcm_counts)
+        for (int i = 0; i < b->n; i++)
+            pcm_counts[i] = kernel_kind_of_mode(b->mode[(size_t)i]) == hrd::K_NONE ? 0u : (uint32_t)npcm;
+    if (bytes == 0) return HRD_OK;
+
+    const int8_t *d_iq = iq;
+    int16_t *d_pcm = pcm;
+    int8_t *d_o256 = out256;
+    size_t d_iq_stride = iq_stride, d_pcm_stride = pcm_stride, d_o_stride = out_stride;
+    const size_t out_row = front_end_only ? n256 * 2 : npcm * sizeof(int16_t);
+    if (mem == HRD_MEM_HOST) {
+        const size_t in_row = (bytes + 31) & ~(size_t)31;
+        rc = ensure_cap(&b->d_in, &b->d_in_cap, in_row * (size_t)b->n);
+        if (!rc) rc = ensure_cap(&b->d_out, &b->d_out_cap, ((out_row + 31) & ~(size_t)31) * (size_t)b->n);
+        if (rc) return rc;
+        HRD_CUDA(cudaMemcpy2DAsync(b->d_in, in_row, iq, iq_stride, bytes, (size_t)b->n, cudaMemcpyHostToDevice, s));
+        d_iq = (const int8_t *)b->d_in;
+        d_iq_stride = in_row;
+        d_pcm = (int16_t *)b->d_out;
+        d_pcm_stride = ((out_row + 31) & ~(size_t)31) / sizeof(int16_t);
+        d_o256 = (int8_t *)b->d_out;
+        d_o_stride = (out_row + 31) & ~(size_t)31;
+    } else {
+        const size_t align = entry == HRD_ENTRY_2048K ? 32 : 4;
+        if (((uintptr_t)iq % align) || (iq_stride % align))
+            return fail(HRD_EINVAL, "device iq pointer/stride must be %zu-byte aligned", align);
+        if (front_end_only && (((uintptr_t)out256 % 4) || (out_stride % 4)))
+            return fail(HRD_EINVAL, "out256 pointer/stride must be 4-byte aligned");
+    }
+
+    hrd::RxParams p;
+    memset(&p, 0, sizeof p);
+    p.iq = d_iq;
+    p.iq_stride = d_iq_stride;
+    p.n256 = (uint32_t)n256;
+    p.pcm = d_pcm;
+    p.pcm_stride = d_pcm_stride;
+    p.state = (hrd::RxState *)b->d_state;
+    p.lsb = b->d_lsb;
+    p.atan2_lut = g_dev_tables[b->device].atan2_lut;
+    if (front_end_only) {
+        p.out256 = d_o256;
+        p.out_stride = d_o_stride;
+        p.stream_ids = b->d_all;
+        p.n_streams = b->n;
+        if (hrd::launch_rx(hrd::K_NONE, HRD_ENTRY_2048K, p, s)) return fail(HRD_ECUDA, "front-end launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        b->launches++;
+    } else {
+        static const int gain_of_kind[5] = {-1, HRD_PARAM_AM_GAIN, HRD_PARAM_FM_GAIN, HRD_PARAM_WBFM_GAIN,
+                                            HRD_PARAM_SSB_GAIN};
+        for (int k = 0; k < 5; k++) {
+            if (!b->group_cnt[k]) continue;
+            if (k == hrd::K_NONE && entry == HRD_ENTRY_256K) continue; // no demodulator selected: nothing runs
+            p.stream_ids = b->d_ids + b->group_off[k];
+            p.n_streams = b->group_cnt[k];
+            p.gain = k ? b->d_param[gain_of_kind[k]] : nullptr;
+            int e = hrd::launch_rx(k, entry, p, s);
+            if (e) return fail(HRD_ECUDA, "rx launch (kind %d) failed: %s", k, cudaGetErrorString((cudaError_t)e));
+            b->launches++;
+        }
+    }
+    if (mem == HRD_MEM_HOST) {
+        if (front_end_only)
+            HRD_CUDA(cudaMemcpy2DAsync(out256, out_stride, b->d_out, d_o_stride, out_row, (size_t)b->n,
+                                       cudaMemcpyDeviceToHost, s));
+        else if (npcm)
+            HRD_CUDA(cudaMemcpy2DAsync(pcm, pcm_stride * sizeof(int16_t), b->d_out, d_pcm_stride * sizeof(int16_t),
+                                       out_row, (size_t)b->n, cudaMemcpyDeviceToHost, s));
+        HRD_CUDA(cudaStreamSynchronize(s));
+    }
+    return HRD_OK;
+}
+
+int hrd_rx_process(hrd_batch_t *b, const int8_t *iq, size_t bytes_per_stream, size_t iq_stride, int entry,
+                   int16_t *pcm, size_t pcm_stride, uint32_t *pcm_counts, int mem, void *cuda_stream)
+{
+    return rx_common(b, iq, bytes_per_stream, iq_stride, entry, pcm, pcm_stride, nullptr, 0, pcm_counts, mem,
+                     cuda_stream, false);
+}
+
+int hrd_rx_front_end(hrd_batch_t *b, const int8_t *iq, size_t bytes_per_stream, size_t iq_stride, int8_t *out256k,
+                     size_t out_stride, int mem, void *cuda_stream)
+{
+    if (!out256k) return fail(HRD_EINVAL, "out256k is null");
+    if (out_stride < bytes_per_stream / 8) return fail(HRD_EINVAL, "out_stride too small");
+    return rx_common(b, iq, bytes_per_stream, iq_stride, HRD_ENTRY_2048K, nullptr, 0, out256k, out_stride, nullptr,
+                     mem, cuda_stream, true);
+}
+
+int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size_t pcm_stride, int8_t *iq,
+                   size_t iq_stride, int mem, void *cuda_stream)
+{
+    if (!b || b->kind != HRD_TX) return fail(HRD_EINVAL, "not a Tx batch");
+    if (!pcm || !iq) return fail(HRD_EINVAL, "null buffer");
+    if (mem != HRD_MEM_HOST && mem != HRD_MEM_DEVICE) return fail(HRD_EINVAL, "bad mem %d", mem);
+    if (n_per_stream > 0x7fffffu) return fail(HRD_EINVAL, "call too long");
+    if (pcm_stride < n_per_stream) return fail(HRD_EINVAL, "pcm_stride too small");
+    const size_t out_row = n_per_stream * 512;
+    if (iq_stride < out_row) return fail(HRD_EINVAL, "iq_stride too small");
+    DeviceGuard guard(b->device);
+    int rc = regroup(b);
+    if (rc) return rc;
+    if (n_per_stream == 0) return HRD_OK;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : (mem == HRD_MEM_HOST ? b->own : (cudaStream_t) nullptr);
+
+    const int16_t *d_pcm = pcm;
+    int8_t *d_iq = iq;
+    size_t d_pcm_stride = pcm_stride, d_iq_stride = iq_stride;
+    if (mem == HRD_MEM_HOST) {
+        const size_t in_row = (n_per_stream * sizeof(int16_t) + 31) & ~(size_t)31;
+        rc = ensure_cap(&b->d_in, &b->d_in_cap, in_row * (size_t)b->n);
+        if (!rc) rc = ensure_cap(&b->d_out, &b->d_out_cap, out_row * (size_t)b->n);
+        if (rc) return rc;
+        HRD_CUDA(cudaMemcpy2DAsync(b->d_in, in_row, pcm, pcm_stride * sizeof(int16_t), n_per_stream * sizeof(int16_t),
+                                   (size_t)b->n, cudaMemcpyHostToDevice, s));
+        d_pcm = (const int16_t *)b->d_in;
+        d_pcm_stride = in_row / sizeof(int16_t);
+        d_iq = (int8_t *)b->d_out;
+        d_iq_stride = out_row;
+    } else {
+        if (((uintptr_t)iq % 32) || (iq_stride % 32))
+            return fail(HRD_EINVAL, "device iq pointer/stride must be 32-byte aligned");
+        if ((uintptr_t)pcm % 2) return fail(HRD_EINVAL, "pcm pointer must be 2-byte aligned");
+    }
+    hrd::TxParams p;
+    memset(&p, 0, sizeof p);
+    p.pcm = d_pcm;
+    p.pcm_stride = d_pcm_stride;
+    p.n8 = (uint32_t)n_per_stream;
+    p.iq = d_iq;
+    p.iq_stride = d_iq_stride;
+    p.state = (hrd::TxState *)b->d_state;
+    p.lsb = b->d_lsb;
+    p.nco_sin = g_dev_tables[b->device].nco_sin;
+    p.nco_cos = g_dev_tables[b->device].nco_cos;
+    static const int param_of_kind[5] = {-1, HRD_PARAM_AM_INDEX, HRD_PARAM_FM_DEV, HRD_PARAM_WBFM_DEV, -1};
+    for (int k = 0; k < 5; k++) {
+        if (!b->group_cnt[k]) continue;
+        p.stream_ids = b->d_ids + b->group_off[k];
+        p.n_streams = b->group_cnt[k];
+        p.param = param_of_kind[k] >= 0 ? b->d_param[param_of_kind[k]] : nullptr;
+        int e = hrd::launch_tx(k, p, s);
+        if (e) return fail(HRD_ECUDA, "tx launch (kind %d) failed: %s", k, cudaGetErrorString((cudaError_t)e));
+        b->launches++;
+    }
+    if (mem == HRD_MEM_HOST) {
+        HRD_CUDA(cudaMemcpy2DAsync(iq, iq_stride, b->d_out, d_iq_stride, out_row, (size_t)b->n,
+                                   cudaMemcpyDeviceToHost, s));
+        HRD_CUDA(cudaStreamSynchronize(s));
+    }
+    return HRD_OK;
+}
+
+} // extern "C"

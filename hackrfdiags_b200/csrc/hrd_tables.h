@@ -1,0 +1,137 @@
+// hrd_tables.h -- coefficient tables, per-stream state records and kernel parameter blocks
+// shared by the host side (hrd_api.cu) and the kernels (hrd_rx.cu, hrd_tx.cu).
+//
+// The float tap values are the reference's filter designs (the data of the spec); they are
+// quantised at library load with the reference's rule (int16_t)round(c*32768) evaluated in
+// float (radioDiags/Filters/Int16/Decimator_int16.cc:56-66) -- including its overflow of
+// 1.0 to -32768 for the SSB delay line.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+
+#include <cuda_runtime.h>
+
+namespace hrd {
+
+// ---------------------------------------------------------------- taps (constant memory)
+struct ConstTables {
+    // Front end, three 3-tap half-band /2 stages (IqDataProcessor.cc:8-27), as dp2a
+    // operand pairs with DOUBLED taps so that the >>15 of the reference becomes ">>16",
+    // i.e. "take bytes 2..3":  A = {2*q[1] (centre, even sample), 2*q[0] (odd sample)},
+    // B = {0, 2*q[2]} applied to the previous word's odd sample.
+    uint32_t fe_a[3], fe_b[3];
+    // FM tuner /4, 32 taps (FmDemodulator.cc:17-51): pair i multiplies ring word 2j+i,
+    // lo half = q[31-2i] (even sample), hi half = q[30-2i] (odd sample)
+    uint32_t fm_tuner[16];
+    // AM/SSB stage 1 /4, 8 taps (AmDemodulator.cc:14-24), same pairing: lo q[7-2i], hi q[6-2i]
+    uint32_t am1[4];
+    // int16-domain decimators, plain taps
+    int32_t am2[12];        // AmDemodulator.cc:27-41    /4
+    int32_t am3[16];        // AmDemodulator.cc:44-62    /2
+    int32_t fm_post[12];    // FmDemodulator.cc:54-68    /4 (also WBFM post-demod 2)
+    int32_t audio40[40];    // FmDemodulator.cc:71-113   /2 (also WBFM audio, Tx stage 1)
+    int32_t wbfm_post1[8];  // WbFmDemodulator.cc:17-27  /4
+    int32_t hilbert[31];    // SsbDemodulator.cc:68-101, SsbModulator.cc:129-162
+    int32_t delay[16];      // SsbDemodulator.cc:65: {0,...,0,-32768}
+    // Tx half-band interpolators (AmModulator.cc:57-123)
+    int32_t tx_hb8[8];      // stages 2,4,5
+    int32_t tx_c3, tx_c7, tx_c8; // outer tap of stages 3&6 / 7 / 8 (8424 / 8249 / 8206)
+    int32_t tx_m3, tx_m7, tx_m8; // their centre taps (16384 each after quantisation)
+};
+
+// ---------------------------------------------------------------- Rx per-stream state
+// Everything a reference IqDataProcessor + its four demodulators remember between calls,
+// as filter HISTORIES (the last N-M inputs of every decimator) instead of ring buffers
+// and indices.  32-bit slots; int16 samples sit in the low half, I/Q pairs are packed
+// {I = low 16, Q = high 16}; 256 kS/s int8 samples are packed two per word as
+// {I[2p], I[2p+1], Q[2p], Q[2p+1]} (the layout dp2a wants).
+struct RxState {
+    // IqDataProcessor stage 1/2/3 decimators: the last word each stage saw
+    uint32_t fe_t, fe_v, fe_u, fe_pad;
+    // AmDemodulator
+    uint32_t am_r256[2];   // 4 samples @256k
+    uint32_t am_d64[8];    // 8 I/Q pairs @64k
+    uint32_t am_a16[14];   // 14 I/Q pairs @16k
+    float am_x1, am_y1;    // DC-removal IIR: x[n-1], y[n-1]
+    // FmDemodulator
+    uint32_t fm_r256[14];  // 28 samples @256k
+    float fm_theta[4];     // differentiator pipeline: theta[n-1..n-4], oldest first
+    int16_t fm_d64[8];     // demodulated int16 @64k
+    int16_t fm_a16[38];    // @16k
+    // WbFmDemodulator
+    float wb_prev_theta;   // previousTheta
+    float wb_x1, wb_y1;    // de-emphasis IIR: x[n-1], y[n-1]
+    uint32_t wb_pad;
+    int16_t wb_d256[4];    // int16 @256k
+    int16_t wb_d64[8];
+    int16_t wb_a16[38];
+    // SsbDemodulator
+    uint32_t ssb_r256[2];
+    uint32_t ssb_d64[8];
+    uint32_t ssb_a16[14];
+    uint32_t ssb_d8[30];   // I/Q pairs @8k for the delay line / Hilbert FIR
+    float ssb_x1, ssb_y1;
+};
+
+// ---------------------------------------------------------------- Tx per-stream state
+struct TxRail8 {           // histories of the eight interpolators of one I/Q pair
+    uint32_t s0[19];       // stage 1 input history @8k   (I/Q pairs)
+    uint32_t s1[3];        // stage 2 input history @16k
+    uint32_t s2[1];        // stage 3 @32k
+    uint32_t s3[3];        // stage 4 @64k
+    uint32_t s4[3];        // stage 5 @128k
+    uint32_t s5[1];        // stage 6 @256k
+    uint32_t s6[1];        // stage 7 @512k
+    uint32_t s7[1];        // stage 8 @1024k
+};
+
+struct TxState {
+    TxRail8 am, fm, ssb;
+    // WbFmModulator: stages 1-5 on the real PCM (low halves used), 6-8 on I/Q
+    TxRail8 wb;
+    float fm_phase;        // PhaseAccumulator::phaseAccumulator of the FM NCO (8 kS/s)
+    float wb_phase;        // ... of the WBFM NCO (256 kS/s)
+    uint32_t ssb_h8[30];   // PCM/2 history for the delay line / Hilbert FIR
+    uint32_t pad[2];
+};
+
+// ---------------------------------------------------------------- kernel parameters
+struct RxParams {
+    const int8_t *iq;
+    size_t iq_stride;          // bytes between streams
+    uint32_t n256;             // 256 kS/s samples per stream in this call (multiple of 32)
+    int16_t *pcm;
+    size_t pcm_stride;         // samples between streams
+    int8_t *out256;            // front-end-only output (may be null)
+    size_t out_stride;
+    RxState *state;
+    const int32_t *stream_ids; // streams of this launch (one mode per launch)
+    int32_t n_streams;
+    const float *gain;         // [n_streams_total] gain of this launch's demodulator
+    const uint8_t *lsb;        // [n_streams_total] SSB sideband flag
+    const float *atan2_lut;    // [256*256]
+};
+
+struct TxParams {
+    const int16_t *pcm;
+    size_t pcm_stride;
+    uint32_t n8;               // PCM samples per stream in this call
+    int8_t *iq;
+    size_t iq_stride;
+    TxState *state;
+    const int32_t *stream_ids;
+    int32_t n_streams;
+    const float *param;        // AM index / FM deviation / WBFM deviation
+    const uint8_t *lsb;
+    const float *nco_sin, *nco_cos;
+};
+
+enum { K_NONE = 0, K_AM = 1, K_FM = 2, K_WBFM = 3, K_SSB = 4 };
+
+void upload_tables(const ConstTables &t);            // hrd_rx.cu (owns the __constant__ copy)
+void upload_tables_tx(const ConstTables &t);         // hrd_tx.cu
+int launch_rx(int kind, int entry, const RxParams &p, cudaStream_t s);
+int launch_tx(int kind, const TxParams &p, cudaStream_t s);
+
+} // namespace hrd

@@ -1,0 +1,163 @@
+/*
+ * hrd.h -- C ABI of libhrd_b200.so: the HackRfDiags baseband DSP hot path on
+ * NVIDIA B200 (sm_100a), batched over thousands of independent streams.
+ *
+ * One "stream" is what one reference object graph processes:
+ *   Rx: one IqDataProcessor plus its AmDemodulator, FmDemodulator,
+ *       WbFmDemodulator and SsbDemodulator
+ *       (radioDiags/hdr_diags/IqDataProcessor.h:21-39,
+ *        radioDiags/{Am,Fm,WbFm,Ssb}Demodulator/*.h)
+ *   Tx: one AmModulator, FmModulator, WbFmModulator and SsbModulator
+ *       (radioDiags/{Am,Fm,WbFm,Ssb}Modulator/*.h) as owned by
+ *       BasebandDataProcessor (radioDiags/hdr_diags/BasebandDataProcessor.h)
+ * A batch owns n_streams of them; every stream keeps its own filter state,
+ * mode and parameters between calls exactly like the reference objects do.
+ *
+ * The reference has no FFI; its boundary is those C++ classes.  The shim
+ * classes in hackrfdiags_b200/shim/ re-create them (same names, signatures,
+ * callback behaviour) on top of this ABI with n_streams = 1; INTEGRATION.md
+ * shows how they drop into buildRadioDiags.sh.
+ *
+ * Conventions: every function returns 0 on success or a negative HRD_E*
+ * code; hrd_last_error() gives the message (thread-local).  No exceptions
+ * cross the boundary.  Calls on one batch must be serialised by the caller
+ * (same rule as the reference objects: one data thread per object).  There
+ * is NO CPU fallback: without a CUDA device hrd_create fails.
+ */
+#ifndef HRD_H
+#define HRD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HRD_ABI_VERSION 1
+
+typedef struct hrd_batch hrd_batch_t;
+
+enum { HRD_RX = 0, HRD_TX = 1 };
+
+/* IqDataProcessor::demodulatorType (IqDataProcessor.h:21); the same numbers
+ * select the modulator on Tx (BasebandDataProcessor.h modulatorType). */
+enum {
+    HRD_MODE_NONE = 0,
+    HRD_MODE_AM = 1,
+    HRD_MODE_FM = 2,
+    HRD_MODE_WBFM = 3,
+    HRD_MODE_LSB = 4,
+    HRD_MODE_USB = 5
+};
+
+/* per-stream scalar parameters and the reference setter each one replaces */
+enum {
+    HRD_PARAM_AM_GAIN = 0,   /* AmDemodulator::setDemodulatorGain   (AmDemodulator.cc:281)   default 300        */
+    HRD_PARAM_FM_GAIN = 1,   /* FmDemodulator::setDemodulatorGain   (FmDemodulator.cc:326)   default 64000/2pi  */
+    HRD_PARAM_WBFM_GAIN = 2, /* WbFmDemodulator::setDemodulatorGain (WbFmDemodulator.cc:316) default 256000/2pi */
+    HRD_PARAM_SSB_GAIN = 3,  /* SsbDemodulator::setDemodulatorGain  (SsbDemodulator.cc:393)  default 300        */
+    HRD_PARAM_AM_INDEX = 4,  /* AmModulator::setModulationIndex     (AmModulator.cc:329)  accepted iff 0<=m<=1, default 0.8 */
+    HRD_PARAM_FM_DEV = 5,    /* FmModulator::setFrequencyDeviation  (FmModulator.cc:336)  guard tests the OLD value vs 0..3500   */
+    HRD_PARAM_WBFM_DEV = 6,  /* WbFmModulator::setFrequencyDeviation(WbFmModulator.cc:318) guard tests the OLD value vs 0..112000 */
+    HRD_PARAM_COUNT = 7
+};
+
+/* which object hrd_reset addresses */
+enum {
+    HRD_UNIT_AM = 0,   /* AmDemodulator::resetDemodulator / AmModulator::resetModulator     */
+    HRD_UNIT_FM = 1,   /* Fm...   (modulator: filters only, the NCO phase is kept)          */
+    HRD_UNIT_WBFM = 2, /* WbFm... (demodulator: the de-emphasis filter is NOT reset)        */
+    HRD_UNIT_SSB = 3,  /* Ssb...                                                            */
+    HRD_UNIT_FRONT_END = 4, /* (ours) IqDataProcessor's three half-band decimators          */
+    HRD_UNIT_ALL = 5        /* (ours) everything, i.e. freshly constructed objects          */
+};
+
+enum { HRD_ENTRY_2048K = 0, /* IqDataProcessor::acceptIqData  (IqDataProcessor.cc:926)  */
+       HRD_ENTRY_256K = 1   /* <X>Demodulator::acceptIqData   (e.g. FmDemodulator.cc:353) */ };
+
+enum { HRD_MEM_HOST = 0, HRD_MEM_DEVICE = 1 };
+
+#define HRD_ALL_STREAMS (-1)
+
+enum {
+    HRD_OK = 0,
+    HRD_EINVAL = -1,   /* bad argument (size not a whole number of PCM samples, bad enum, ...) */
+    HRD_ENODEV = -2,   /* no usable CUDA device / wrong architecture */
+    HRD_ECUDA = -3,    /* CUDA runtime error, see hrd_last_error()   */
+    HRD_ENOMEM = -4
+};
+
+/* ---- lifetime ------------------------------------------------------- */
+int hrd_abi_version(void);
+int hrd_create(int device, int n_streams, int kind, hrd_batch_t **out);
+int hrd_destroy(hrd_batch_t *b);
+const char *hrd_last_error(void);
+
+/* ---- control (replaces the reference's unsynchronised member writes) - */
+/* IqDataProcessor::setDemodulatorMode (IqDataProcessor.cc:346-372; LSB/USB
+ * also flip the SSB demodulator's sideband) or, on a Tx batch,
+ * BasebandDataProcessor::setModulatorMode (+ Ssb set{Lsb,Usb}ModulationMode). */
+int hrd_set_mode(hrd_batch_t *b, int stream, int mode);
+int hrd_get_mode(hrd_batch_t *b, int stream, int *mode);
+int hrd_set_param(hrd_batch_t *b, int stream, int param, float value);
+int hrd_get_param(hrd_batch_t *b, int stream, int param, float *value);
+int hrd_reset(hrd_batch_t *b, int stream, int unit);
+
+/* ---- receive --------------------------------------------------------- */
+/*
+ * One call = one reference call on every stream:
+ *   entry 2048K: IqDataProcessor::acceptIqData(ts, iq, bytes_per_stream)
+ *   entry 256K : <mode's demodulator>::acceptIqData(iq, bytes_per_stream)
+ * iq        int8 interleaved I,Q; stream s starts at iq + s*iq_stride bytes
+ *           (16-byte aligned starts)
+ * bytes_per_stream  multiple of 512 (2048K) or 64 (256K): whole PCM samples.
+ *           Unlike the reference there is no 262144 / 32768 byte ceiling.
+ * pcm       int16 out; stream s starts at pcm + s*pcm_stride samples; gets
+ *           bytes_per_stream/512 (resp. /64) samples, 0 when the mode is NONE
+ * pcm_counts  optional, host memory, n_streams entries
+ * mem       HRD_MEM_HOST: pointers are host memory, copied through pinned
+ *           staging inside the call (the call returns when pcm is ready);
+ *           HRD_MEM_DEVICE: device pointers, work is queued on cuda_stream
+ *           and the call returns without synchronising
+ * cuda_stream  a cudaStream_t (NULL = the legacy default stream)
+ */
+int hrd_rx_process(hrd_batch_t *b, const int8_t *iq, size_t bytes_per_stream, size_t iq_stride,
+                   int entry, int16_t *pcm, size_t pcm_stride, uint32_t *pcm_counts, int mem,
+                   void *cuda_stream);
+
+/* IqDataProcessor::reduceSampleRate + upconvertByFsOver4 only
+ * (IqDataProcessor.cc:429-500, 771-815): the 256 kS/s int8 I,Q stream the
+ * reference can dump over UDP.  out256k gets bytes_per_stream/8 bytes per
+ * stream at out_stride.  Advances the front-end state like the real call. */
+int hrd_rx_front_end(hrd_batch_t *b, const int8_t *iq, size_t bytes_per_stream, size_t iq_stride,
+                     int8_t *out256k, size_t out_stride, int mem, void *cuda_stream);
+
+/* ---- transmit -------------------------------------------------------- */
+/*
+ * One call = <mode's modulator>::acceptData(pcm, n_per_stream, iq, &len) on
+ * every stream (e.g. AmModulator.cc:366-381).  pcm is int16 at 8 kS/s,
+ * stream s at pcm + s*pcm_stride samples; iq gets n_per_stream*512 bytes of
+ * int8 I,Q at 2.048 MS/s at iq + s*iq_stride bytes (32-byte aligned starts).
+ * Mode NONE writes the idle carrier BasebandDataProcessor uses: every byte
+ * 64 (BasebandDataProcessor.cc:689-694).  No 512-sample ceiling.
+ */
+int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size_t pcm_stride,
+                   int8_t *iq, size_t iq_stride, int mem, void *cuda_stream);
+
+/* ---- introspection (tests, bench) ------------------------------------ */
+int hrd_synchronize(hrd_batch_t *b);
+/* kernels this batch has launched so far (bench.py's gpu_launches) */
+int hrd_launch_count(hrd_batch_t *b, uint64_t *count);
+/* copy a device table back: 0 = atan2 LUT (65536 floats), 1 = NCO sin,
+ * 2 = NCO cos (16384 floats each) */
+int hrd_get_table(hrd_batch_t *b, int which, float *out, size_t n);
+/* quantised taps as uploaded, same numbering as oracle/hrd_oracle.h HRO_TAPS_* */
+int hrd_get_taps(int which, int16_t *out, int cap);
+/* bytes of per-stream state the batch keeps in HBM */
+size_t hrd_state_bytes_per_stream(int kind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HRD_H */

@@ -1,0 +1,118 @@
+"""GPU parity, small sizes: CUDA path (through the C ABI) vs the CPU oracle, bit for bit."""
+import numpy as np
+import pytest
+
+from hackrfdiags_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+RX_MODES = [capi.MODE_AM, capi.MODE_FM, capi.MODE_WBFM, capi.MODE_LSB, capi.MODE_USB]
+NAMES = {1: "am", 2: "fm", 3: "wbfm", 4: "lsb", 5: "usb"}
+
+
+def _diff(a, b):
+    d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+    return int(d.max()) if d.size else 0, int((d != 0).sum())
+
+
+def test_tables_match_oracle(oracle):
+    b = capi.Batch(1, capi.RX)
+    assert np.array_equal(b.get_table(0).view(np.uint32), oracle.atan2_table().ravel().view(np.uint32))
+    s, c = oracle.nco_tables()
+    assert np.array_equal(b.get_table(1).view(np.uint32), s.view(np.uint32))
+    assert np.array_equal(b.get_table(2).view(np.uint32), c.view(np.uint32))
+    for i in range(13):
+        assert np.array_equal(capi.get_taps(i), oracle.taps(i))
+
+
+def test_front_end_bit_exact(oracle):
+    n_streams, n = 12, 131072 + 4096
+    iq = synth.rx_batch(capi.MODE_FM, n_streams, n)
+    b = capi.Batch(n_streams, capi.RX)
+    got = [b.rx_front_end(iq[:, :2 * 131072]), b.rx_front_end(iq[:, 2 * 131072:])]
+    for s in range(n_streams):
+        h = oracle.rx_new()
+        w0 = oracle.rx_front_end(h, iq[s, :2 * 131072])
+        w1 = oracle.rx_front_end(h, iq[s, 2 * 131072:])
+        oracle.rx_free(h)
+        assert np.array_equal(got[0][s], w0), f"stream {s} call 0"
+        assert np.array_equal(got[1][s], w1), f"stream {s} call 1"
+
+
+@pytest.mark.parametrize("mode", RX_MODES)
+def test_rx_2048k_bit_exact(oracle, mode):
+    n_streams, n = 16, 2 * 131072 + 8192 + 256
+    iq = synth.rx_batch(mode, n_streams, n)
+    b = capi.Batch(n_streams, capi.RX)
+    b.set_mode(mode)
+    got = b.rx(iq)
+    assert got.shape == (n_streams, n // 256)
+    for s in range(n_streams):
+        want = oracle.run_rx(mode, iq[s])
+        mx, cnt = _diff(got[s], want)
+        assert mx == 0, f"{NAMES[mode]} stream {s}: max abs err {mx}, {cnt} mismatches of {want.size}"
+
+
+@pytest.mark.parametrize("mode", RX_MODES)
+def test_rx_256k_bit_exact(oracle, mode):
+    n_streams, n = 8, 3 * 16384 + 32 * 5
+    iq = synth.rx_batch(mode, n_streams, n, entry="256k")
+    b = capi.Batch(n_streams, capi.RX)
+    b.set_mode(mode)
+    got = b.rx(iq, entry=capi.ENTRY_256K)
+    for s in range(n_streams):
+        want = oracle.run_rx(mode, iq[s], entry="256k")
+        mx, cnt = _diff(got[s], want)
+        assert mx == 0, f"{NAMES[mode]} stream {s}: max abs err {mx}, {cnt} mismatches"
+
+
+@pytest.mark.parametrize("mode", RX_MODES)
+def test_rx_streaming_state(oracle, mode):
+    """Many calls of odd sizes == one long call == the oracle."""
+    n_streams = 6
+    sizes = [256, 512, 131072, 256 * 33, 8192, 256 * 7]
+    iq = synth.rx_batch(mode, n_streams, sum(sizes), config=1)
+    b = capi.Batch(n_streams, capi.RX)
+    b.set_mode(mode)
+    parts, off = [], 0
+    for sz in sizes:
+        parts.append(b.rx(np.ascontiguousarray(iq[:, 2 * off:2 * (off + sz)])))
+        off += sz
+    got = np.concatenate(parts, axis=1)
+    for s in range(n_streams):
+        want = oracle.run_rx(mode, iq[s])
+        mx, cnt = _diff(got[s], want)
+        assert mx == 0, f"{NAMES[mode]} stream {s}: max abs err {mx}, {cnt} mismatches"
+
+
+@pytest.mark.parametrize("mode", RX_MODES)
+def test_tx(oracle, mode):
+    n_streams, n = 10, 32 * 5 + 17
+    pcm = synth.tx_batch(n_streams, n)
+    b = capi.Batch(n_streams, capi.TX)
+    b.set_mode(mode)
+    got = b.tx(pcm)
+    tol = 1 if mode == capi.MODE_FM else 0  # Nco::run calls libm sinf/cosf: <= 1 LSB allowed
+    for s in range(n_streams):
+        want = oracle.run_tx(mode, pcm[s])
+        mx, cnt = _diff(got[s], want)
+        assert mx <= tol, f"{NAMES[mode]} stream {s}: max abs err {mx}, {cnt} mismatches of {want.size}"
+
+
+@pytest.mark.parametrize("mode", RX_MODES)
+def test_tx_streaming_state(oracle, mode):
+    n_streams = 5
+    sizes = [1, 31, 32, 33, 512, 100]
+    pcm = synth.tx_batch(n_streams, sum(sizes), config=2)
+    b = capi.Batch(n_streams, capi.TX)
+    b.set_mode(mode)
+    parts, off = [], 0
+    for sz in sizes:
+        parts.append(b.tx(np.ascontiguousarray(pcm[:, off:off + sz])))
+        off += sz
+    got = np.concatenate(parts, axis=1)
+    tol = 1 if mode == capi.MODE_FM else 0
+    for s in range(n_streams):
+        want = oracle.run_tx(mode, pcm[s])
+        mx, cnt = _diff(got[s], want)
+        assert mx <= tol, f"{NAMES[mode]} stream {s}: max abs err {mx}, {cnt} mismatches"
