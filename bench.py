@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for the HackRfDiags baseband DSP hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (ours: CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  (the reference's own CPU chain)
+
+Workload at every N (weak scaling, per GPU): BASELINE.json configs[1], "batched AM and SSB
+demod: 1024 independent synthetic IQ streams on 1 B200" -- 512 AM + 256 LSB + 256 USB streams,
+1 s of int8 IQ at 2.048 MS/s each (4.29 GB in, 16.8 MB of PCM out per step), entered at
+IqDataProcessor::acceptIqData.  A step is one pass over that batch; stream state carries from
+step to step exactly as consecutive reference calls would.  `value` is input IQ MS/s with the
+inputs resident in HBM; `e2e` is the same through hrd_rx_process with pinned HOST buffers
+(H2D of all IQ and D2H of all PCM inside the timed region).  Extra keys give every other
+mode (Rx and Tx, 4096 streams) with its own roofline fraction.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+FS = 2_048_000
+BYTES_PER_IN_SAMPLE_RX = 2.0 + 2.0 / 256.0
+BYTES_PER_OUT_SAMPLE_TX = 2.0 + 2.0 / 256.0
+METRIC = "aggregate input IQ MS/s (config 2: AM+SSB demod, 1024 streams/GPU, 2.048 MS/s entry)"
+UNIT = "MS/s"
+
+MODE_NAMES = {1: "am", 2: "fm", 3: "wbfm", 4: "lsb", 5: "usb"}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------
+# synthetic inputs generated on the device (same signal classes as hackrfdiags_b200/synth.py)
+# ----------------------------------------------------------------------------------------
+def make_rx_iq_device(torch, mode, n_distinct, n_samples, device, seed):
+    """[n_distinct, 2*n_samples] int8: carrier at -64 kHz, signal of `mode`, amplitude / noise cycled."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    t = torch.arange(n_samples, device=device, dtype=torch.float64) / FS
+    two_pi = 2.0 * 3.141592653589793
+    out = torch.empty((n_distinct, 2 * n_samples), dtype=torch.int8, device=device)
+    amps = (20.0, 60.0, 100.0, 127.0)
+    sigmas = (1.0, 3.0, 10.0)
+    for s in range(n_distinct):
+        amp, sigma = amps[s % 4], sigmas[(s // 4) % 3]
+        if mode == 1:
+            env = (1.0 + 0.8 * torch.sin(two_pi * 1000.0 * t)) / 1.8
+            ph = torch.zeros_like(t)
+        elif mode == 2:
+            env = torch.ones_like(t)
+            ph = 3.0 * (1.0 - torch.cos(two_pi * 1000.0 * t))
+        elif mode == 3:
+            env = torch.ones_like(t)
+            ph = 45.0 * (1.0 - torch.cos(two_pi * 1000.0 * t)) + 3.0 * (1.0 - torch.cos(two_pi * 10000.0 * t))
+        else:
+            sign = -1.0 if mode == 4 else 1.0
+            a, b = sign * two_pi * 700.0 * t, sign * two_pi * 1900.0 * t
+            re, im = 0.5 * (torch.cos(a) + torch.cos(b)), 0.5 * (torch.sin(a) + torch.sin(b))
+            env = torch.sqrt(re * re + im * im)
+            ph = torch.atan2(im, re)
+        ph = ph + two_pi * (-64000.0) * t
+        i = amp * env * torch.cos(ph) + sigma * torch.randn(n_samples, device=device, dtype=torch.float64, generator=g)
+        q = amp * env * torch.sin(ph) + sigma * torch.randn(n_samples, device=device, dtype=torch.float64, generator=g)
+        out[s, 0::2] = torch.clamp(torch.round(i), -128, 127).to(torch.int8)
+        out[s, 1::2] = torch.clamp(torch.round(q), -128, 127).to(torch.int8)
+    return out
+
+
+def make_tx_pcm_device(torch, n_distinct, n_samples, device, seed):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    t = torch.arange(n_samples, device=device, dtype=torch.float64) / 8000.0
+    out = torch.empty((n_distinct, n_samples), dtype=torch.int16, device=device)
+    for s in range(n_distinct):
+        k = s % 3
+        if k == 0:
+            x = -32768.0 * torch.cos(2 * 3.141592653589793 * (300.0 + 97.0 * s % 3100.0) * t)
+        elif k == 1:
+            x = torch.randint(-32768, 32768, (n_samples,), device=device, generator=g).to(torch.float64)
+        else:
+            x = 12000.0 * torch.sin(2 * 3.141592653589793 * 440.0 * t) * (0.5 + 0.5 * torch.sin(2 * 3.141592653589793 * 3.0 * t))
+        out[s] = torch.clamp(torch.round(x), -32768, 32767).to(torch.int16)
+    return out
+
+
+def tile_rows(torch, distinct, n_rows):
+    reps = (n_rows + distinct.shape[0] - 1) // distinct.shape[0]
+    return distinct.repeat(reps, 1)[:n_rows].contiguous()
+
+
+# ----------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(gpu_index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.tmp.read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------
+def time_calls(torch, calls, steps, warmup):
+    """calls: list of zero-arg launchers (one kernel each).  Returns (ms_per_step, [ms per call])."""
+    for _ in range(warmup):
+        for c in calls:
+            c()
+    torch.cuda.synchronize()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(calls) + 1)] for _ in range(steps)]
+    for k in range(steps):
+        ev[k][0].record()
+        for j, c in enumerate(calls):
+            c()
+            ev[k][j + 1].record()
+    torch.cuda.synchronize()
+    total = ev[0][0].elapsed_time(ev[-1][-1])
+    per_call = [sum(ev[k][j].elapsed_time(ev[k][j + 1]) for k in range(steps)) / steps for j in range(len(calls))]
+    return total / steps, per_call
+
+
+def bench_rx_modes(torch, capi, device, groups, n_samples, steps, warmup, seed):
+    """groups: list of (mode, n_streams).  One batch (= one kernel launch per step) per group."""
+    stream = torch.cuda.current_stream().cuda_stream
+    calls, keep = [], []
+    for mode, n in groups:
+        distinct = make_rx_iq_device(torch, mode, min(n, 32), n_samples, device, seed + mode)
+        iq = tile_rows(torch, distinct, n)
+        del distinct
+        pcm = torch.zeros((n, n_samples // 256), dtype=torch.int16, device=device)
+        b = capi.Batch(n, capi.RX, device.index or 0)
+        b.set_mode(mode)
+        keep.append((b, iq, pcm))
+        calls.append(lambda b=b, iq=iq, pcm=pcm: b.rx_device(iq.data_ptr(), iq.shape[1], iq.stride(0), pcm.data_ptr(),
+                                                             pcm.stride(0), capi.ENTRY_2048K, stream))
+    ms_step, per_call = time_calls(torch, calls, steps, warmup)
+    launches = sum(k[0].launch_count() for k in keep)
+    return ms_step, per_call, launches, keep
+
+
+def bench_tx_mode(torch, capi, device, mode, n, n_pcm, steps, warmup, seed):
+    stream = torch.cuda.current_stream().cuda_stream
+    distinct = make_tx_pcm_device(torch, min(n, 32), n_pcm, device, seed)
+    pcm = tile_rows(torch, distinct, n)
+    iq = torch.empty((n, n_pcm * 512), dtype=torch.int8, device=device)
+    b = capi.Batch(n, capi.TX, device.index or 0)
+    b.set_mode(mode)
+    call = lambda: b.tx_device(pcm.data_ptr(), n_pcm, pcm.stride(0), iq.data_ptr(), iq.stride(0), stream)
+    ms_step, per_call = time_calls(torch, [call], steps, warmup)
+    return ms_step
+
+
+def run_ours(args):
+    import torch
+    from hackrfdiags_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    peak, peak_src = measured_peak_gbs()
+
+    n_samples = int(args.seconds * FS) // 8192 * 8192
+    groups = [(1, args.streams // 2), (4, args.streams // 4), (5, args.streams - args.streams // 2 - args.streams // 4)]
+    in_samples_per_step = args.streams * n_samples
+
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_step, per_call, launches, keep = bench_rx_modes(torch, capi, device, groups, n_samples, args.steps, args.warmup,
+                                                       seed=1234 + rank)
+    torch.cuda.synchronize()
+    t_local = torch.tensor([ms_step], device=device, dtype=torch.float64)
+    if dist:
+        dist.barrier()
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+    ms_max = float(t_local.item())
+    clocks = sampler.stop() if sampler else None
+    value = world * in_samples_per_step / (ms_max * 1e-3) / 1e6
+
+    # roofline of the dominant kernel: the AM launch (half the streams, the longest launch)
+    dom = max(range(len(groups)), key=lambda j: per_call[j])
+    dom_bytes = groups[dom][1] * n_samples * BYTES_PER_IN_SAMPLE_RX
+    achieved = dom_bytes / (per_call[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": f"rx_kernel<{MODE_NAMES[groups[dom][0]].upper()},2048k>",
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": round(per_call[dom], 4)}
+
+    out = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_max, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int8 in / int32 accumulate (Q15) / f32 IIR", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: 1024 streams/GPU = 512 AM + 256 LSB + 256 USB, "
+                               f"{n_samples / FS:.3f} s of int8 IQ @2.048 MS/s each, IqDataProcessor entry",
+                   "streams_per_gpu": args.streams, "input_bytes_per_step_per_gpu": 2 * in_samples_per_step,
+                   "l2": "inputs per step exceed the 126 MB L2 many times over; no flush needed",
+                   "sharding": "disjoint stream sets per GPU, no collective"},
+        "roofline": roofline, "gpu_launches": launches * world,
+    }
+    if clocks:
+        out["clocks"] = clocks
+    del keep
+    torch.cuda.empty_cache()
+
+    if rank == 0 and not args.quick:
+        out["e2e"] = run_e2e(torch, capi, device, args, groups, n_samples, world)
+        if world == 1:
+            out["modes"] = run_mode_sweep(torch, capi, device, args, peak)
+            out["cpu_baseline"] = cpu_baseline(args, groups)
+    elif rank == 0:
+        out["e2e"] = run_e2e(torch, capi, device, args, groups, n_samples, world)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def run_e2e(torch, capi, device, args, groups, n_samples, world):
+    """Same workload through the C ABI with pinned HOST buffers: H2D + kernels + D2H per step."""
+    steps = max(2, min(args.steps, 5))
+    bufs = []
+    for mode, n in groups:
+        distinct = make_rx_iq_device(torch, mode, min(n, 32), n_samples, device, 99 + mode)
+        host_iq = torch.empty((n, 2 * n_samples), dtype=torch.int8, pin_memory=True)
+        host_iq.copy_(tile_rows(torch, distinct, n))
+        host_pcm = torch.empty((n, n_samples // 256), dtype=torch.int16, pin_memory=True)
+        b = capi.Batch(n, capi.RX, device.index or 0)
+        b.set_mode(mode)
+        bufs.append((b, host_iq, host_pcm))
+        del distinct
+    torch.cuda.synchronize()
+
+    def step():
+        for b, hi, hp in bufs:
+            b.rx_host_ptr(hi.data_ptr(), hi.shape[1], hi.stride(0), hp.data_ptr(), hp.stride(0))
+
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()  # each call returns only when its PCM is in host memory
+    dt = (time.perf_counter() - t0) / steps
+    h2d = sum(hi.numel() for _, hi, _ in bufs)
+    d2h = sum(hp.numel() * 2 for _, _, hp in bufs)
+    value = args.streams * n_samples / dt / 1e6
+    return {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": round(dt * 1e3, 3), "steps": steps,
+            "note": "hrd_rx_process(HRD_MEM_HOST) on pinned buffers, per GPU; this rank only"}
+
+
+def run_mode_sweep(torch, capi, device, args, peak):
+    """Every other chain at 4096 streams: MS/s and fraction of the HBM roofline."""
+    res = {}
+    n_streams = args.sweep_streams
+    n_samples = int(args.sweep_seconds * FS) // 8192 * 8192
+    for mode in (1, 2, 3, 4):
+        ms, per_call, _, keep = bench_rx_modes(torch, capi, device, [(mode, n_streams)], n_samples, 3, 2, seed=7)
+        del keep
+        torch.cuda.empty_cache()
+        sps = n_streams * n_samples / (ms * 1e-3)
+        res[f"rx_{MODE_NAMES[mode]}"] = {"streams": n_streams, "MS/s": round(sps / 1e6, 1), "ms": round(ms, 3),
+                                         "hbm_frac": round(sps * BYTES_PER_IN_SAMPLE_RX / 1e9 / peak, 4)}
+    n_pcm = n_samples // 256
+    for mode in (1, 2, 3, 4):
+        ms = bench_tx_mode(torch, capi, device, mode, n_streams, n_pcm, 3, 2, seed=11)
+        torch.cuda.empty_cache()
+        sps = n_streams * n_pcm * 256 / (ms * 1e-3)
+        res[f"tx_{MODE_NAMES[mode]}"] = {"streams": n_streams, "MS/s": round(sps / 1e6, 1), "ms": round(ms, 3),
+                                         "hbm_frac": round(sps * BYTES_PER_OUT_SAMPLE_TX / 1e9 / peak, 4)}
+    return res
+
+
+# ----------------------------------------------------------------------------------------
+# CPU arms (the compiled reference, oracle/_ref/libhrd_ref.so; falls back to nothing else)
+# ----------------------------------------------------------------------------------------
+def cpu_sample(groups, n_streams_total, seconds):
+    """A bounded sample of the same workload: same mode mix, fewer streams."""
+    import numpy as np
+    from hackrfdiags_b200 import synth
+    n_samples = int(seconds * FS) // 8192 * 8192
+    total = sum(n for _, n in groups)
+    parts = []
+    for mode, n in groups:
+        k = max(1, round(n_streams_total * n / total))
+        distinct = np.stack([synth.rx_stream(mode, n_samples, stream=s) for s in range(min(k, 4))])
+        parts.append((mode, np.ascontiguousarray(np.tile(distinct, ((k + 3) // 4, 1))[:k])))
+    return parts, n_samples
+
+
+def time_reference(parts, n_samples, cores):
+    from cpu_checkers import Ref
+    ref = Ref()
+    t = 0.0
+    for mode, iq in parts:
+        dt, _ = ref.bench_rx(mode, iq, cores)
+        t += dt
+    n = sum(iq.shape[0] for _, iq in parts)
+    return n * n_samples / t / 1e6, t
+
+
+def cpu_baseline(args, groups):
+    cores = os.cpu_count() or 1
+    try:
+        parts, n_samples = cpu_sample(groups, 16 * cores, 1.0)
+        time_reference(parts, n_samples, cores)  # warm
+        value, t = time_reference(parts, n_samples, cores)
+        return {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": f"{sum(p[1].shape[0] for p in parts)} streams x {n_samples / FS:.3f} s, same AM/LSB/USB mix, "
+                          f"unmodified reference classes (oracle/_ref), one object graph per stream, "
+                          f"{cores} threads, {t:.2f} s wall"}
+    except Exception as e:  # the checker library is missing: report, do not substitute anything
+        return {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": f"unavailable: {e}"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    groups = [(1, args.streams // 2), (4, args.streams // 4), (5, args.streams - args.streams // 2 - args.streams // 4)]
+    parts, n_samples = cpu_sample(groups, 16 * cores, 1.0)
+    for _ in range(max(1, min(args.warmup, 2))):
+        time_reference(parts, n_samples, cores)
+    t_tot, n_tot = 0.0, 0
+    for _ in range(args.steps):
+        v, t = time_reference(parts, n_samples, cores)
+        t_tot += t
+        n_tot += sum(p[1].shape[0] for p in parts) * n_samples
+    value = n_tot / t_tot / 1e6
+    sample = (f"each step: {sum(p[1].shape[0] for p in parts)} streams x {n_samples / FS:.3f} s of the same "
+              f"AM/LSB/USB mix through the unmodified reference classes (oracle/_ref/libhrd_ref.so), "
+              f"{cores} host threads")
+    out = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT,
+           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": round(t_tot / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "int16 Q15 / f32 (reference CPU arithmetic)", "data": "synthetic",
+           "config": {"workload": "BASELINE configs[1] mode mix, bounded sample (see cpu_baseline.sample)"},
+           "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "reference",
+                            "sample": sample},
+           "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=1024, help="streams per GPU (config 2)")
+    ap.add_argument("--seconds", type=float, default=1.0, help="signal seconds per stream per step")
+    ap.add_argument("--sweep-streams", type=int, default=4096)
+    ap.add_argument("--sweep-seconds", type=float, default=0.5)
+    ap.add_argument("--quick", action="store_true", help="skip the mode sweep and the CPU baseline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
