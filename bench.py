@@ -31,6 +31,9 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 FS = 2_048_000
 BYTES_PER_IN_SAMPLE_RX = 2.0 + 2.0 / 256.0
 BYTES_PER_OUT_SAMPLE_TX = 2.0 + 2.0 / 256.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one rx_kernel<AM+SSB> launch of this workload, from the
+# committed ncu --set full capture (profiles/); None until one has been taken for the current kernel
+NCU_TRAFFIC_BYTES = None
 METRIC = "aggregate input IQ MS/s (config 2: AM+SSB demod, 1024 streams/GPU, 2.048 MS/s entry)"
 UNIT = "MS/s"
 
@@ -160,7 +163,7 @@ class ClockSampler:
 # our arm
 # ----------------------------------------------------------------------------------------
 def time_calls(torch, calls, steps, warmup):
-    """calls: list of zero-arg launchers (one kernel each).  Returns (ms_per_step, [ms per call])."""
+    """calls: list of zero-arg launchers.  Returns (ms_per_step, [ms per call])."""
     for _ in range(warmup):
         for c in calls:
             c()
@@ -177,23 +180,39 @@ def time_calls(torch, calls, steps, warmup):
     return total / steps, per_call
 
 
-def bench_rx_modes(torch, capi, device, groups, n_samples, steps, warmup, seed):
-    """groups: list of (mode, n_streams).  One batch (= one kernel launch per step) per group."""
-    stream = torch.cuda.current_stream().cuda_stream
-    calls, keep = [], []
-    for mode, n in groups:
-        distinct = make_rx_iq_device(torch, mode, min(n, 32), n_samples, device, seed + mode)
-        iq = tile_rows(torch, distinct, n)
+def make_rx_batch(torch, capi, device, groups, n_samples, seed):
+    """ONE batch holding every group's streams: groups = [(mode, n_streams)]; returns (batch, iq, pcm)."""
+    n = sum(g[1] for g in groups)
+    iq = torch.empty((n, 2 * n_samples), dtype=torch.int8, device=device)
+    b = capi.Batch(n, capi.RX, device.index or 0)
+    at = 0
+    for mode, cnt in groups:
+        distinct = make_rx_iq_device(torch, mode, min(cnt, 32), n_samples, device, seed + mode)
+        iq[at:at + cnt] = tile_rows(torch, distinct, cnt)
         del distinct
-        pcm = torch.zeros((n, n_samples // 256), dtype=torch.int16, device=device)
-        b = capi.Batch(n, capi.RX, device.index or 0)
-        b.set_mode(mode)
-        keep.append((b, iq, pcm))
-        calls.append(lambda b=b, iq=iq, pcm=pcm: b.rx_device(iq.data_ptr(), iq.shape[1], iq.stride(0), pcm.data_ptr(),
-                                                             pcm.stride(0), capi.ENTRY_2048K, stream))
-    ms_step, per_call = time_calls(torch, calls, steps, warmup)
-    launches = sum(k[0].launch_count() for k in keep)
-    return ms_step, per_call, launches, keep
+        for s in range(at, at + cnt):
+            b.set_mode(mode, s)
+        at += cnt
+    pcm = torch.zeros((n, n_samples // 256), dtype=torch.int16, device=device)
+    return b, iq, pcm
+
+
+def bench_rx_modes(torch, capi, device, groups, n_samples, steps, warmup, seed):
+    """One batch, one hrd_rx_process call per step.  Returns (ms_per_step, kernel_ms, tail_ms, launches, keep):
+    kernel_ms = the tile kernel(s) alone, tail_ms = the AM/SSB IIR pass, both from CUDA events the
+    library records on the launching stream inside the timed steps (HRD_OPT_PROFILE)."""
+    stream = torch.cuda.current_stream().cuda_stream
+    b, iq, pcm = make_rx_batch(torch, capi, device, groups, n_samples, seed)
+    b.set_option(capi.OPT_PROFILE, 1)
+    call = lambda: b.rx_device(iq.data_ptr(), iq.shape[1], iq.stride(0), pcm.data_ptr(), pcm.stride(0),
+                               capi.ENTRY_2048K, stream)
+    l0 = b.launch_count()
+    ms_step, _ = time_calls(torch, [call], steps, warmup)
+    launches = (b.launch_count() - l0) * steps // (steps + warmup)
+    k = min(steps, 32)
+    kernel_ms = sum(b.kernel_ms(0, a) for a in range(k)) / k
+    tail_ms = sum(b.kernel_ms(1, a) for a in range(k)) / k
+    return ms_step, kernel_ms, tail_ms, launches, (b, iq, pcm)
 
 
 def bench_tx_mode(torch, capi, device, mode, n, n_pcm, steps, warmup, seed):
@@ -233,8 +252,8 @@ def run_ours(args):
         dist.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_step, per_call, launches, keep = bench_rx_modes(torch, capi, device, groups, n_samples, args.steps, args.warmup,
-                                                       seed=1234 + rank)
+    ms_step, kernel_ms, tail_ms, launches, keep = bench_rx_modes(torch, capi, device, groups, n_samples, args.steps,
+                                                                 args.warmup, seed=1234 + rank)
     torch.cuda.synchronize()
     t_local = torch.tensor([ms_step], device=device, dtype=torch.float64)
     if dist:
@@ -244,14 +263,14 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     value = world * in_samples_per_step / (ms_max * 1e-3) / 1e6
 
-    # roofline of the dominant kernel: the AM launch (half the streams, the longest launch)
-    dom = max(range(len(groups)), key=lambda j: per_call[j])
-    dom_bytes = groups[dom][1] * n_samples * BYTES_PER_IN_SAMPLE_RX
-    achieved = dom_bytes / (per_call[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": f"rx_kernel<{MODE_NAMES[groups[dom][0]].upper()},2048k>",
+    # roofline of the dominant kernel: the AM+SSB tile kernel (one launch covers all 1024 streams)
+    dom_bytes = in_samples_per_step * BYTES_PER_IN_SAMPLE_RX
+    achieved = dom_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "rx_kernel<AM+SSB, 2048k entry>",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": round(per_call[dom], 4)}
+                "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": round(kernel_ms, 4),
+                "tail_kernel": {"name": "rx_dc_iir_kernel", "avg_launch_ms": round(tail_ms, 4)}}
 
     out = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -263,6 +282,7 @@ def run_ours(args):
                    "l2": "inputs per step exceed the 126 MB L2 many times over; no flush needed",
                    "sharding": "disjoint stream sets per GPU, no collective"},
         "roofline": roofline, "gpu_launches": launches * world,
+        "call_ms": {"tile_kernel": round(kernel_ms, 4), "iir_tail": round(tail_ms, 4)},
     }
     if clocks:
         out["clocks"] = clocks
@@ -286,32 +306,24 @@ def run_ours(args):
 def run_e2e(torch, capi, device, args, groups, n_samples, world):
     """Same workload through the C ABI with pinned HOST buffers: H2D + kernels + D2H per step."""
     steps = max(2, min(args.steps, 5))
-    bufs = []
-    for mode, n in groups:
-        distinct = make_rx_iq_device(torch, mode, min(n, 32), n_samples, device, 99 + mode)
-        host_iq = torch.empty((n, 2 * n_samples), dtype=torch.int8, pin_memory=True)
-        host_iq.copy_(tile_rows(torch, distinct, n))
-        host_pcm = torch.empty((n, n_samples // 256), dtype=torch.int16, pin_memory=True)
-        b = capi.Batch(n, capi.RX, device.index or 0)
-        b.set_mode(mode)
-        bufs.append((b, host_iq, host_pcm))
-        del distinct
+    b, iq, pcm = make_rx_batch(torch, capi, device, groups, n_samples, 99)
+    host_iq = torch.empty(iq.shape, dtype=torch.int8, pin_memory=True)
+    host_iq.copy_(iq)
+    host_pcm = torch.empty(pcm.shape, dtype=torch.int16, pin_memory=True)
+    del iq, pcm
     torch.cuda.synchronize()
 
-    def step():
-        for b, hi, hp in bufs:
-            b.rx_host_ptr(hi.data_ptr(), hi.shape[1], hi.stride(0), hp.data_ptr(), hp.stride(0))
+    def step():  # returns only when the PCM is in host memory
+        b.rx_host_ptr(host_iq.data_ptr(), host_iq.shape[1], host_iq.stride(0), host_pcm.data_ptr(), host_pcm.stride(0))
 
     step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        step()  # each call returns only when its PCM is in host memory
+        step()
     dt = (time.perf_counter() - t0) / steps
-    h2d = sum(hi.numel() for _, hi, _ in bufs)
-    d2h = sum(hp.numel() * 2 for _, _, hp in bufs)
     value = args.streams * n_samples / dt / 1e6
-    return {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "ms_per_step": round(dt * 1e3, 3), "steps": steps,
+    return {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": host_iq.numel(),
+            "d2h_bytes_per_step": host_pcm.numel() * 2, "ms_per_step": round(dt * 1e3, 3), "steps": steps,
             "note": "hrd_rx_process(HRD_MEM_HOST) on pinned buffers, per GPU; this rank only"}
 
 
@@ -321,12 +333,13 @@ def run_mode_sweep(torch, capi, device, args, peak):
     n_streams = args.sweep_streams
     n_samples = int(args.sweep_seconds * FS) // 8192 * 8192
     for mode in (1, 2, 3, 4):
-        ms, per_call, _, keep = bench_rx_modes(torch, capi, device, [(mode, n_streams)], n_samples, 3, 2, seed=7)
+        ms, kms, tms, _, keep = bench_rx_modes(torch, capi, device, [(mode, n_streams)], n_samples, 3, 2, seed=7)
         del keep
         torch.cuda.empty_cache()
         sps = n_streams * n_samples / (ms * 1e-3)
         res[f"rx_{MODE_NAMES[mode]}"] = {"streams": n_streams, "MS/s": round(sps / 1e6, 1), "ms": round(ms, 3),
-                                         "hbm_frac": round(sps * BYTES_PER_IN_SAMPLE_RX / 1e9 / peak, 4)}
+                                         "hbm_frac": round(sps * BYTES_PER_IN_SAMPLE_RX / 1e9 / peak, 4),
+                                         "kernel_ms": round(kms, 3), "tail_ms": round(tms, 3)}
     n_pcm = n_samples // 256
     for mode in (1, 2, 3, 4):
         ms = bench_tx_mode(torch, capi, device, mode, n_streams, n_pcm, 3, 2, seed=11)

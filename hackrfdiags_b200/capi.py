@@ -22,12 +22,13 @@ UNIT_AM, UNIT_FM, UNIT_WBFM, UNIT_SSB, UNIT_FRONT_END, UNIT_ALL = range(6)
 ENTRY_2048K, ENTRY_256K = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 ALL_STREAMS = -1
+OPT_RX_TILE_BATCHES, OPT_RX_WBFM_TILING, OPT_TX_TILE_SAMPLES, OPT_PROFILE = range(4)
 
 # every symbol include/hrd.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "hrd_abi_version", "hrd_create", "hrd_destroy", "hrd_last_error", "hrd_set_mode", "hrd_get_mode",
-    "hrd_set_param", "hrd_get_param", "hrd_reset", "hrd_rx_process", "hrd_rx_front_end", "hrd_tx_process",
-    "hrd_synchronize", "hrd_launch_count", "hrd_get_table", "hrd_get_taps", "hrd_state_bytes_per_stream",
+    "hrd_set_param", "hrd_get_param", "hrd_reset", "hrd_set_option", "hrd_get_option", "hrd_rx_process", "hrd_rx_front_end", "hrd_tx_process",
+    "hrd_synchronize", "hrd_launch_count", "hrd_kernel_ms", "hrd_get_table", "hrd_get_taps", "hrd_state_bytes_per_stream",
 ]
 
 
@@ -56,11 +57,14 @@ def load():
     lib.hrd_set_param.argtypes = [vp, i, i, C.c_float]
     lib.hrd_get_param.argtypes = [vp, i, i, C.POINTER(C.c_float)]
     lib.hrd_reset.argtypes = [vp, i, i]
+    lib.hrd_set_option.argtypes = [vp, i, i]
+    lib.hrd_get_option.argtypes = [vp, i, C.POINTER(i)]
     lib.hrd_rx_process.argtypes = [vp, vp, sz, sz, i, vp, sz, vp, i, vp]
     lib.hrd_rx_front_end.argtypes = [vp, vp, sz, sz, vp, sz, i, vp]
     lib.hrd_tx_process.argtypes = [vp, vp, sz, sz, vp, sz, i, vp]
     lib.hrd_synchronize.argtypes = [vp]
     lib.hrd_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+    lib.hrd_kernel_ms.argtypes = [vp, i, i, C.POINTER(C.c_float)]
     lib.hrd_get_table.argtypes = [vp, i, vp, sz]
     lib.hrd_get_taps.argtypes = [i, vp, i]
     lib.hrd_state_bytes_per_stream.argtypes = [i]
@@ -123,6 +127,14 @@ class Batch:
     def reset(self, unit: int = UNIT_ALL, stream: int = ALL_STREAMS):
         _check(self.lib.hrd_reset(self.h, int(stream), int(unit)))
 
+    def set_option(self, option: int, value: int):
+        _check(self.lib.hrd_set_option(self.h, int(option), int(value)))
+
+    def get_option(self, option: int) -> int:
+        v = C.c_int()
+        _check(self.lib.hrd_get_option(self.h, int(option), C.byref(v)))
+        return v.value
+
     def synchronize(self):
         _check(self.lib.hrd_synchronize(self.h))
 
@@ -130,6 +142,11 @@ class Batch:
         c = C.c_uint64()
         _check(self.lib.hrd_launch_count(self.h, C.byref(c)))
         return c.value
+
+    def kernel_ms(self, which: int = 0, age: int = 0) -> float:
+        v = C.c_float()
+        _check(self.lib.hrd_kernel_ms(self.h, int(which), int(age), C.byref(v)))
+        return v.value
 
     def get_table(self, which: int) -> np.ndarray:
         n = 65536 if which == 0 else 16384

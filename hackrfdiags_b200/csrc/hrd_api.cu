@@ -183,22 +183,34 @@ int kernel_kind_of_mode(int mode)
 
 } // namespace
 
+#define HRD_PROFILE_RING 32
+
 struct hrd_batch {
     int device = 0, n = 0, kind = HRD_RX;
     std::vector<int32_t> mode;
     std::vector<uint8_t> lsb;
     std::vector<float> param[HRD_PARAM_COUNT];
     bool dirty = true;
-    void *d_state = nullptr;
+    void *d_state[2] = {nullptr, nullptr}; // Rx: double-buffered, see hrd::RxParams; Tx uses [0] only
+    int cur = 0;                           // the half the next call reads
+    int sm_count = 148;
+    int opt[HRD_OPT_COUNT] = {};
+    int32_t *d_pre = nullptr;              // Rx AM/SSB: IIR input scratch, [n][pre_stride]
+    size_t d_pre_cap = 0, pre_stride = 0;
     int32_t *d_ids = nullptr; // streams grouped by kernel kind
     int32_t *d_all = nullptr; // 0..n-1
     uint8_t *d_lsb = nullptr;
+    uint8_t *d_kind = nullptr; // kernel kind (hrd::K_*) of every stream
     float *d_param[HRD_PARAM_COUNT] = {};
     int group_off[5] = {}, group_cnt[5] = {};
     void *d_in = nullptr, *d_out = nullptr;
     size_t d_in_cap = 0, d_out_cap = 0;
     cudaStream_t own = nullptr;
     uint64_t launches = 0;
+    // HRD_OPT_PROFILE: events around the hot kernel(s) of the latest call and around its tail kernel
+    // (a ring of the last HRD_PROFILE_RING calls, so back-to-back timed steps can all be read)
+    cudaEvent_t ev[HRD_PROFILE_RING][3] = {};
+    uint64_t ev_calls = 0;
 };
 
 namespace {
@@ -211,12 +223,18 @@ int regroup(hrd_batch *b)
     HRD_CUDA(cudaDeviceSynchronize()); // earlier launches may still be reading the old tables
     std::vector<int32_t> ids;
     ids.reserve((size_t)b->n);
-    for (int k = 0; k < 5; k++) {
+    std::vector<uint8_t> kinds((size_t)b->n);
+    for (int s = 0; s < b->n; s++) kinds[(size_t)s] = (uint8_t)kernel_kind_of_mode(b->mode[(size_t)s]);
+    // AM and SSB streams sit next to each other: on Rx one launch runs both
+    static const int order[5] = {hrd::K_NONE, hrd::K_FM, hrd::K_WBFM, hrd::K_AM, hrd::K_SSB};
+    for (int o = 0; o < 5; o++) {
+        const int k = order[o];
         b->group_off[k] = (int)ids.size();
         for (int s = 0; s < b->n; s++)
-            if (kernel_kind_of_mode(b->mode[(size_t)s]) == k) ids.push_back(s);
+            if (kinds[(size_t)s] == k) ids.push_back(s);
         b->group_cnt[k] = (int)ids.size() - b->group_off[k];
     }
+    HRD_CUDA(cudaMemcpy(b->d_kind, kinds.data(), (size_t)b->n, cudaMemcpyHostToDevice));
     HRD_CUDA(cudaMemcpy(b->d_ids, ids.data(), (size_t)b->n * sizeof(int32_t), cudaMemcpyHostToDevice));
     HRD_CUDA(cudaMemcpy(b->d_lsb, b->lsb.data(), (size_t)b->n, cudaMemcpyHostToDevice));
     for (int p = 0; p < HRD_PARAM_COUNT; p++)
@@ -261,12 +279,50 @@ int check_stream_arg(hrd_batch *b, int stream)
 int zero_state(hrd_batch *b, int stream, size_t off, size_t len)
 {
     const size_t pitch = state_size(b->kind);
-    char *base = (char *)b->d_state + off;
+    char *base = (char *)b->d_state[b->kind == HRD_RX ? b->cur : 0] + off;
     if (stream == HRD_ALL_STREAMS)
         HRD_CUDA(cudaMemset2DAsync(base, pitch, 0, len, (size_t)b->n, b->own));
     else
         HRD_CUDA(cudaMemsetAsync(base + (size_t)stream * pitch, 0, len, b->own));
     return HRD_OK;
+}
+
+// How a call is cut into time tiles (hrd_rx.cu header).  Auto mode searches the tile count
+// that wastes least: slots left empty in the last wave of warps plus the halo every tile after
+// the first re-reads and recomputes.
+void choose_tiles(hrd_batch *b, int kind, int entry, int n_streams, uint32_t n_batches, int32_t *n_tiles,
+                  uint32_t *tile_batches)
+{
+    const uint32_t halo = (uint32_t)hrd::rx_halo_batches(kind);
+    uint32_t tb = n_batches ? n_batches : 1;
+    const bool allowed = kind != hrd::K_WBFM || b->opt[HRD_OPT_RX_WBFM_TILING];
+    if (allowed && n_batches > 1) {
+        if (b->opt[HRD_OPT_RX_TILE_BATCHES] > 0) {
+            tb = (uint32_t)b->opt[HRD_OPT_RX_TILE_BATCHES];
+            if (tb < halo) tb = halo;
+        } else {
+            const double slots = (double)b->sm_count * hrd::rx_resident_warps_per_sm(kind, entry);
+            double best = -1.0;
+            for (uint32_t t = 1; t <= 512 && t <= n_batches; t++) {
+                const uint32_t cand = (n_batches + t - 1) / t; // batches per tile
+                if (t > 1 && cand < 2 * halo) break;           // halo would exceed half a tile
+                const uint32_t tiles = (n_batches + cand - 1) / cand;
+                const double items = (double)tiles * n_streams;
+                const double waves = ceil(items / slots);
+                const double fill = items / (waves * slots);
+                const double useful = (double)cand / (double)(cand + (tiles > 1 ? halo : 0));
+                const double score = fill * useful;
+                if (score > best + 1e-9) {
+                    best = score;
+                    tb = cand;
+                }
+            }
+        }
+        if (tb > n_batches) tb = n_batches;
+    }
+    *tile_batches = tb;
+    *n_tiles = (int32_t)((n_batches + tb - 1) / tb);
+    if (*n_tiles < 1) *n_tiles = 1;
 }
 
 } // namespace
@@ -323,11 +379,15 @@ int hrd_create(int device, int n_streams, int kind, hrd_batch_t **out)
     cudaError_t e = cudaSuccess;
     const size_t ssz = state_size(kind) * (size_t)n_streams;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->own, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&b->d_state, ssz);
-    if (e == cudaSuccess) e = cudaMemset(b->d_state, 0, ssz);
+    b->sm_count = prop.multiProcessorCount;
+    for (int h = 0; h < (kind == HRD_RX ? 2 : 1); h++) {
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_state[h], ssz);
+        if (e == cudaSuccess) e = cudaMemset(b->d_state[h], 0, ssz);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&b->d_ids, (size_t)n_streams * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_all, (size_t)n_streams * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_lsb, (size_t)n_streams);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_kind, (size_t)n_streams);
     for (int p = 0; p < HRD_PARAM_COUNT && e == cudaSuccess; p++)
         e = cudaMalloc(&b->d_param[p], (size_t)n_streams * sizeof(float));
     if (e == cudaSuccess) {
@@ -348,13 +408,19 @@ int hrd_destroy(hrd_batch_t *b)
     if (!b) return HRD_OK;
     DeviceGuard guard(b->device);
     if (b->own) cudaStreamSynchronize(b->own);
-    cudaFree(b->d_state);
+    cudaFree(b->d_state[0]);
+    cudaFree(b->d_state[1]);
+    cudaFree(b->d_pre);
     cudaFree(b->d_ids);
     cudaFree(b->d_all);
     cudaFree(b->d_lsb);
+    cudaFree(b->d_kind);
     for (int p = 0; p < HRD_PARAM_COUNT; p++) cudaFree(b->d_param[p]);
     cudaFree(b->d_in);
     cudaFree(b->d_out);
+    for (int r = 0; r < HRD_PROFILE_RING; r++)
+        for (int i = 0; i < 3; i++)
+            if (b->ev[r][i]) cudaEventDestroy(b->ev[r][i]);
     if (b->own) cudaStreamDestroy(b->own);
     delete b;
     return HRD_OK;
@@ -421,6 +487,23 @@ int hrd_get_param(hrd_batch_t *b, int stream, int param, float *value)
     return HRD_OK;
 }
 
+int hrd_set_option(hrd_batch_t *b, int option, int value)
+{
+    if (!b) return fail(HRD_EINVAL, "null batch");
+    if (option < 0 || option >= HRD_OPT_COUNT) return fail(HRD_EINVAL, "bad option %d", option);
+    if (value < 0) return fail(HRD_EINVAL, "option values are non-negative");
+    b->opt[option] = value;
+    return HRD_OK;
+}
+
+int hrd_get_option(hrd_batch_t *b, int option, int *value)
+{
+    if (!b || !value) return fail(HRD_EINVAL, "null argument");
+    if (option < 0 || option >= HRD_OPT_COUNT) return fail(HRD_EINVAL, "bad option %d", option);
+    *value = b->opt[option];
+    return HRD_OK;
+}
+
 int hrd_reset(hrd_batch_t *b, int stream, int unit)
 {
     int rc = check_stream_arg(b, stream);
@@ -432,16 +515,16 @@ int hrd_reset(hrd_batch_t *b, int stream, int unit)
 #define RANGE(T, first, next) offsetof(T, first), offsetof(T, next) - offsetof(T, first)
     if (b->kind == HRD_RX) {
         switch (unit) {
-        case HRD_UNIT_AM: rc = zero_state(b, stream, RANGE(RxState, am_r256, fm_r256)); break;
+        case HRD_UNIT_AM: rc = zero_state(b, stream, RANGE(RxState, am, fm_r256)); break;
         case HRD_UNIT_FM: rc = zero_state(b, stream, RANGE(RxState, fm_r256, wb_prev_theta)); break;
         case HRD_UNIT_WBFM: // WbFmDemodulator.cc:284-298: decimators and previousTheta, not the IIR
             rc = zero_state(b, stream, RANGE(RxState, wb_prev_theta, wb_x1));
-            if (!rc) rc = zero_state(b, stream, RANGE(RxState, wb_d256, ssb_r256));
+            if (!rc) rc = zero_state(b, stream, RANGE(RxState, wb_d256, ssb));
             break;
         case HRD_UNIT_SSB:
-            rc = zero_state(b, stream, offsetof(RxState, ssb_r256), sizeof(RxState) - offsetof(RxState, ssb_r256));
+            rc = zero_state(b, stream, offsetof(RxState, ssb), sizeof(RxState) - offsetof(RxState, ssb));
             break;
-        case HRD_UNIT_FRONT_END: rc = zero_state(b, stream, RANGE(RxState, fe_t, am_r256)); break;
+        case HRD_UNIT_FRONT_END: rc = zero_state(b, stream, RANGE(RxState, fe_t, am)); break;
         case HRD_UNIT_ALL: rc = zero_state(b, stream, 0, sizeof(RxState)); break;
         default: return fail(HRD_EINVAL, "bad unit %d", unit);
         }
@@ -476,6 +559,19 @@ int hrd_launch_count(hrd_batch_t *b, uint64_t *count)
 {
     if (!b || !count) return fail(HRD_EINVAL, "null argument");
     *count = b->launches;
+    return HRD_OK;
+}
+
+int hrd_kernel_ms(hrd_batch_t *b, int which, int age, float *ms)
+{
+    if (!b || !ms) return fail(HRD_EINVAL, "null argument");
+    if (which < 0 || which > 1) return fail(HRD_EINVAL, "which must be 0 (main kernels) or 1 (tail kernel)");
+    if (age < 0 || age >= HRD_PROFILE_RING || (uint64_t)age >= b->ev_calls)
+        return fail(HRD_EINVAL, "no profiled call of age %d: set HRD_OPT_PROFILE before the process calls", age);
+    DeviceGuard guard(b->device);
+    cudaEvent_t *e = b->ev[(b->ev_calls - 1 - (uint64_t)age) % HRD_PROFILE_RING];
+    HRD_CUDA(cudaEventSynchronize(e[2]));
+    HRD_CUDA(cudaEventElapsedTime(ms, e[which], e[which + 1]));
     return HRD_OK;
 }
 
@@ -548,30 +644,77 @@ static int rx_common(hrd_batch_t *b, const int8_t *iq, size_t bytes, size_t iq_s
     p.n256 = (uint32_t)n256;
     p.pcm = d_pcm;
     p.pcm_stride = d_pcm_stride;
-    p.state = (hrd::RxState *)b->d_state;
+    p.state_in = (const hrd::RxState *)b->d_state[b->cur];
+    p.state_out = (hrd::RxState *)b->d_state[b->cur ^ 1];
     p.lsb = b->d_lsb;
     p.atan2_lut = g_dev_tables[b->device].atan2_lut;
+    const uint32_t n_batches = (uint32_t)((n256 + 1023) / 1024);
     if (front_end_only) {
         p.out256 = d_o256;
         p.out_stride = d_o_stride;
         p.stream_ids = b->d_all;
         p.n_streams = b->n;
+        choose_tiles(b, hrd::K_NONE, HRD_ENTRY_2048K, b->n, n_batches, &p.n_tiles, &p.tile_batches);
         if (hrd::launch_rx(hrd::K_NONE, HRD_ENTRY_2048K, p, s)) return fail(HRD_ECUDA, "front-end launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         b->launches++;
     } else {
         static const int gain_of_kind[5] = {-1, HRD_PARAM_AM_GAIN, HRD_PARAM_FM_GAIN, HRD_PARAM_WBFM_GAIN,
                                             HRD_PARAM_SSB_GAIN};
-        for (int k = 0; k < 5; k++) {
-            if (!b->group_cnt[k]) continue;
-            if (k == hrd::K_NONE && entry == HRD_ENTRY_256K) continue; // no demodulator selected: nothing runs
+        if (b->group_cnt[hrd::K_AM] || b->group_cnt[hrd::K_SSB]) {
+            // the DC-removal IIR's input, one int32 per PCM sample (rows 32-byte aligned)
+            const size_t stride = (npcm + 7) & ~(size_t)7;
+            if (b->pre_stride < stride) {
+                rc = ensure_cap((void **)&b->d_pre, &b->d_pre_cap, stride * sizeof(int32_t) * (size_t)b->n);
+                if (rc) return rc;
+                b->pre_stride = stride;
+            }
+            p.pre_iir = b->d_pre;
+            p.pre_stride = b->pre_stride;
+        }
+        if (b->group_cnt[hrd::K_NONE] && entry == HRD_ENTRY_256K)
+            // no demodulator selected: nothing runs for those streams, their state just carries over
+            HRD_CUDA(cudaMemcpyAsync(b->d_state[b->cur ^ 1], b->d_state[b->cur], sizeof(hrd::RxState) * (size_t)b->n,
+                                     cudaMemcpyDeviceToDevice, s));
+        p.kind_of = b->d_kind;
+        p.gain_ssb = b->d_param[HRD_PARAM_SSB_GAIN];
+        const bool prof = b->opt[HRD_OPT_PROFILE] != 0;
+        cudaEvent_t *ev = b->ev[b->ev_calls % HRD_PROFILE_RING];
+        if (prof) {
+            for (int i = 0; i < 3; i++)
+                if (!ev[i]) HRD_CUDA(cudaEventCreate(&ev[i]));
+            HRD_CUDA(cudaEventRecord(ev[0], s));
+        }
+        hrd::RxParams iir_p;
+        bool iir = false;
+        for (int k = 0; k < 4; k++) { // K_NONE, K_AM (+ K_SSB), K_FM, K_WBFM
+            int cnt = b->group_cnt[k];
+            if (k == hrd::K_AM) cnt += b->group_cnt[hrd::K_SSB]; // adjacent in d_ids, one launch
+            if (!cnt) continue;
+            if (k == hrd::K_NONE && entry == HRD_ENTRY_256K) continue;
             p.stream_ids = b->d_ids + b->group_off[k];
-            p.n_streams = b->group_cnt[k];
+            p.n_streams = cnt;
             p.gain = k ? b->d_param[gain_of_kind[k]] : nullptr;
+            choose_tiles(b, k, entry, p.n_streams, n_batches, &p.n_tiles, &p.tile_batches);
             int e = hrd::launch_rx(k, entry, p, s);
             if (e) return fail(HRD_ECUDA, "rx launch (kind %d) failed: %s", k, cudaGetErrorString((cudaError_t)e));
             b->launches++;
+            if (k == hrd::K_AM) {
+                iir_p = p;
+                iir = true;
+            }
+        }
+        if (prof) HRD_CUDA(cudaEventRecord(ev[1], s));
+        if (iir) { // the serial 8 kS/s recurrence of the AM/SSB streams, after every tile kernel
+            int e = hrd::launch_rx_dc_iir(iir_p, s);
+            if (e) return fail(HRD_ECUDA, "rx IIR launch failed: %s", cudaGetErrorString((cudaError_t)e));
+            b->launches++;
+        }
+        if (prof) {
+            HRD_CUDA(cudaEventRecord(ev[2], s));
+            b->ev_calls++;
         }
     }
+    b->cur ^= 1; // what this call wrote is what the next one reads
     if (mem == HRD_MEM_HOST) {
         if (front_end_only)
             HRD_CUDA(cudaMemcpy2DAsync(out256, out_stride, b->d_out, d_o_stride, out_row, (size_t)b->n,
@@ -642,7 +785,7 @@ int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size
     p.n8 = (uint32_t)n_per_stream;
     p.iq = d_iq;
     p.iq_stride = d_iq_stride;
-    p.state = (hrd::TxState *)b->d_state;
+    p.state = (hrd::TxState *)b->d_state[0];
     p.lsb = b->d_lsb;
     p.nco_sin = g_dev_tables[b->device].nco_sin;
     p.nco_cos = g_dev_tables[b->device].nco_cos;

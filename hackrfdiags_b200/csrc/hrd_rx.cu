@@ -7,16 +7,32 @@
 //   WbFmDemodulator/WbFmDemodulator.cc:341-500, SsbDemodulator/SsbDemodulator.cc:420-598
 // and underneath them Filters/Int16/{Decimator,FirFilter}_int16.cc, Filters/{Fir,Iir}Filter.cc.
 //
-// One warp owns one stream.  Work is cut into BATCHES of 1024 samples at 256 kS/s (= 8192
-// input samples = 32 PCM samples):
+// Work decomposition.  A call is cut, per stream, into TIME TILES of
+// tile_batches batches; one batch is 1024 samples at 256 kS/s (= 8192 input samples = 32 PCM
+// samples).  One warp owns one (stream, tile):
+//   * tile 0 starts from the stream's saved state (filter histories of the previous call);
+//   * a later tile starts HALO batches before its first output with all-zero histories.  Every
+//     stage up to the detector is an FIR, so after the halo its histories hold exactly what a
+//     serial run would hold (the halo is longer than the summed look-back of the cascade); the
+//     halo's own outputs are simply not stored;
+//   * the last tile writes the stream's state for the next call (into the other half of the
+//     double-buffered state array, see RxParams).
+// The two float recurrences are the exception: the AM/SSB DC-removal IIR (8 kS/s) has no finite
+// look-back, so the tile kernel stops at the IIR's INPUT (one int32 per PCM sample) and
+// rx_dc_iir_kernel runs the recurrence afterwards, one thread per stream, serially, exactly as
+// the reference does.  The WBFM de-emphasis IIR (256 kS/s) runs inside the tile kernel on one
+// lane; WBFM calls are therefore only tiled when the caller opts in (the warm-started
+// recurrence converges to the serial one within the halo, but that is a numerical argument,
+// not an identity).
+//
+// Inside a batch:
 //   A. front end, 16 iterations: every lane takes 32 input bytes (16 I,Q samples, one
-//      LDG.E.256) through the three /2 stages with dp2a on packed int8, passes the one
-//      boundary sample each stage needs to its neighbour lane by shuffle, applies the Fs/4
-//      rotation and the (int8_t) wrap, and appends one packed word (2 samples) to a
-//      shared-memory ring;
+//      LDG.E.256, software-prefetched DEPTH iterations ahead) through the three /2 stages with
+//      dp2a on packed int8, passes the one boundary sample each stage needs to its neighbour
+//      lane by shuffle, applies the Fs/4 rotation and the (int8_t) wrap, and appends one packed
+//      word (2 samples) to a shared-memory ring;
 //   B. the mode's demodulator runs lane-parallel over the ring at 64 k, 16 k and 8 kS/s;
-//      the only serial pieces are the float IIR recurrences, run by one lane;
-//   C. 32 PCM samples leave with one coalesced 64-byte store.
+//   C. 32 PCM samples (or IIR inputs) leave with one coalesced store.
 // Integer sections are bit-exact by construction (same Q15 arithmetic, same wrap-around);
 // float sections use the reference's operation order with FMA contraction disabled
 // (-fmad=false) and IEEE division.
@@ -32,6 +48,13 @@ namespace {
 
 constexpr int BATCH256 = 1024; // 256 kS/s samples per batch
 constexpr int IT_SAMPLES = 64; // 256 kS/s samples per warp iteration
+constexpr int RX_DEPTH = 2;    // input iterations in flight per warp (software prefetch)
+
+// batches a tile > 0 runs ahead of its first stored output.  Look-back of each cascade in PCM
+// periods (one batch = 32): AM 10, FM 23, SSB 40 (the 31-tap Hilbert FIR at 8 kS/s),
+// WBFM 22 after the de-emphasis IIR plus >= 1024 samples at 256 kS/s of IIR warm-up.
+template <int KIND> struct HaloOf { static constexpr int value = 1; };
+template <> struct HaloOf<K_WBFM> { static constexpr int value = 2; };
 
 // ------------------------------------------------------------------------------------
 // per-warp shared memory, by mode
@@ -39,18 +62,11 @@ constexpr int IT_SAMPLES = 64; // 256 kS/s samples per warp iteration
 struct SmemNone {
     uint32_t dummy[4];
 };
-struct SmemAm {
+struct SmemAm { // AM and SSB streams (one launch runs both)
     uint32_t r256[2 + BATCH256 / 2]; // packed int8 words, 2 samples each
     uint32_t d64[8 + BATCH256 / 4];  // I/Q int16 pairs
     uint32_t a16[14 + BATCH256 / 16];
-    float f8[32];
-};
-struct SmemSsb {
-    uint32_t r256[2 + BATCH256 / 2];
-    uint32_t d64[8 + BATCH256 / 4];
-    uint32_t a16[14 + BATCH256 / 16];
-    uint32_t d8[30 + 32];
-    float f8[32];
+    uint32_t d8[30 + 32];            // SSB only: I/Q pairs at 8 kS/s
 };
 struct SmemFm {
     uint32_t r256[14 + BATCH256 / 2];
@@ -70,13 +86,16 @@ template <> struct SmemOf<K_NONE> { typedef SmemNone type; };
 template <> struct SmemOf<K_AM> { typedef SmemAm type; };
 template <> struct SmemOf<K_FM> { typedef SmemFm type; };
 template <> struct SmemOf<K_WBFM> { typedef SmemWbfm type; };
-template <> struct SmemOf<K_SSB> { typedef SmemSsb type; };
 
 // ------------------------------------------------------------------------------------
 // A. front end
 // ------------------------------------------------------------------------------------
 struct FeCarry {
     uint32_t t, v, u; // last transposed word of stage 1/2/3 input, as seen by this lane
+};
+
+struct FeTaps {
+    uint32_t a0, b0, a1, b1, a2, b2;
 };
 
 // byte 2 of a and byte 2 of b into bytes 0,1 (the >>16 of the doubled-tap accumulators)
@@ -110,35 +129,34 @@ __device__ __forceinline__ void halfband_stage(const uint32_t (&in)[N], uint32_t
 
 // 16 input samples (8 raw words {I,Q,I,Q}) -> one ring word {I0,I1,Q0,Q1} at 256 kS/s,
 // rotated by +Fs/4 (IqDataProcessor.cc:771-815) and narrowed like (int8_t) does.
-__device__ __forceinline__ uint32_t front_end_iter(const u32x8 &w, FeCarry &c, int lane)
+// t[] is the raw input already transposed to {I_e, I_o, Q_e, Q_o} (the caller does that first
+// so that the raw registers are free to receive the next prefetch in place).
+__device__ __forceinline__ uint32_t front_end_iter(const uint32_t (&t)[8], FeCarry &c, const FeTaps &k, int lane)
 {
-    uint32_t t[8];
-#pragma unroll
-    for (int r = 0; r < 8; r++) t[r] = __byte_perm(w.v[r], 0, 0x3120);
     int pi8[8], pq8[8];
-    halfband_stage<8>(t, from_left(t[7], c.t, lane), c_tab.fe_a[0], c_tab.fe_b[0], pi8, pq8);
+    halfband_stage<8>(t, from_left(t[7], c.t, lane), k.a0, k.b0, pi8, pq8);
     uint32_t v[4];
 #pragma unroll
     for (int j = 0; j < 4; j++)
         v[j] = merge16(pack_b2(pi8[2 * j], pi8[2 * j + 1]), pack_b2(pq8[2 * j], pq8[2 * j + 1]));
     int pi4[4], pq4[4];
-    halfband_stage<4>(v, from_left(v[3], c.v, lane), c_tab.fe_a[1], c_tab.fe_b[1], pi4, pq4);
+    halfband_stage<4>(v, from_left(v[3], c.v, lane), k.a1, k.b1, pi4, pq4);
     uint32_t u[2];
 #pragma unroll
-    for (int k = 0; k < 2; k++)
-        u[k] = merge16(pack_b2(pi4[2 * k], pi4[2 * k + 1]), pack_b2(pq4[2 * k], pq4[2 * k + 1]));
+    for (int j = 0; j < 2; j++)
+        u[j] = merge16(pack_b2(pi4[2 * j], pi4[2 * j + 1]), pack_b2(pq4[2 * j], pq4[2 * j + 1]));
     int pi2[2], pq2[2];
-    halfband_stage<2>(u, from_left(u[1], c.u, lane), c_tab.fe_a[2], c_tab.fe_b[2], pi2, pq2);
+    halfband_stage<2>(u, from_left(u[1], c.u, lane), k.a2, k.b2, pi2, pq2);
     // rotation: this lane's samples are number 2*lane and 2*lane+1 of the iteration, so
     // their phases are {0,1} on even lanes and {2,3} on odd lanes:
     //   0:(x,y) 1:(-y,x) 2:(-x,-y) 3:(y,-x).  Negating "acc>>16" is (65535-acc)>>16.
     const int s = (lane & 1) ? -1 : 1;
-    const int k = (lane & 1) ? 65535 : 0;
+    const int kk = (lane & 1) ? 65535 : 0;
     const int kn = (lane & 1) ? 0 : 65535;
-    int i0 = pi2[0] * s + k;
-    int q0 = pq2[0] * s + k;
+    int i0 = pi2[0] * s + kk;
+    int q0 = pq2[0] * s + kk;
     int i1 = pq2[1] * (-s) + kn;
-    int q1 = pi2[1] * s + k;
+    int q1 = pi2[1] * s + kk;
     return merge16(pack_b2(i0, i1), pack_b2(q0, q1));
 }
 
@@ -165,8 +183,8 @@ __device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xffff
 __device__ __forceinline__ int hi16(uint32_t w) { return ((int)w) >> 16; }
 __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
 
-// I/Q int16 pairs, N taps, decimate by M: output k reads ring[M*k + (N-1) - t + (hist-(N-M))]
-// with hist == N-M, i.e. ring[M*k + N - 1 - t].
+// I/Q int16 pairs, N taps, decimate by M: output k reads ring[M*k + N - 1 - t]
+// (the ring keeps hist == N-M old samples in front of the new ones).
 template <int N, int M>
 __device__ __forceinline__ uint32_t dec_pairs(const uint32_t *ring, const int32_t *taps, int k)
 {
@@ -202,105 +220,150 @@ __device__ __forceinline__ float iir_serial(float *f, int n, float a0, float y1)
     return y1;
 }
 
+template <typename T>
+__device__ __forceinline__ void ring_init(T *ring, const T *state, int hist, int lane, bool from_state)
+{
+    for (int i = lane; i < hist; i += 32) ring[i] = from_state ? state[i] : T();
+}
+
+// input of one warp iteration: 32 bytes per lane at the 2.048 MS/s entry, 4 at the 256 kS/s one
+template <int ENTRY> struct RawOf { typedef u32x8 type; };
+template <> struct RawOf<1> { typedef uint32_t type; };
+
+// Unconditional load at a clamped offset: lanes past the end of the tile re-read its last
+// chunk instead of being predicated off (a predicated LDG.256 costs 16 register moves to keep
+// the old value alive).  What they compute is never stored and never reaches a live lane:
+// data only flows from lower to higher lanes, and a partly filled iteration is the tile's last.
+template <int ENTRY>
+__device__ __forceinline__ typename RawOf<ENTRY>::type load_raw(const int8_t *src, uint32_t off, uint32_t off_last)
+{
+    const uint32_t o = min(off, off_last);
+    if constexpr (ENTRY == 0)
+        return ldg_stream_256(src + o);
+    else
+        return __ldg(reinterpret_cast<const uint32_t *>(src + o));
+}
+
 // ------------------------------------------------------------------------------------
-// the kernel
+// the tile kernel
 // ------------------------------------------------------------------------------------
 template <int KIND, int ENTRY>
-__global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) rx_kernel(const RxParams p)
+__global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxParams p)
 {
     typedef typename SmemOf<KIND>::type Smem;
+    typedef typename RawOf<ENTRY>::type Raw;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int slot = blockIdx.x * HRD_WARPS_PER_CTA + warp;
-    if (slot >= p.n_streams) return;
+    const int item = blockIdx.x * HRD_WARPS_PER_CTA + warp;
+    if (item >= p.n_streams * p.n_tiles) return;
+    const int tile = item / p.n_streams;
+    const int slot = item - tile * p.n_streams;
     const int sid = p.stream_ids[slot];
+    const bool first = tile == 0, last = tile == p.n_tiles - 1;
+    // the K_AM instance runs the AM and the SSB streams of a batch (same /32 decimator chain)
+    const bool ssb = KIND == K_AM && p.kind_of[sid] == K_SSB;
+    const uint32_t halo = (KIND == K_AM && ssb) ? 2u : (uint32_t)HaloOf<KIND>::value;
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw + (size_t)warp * sizeof(Smem));
-    RxState &st = p.state[sid];
+    const RxState &st = p.state_in[sid];
     const int8_t *src = p.iq + (size_t)sid * p.iq_stride;
+    asm volatile("" : "+l"(src)); // keep the row pointer in registers (else it is recomputed per load)
 
-    // ---- load state -------------------------------------------------------------
+    // ---- this tile's range, in 256 kS/s samples --------------------------------------
+    const uint32_t tile_len = p.tile_batches * BATCH256;
+    const uint32_t emit_from = (uint32_t)tile * tile_len; // outputs before this are the halo's
+    const uint32_t end256 = min(p.n256, emit_from + tile_len);
+    uint32_t done256 = first ? 0u : emit_from - halo * BATCH256;
+
+    // ---- start state: saved (tile 0) or all-zero (later tiles, rebuilt by the halo) -----
     FeCarry fc;
-    fc.t = st.fe_t;
-    fc.v = st.fe_v;
-    fc.u = st.fe_u;
+    fc.t = first ? st.fe_t : 0u;
+    fc.v = first ? st.fe_v : 0u;
+    fc.u = first ? st.fe_u : 0u;
+    FeTaps fk;
+    fk.a0 = c_tab.fe_a[0]; fk.b0 = c_tab.fe_b[0];
+    fk.a1 = c_tab.fe_a[1]; fk.b1 = c_tab.fe_b[1];
+    fk.a2 = c_tab.fe_a[2]; fk.b2 = c_tab.fe_b[2];
     float gain = 0.f, scale = 0.f;
     float x1 = 0.f, y1 = 0.f, th_keep = 0.f, v_keep = 0.f;
     bool lsb = true;
-    if constexpr (KIND != K_NONE) gain = p.gain[sid];
+    if constexpr (KIND == K_FM || KIND == K_WBFM) gain = p.gain[sid];
     if constexpr (KIND == K_AM) {
-        ring_load_hist(sm.r256, st.am_r256, 2, lane);
-        ring_load_hist(sm.d64, st.am_d64, 8, lane);
-        ring_load_hist(sm.a16, st.am_a16, 14, lane);
-        x1 = st.am_x1;
-        y1 = st.am_y1;
-    }
-    if constexpr (KIND == K_SSB) {
-        ring_load_hist(sm.r256, st.ssb_r256, 2, lane);
-        ring_load_hist(sm.d64, st.ssb_d64, 8, lane);
-        ring_load_hist(sm.a16, st.ssb_a16, 14, lane);
-        ring_load_hist(sm.d8, st.ssb_d8, 30, lane);
-        x1 = st.ssb_x1;
-        y1 = st.ssb_y1;
-        lsb = p.lsb[sid] != 0;
+        const RxDec32 &d = ssb ? st.ssb : st.am;
+        ring_init(sm.r256, d.r256, 2, lane, first);
+        ring_init(sm.d64, d.d64, 8, lane, first);
+        ring_init(sm.a16, d.a16, 14, lane, first);
+        if (ssb) {
+            ring_init(sm.d8, st.ssb_d8, 30, lane, first);
+            lsb = p.lsb[sid] != 0;
+        }
     }
     if constexpr (KIND == K_FM) {
-        ring_load_hist(sm.r256, st.fm_r256, 14, lane);
-        ring_load_hist(sm.th, st.fm_theta, 4, lane);
-        ring_load_hist(sm.d64, st.fm_d64, 8, lane);
-        ring_load_hist(sm.a16, st.fm_a16, 38, lane);
+        ring_init(sm.r256, st.fm_r256, 14, lane, first);
+        ring_init(sm.th, st.fm_theta, 4, lane, first);
+        ring_init(sm.d64, st.fm_d64, 8, lane, first);
+        ring_init(sm.a16, st.fm_a16, 38, lane, first);
         // FmDemodulator.cc:488-491
         scale = __fmul_rn(__fdiv_rn(gain, 15000.f), 32767.f);
     }
     if constexpr (KIND == K_WBFM) {
-        ring_load_hist(sm.d256, st.wb_d256, 4, lane);
-        ring_load_hist(sm.d64, st.wb_d64, 8, lane);
-        ring_load_hist(sm.a16, st.wb_a16, 38, lane);
-        x1 = st.wb_x1;
-        y1 = st.wb_y1;
-        th_keep = st.wb_prev_theta;
+        ring_init(sm.d256, st.wb_d256, 4, lane, first);
+        ring_init(sm.d64, st.wb_d64, 8, lane, first);
+        ring_init(sm.a16, st.wb_a16, 38, lane, first);
+        x1 = first ? st.wb_x1 : 0.f;
+        y1 = first ? st.wb_y1 : 0.f;
+        th_keep = first ? st.wb_prev_theta : 0.f;
         v_keep = x1;
         // WbFmDemodulator.cc:392-395
         scale = __fmul_rn(__fdiv_rn(gain, 75000.f), 32767.f);
     }
     __syncwarp();
 
-    const uint32_t n256 = p.n256;
-    uint32_t done256 = 0;
+    // ---- software prefetch: RX_DEPTH iterations of input in flight ------------------------
+    constexpr uint32_t BPS = ENTRY == 0 ? 16 : 2;           // input bytes per 256 kS/s sample
+    uint32_t pf = (done256 + 2 * lane) * BPS;               // this lane's next prefetch offset
+    const uint32_t pf_last = (end256 - 2) * BPS;            // its clamp: the tile's last lane chunk
+    Raw buf[RX_DEPTH];
+#pragma unroll
+    for (int d = 0; d < RX_DEPTH; d++) {
+        buf[d] = load_raw<ENTRY>(src, pf, pf_last);
+        pf += IT_SAMPLES * BPS;
+    }
+
     uint32_t last_active = 32;
 
-    while (done256 < n256) {
-        const uint32_t nb = min((uint32_t)BATCH256, n256 - done256); // multiple of 32
+    while (done256 < end256) {
+        const uint32_t nb = min((uint32_t)BATCH256, end256 - done256); // multiple of 32
         const uint32_t n_it = (nb + IT_SAMPLES - 1) / IT_SAMPLES;
+        const bool emit = done256 >= emit_from;
+        last_active = min(32u, (nb - (n_it - 1) * IT_SAMPLES) / 2);
 
         // ---- A. front end (or plain load at the 256 kS/s entry) ----------------------
-        for (uint32_t it = 0; it < n_it; it++) {
-            const uint32_t s0 = done256 + it * IT_SAMPLES + 2 * lane; // first sample of this lane
-            const bool active = s0 < n256;
-            if (it + 1 == n_it) last_active = min(32u, (nb - it * IT_SAMPLES) / 2);
+        // one iteration: consume b (loaded RX_DEPTH iterations ago), refill it in place
+        auto step = [&](Raw &b, const uint32_t it) {
             uint32_t word;
             if constexpr (ENTRY == 0) {
-                u32x8 w;
-                if (active) {
-                    w = ldg_stream_256(src + (size_t)s0 * 16);
-                } else {
+                uint32_t t[8];
 #pragma unroll
-                    for (int r = 0; r < 8; r++) w.v[r] = 0;
-                }
-                word = front_end_iter(w, fc, lane);
+                for (int r = 0; r < 8; r++) t[r] = __byte_perm(b.v[r], 0, 0x3120);
+                b = load_raw<ENTRY>(src, pf, pf_last); // in place: b is dead now
+                word = front_end_iter(t, fc, fk, lane);
             } else {
-                uint32_t raw = active ? __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)s0 * 2)) : 0u;
-                word = __byte_perm(raw, 0, 0x3120);
+                word = __byte_perm(b, 0, 0x3120);
+                b = load_raw<ENTRY>(src, pf, pf_last);
             }
+            pf += IT_SAMPLES * BPS;
             const uint32_t widx = it * 32 + lane; // word index inside the batch
+            // lanes past the end of the tile write ring slots nothing reads
             if constexpr (KIND == K_NONE) {
-                if (p.out256 && active)
+                const uint32_t s0 = done256 + it * IT_SAMPLES + 2 * lane;
+                if (p.out256 && s0 < end256 && emit)
                     *reinterpret_cast<uint32_t *>(p.out256 + (size_t)sid * p.out_stride + (size_t)s0 * 2) =
                         __byte_perm(word, 0, 0x3120);
-            } else if constexpr (KIND == K_AM || KIND == K_SSB) {
-                if (active) sm.r256[2 + widx] = word;
+            } else if constexpr (KIND == K_AM) {
+                sm.r256[2 + widx] = word;
             } else if constexpr (KIND == K_FM) {
-                if (active) sm.r256[14 + widx] = word;
+                sm.r256[14 + widx] = word;
             } else { // K_WBFM: discriminator + the FIR half of the de-emphasis filter, in place
                 // uint8_t idx = (uint8_t)sample + 128  (WbFmDemodulator.cc:403-404)
                 uint32_t x = word ^ 0x80808080u;
@@ -314,27 +377,34 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) rx_kernel(const RxPara
                 float v0 = __fmul_rn(scale, d0), v1 = __fmul_rn(scale, d1);
                 float selv = (lane == 31) ? v_keep : v1;
                 float vp = __shfl_sync(HRD_FULL_MASK, selv, (lane + 31) & 31);
-                if (active) {
-                    th_keep = th1;
-                    v_keep = v1;
-                }
+                th_keep = th1; // the state save reads them from the last live lane
+                v_keep = v1;
                 // FirFilter::filterData order: y = 0 + b0*x[n]; y = y + b1*x[n-1]
-                const float b = 0.0253863f;
-                float f0 = __fadd_rn(__fmul_rn(b, v0), __fmul_rn(b, vp));
-                float f1 = __fadd_rn(__fmul_rn(b, v1), __fmul_rn(b, v0));
-                if (active) {
-                    sm.f256[2 * widx] = f0;
-                    sm.f256[2 * widx + 1] = f1;
-                }
+                const float bb = 0.0253863f;
+                float f0 = __fadd_rn(__fmul_rn(bb, v0), __fmul_rn(bb, vp));
+                float f1 = __fadd_rn(__fmul_rn(bb, v1), __fmul_rn(bb, v0));
+                sm.f256[2 * widx] = f0;
+                sm.f256[2 * widx + 1] = f1;
             }
+        };
+        // Full batches have 16 iterations, a multiple of RX_DEPTH, so the buffers keep their
+        // roles from batch to batch; only the tile's last batch can leave a remainder.
+        uint32_t it = 0;
+        for (; it + RX_DEPTH <= n_it; it += RX_DEPTH) {
+#pragma unroll
+            for (int d = 0; d < RX_DEPTH; d++) step(buf[d], it + d);
         }
+#pragma unroll
+        for (int d = 0; d < RX_DEPTH - 1; d++)
+            if (it + d < n_it) step(buf[d], it + d);
         __syncwarp();
 
         const int n64 = nb / 4, n16 = nb / 16, n8 = nb / 32;
-        int16_t *pcm_out = p.pcm + (size_t)sid * p.pcm_stride + done256 / 32;
+        const size_t pcm_at = done256 / 32;
+        int16_t *pcm_out = p.pcm + (size_t)sid * p.pcm_stride + pcm_at;
 
         // ---- B. demodulators ----------------------------------------------------------
-        if constexpr (KIND == K_AM || KIND == K_SSB) {
+        if constexpr (KIND == K_AM) {
             // AmDemodulator.cc:339-408 / SsbDemodulator.cc:462-529: /4 (8) /4 (12) /2 (16)
             for (int j = lane; j < n64; j += 32) {
                 int yi, yq;
@@ -346,20 +416,14 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) rx_kernel(const RxPara
             __syncwarp();
             uint32_t iq8 = 0;
             if (lane < n8) iq8 = dec_pairs<16, 2>(sm.a16, c_tab.am3, lane);
-            float fir = 0.f;
-            if constexpr (KIND == K_AM) {
+            int x = 0; // what enters the DC-removal IIR (as float) in the reference
+            if (!ssb) {
                 // AmDemodulator.cc:444-458: |I|,|Q| narrowed to int16, max + min/2
                 int im = (int)(short)abs(lo16(iq8)), qm = (int)(short)abs(hi16(iq8));
-                int mag = (im > qm) ? (int)(short)(im + (qm >> 1)) : (int)(short)(qm + (im >> 1));
-                float x = (float)mag;
-                float xp = __shfl_up_sync(HRD_FULL_MASK, x, 1);
-                if (lane == 0) xp = x1;
-                x1 = __shfl_sync(HRD_FULL_MASK, x, n8 - 1);
-                fir = __fsub_rn(x, xp); // b = {1,-1}: 0 + 1*x[n], then + (-1)*x[n-1]
+                x = (im > qm) ? (int)(short)(im + (qm >> 1)) : (int)(short)(qm + (im >> 1));
             } else {
                 if (lane < n8) sm.d8[30 + lane] = iq8;
                 __syncwarp();
-                float x = 0.f;
                 if (lane < n8) {
                     // SsbDemodulator.cc:576-590: delay line (= -I[n-15]) and 31-tap Hilbert on Q
                     const uint32_t *r = sm.d8 + lane; // r[30] is sample n
@@ -368,24 +432,15 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) rx_kernel(const RxPara
 #pragma unroll
                     for (int t = 0; t < 31; t += 2) acc += (unsigned)(c_tab.hilbert[t] * hi16(r[30 - t]));
                     int qh = q15((int)acc);
-                    x = lsb ? (float)(id - qh) : (float)(id + qh);
+                    x = lsb ? (id - qh) : (id + qh);
                 }
-                float xp = __shfl_up_sync(HRD_FULL_MASK, x, 1);
-                if (lane == 0) xp = x1;
-                x1 = __shfl_sync(HRD_FULL_MASK, x, n8 - 1);
-                fir = __fsub_rn(x, xp);
             }
-            sm.f8[lane] = fir;
-            __syncwarp();
-            if (lane == 0) y1 = iir_serial(sm.f8, n8, -0.95f, y1);
-            y1 = __shfl_sync(HRD_FULL_MASK, y1, 0);
-            __syncwarp();
-            if (lane < n8) pcm_out[lane] = (int16_t)f32_to_i16(__fmul_rn(gain, sm.f8[lane]));
+            if (emit && lane < n8) p.pre_iir[(size_t)sid * p.pre_stride + pcm_at + lane] = x;
             __syncwarp();
             ring_shift(sm.r256, 2, nb / 2, lane);
             ring_shift(sm.d64, 8, n64, lane);
             ring_shift(sm.a16, 14, n16, lane);
-            if constexpr (KIND == K_SSB) ring_shift(sm.d8, 30, n8, lane);
+            if (ssb) ring_shift(sm.d8, 30, n8, lane);
         }
 
         if constexpr (KIND == K_FM) {
@@ -406,7 +461,7 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) rx_kernel(const RxPara
             // FmDemodulator.cc:551-585: /4 (12 taps) then /2 (40 taps)
             for (int k = lane; k < n16; k += 32) sm.a16[38 + k] = (int16_t)dec_real<12, 4>(sm.d64, c_tab.fm_post, k);
             __syncwarp();
-            if (lane < n8) pcm_out[lane] = (int16_t)dec_real<40, 2>(sm.a16, c_tab.audio40, lane);
+            if (emit && lane < n8) pcm_out[lane] = (int16_t)dec_real<40, 2>(sm.a16, c_tab.audio40, lane);
             __syncwarp();
             ring_shift(sm.r256, 14, nb / 2, lane);
             ring_shift(sm.th, 4, n64, lane);
@@ -426,7 +481,7 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) rx_kernel(const RxPara
             __syncwarp();
             for (int k = lane; k < n16; k += 32) sm.a16[38 + k] = (int16_t)dec_real<12, 4>(sm.d64, c_tab.fm_post, k);
             __syncwarp();
-            if (lane < n8) pcm_out[lane] = (int16_t)dec_real<40, 2>(sm.a16, c_tab.audio40, lane);
+            if (emit && lane < n8) pcm_out[lane] = (int16_t)dec_real<40, 2>(sm.a16, c_tab.audio40, lane);
             __syncwarp();
             ring_shift(sm.d256, 4, (int)nb, lane);
             ring_shift(sm.d64, 8, n64, lane);
@@ -435,48 +490,174 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) rx_kernel(const RxPara
         done256 += nb;
     }
 
-    // ---- save state ------------------------------------------------------------------
+    // ---- the last tile leaves the stream's state for the next call -----------------------
+    if (!last) return;
+    RxState &so = p.state_out[sid];
+    {
+        // everything this launch does not own (other demodulators, the IIR pair of AM/SSB)
+        // is carried over unchanged
+        const uint32_t *a = reinterpret_cast<const uint32_t *>(&st);
+        uint32_t *b = reinterpret_cast<uint32_t *>(&so);
+        for (int i = lane; i < (int)(sizeof(RxState) / 4); i += 32) b[i] = a[i];
+    }
+    __syncwarp();
     if constexpr (ENTRY == 0) {
         if (lane == (int)last_active - 1) {
-            st.fe_t = fc.t;
-            st.fe_v = fc.v;
-            st.fe_u = fc.u;
+            so.fe_t = fc.t;
+            so.fe_v = fc.v;
+            so.fe_u = fc.u;
         }
     }
     if constexpr (KIND == K_AM) {
-        ring_save_hist(sm.r256, st.am_r256, 2, lane);
-        ring_save_hist(sm.d64, st.am_d64, 8, lane);
-        ring_save_hist(sm.a16, st.am_a16, 14, lane);
-        if (lane == 0) {
-            st.am_x1 = x1;
-            st.am_y1 = y1;
-        }
-    }
-    if constexpr (KIND == K_SSB) {
-        ring_save_hist(sm.r256, st.ssb_r256, 2, lane);
-        ring_save_hist(sm.d64, st.ssb_d64, 8, lane);
-        ring_save_hist(sm.a16, st.ssb_a16, 14, lane);
-        ring_save_hist(sm.d8, st.ssb_d8, 30, lane);
-        if (lane == 0) {
-            st.ssb_x1 = x1;
-            st.ssb_y1 = y1;
-        }
+        RxDec32 &d = ssb ? so.ssb : so.am;
+        ring_save_hist(sm.r256, d.r256, 2, lane);
+        ring_save_hist(sm.d64, d.d64, 8, lane);
+        ring_save_hist(sm.a16, d.a16, 14, lane);
+        if (ssb) ring_save_hist(sm.d8, so.ssb_d8, 30, lane);
     }
     if constexpr (KIND == K_FM) {
-        ring_save_hist(sm.r256, st.fm_r256, 14, lane);
-        ring_save_hist(sm.th, st.fm_theta, 4, lane);
-        ring_save_hist(sm.d64, st.fm_d64, 8, lane);
-        ring_save_hist(sm.a16, st.fm_a16, 38, lane);
+        ring_save_hist(sm.r256, so.fm_r256, 14, lane);
+        ring_save_hist(sm.th, so.fm_theta, 4, lane);
+        ring_save_hist(sm.d64, so.fm_d64, 8, lane);
+        ring_save_hist(sm.a16, so.fm_a16, 38, lane);
     }
     if constexpr (KIND == K_WBFM) {
-        ring_save_hist(sm.d256, st.wb_d256, 4, lane);
-        ring_save_hist(sm.d64, st.wb_d64, 8, lane);
-        ring_save_hist(sm.a16, st.wb_a16, 38, lane);
+        ring_save_hist(sm.d256, so.wb_d256, 4, lane);
+        ring_save_hist(sm.d64, so.wb_d64, 8, lane);
+        ring_save_hist(sm.a16, so.wb_a16, 38, lane);
         if (lane == (int)last_active - 1) {
-            st.wb_prev_theta = th_keep;
-            st.wb_x1 = v_keep;
+            so.wb_prev_theta = th_keep;
+            so.wb_x1 = v_keep;
         }
-        if (lane == 0) st.wb_y1 = y1;
+        if (lane == 0) so.wb_y1 = y1;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// AM / SSB DC-removal IIR (AmDemodulator.cc:67-68,460-465, SsbDemodulator.cc:104-105,586-592;
+// Filters/IirFilter.cc:161-176): one thread per stream walks the call's PCM samples in order,
+//   fir = x[n] - x[n-1];  y = fir - (-0.95f * y[n-1]);  pcm = (int16_t)(gain * y)
+// every operation a rounded fp32 one, as the reference evaluates it.  Must run after the tile
+// kernel of the same call (same CUDA stream); it finishes the state record the tile kernel
+// started in state_out.
+// ------------------------------------------------------------------------------------
+// One warp runs 32 streams, one per lane.  The IIR inputs are staged through shared memory so
+// that global traffic is coalesced (a lane reading its own row would touch 32 different lines
+// per load instruction): cp.async brings [32 rows][64 samples] chunks in, IIR_STAGES deep, each
+// lane then walks its own row (LDS.128, pitch 68 words = conflict-free), and the PCM leaves
+// through a second staging buffer as 16-byte row segments.
+constexpr int IIR_CHUNK = 64;   // samples per stream per stage
+constexpr int IIR_STAGES = 4;
+constexpr int IIR_PITCH = 68;   // int32 words per staged row (16-byte aligned, odd multiple of 4)
+constexpr int IIR_OPITCH = 72;  // int16 per staged output row
+
+struct SmemIir {
+    int32_t in[IIR_STAGES][32][IIR_PITCH];
+    int16_t out[32][IIR_OPITCH];
+    const int32_t *xrow[32];
+    int16_t *prow[32];
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(32) rx_dc_iir_kernel(const RxParams p)
+{
+    __shared__ __align__(16) SmemIir sm;
+    const int lane = threadIdx.x;
+    const int slot = blockIdx.x * 32 + lane;
+    const bool live = slot < p.n_streams;
+    const int sid = p.stream_ids[live ? slot : p.n_streams - 1]; // idle lanes shadow the last stream, store nothing
+    const bool ssb = p.kind_of[sid] == K_SSB;
+    const RxDec32 &si = ssb ? p.state_in[sid].ssb : p.state_in[sid].am;
+    const float gain = ssb ? p.gain_ssb[sid] : p.gain[sid];
+    float x1 = si.x1, y1 = si.y1;
+    const uint32_t n = p.n256 / 32;
+    const uint32_t n_pad = (n + 7) & ~7u; // rows of pre_iir are padded to 8 samples
+    int16_t *pcm = p.pcm + (size_t)sid * p.pcm_stride;
+    sm.xrow[lane] = p.pre_iir + (size_t)sid * p.pre_stride;
+    sm.prow[lane] = pcm;
+    // 16-byte output segments need every row 16-byte aligned
+    const bool vec_out = __all_sync(HRD_FULL_MASK, (reinterpret_cast<uintptr_t>(pcm) & 15) == 0);
+    __syncwarp();
+
+    const uint32_t n_chunks = (n + IIR_CHUNK - 1) / IIR_CHUNK;
+    auto issue = [&](uint32_t c) { // chunk c -> stage c % IIR_STAGES; 16 segments of 16 bytes per row
+        if (c < n_chunks) {
+            int32_t(*dst)[IIR_PITCH] = sm.in[c % IIR_STAGES];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int row = 2 * i + (lane >> 4), part = lane & 15;
+                const uint32_t at = c * IIR_CHUNK + part * 4;
+                if (at < n_pad) cp_async16(&dst[row][part * 4], sm.xrow[row] + at);
+            }
+        }
+        cp_async_commit(); // an empty group keeps the wait arithmetic uniform
+    };
+#pragma unroll
+    for (int c = 0; c < IIR_STAGES - 1; c++) issue(c);
+
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        issue(c + IIR_STAGES - 1);
+        cp_async_wait<IIR_STAGES - 1>();
+        __syncwarp();
+        const int32_t *row = sm.in[c % IIR_STAGES][lane];
+        const uint32_t base = c * IIR_CHUNK;
+#pragma unroll
+        for (int g = 0; g < IIR_CHUNK / 8; g++) {
+            const int4 a = *reinterpret_cast<const int4 *>(row + 8 * g);
+            const int4 b = *reinterpret_cast<const int4 *>(row + 8 * g + 4);
+            const int v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            int o[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float xf = (float)v[k];
+                const float fir = __fsub_rn(xf, x1); // b = {1,-1}: 0 + 1*x[n], then + (-1)*x[n-1]
+                const float y = __fsub_rn(fir, __fmul_rn(-0.95f, y1));
+                if (base + 8 * g + k < n) { // the padding past the call's end must not advance the state
+                    x1 = xf;
+                    y1 = y;
+                }
+                o[k] = f32_to_i16(__fmul_rn(gain, y));
+            }
+            int4 w;
+            w.x = (int)(((uint32_t)o[0] & 0xffffu) | ((uint32_t)o[1] << 16));
+            w.y = (int)(((uint32_t)o[2] & 0xffffu) | ((uint32_t)o[3] << 16));
+            w.z = (int)(((uint32_t)o[4] & 0xffffu) | ((uint32_t)o[5] << 16));
+            w.w = (int)(((uint32_t)o[6] & 0xffffu) | ((uint32_t)o[7] << 16));
+            *reinterpret_cast<int4 *>(&sm.out[lane][8 * g]) = w;
+        }
+        __syncwarp();
+        const int rows_live = min(32, p.n_streams - (int)blockIdx.x * 32);
+        if (vec_out) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) { // 32 rows x 8 segments of 8 samples
+                const int r = 4 * i + (lane >> 3), part = lane & 7;
+                const uint32_t at = base + part * 8;
+                if (r < rows_live && at < n) {
+                    const int4 w = *reinterpret_cast<const int4 *>(&sm.out[r][part * 8]);
+                    if (at + 8 <= n) {
+                        *reinterpret_cast<int4 *>(sm.prow[r] + at) = w;
+                    } else { // the call's last, partial group of 8
+                        const int16_t *q = &sm.out[r][part * 8];
+                        for (uint32_t k = 0; at + k < n; k++) sm.prow[r][at + k] = q[k];
+                    }
+                }
+            }
+        } else if (live) {
+            for (uint32_t k = 0; k < IIR_CHUNK && base + k < n; k++) pcm[base + k] = sm.out[lane][k];
+        }
+        __syncwarp(); // the stage and the output buffer are free again
+    }
+    if (live) {
+        RxDec32 &so = ssb ? p.state_out[sid].ssb : p.state_out[sid].am;
+        so.x1 = x1;
+        so.y1 = y1;
     }
 }
 
@@ -484,7 +665,8 @@ template <int KIND, int ENTRY>
 int launch_one(const RxParams &p, cudaStream_t s)
 {
     typedef typename SmemOf<KIND>::type Smem;
-    const int grid = (p.n_streams + HRD_WARPS_PER_CTA - 1) / HRD_WARPS_PER_CTA;
+    const long long items = (long long)p.n_streams * p.n_tiles;
+    const int grid = (int)((items + HRD_WARPS_PER_CTA - 1) / HRD_WARPS_PER_CTA);
     const size_t smem = sizeof(Smem) * HRD_WARPS_PER_CTA;
     rx_kernel<KIND, ENTRY><<<grid, HRD_WARPS_PER_CTA * 32, smem, s>>>(p);
     return (int)cudaGetLastError();
@@ -492,6 +674,45 @@ int launch_one(const RxParams &p, cudaStream_t s)
 
 } // namespace
 
+int rx_halo_batches(int kind)
+{
+    switch (kind) {
+    case K_AM: return 2; // the AM launch also carries the SSB streams (31-tap Hilbert at 8 kS/s)
+    case K_WBFM: return HaloOf<K_WBFM>::value;
+    default: return 1;
+    }
+}
+
+template <int KIND, int ENTRY>
+int resident_warps()
+{
+    typedef typename SmemOf<KIND>::type Smem;
+    int blocks = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, rx_kernel<KIND, ENTRY>, HRD_WARPS_PER_CTA * 32,
+                                                      sizeof(Smem) * HRD_WARPS_PER_CTA) != cudaSuccess || blocks < 1)
+        blocks = 1;
+    return blocks * HRD_WARPS_PER_CTA;
+}
+
+int rx_resident_warps_per_sm(int kind, int entry)
+{
+    static int cache[5][2] = {};
+    if (kind < 0 || kind > 4 || entry < 0 || entry > 1) return HRD_WARPS_PER_CTA;
+    if (cache[kind][entry]) return cache[kind][entry];
+    int w = HRD_WARPS_PER_CTA;
+#define HRD_RW(K, E) (w = resident_warps<K, E>())
+    switch (kind) {
+    case K_NONE: entry == 0 ? HRD_RW(K_NONE, 0) : HRD_RW(K_NONE, 1); break;
+    case K_AM: entry == 0 ? HRD_RW(K_AM, 0) : HRD_RW(K_AM, 1); break;
+    case K_FM: entry == 0 ? HRD_RW(K_FM, 0) : HRD_RW(K_FM, 1); break;
+    case K_WBFM: entry == 0 ? HRD_RW(K_WBFM, 0) : HRD_RW(K_WBFM, 1); break;
+    }
+#undef HRD_RW
+    cache[kind][entry] = w;
+    return w;
+}
+
+// kind: K_NONE, K_AM (AM and SSB streams together), K_FM or K_WBFM
 int launch_rx(int kind, int entry, const RxParams &p, cudaStream_t s)
 {
     if (p.n_streams <= 0) return 0;
@@ -503,10 +724,17 @@ int launch_rx(int kind, int entry, const RxParams &p, cudaStream_t s)
         HRD_RX_CASE(K_AM)
         HRD_RX_CASE(K_FM)
         HRD_RX_CASE(K_WBFM)
-        HRD_RX_CASE(K_SSB)
     }
 #undef HRD_RX_CASE
     return (int)cudaErrorInvalidValue;
+}
+
+int launch_rx_dc_iir(const RxParams &p, cudaStream_t s)
+{
+    if (p.n_streams <= 0 || p.n256 == 0) return 0;
+    const int grid = (p.n_streams + 31) / 32;
+    rx_dc_iir_kernel<<<grid, 32, 0, s>>>(p);
+    return (int)cudaGetLastError();
 }
 
 } // namespace hrd

@@ -46,14 +46,19 @@ struct ConstTables {
 // and indices.  32-bit slots; int16 samples sit in the low half, I/Q pairs are packed
 // {I = low 16, Q = high 16}; 256 kS/s int8 samples are packed two per word as
 // {I[2p], I[2p+1], Q[2p], Q[2p+1]} (the layout dp2a wants).
+// AmDemodulator and SsbDemodulator share the /4 /4 /2 decimator chain and the DC-removal IIR
+struct RxDec32 {
+    uint32_t r256[2];      // 4 samples @256k
+    uint32_t d64[8];       // 8 I/Q pairs @64k
+    uint32_t a16[14];      // 14 I/Q pairs @16k
+    float x1, y1;          // DC-removal IIR: x[n-1], y[n-1]
+};
+
 struct RxState {
     // IqDataProcessor stage 1/2/3 decimators: the last word each stage saw
     uint32_t fe_t, fe_v, fe_u, fe_pad;
     // AmDemodulator
-    uint32_t am_r256[2];   // 4 samples @256k
-    uint32_t am_d64[8];    // 8 I/Q pairs @64k
-    uint32_t am_a16[14];   // 14 I/Q pairs @16k
-    float am_x1, am_y1;    // DC-removal IIR: x[n-1], y[n-1]
+    RxDec32 am;
     // FmDemodulator
     uint32_t fm_r256[14];  // 28 samples @256k
     float fm_theta[4];     // differentiator pipeline: theta[n-1..n-4], oldest first
@@ -67,11 +72,8 @@ struct RxState {
     int16_t wb_d64[8];
     int16_t wb_a16[38];
     // SsbDemodulator
-    uint32_t ssb_r256[2];
-    uint32_t ssb_d64[8];
-    uint32_t ssb_a16[14];
+    RxDec32 ssb;
     uint32_t ssb_d8[30];   // I/Q pairs @8k for the delay line / Hilbert FIR
-    float ssb_x1, ssb_y1;
 };
 
 // ---------------------------------------------------------------- Tx per-stream state
@@ -105,12 +107,28 @@ struct RxParams {
     size_t pcm_stride;         // samples between streams
     int8_t *out256;            // front-end-only output (may be null)
     size_t out_stride;
-    RxState *state;
+    // Per-stream state is double-buffered: a call reads state_in and writes state_out, so the
+    // warp that finishes a stream's LAST time tile can never overwrite what the warp of its
+    // FIRST tile has yet to read.  The host swaps the two after every call.
+    const RxState *state_in;
+    RxState *state_out;
     const int32_t *stream_ids; // streams of this launch (one mode per launch)
     int32_t n_streams;
     const float *gain;         // [n_streams_total] gain of this launch's demodulator
     const uint8_t *lsb;        // [n_streams_total] SSB sideband flag
+    const uint8_t *kind_of;    // [n_streams_total] K_* of every stream (the AM launch also runs SSB streams)
+    const float *gain_ssb;     // [n_streams_total] SSB gain (AM/SSB launch: gain is the AM one)
     const float *atan2_lut;    // [256*256]
+    // Time tiling: every stream's call is cut into n_tiles tiles of
+    // tile_batches batches (1 batch = 1024 samples at 256 kS/s = 32 PCM samples); one warp owns
+    // one (stream, tile).  Tile 0 starts from the saved state, later tiles rebuild the FIR
+    // histories by running HALO batches ahead of their first output.
+    int32_t n_tiles;
+    uint32_t tile_batches;
+    // AM / SSB: the value that enters the DC-removal IIR, one int32 per PCM sample.  The
+    // recurrence itself is serial per stream and runs in rx_dc_iir_kernel afterwards.
+    int32_t *pre_iir;
+    size_t pre_stride;         // int32 elements between streams
 };
 
 struct TxParams {
@@ -132,6 +150,9 @@ enum { K_NONE = 0, K_AM = 1, K_FM = 2, K_WBFM = 3, K_SSB = 4 };
 void upload_tables(const ConstTables &t);            // hrd_rx.cu (owns the __constant__ copy)
 void upload_tables_tx(const ConstTables &t);         // hrd_tx.cu
 int launch_rx(int kind, int entry, const RxParams &p, cudaStream_t s);
+int launch_rx_dc_iir(const RxParams &p, cudaStream_t s);  // AM + SSB streams, after their launch_rx
+int rx_halo_batches(int kind);                            // batches a tile > 0 runs ahead
+int rx_resident_warps_per_sm(int kind, int entry);        // occupancy of that kernel (cached)
 int launch_tx(int kind, const TxParams &p, cudaStream_t s);
 
 } // namespace hrd

@@ -6,9 +6,9 @@
  *   Rx: one IqDataProcessor plus its AmDemodulator, FmDemodulator,
  *       WbFmDemodulator and SsbDemodulator
  *       (radioDiags/hdr_diags/IqDataProcessor.h:21-39,
- *        radioDiags/{Am,Fm,WbFm,Ssb}Demodulator/*.h)
+ *        radioDiags/{Am,Fm,WbFm,Ssb}Demodulator/ headers)
  *   Tx: one AmModulator, FmModulator, WbFmModulator and SsbModulator
- *       (radioDiags/{Am,Fm,WbFm,Ssb}Modulator/*.h) as owned by
+ *       (radioDiags/{Am,Fm,WbFm,Ssb}Modulator/ headers) as owned by
  *       BasebandDataProcessor (radioDiags/hdr_diags/BasebandDataProcessor.h)
  * A batch owns n_streams of them; every stream keeps its own filter state,
  * mode and parameters between calls exactly like the reference objects do.
@@ -78,6 +78,26 @@ enum { HRD_ENTRY_2048K = 0, /* IqDataProcessor::acceptIqData  (IqDataProcessor.c
 
 enum { HRD_MEM_HOST = 0, HRD_MEM_DEVICE = 1 };
 
+/* Execution options (ours; they change how a call is scheduled on the GPU, never its result,
+ * with the one documented exception).  The reference has no counterpart: its objects are
+ * single-stream and single-threaded. */
+enum {
+    /* Rx: batches (of 8192 input samples = 32 PCM samples) per time tile; one warp owns one
+     * (stream, tile).  0 = choose from the stream count and the SM count. */
+    HRD_OPT_RX_TILE_BATCHES = 0,
+    /* Rx WBFM: allow time tiling.  Off (default): a WBFM stream's call is one tile and the
+     * 256 kS/s de-emphasis recurrence is evaluated serially from the saved state, bit-exact.
+     * On: tiles after the first warm the recurrence up over >= 1024 samples from zero, which
+     * converges to the serial value (pole 0.949) but is not an identity: <= 1 LSB of PCM. */
+    HRD_OPT_RX_WBFM_TILING = 1,
+    /* Tx: PCM samples per time tile (multiple of 32).  0 = choose automatically. */
+    HRD_OPT_TX_TILE_SAMPLES = 2,
+    /* record CUDA events around the kernels of every process call (bench.py's roofline):
+     * hrd_kernel_ms() then reports the main and tail kernel times of the latest calls */
+    HRD_OPT_PROFILE = 3,
+    HRD_OPT_COUNT = 4
+};
+
 #define HRD_ALL_STREAMS (-1)
 
 enum {
@@ -103,6 +123,8 @@ int hrd_get_mode(hrd_batch_t *b, int stream, int *mode);
 int hrd_set_param(hrd_batch_t *b, int stream, int param, float value);
 int hrd_get_param(hrd_batch_t *b, int stream, int param, float *value);
 int hrd_reset(hrd_batch_t *b, int stream, int unit);
+int hrd_set_option(hrd_batch_t *b, int option, int value);
+int hrd_get_option(hrd_batch_t *b, int option, int *value);
 
 /* ---- receive --------------------------------------------------------- */
 /*
@@ -147,6 +169,10 @@ int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size
 
 /* ---- introspection (tests, bench) ------------------------------------ */
 int hrd_synchronize(hrd_batch_t *b);
+/* with HRD_OPT_PROFILE set: device time of a recent process call's kernels; age 0 = the latest
+ * call, up to 31 calls back; which = 0 the main kernels (Rx tile kernels / Tx kernels), 1 the
+ * tail kernel (Rx AM/SSB IIR pass).  Waits for that call to finish. */
+int hrd_kernel_ms(hrd_batch_t *b, int which, int age, float *ms);
 /* kernels this batch has launched so far (bench.py's gpu_launches) */
 int hrd_launch_count(hrd_batch_t *b, uint64_t *count);
 /* copy a device table back: 0 = atan2 LUT (65536 floats), 1 = NCO sin,

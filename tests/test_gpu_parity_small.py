@@ -116,3 +116,76 @@ def test_tx_streaming_state(oracle, mode):
         want = oracle.run_tx(mode, pcm[s])
         mx, cnt = _diff(got[s], want)
         assert mx <= tol, f"{NAMES[mode]} stream {s}: max abs err {mx}, {cnt} mismatches"
+
+
+# ---- time tiling: every tile size must give what one tile (= the serial order) gives -----
+@pytest.mark.parametrize("mode", [capi.MODE_AM, capi.MODE_FM, capi.MODE_LSB, capi.MODE_USB])
+@pytest.mark.parametrize("tile_batches", [1, 2, 3, 5])
+def test_rx_time_tiles_bit_exact(oracle, mode, tile_batches):
+    """Tiles of 1..5 batches (halo 1-2 batches each), ragged last tile, two calls in a row."""
+    n_streams = 9
+    sizes = [8192 * 7 + 256 * 3, 8192 * 4, 256 * 5]
+    iq = synth.rx_batch(mode, n_streams, sum(sizes), config=3)
+    b = capi.Batch(n_streams, capi.RX)
+    b.set_mode(mode)
+    b.set_option(capi.OPT_RX_TILE_BATCHES, tile_batches)
+    parts, off = [], 0
+    for sz in sizes:
+        parts.append(b.rx(np.ascontiguousarray(iq[:, 2 * off:2 * (off + sz)])))
+        off += sz
+    got = np.concatenate(parts, axis=1)
+    for s in range(n_streams):
+        want = oracle.run_rx(mode, iq[s])
+        mx, cnt = _diff(got[s], want)
+        assert mx == 0, f"{NAMES[mode]} tile={tile_batches} stream {s}: max abs err {mx}, {cnt} mismatches"
+
+
+@pytest.mark.parametrize("tile_batches", [2, 3])
+def test_rx_front_end_time_tiles(oracle, tile_batches):
+    n_streams, n = 6, 8192 * 9 + 512
+    iq = synth.rx_batch(capi.MODE_FM, n_streams, n, config=4)
+    b = capi.Batch(n_streams, capi.RX)
+    b.set_option(capi.OPT_RX_TILE_BATCHES, tile_batches)
+    got = b.rx_front_end(iq)
+    for s in range(n_streams):
+        h = oracle.rx_new()
+        want = oracle.rx_front_end(h, iq[s])
+        oracle.rx_free(h)
+        assert np.array_equal(got[s], want), f"stream {s}"
+
+
+def test_rx_wbfm_time_tiles_within_one_lsb(oracle):
+    """Opt-in WBFM tiling warm-starts the 256 kS/s de-emphasis recurrence: <= 1 LSB, reported."""
+    n_streams, n = 8, 8192 * 12
+    iq = synth.rx_batch(capi.MODE_WBFM, n_streams, n, config=5)
+    b = capi.Batch(n_streams, capi.RX)
+    b.set_mode(capi.MODE_WBFM)
+    b.set_option(capi.OPT_RX_WBFM_TILING, 1)
+    b.set_option(capi.OPT_RX_TILE_BATCHES, 3)
+    got = b.rx(iq)
+    worst = 0
+    for s in range(n_streams):
+        want = oracle.run_rx(capi.MODE_WBFM, iq[s])
+        d = np.abs(got[s].astype(np.int32) - want.astype(np.int32))
+        d = np.minimum(d, 65536 - d)  # (int16_t) narrowing wraps: compare modulo 2^16
+        worst = max(worst, int(d.max()))
+    print(f"wbfm tiled: max abs err {worst} LSB")
+    assert worst <= 1
+
+
+def test_rx_mixed_modes_one_batch(oracle):
+    """All five modes plus NONE in one batch and one call; auto tiling."""
+    modes = [capi.MODE_AM, capi.MODE_FM, capi.MODE_WBFM, capi.MODE_LSB, capi.MODE_USB, capi.MODE_NONE] * 2
+    n = 8192 * 6
+    iq = np.stack([synth.rx_stream(m if m else capi.MODE_AM, n, stream=i, config=6) for i, m in enumerate(modes)])
+    b = capi.Batch(len(modes), capi.RX)
+    for i, m in enumerate(modes):
+        b.set_mode(m, i)
+    got = [b.rx(np.ascontiguousarray(iq[:, :2 * 8192 * 4])), b.rx(np.ascontiguousarray(iq[:, 2 * 8192 * 4:]))]
+    got = np.concatenate(got, axis=1)
+    for i, m in enumerate(modes):
+        if m == capi.MODE_NONE:
+            assert b.last_counts[i] == 0
+            continue
+        want = oracle.run_rx(m, iq[i])
+        assert np.array_equal(got[i], want), f"stream {i} mode {m}"
