@@ -195,7 +195,7 @@ struct hrd_batch {
     int cur = 0;                           // the half the next call reads
     int sm_count = 148;
     int opt[HRD_OPT_COUNT] = {};
-    int32_t *d_pre = nullptr;              // Rx AM/SSB: IIR input scratch, [n][pre_stride]
+    float *d_pre = nullptr;                // Rx AM/SSB: IIR input scratch, [n][pre_stride]
     size_t d_pre_cap = 0, pre_stride = 0;
     int32_t *d_ids = nullptr; // streams grouped by kernel kind
     int32_t *d_all = nullptr; // 0..n-1
@@ -661,10 +661,12 @@ static int rx_common(hrd_batch_t *b, const int8_t *iq, size_t bytes, size_t iq_s
         static const int gain_of_kind[5] = {-1, HRD_PARAM_AM_GAIN, HRD_PARAM_FM_GAIN, HRD_PARAM_WBFM_GAIN,
                                             HRD_PARAM_SSB_GAIN};
         if (b->group_cnt[hrd::K_AM] || b->group_cnt[hrd::K_SSB]) {
-            // the DC-removal IIR's input, one int32 per PCM sample (rows 32-byte aligned)
+            // the DC-removal IIR's input, one float per PCM sample (rows 32-byte aligned)
             const size_t stride = (npcm + 7) & ~(size_t)7;
+            if (stride * (size_t)b->n >= ((size_t)1 << 32))
+                return fail(HRD_EINVAL, "call too long for %d AM/SSB streams (IIR scratch is indexed with 32 bits)", b->n);
             if (b->pre_stride < stride) {
-                rc = ensure_cap((void **)&b->d_pre, &b->d_pre_cap, stride * sizeof(int32_t) * (size_t)b->n);
+                rc = ensure_cap((void **)&b->d_pre, &b->d_pre_cap, stride * sizeof(float) * (size_t)b->n);
                 if (rc) return rc;
                 b->pre_stride = stride;
             }

@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
             ring_init(sm.d8, st.ssb_d8, 30, lane, first);
             lsb = p.lsb[sid] != 0;
         }
+        x1 = first ? d.x1 : 0.f; // (float)x[n-1] of the DC-removal filter; a halo rebuilds it
     }
     if constexpr (KIND == K_FM) {
         ring_init(sm.r256, st.fm_r256, 14, lane, first);
@@ -435,7 +436,13 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
                     x = lsb ? (id - qh) : (id + qh);
                 }
             }
-            if (emit && lane < n8) p.pre_iir[(size_t)sid * p.pre_stride + pcm_at + lane] = x;
+            // the FIR half of the DC-removal filter (IirFilter.cc:161-164, b = {1,-1}):
+            // 0 + 1*x[n], then + (-1)*x[n-1], all floats
+            const float xf = (float)x;
+            float xp = __shfl_up_sync(HRD_FULL_MASK, xf, 1);
+            if (lane == 0) xp = x1;
+            x1 = __shfl_sync(HRD_FULL_MASK, xf, n8 - 1);
+            if (emit && lane < n8) p.pre_iir[(size_t)sid * p.pre_stride + pcm_at + lane] = __fsub_rn(xf, xp);
             __syncwarp();
             ring_shift(sm.r256, 2, nb / 2, lane);
             ring_shift(sm.d64, 8, n64, lane);
@@ -514,6 +521,7 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
         ring_save_hist(sm.d64, d.d64, 8, lane);
         ring_save_hist(sm.a16, d.a16, 14, lane);
         if (ssb) ring_save_hist(sm.d8, so.ssb_d8, 30, lane);
+        if (lane == 0) d.x1 = x1; // y1 follows from rx_dc_iir_kernel
     }
     if constexpr (KIND == K_FM) {
         ring_save_hist(sm.r256, so.fm_r256, 14, lane);
@@ -541,21 +549,23 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
 // kernel of the same call (same CUDA stream); it finishes the state record the tile kernel
 // started in state_out.
 // ------------------------------------------------------------------------------------
-// One warp runs 32 streams, one per lane.  The IIR inputs are staged through shared memory so
-// that global traffic is coalesced (a lane reading its own row would touch 32 different lines
-// per load instruction): cp.async brings [32 rows][64 samples] chunks in, IIR_STAGES deep, each
-// lane then walks its own row (LDS.128, pitch 68 words = conflict-free), and the PCM leaves
-// through a second staging buffer as 16-byte row segments.
-constexpr int IIR_CHUNK = 64;   // samples per stream per stage
-constexpr int IIR_STAGES = 4;
-constexpr int IIR_PITCH = 68;   // int32 words per staged row (16-byte aligned, odd multiple of 4)
-constexpr int IIR_OPITCH = 72;  // int16 per staged output row
+// One CTA runs 32 streams.  The recurrence is a dependent FMUL+FSUB per sample, so the time of
+// a call is (samples per stream) x (chain latency) no matter how many streams there are; what
+// can be done is to keep everything else OFF the warp that walks the chain.  Four warps form a
+// software pipeline over chunks of 64 samples per stream, one __syncthreads per step:
+//   warp 0   loader: cp.async brings chunk t+3 in ([32 rows][64 floats], coalesced);
+//   warp 1   chain: lane r walks row r of chunk t in place, y = fir - (-0.95f * y1), reading
+//            and writing shared memory 16 bytes at a time (pitch 68 words: conflict-free);
+//   warps 2,3 post: chunk t-1, element-parallel: pcm = (int16_t)(gain * y), 16-byte stores.
+constexpr int IIR_CHUNK = 64;   // samples per stream per pipeline step
+constexpr int IIR_AHEAD = 3;    // chunks in flight ahead of the chain
+constexpr int IIR_STAGES = IIR_AHEAD + 2;
+constexpr int IIR_PITCH = 68;   // words per staged row (16-byte aligned, 17 x 4: conflict-free LDS.128)
 
 struct SmemIir {
-    int32_t in[IIR_STAGES][32][IIR_PITCH];
-    int16_t out[32][IIR_OPITCH];
-    const int32_t *xrow[32];
+    float f[IIR_STAGES][32][IIR_PITCH];
     int16_t *prow[32];
+    float gain[32];
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
@@ -566,98 +576,129 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(32) rx_dc_iir_kernel(const RxParams p)
+__global__ void __launch_bounds__(128) rx_dc_iir_kernel(const RxParams p)
 {
-    __shared__ __align__(16) SmemIir sm;
-    const int lane = threadIdx.x;
-    const int slot = blockIdx.x * 32 + lane;
-    const bool live = slot < p.n_streams;
-    const int sid = p.stream_ids[live ? slot : p.n_streams - 1]; // idle lanes shadow the last stream, store nothing
-    const bool ssb = p.kind_of[sid] == K_SSB;
-    const RxDec32 &si = ssb ? p.state_in[sid].ssb : p.state_in[sid].am;
-    const float gain = ssb ? p.gain_ssb[sid] : p.gain[sid];
-    float x1 = si.x1, y1 = si.y1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemIir &sm = *reinterpret_cast<SmemIir *>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int rows_live = min(32, p.n_streams - (int)blockIdx.x * 32);
     const uint32_t n = p.n256 / 32;
     const uint32_t n_pad = (n + 7) & ~7u; // rows of pre_iir are padded to 8 samples
-    int16_t *pcm = p.pcm + (size_t)sid * p.pcm_stride;
-    sm.xrow[lane] = p.pre_iir + (size_t)sid * p.pre_stride;
-    sm.prow[lane] = pcm;
-    // 16-byte output segments need every row 16-byte aligned
-    const bool vec_out = __all_sync(HRD_FULL_MASK, (reinterpret_cast<uintptr_t>(pcm) & 15) == 0);
-    __syncwarp();
-
     const uint32_t n_chunks = (n + IIR_CHUNK - 1) / IIR_CHUNK;
-    auto issue = [&](uint32_t c) { // chunk c -> stage c % IIR_STAGES; 16 segments of 16 bytes per row
-        if (c < n_chunks) {
-            int32_t(*dst)[IIR_PITCH] = sm.in[c % IIR_STAGES];
+
+    float y1 = 0.f; // warp 1: the recurrence state of row `lane`
+    bool vec_out = true;
+    // warp 0: element offsets of the 16 rows this lane copies segments of (rows 2i + lane/16)
+    uint32_t row_off[16];
+    {
+        // rows past the end of the launch shadow its last stream and store nothing
+        const int sid = p.stream_ids[blockIdx.x * 32 + min(lane, rows_live - 1)];
+        const bool ssb = p.kind_of[sid] == K_SSB;
+        int16_t *pcm = p.pcm + (size_t)sid * p.pcm_stride;
+        vec_out = __all_sync(HRD_FULL_MASK, (reinterpret_cast<uintptr_t>(pcm) & 15) == 0);
+        if (warp == 0) {
+            sm.prow[lane] = pcm;
+            sm.gain[lane] = ssb ? p.gain_ssb[sid] : p.gain[sid];
+        }
+        y1 = ssb ? p.state_in[sid].ssb.y1 : p.state_in[sid].am.y1;
+        const uint32_t my_row = (uint32_t)((size_t)sid * p.pre_stride); // the host keeps n * pre_stride < 2^32
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const int row = 2 * i + (lane >> 4), part = lane & 15;
-                const uint32_t at = c * IIR_CHUNK + part * 4;
-                if (at < n_pad) cp_async16(&dst[row][part * 4], sm.xrow[row] + at);
+        for (int i = 0; i < 16; i++) // row 2i + lane/16 belongs to lane 2i + lane/16; keep this lane's column
+            row_off[i] = __shfl_sync(HRD_FULL_MASK, my_row, 2 * i + (lane >> 4)) + (uint32_t)(lane & 15) * 4;
+    }
+
+    auto issue = [&](uint32_t c) { // warp 0: chunk c -> f[c % IIR_STAGES], 16 x 16 bytes per row
+        if (c < n_chunks) {
+            float(*dst)[IIR_PITCH] = sm.f[c % IIR_STAGES];
+            const uint32_t at = c * IIR_CHUNK + (lane & 15) * 4;
+            if (at < n_pad) {
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    cp_async16(&dst[2 * i + (lane >> 4)][(lane & 15) * 4], p.pre_iir + row_off[i] + c * IIR_CHUNK);
             }
         }
         cp_async_commit(); // an empty group keeps the wait arithmetic uniform
     };
+    if (warp == 0) {
 #pragma unroll
-    for (int c = 0; c < IIR_STAGES - 1; c++) issue(c);
+        for (int c = 0; c < IIR_AHEAD; c++) issue(c);
+        cp_async_wait<IIR_AHEAD - 1>(); // chunk 0 has landed
+    }
+    __syncthreads();
 
-    for (uint32_t c = 0; c < n_chunks; c++) {
-        issue(c + IIR_STAGES - 1);
-        cp_async_wait<IIR_STAGES - 1>();
-        __syncwarp();
-        const int32_t *row = sm.in[c % IIR_STAGES][lane];
-        const uint32_t base = c * IIR_CHUNK;
+    for (uint32_t t = 0; t < n_chunks + 1; t++) {
+        if (warp == 0) {
+            issue(t + IIR_AHEAD);
+            cp_async_wait<IIR_AHEAD - 1>(); // chunk t+1 has landed (visible to the others after the barrier)
+        } else if (warp == 1) {
+            if (t < n_chunks) {
+                float *row = sm.f[t % IIR_STAGES][lane];
+                const uint32_t m = min((uint32_t)IIR_CHUNK, n - t * IIR_CHUNK); // valid samples in this chunk
+                uint32_t k = 0;
+                if (m == IIR_CHUNK) {
+                    // the whole row into registers first: one shared-memory latency per chunk, then
+                    // nothing but the dependent FMUL+FSUB pairs (IirFilter.cc:161-176, a0 = -0.95f)
+                    float4 v[IIR_CHUNK / 4];
 #pragma unroll
-        for (int g = 0; g < IIR_CHUNK / 8; g++) {
-            const int4 a = *reinterpret_cast<const int4 *>(row + 8 * g);
-            const int4 b = *reinterpret_cast<const int4 *>(row + 8 * g + 4);
-            const int v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            int o[8];
+                    for (int g = 0; g < IIR_CHUNK / 4; g++) v[g] = *reinterpret_cast<float4 *>(row + 4 * g);
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const float xf = (float)v[k];
-                const float fir = __fsub_rn(xf, x1); // b = {1,-1}: 0 + 1*x[n], then + (-1)*x[n-1]
-                const float y = __fsub_rn(fir, __fmul_rn(-0.95f, y1));
-                if (base + 8 * g + k < n) { // the padding past the call's end must not advance the state
-                    x1 = xf;
-                    y1 = y;
+                    for (int g = 0; g < IIR_CHUNK / 4; g++) {
+                        v[g].x = y1 = __fsub_rn(v[g].x, __fmul_rn(-0.95f, y1));
+                        v[g].y = y1 = __fsub_rn(v[g].y, __fmul_rn(-0.95f, y1));
+                        v[g].z = y1 = __fsub_rn(v[g].z, __fmul_rn(-0.95f, y1));
+                        v[g].w = y1 = __fsub_rn(v[g].w, __fmul_rn(-0.95f, y1));
+                        *reinterpret_cast<float4 *>(row + 4 * g) = v[g];
+                    }
+                    k = IIR_CHUNK;
                 }
-                o[k] = f32_to_i16(__fmul_rn(gain, y));
+                for (; k < m; k++) row[k] = y1 = __fsub_rn(row[k], __fmul_rn(-0.95f, y1));
             }
-            int4 w;
-            w.x = (int)(((uint32_t)o[0] & 0xffffu) | ((uint32_t)o[1] << 16));
-            w.y = (int)(((uint32_t)o[2] & 0xffffu) | ((uint32_t)o[3] << 16));
-            w.z = (int)(((uint32_t)o[4] & 0xffffu) | ((uint32_t)o[5] << 16));
-            w.w = (int)(((uint32_t)o[6] & 0xffffu) | ((uint32_t)o[7] << 16));
-            *reinterpret_cast<int4 *>(&sm.out[lane][8 * g]) = w;
-        }
-        __syncwarp();
-        const int rows_live = min(32, p.n_streams - (int)blockIdx.x * 32);
-        if (vec_out) {
+        } else {
+            if (t >= 1) {
+                const uint32_t c = t - 1;
+                const float(*src)[IIR_PITCH] = sm.f[c % IIR_STAGES];
+                const uint32_t base = c * IIR_CHUNK;
+                const int pl = threadIdx.x - 64; // 0..63: 4 x (row, 8 samples) each
 #pragma unroll
-            for (int i = 0; i < 8; i++) { // 32 rows x 8 segments of 8 samples
-                const int r = 4 * i + (lane >> 3), part = lane & 7;
-                const uint32_t at = base + part * 8;
-                if (r < rows_live && at < n) {
-                    const int4 w = *reinterpret_cast<const int4 *>(&sm.out[r][part * 8]);
-                    if (at + 8 <= n) {
-                        *reinterpret_cast<int4 *>(sm.prow[r] + at) = w;
-                    } else { // the call's last, partial group of 8
-                        const int16_t *q = &sm.out[r][part * 8];
-                        for (uint32_t k = 0; at + k < n; k++) sm.prow[r][at + k] = q[k];
+                for (int i = 0; i < 4; i++) {
+                    const int r = 8 * i + (pl >> 3), part = pl & 7;
+                    const uint32_t at = base + part * 8;
+                    if (r < rows_live && at < n) {
+                        const float g = sm.gain[r];
+                        const float4 a = *reinterpret_cast<const float4 *>(&src[r][part * 8]);
+                        const float4 b = *reinterpret_cast<const float4 *>(&src[r][part * 8 + 4]);
+                        // AmDemodulator.cc:465 / SsbDemodulator.cc:592: (int16_t)(gain * y)
+                        const int o0 = f32_to_i16(__fmul_rn(g, a.x)), o1 = f32_to_i16(__fmul_rn(g, a.y));
+                        const int o2 = f32_to_i16(__fmul_rn(g, a.z)), o3 = f32_to_i16(__fmul_rn(g, a.w));
+                        const int o4 = f32_to_i16(__fmul_rn(g, b.x)), o5 = f32_to_i16(__fmul_rn(g, b.y));
+                        const int o6 = f32_to_i16(__fmul_rn(g, b.z)), o7 = f32_to_i16(__fmul_rn(g, b.w));
+                        int16_t *dst = sm.prow[r] + at;
+                        if (vec_out && at + 8 <= n) {
+                            int4 w;
+                            w.x = (int)(((uint32_t)o0 & 0xffffu) | ((uint32_t)o1 << 16));
+                            w.y = (int)(((uint32_t)o2 & 0xffffu) | ((uint32_t)o3 << 16));
+                            w.z = (int)(((uint32_t)o4 & 0xffffu) | ((uint32_t)o5 << 16));
+                            w.w = (int)(((uint32_t)o6 & 0xffffu) | ((uint32_t)o7 << 16));
+                            *reinterpret_cast<int4 *>(dst) = w;
+                        } else {
+                            const int o[8] = {o0, o1, o2, o3, o4, o5, o6, o7};
+#pragma unroll
+                            for (int k = 0; k < 8; k++)
+                                if (at + k < n) dst[k] = (int16_t)o[k];
+                        }
                     }
                 }
             }
-        } else if (live) {
-            for (uint32_t k = 0; k < IIR_CHUNK && base + k < n; k++) pcm[base + k] = sm.out[lane][k];
         }
-        __syncwarp(); // the stage and the output buffer are free again
+        __syncthreads();
     }
-    if (live) {
-        RxDec32 &so = ssb ? p.state_out[sid].ssb : p.state_out[sid].am;
-        so.x1 = x1;
-        so.y1 = y1;
+
+    // y[n-1] for the next call (x[n-1] was left by the tile kernel)
+    if (warp == 1 && lane < rows_live) {
+        const int sid = p.stream_ids[blockIdx.x * 32 + lane];
+        const bool ssb = p.kind_of[sid] == K_SSB;
+        (ssb ? p.state_out[sid].ssb : p.state_out[sid].am).y1 = y1;
     }
 }
 
@@ -733,7 +774,12 @@ int launch_rx_dc_iir(const RxParams &p, cudaStream_t s)
 {
     if (p.n_streams <= 0 || p.n256 == 0) return 0;
     const int grid = (p.n_streams + 31) / 32;
-    rx_dc_iir_kernel<<<grid, 32, 0, s>>>(p);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(rx_dc_iir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemIir));
+        attr_set = true;
+    }
+    rx_dc_iir_kernel<<<grid, 128, sizeof(SmemIir), s>>>(p);
     return (int)cudaGetLastError();
 }
 

@@ -125,10 +125,11 @@ struct RxParams {
     // histories by running HALO batches ahead of their first output.
     int32_t n_tiles;
     uint32_t tile_batches;
-    // AM / SSB: the value that enters the DC-removal IIR, one int32 per PCM sample.  The
-    // recurrence itself is serial per stream and runs in rx_dc_iir_kernel afterwards.
-    int32_t *pre_iir;
-    size_t pre_stride;         // int32 elements between streams
+    // AM / SSB: the FIR half of the DC-removal filter, fir[n] = x[n] - x[n-1] as floats, one per
+    // PCM sample.  The recurrence itself is serial per stream and runs in rx_dc_iir_kernel
+    // afterwards.
+    float *pre_iir;
+    size_t pre_stride;         // elements between streams (multiple of 8)
 };
 
 struct TxParams {

@@ -1,0 +1,346 @@
+//**************************************************************************
+// file name: hrd_shim.cc
+//**************************************************************************
+// The reference's eight modulator / demodulator classes re-created on top of
+// the libhrd_b200 C ABI (include/hrd.h) as batches of ONE stream, so that
+// IqDataProcessor.cc, BasebandDataProcessor.cc, Radio.cc and the stand-alone
+// test programs (am.cc, fm.cc, wbfm.cc, ssb.cc) compile and link unchanged.
+//
+// What each member replaces (reference paths relative to radioDiags/):
+//   <X>Demodulator::acceptIqData      AmDemodulator.cc:297-315, FmDemodulator.cc:353-371,
+//                                     WbFmDemodulator.cc:341-356, SsbDemodulator.cc:420-438
+//   <X>Demodulator::resetDemodulator  AmDemodulator.cc:249-263, FmDemodulator.cc:296-308,
+//                                     WbFmDemodulator.cc:284-298, SsbDemodulator.cc:297-313
+//   <X>Demodulator::setDemodulatorGain  AmDemodulator.cc:281, FmDemodulator.cc:326, ...
+//   <X>Modulator::acceptData          AmModulator.cc:366-381, FmModulator.cc:353-368,
+//                                     WbFmModulator.cc:347-365, SsbModulator.cc:430-445
+//   setModulationIndex / setFrequencyDeviation / set{Lsb,Usb}ModulationMode and their guards
+//                                     AmModulator.cc:329-339, FmModulator.cc:336-346,
+//                                     WbFmModulator.cc:318-328, SsbModulator.cc:379-411
+// The objects keep the reference's threading rule: one data thread per object;
+// setters may arrive from another thread and take effect at the next call.
+//
+// No signal processing happens here.  Without a usable B200 the constructors
+// print the library's error and abort: there is deliberately no CPU fallback.
+//**************************************************************************
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/hrd.h"
+
+#include "AmDemodulator.h"
+#include "FmDemodulator.h"
+#include "WbFmDemodulator.h"
+#include "SsbDemodulator.h"
+#include "AmModulator.h"
+#include "FmModulator.h"
+#include "WbFmModulator.h"
+#include "SsbModulator.h"
+
+// supplied by the host application, exactly as for the reference classes
+// (diagUi.cc:2881; the test programs define their own, am.cc:93-110)
+extern void nprintf(FILE *s,const char *formatPtr, ...);
+
+static int shimDevice(void)
+{
+  const char *e = getenv("HRD_DEVICE");
+  return (e != NULL) ? atoi(e) : 0;
+}
+
+static void shimDie(const char *what)
+{
+  fprintf(stderr,"libhrdshim: %s failed: %s\n",what,hrd_last_error());
+  fprintf(stderr,"libhrdshim: this build has no CPU fallback (needs an NVIDIA B200, sm_100)\n");
+  abort();
+}
+
+//**************************************************************************
+// Receive side.
+//**************************************************************************
+struct HrdShimRx
+{
+  hrd_batch_t *batchPtr;
+  int mode;
+  int gainParameter;
+  int resetUnit;
+  float demodulatorGain;
+  bool lsbDemodulationMode;
+  void (*pcmCallbackPtr)(int16_t *bufferPtr,uint32_t bufferLength);
+
+  // acceptIqData() hands whole PCM samples (64 bytes of IQ at 256000 S/s) to
+  // the library; a shorter tail waits here for the next call.  The reference's
+  // own caller always passes 32768 bytes, so this never triggers there.
+  std::vector<int8_t> pending;
+  std::vector<int8_t> work;
+  std::vector<int16_t> pcmData;
+};
+
+static HrdShimRx *rxCreate(int mode,int gainParameter,int resetUnit,
+    void (*pcmCallbackPtr)(int16_t *bufferPtr,uint32_t bufferLength))
+{
+  HrdShimRx *p = new HrdShimRx;
+  p->batchPtr = NULL;
+  p->mode = mode;
+  p->gainParameter = gainParameter;
+  p->resetUnit = resetUnit;
+  p->lsbDemodulationMode = true;
+  p->pcmCallbackPtr = pcmCallbackPtr;
+  if (hrd_create(shimDevice(),1,HRD_RX,&p->batchPtr) != HRD_OK) shimDie("hrd_create");
+  if (hrd_set_mode(p->batchPtr,0,mode) != HRD_OK) shimDie("hrd_set_mode");
+  if (hrd_get_param(p->batchPtr,0,gainParameter,&p->demodulatorGain) != HRD_OK)
+    shimDie("hrd_get_param");
+  return (p);
+}
+
+static void rxDestroy(HrdShimRx *p)
+{
+  if (p != NULL)
+  {
+    hrd_destroy(p->batchPtr);
+    delete p;
+  }
+}
+
+static void rxAccept(HrdShimRx *p,int8_t *bufferPtr,uint32_t bufferLength)
+{
+  const int8_t *src = bufferPtr;
+  size_t total = bufferLength;
+
+  if (!p->pending.empty())
+  {
+    p->work.assign(p->pending.begin(),p->pending.end());
+    p->work.insert(p->work.end(),bufferPtr,bufferPtr + bufferLength);
+    src = p->work.data();
+    total = p->work.size();
+  }
+
+  const size_t whole = total - (total % 64);
+  const size_t sampleCount = whole / 64;
+
+  if (p->pcmData.size() < sampleCount + 1) p->pcmData.resize(sampleCount + 1);
+
+  if (whole > 0)
+  {
+    if (hrd_rx_process(p->batchPtr,src,whole,whole,HRD_ENTRY_256K,p->pcmData.data(),
+                       p->pcmData.size(),NULL,HRD_MEM_HOST,NULL) != HRD_OK)
+      shimDie("hrd_rx_process");
+  }
+
+  p->pending.assign(src + whole,src + total);
+
+  // The reference calls back once per acceptIqData(), even with 0 samples.
+  if (p->pcmCallbackPtr != NULL)
+    p->pcmCallbackPtr(p->pcmData.data(),(uint32_t)sampleCount);
+}
+
+static void rxSetGain(HrdShimRx *p,float gain)
+{
+  p->demodulatorGain = gain;
+  if (hrd_set_param(p->batchPtr,0,p->gainParameter,gain) != HRD_OK) shimDie("hrd_set_param");
+}
+
+static void rxReset(HrdShimRx *p)
+{
+  p->pending.clear();
+  if (hrd_reset(p->batchPtr,0,p->resetUnit) != HRD_OK) shimDie("hrd_reset");
+}
+
+#define HRD_SHIM_DEMODULATOR(Class,Title,Mode,Gain,Unit)                          \
+  Class::Class(void (*pcmCallbackPtr)(int16_t *bufferPtr,uint32_t bufferLength))  \
+  { implPtr = rxCreate(Mode,Gain,Unit,pcmCallbackPtr); }                          \
+  Class::~Class(void) { rxDestroy(implPtr); }                                     \
+  void Class::resetDemodulator(void) { rxReset(implPtr); }                        \
+  void Class::setDemodulatorGain(float gain) { rxSetGain(implPtr,gain); }         \
+  void Class::acceptIqData(int8_t *bufferPtr,uint32_t bufferLength)               \
+  { rxAccept(implPtr,bufferPtr,bufferLength); }
+
+HRD_SHIM_DEMODULATOR(AmDemodulator,"AM",HRD_MODE_AM,HRD_PARAM_AM_GAIN,HRD_UNIT_AM)
+HRD_SHIM_DEMODULATOR(FmDemodulator,"FM",HRD_MODE_FM,HRD_PARAM_FM_GAIN,HRD_UNIT_FM)
+HRD_SHIM_DEMODULATOR(WbFmDemodulator,"Wideband FM",HRD_MODE_WBFM,HRD_PARAM_WBFM_GAIN,HRD_UNIT_WBFM)
+HRD_SHIM_DEMODULATOR(SsbDemodulator,"SSB",HRD_MODE_LSB,HRD_PARAM_SSB_GAIN,HRD_UNIT_SSB)
+
+void SsbDemodulator::setLsbDemodulationMode(void)
+{
+  implPtr->lsbDemodulationMode = true;
+  if (hrd_set_mode(implPtr->batchPtr,0,HRD_MODE_LSB) != HRD_OK) shimDie("hrd_set_mode");
+}
+
+void SsbDemodulator::setUsbDemodulationMode(void)
+{
+  implPtr->lsbDemodulationMode = false;
+  if (hrd_set_mode(implPtr->batchPtr,0,HRD_MODE_USB) != HRD_OK) shimDie("hrd_set_mode");
+}
+
+// Same text as the reference prints (AmDemodulator.cc:553-563 and siblings).
+static void rxDisplay(const char *titlePtr,float gain)
+{
+  nprintf(stderr,"\n--------------------------------------------\n");
+  nprintf(stderr,"%s Demodulator Internal Information\n",titlePtr);
+  nprintf(stderr,"--------------------------------------------\n");
+  nprintf(stderr,"Demodulator Gain         : %f\n",gain);
+}
+
+void AmDemodulator::displayInternalInformation(void) { rxDisplay("AM",implPtr->demodulatorGain); }
+void FmDemodulator::displayInternalInformation(void) { rxDisplay("FM",implPtr->demodulatorGain); }
+void WbFmDemodulator::displayInternalInformation(void) { rxDisplay("Wideband FM",implPtr->demodulatorGain); }
+
+void SsbDemodulator::displayInternalInformation(void)
+{
+  nprintf(stderr,"\n--------------------------------------------\n");
+  nprintf(stderr,"SSB Demodulator Internal Information\n");
+  nprintf(stderr,"--------------------------------------------\n");
+  nprintf(stderr,"Demodulation Mode        : ");
+  if (implPtr->lsbDemodulationMode)
+  {
+    nprintf(stderr,"LSB\n");
+  }
+  else
+  {
+    nprintf(stderr,"USB\n");
+  }
+  nprintf(stderr,"Demodulator Gain         : %f\n",implPtr->demodulatorGain);
+}
+
+//**************************************************************************
+// Transmit side.
+//**************************************************************************
+struct HrdShimTx
+{
+  hrd_batch_t *batchPtr;
+  int mode;
+  int resetUnit;
+  bool lsbModulationMode;
+};
+
+static HrdShimTx *txCreate(int mode,int resetUnit)
+{
+  HrdShimTx *p = new HrdShimTx;
+  p->batchPtr = NULL;
+  p->mode = mode;
+  p->resetUnit = resetUnit;
+  p->lsbModulationMode = true;
+  if (hrd_create(shimDevice(),1,HRD_TX,&p->batchPtr) != HRD_OK) shimDie("hrd_create");
+  if (hrd_set_mode(p->batchPtr,0,mode) != HRD_OK) shimDie("hrd_set_mode");
+  return (p);
+}
+
+static void txDestroy(HrdShimTx *p)
+{
+  if (p != NULL)
+  {
+    hrd_destroy(p->batchPtr);
+    delete p;
+  }
+}
+
+static void txAccept(HrdShimTx *p,int16_t *bufferPtr,uint32_t bufferLength,
+                     int8_t *outputBufferPtr,uint32_t *outputBufferLengthPtr)
+{
+  // bufferLength PCM samples -> bufferLength * 256 IQ samples = * 512 bytes,
+  // whatever the caller's buffer size argument said (AmModulator.cc:410-530)
+  const size_t outputLength = (size_t)bufferLength * 512;
+  if (bufferLength > 0)
+  {
+    if (hrd_tx_process(p->batchPtr,bufferPtr,bufferLength,bufferLength,outputBufferPtr,
+                       outputLength,HRD_MEM_HOST,NULL) != HRD_OK)
+      shimDie("hrd_tx_process");
+  }
+  *outputBufferLengthPtr = (uint32_t)outputLength;
+}
+
+static float txParameter(HrdShimTx *p,int parameter)
+{
+  float value = 0;
+  if (hrd_get_param(p->batchPtr,0,parameter,&value) != HRD_OK) shimDie("hrd_get_param");
+  return (value);
+}
+
+#define HRD_SHIM_MODULATOR(Class,Mode,Unit)                                       \
+  Class::Class(void) { implPtr = txCreate(Mode,Unit); }                           \
+  Class::~Class(void) { txDestroy(implPtr); }                                     \
+  void Class::resetModulator(void)                                                \
+  { if (hrd_reset(implPtr->batchPtr,0,Unit) != HRD_OK) shimDie("hrd_reset"); }    \
+  void Class::acceptData(int16_t *bufferPtr,uint32_t bufferLength,                \
+                         int8_t *outputBufferPtr,uint32_t *outputBufferLengthPtr) \
+  { txAccept(implPtr,bufferPtr,bufferLength,outputBufferPtr,outputBufferLengthPtr); }
+
+HRD_SHIM_MODULATOR(AmModulator,HRD_MODE_AM,HRD_UNIT_AM)
+HRD_SHIM_MODULATOR(FmModulator,HRD_MODE_FM,HRD_UNIT_FM)
+HRD_SHIM_MODULATOR(WbFmModulator,HRD_MODE_WBFM,HRD_UNIT_WBFM)
+HRD_SHIM_MODULATOR(SsbModulator,HRD_MODE_LSB,HRD_UNIT_SSB)
+
+// The range checks (and the reference's quirk of testing the OLD deviation,
+// FmModulator.cc:336-346) live behind hrd_set_param so that batched callers
+// get them too.
+void AmModulator::setModulationIndex(float modulationIndex)
+{
+  if (hrd_set_param(implPtr->batchPtr,0,HRD_PARAM_AM_INDEX,modulationIndex) != HRD_OK)
+    shimDie("hrd_set_param");
+}
+
+void FmModulator::setFrequencyDeviation(float deviation)
+{
+  if (hrd_set_param(implPtr->batchPtr,0,HRD_PARAM_FM_DEV,deviation) != HRD_OK)
+    shimDie("hrd_set_param");
+}
+
+void WbFmModulator::setFrequencyDeviation(float deviation)
+{
+  if (hrd_set_param(implPtr->batchPtr,0,HRD_PARAM_WBFM_DEV,deviation) != HRD_OK)
+    shimDie("hrd_set_param");
+}
+
+void SsbModulator::setLsbModulationMode(void)
+{
+  implPtr->lsbModulationMode = true;
+  if (hrd_set_mode(implPtr->batchPtr,0,HRD_MODE_LSB) != HRD_OK) shimDie("hrd_set_mode");
+}
+
+void SsbModulator::setUsbModulationMode(void)
+{
+  implPtr->lsbModulationMode = false;
+  if (hrd_set_mode(implPtr->batchPtr,0,HRD_MODE_USB) != HRD_OK) shimDie("hrd_set_mode");
+}
+
+void AmModulator::displayInternalInformation(void)
+{
+  nprintf(stderr,"\n--------------------------------------------\n");
+  nprintf(stderr,"AM Modulator Internal Information\n");
+  nprintf(stderr,"--------------------------------------------\n");
+  nprintf(stderr,"Modulator Index          : %f\n",txParameter(implPtr,HRD_PARAM_AM_INDEX));
+}
+
+void FmModulator::displayInternalInformation(void)
+{
+  nprintf(stderr,"\n--------------------------------------------\n");
+  nprintf(stderr,"FM Modulator Internal Information\n");
+  nprintf(stderr,"--------------------------------------------\n");
+  nprintf(stderr,"Frequency Deviation:      : %fHz\n",txParameter(implPtr,HRD_PARAM_FM_DEV));
+}
+
+void WbFmModulator::displayInternalInformation(void)
+{
+  nprintf(stderr,"\n--------------------------------------------\n");
+  nprintf(stderr,"Wideband FM Modulator Internal Information\n");
+  nprintf(stderr,"--------------------------------------------\n");
+  nprintf(stderr,"Frequency Deviation:      : %fHz\n",txParameter(implPtr,HRD_PARAM_WBFM_DEV));
+}
+
+void SsbModulator::displayInternalInformation(void)
+{
+  nprintf(stderr,"\n--------------------------------------------\n");
+  nprintf(stderr,"SSB Modulator Internal Information\n");
+  nprintf(stderr,"--------------------------------------------\n");
+  nprintf(stderr,"Modulation Mode        : ");
+  if (implPtr->lsbModulationMode)
+  {
+    nprintf(stderr,"LSB\n");
+  }
+  else
+  {
+    nprintf(stderr,"USB\n");
+  }
+}
