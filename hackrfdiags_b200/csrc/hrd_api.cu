@@ -111,6 +111,8 @@ int build_tables(hrd::ConstTables &t)
     for (int i = 0; i < 31; i++) t.hilbert[i] = quantise(k_hilbert31[i]);
     for (int i = 0; i < 16; i++) t.delay[i] = quantise(k_delay16[i]);
     for (int i = 0; i < 8; i++) t.tx_hb8[i] = quantise(k_tx_hb8[i]);
+    t.k_one = 1;
+    t.k_32768 = 32768;
     t.tx_c3 = quantise(k_fe3[0]);
     t.tx_m3 = quantise(k_fe3[1]);
     t.tx_c7 = quantise(k_fe2[0]);
@@ -122,7 +124,17 @@ int build_tables(hrd::ConstTables &t)
         if (t.hilbert[i] != 0) return fail(HRD_EINVAL, "Hilbert odd taps expected to be zero");
     for (int i = 0; i < 15; i++)
         if (t.delay[i] != 0) return fail(HRD_EINVAL, "delay-line taps expected to be zero");
-    if (t.tx_hb8[7] != 0) return fail(HRD_EINVAL, "Tx half-band tap 7 expected to be zero");
+    // Tx half-band designs: 8 taps {a,0,b,16384,b,0,a,0} and 4 taps {c,16384,c,0} with 0 < c <= 16384.
+    // With that structure the odd branches are (x+1)>>1 and no stage output can leave int16
+    // (hrd_tx.cu hb4_even / hb4_odd / interp8 rely on it).
+    const int32_t *h = t.tx_hb8;
+    if (h[1] || h[5] || h[7] || h[3] != 16384 || h[0] != h[6] || h[2] != h[4] ||
+        2 * (abs(h[0]) + abs(h[2])) > 32767)
+        return fail(HRD_EINVAL, "Tx 8-tap half-band does not have the expected structure");
+    if (t.tx_m3 != 16384 || t.tx_m7 != 16384 || t.tx_m8 != 16384)
+        return fail(HRD_EINVAL, "Tx 4-tap half-band centre taps expected to be 16384");
+    if (t.tx_c3 <= 0 || t.tx_c3 > 16384 || t.tx_c7 <= 0 || t.tx_c7 > 16384 || t.tx_c8 <= 0 || t.tx_c8 > 16384)
+        return fail(HRD_EINVAL, "Tx 4-tap half-band outer taps out of the supported range");
     return HRD_OK;
 }
 
@@ -131,6 +143,8 @@ struct DeviceTables {
     bool ready = false;
     float *atan2_lut = nullptr;
     float *nco_sin = nullptr, *nco_cos = nullptr;
+    uint32_t *nco_iq900 = nullptr;
+    float *nco_thr = nullptr;
 };
 std::mutex g_tab_mutex;
 DeviceTables g_dev_tables[64];
@@ -165,6 +179,30 @@ int ensure_tables(int device)
     HRD_CUDA(cudaMemcpy(d.atan2_lut, lut.data(), 65536 * sizeof(float), cudaMemcpyHostToDevice));
     HRD_CUDA(cudaMemcpy(d.nco_sin, s.data(), 16384 * sizeof(float), cudaMemcpyHostToDevice));
     HRD_CUDA(cudaMemcpy(d.nco_cos, c.data(), 16384 * sizeof(float), cudaMemcpyHostToDevice));
+    // WbFmModulator.cc:606-626: iSample *= 900; (int16_t)iSample -- a pure function of the table
+    // entry, so it is tabulated too (float multiply, truncation toward zero; |v| <= 900)
+    std::vector<uint32_t> iq900(16384);
+    for (int i = 0; i < 16384; i++) {
+        volatile float ci = c[i] * 900.0f, si = s[i] * 900.0f;
+        iq900[i] = pair16((int16_t)(int32_t)ci, (int16_t)(int32_t)si);
+    }
+    // Nco::runFast (Nco.cc:231-233): thr[k] = the smallest float phase >= 0 for which the
+    // reference's own expression gives an index offset >= k; found by walking floats around
+    // 2*pi*k/16384, so the table is exact by construction (hrd_tx.cu nco_index searches it)
+    std::vector<float> thr(8194);
+    auto ref_index = [](float ph) { return (int)(int16_t)(int32_t)((double)(ph * 16384.0f) / (2 * M_PI)); };
+    thr[0] = 0.0f;
+    for (int k = 1; k <= 8192; k++) {
+        float ph = (float)(2 * M_PI * k / 16384.0);
+        while (ref_index(ph) >= k) ph = nextafterf(ph, 0.0f);
+        while (ref_index(ph) < k) ph = nextafterf(ph, 100.0f);
+        thr[(size_t)k] = ph;
+    }
+    thr[8193] = INFINITY;
+    HRD_CUDA(cudaMalloc(&d.nco_thr, thr.size() * sizeof(float)));
+    HRD_CUDA(cudaMemcpy(d.nco_thr, thr.data(), thr.size() * sizeof(float), cudaMemcpyHostToDevice));
+    HRD_CUDA(cudaMalloc(&d.nco_iq900, 16384 * sizeof(uint32_t)));
+    HRD_CUDA(cudaMemcpy(d.nco_iq900, iq900.data(), 16384 * sizeof(uint32_t), cudaMemcpyHostToDevice));
     d.ready = true;
     return HRD_OK;
 }
@@ -791,6 +829,8 @@ int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size
     p.lsb = b->d_lsb;
     p.nco_sin = g_dev_tables[b->device].nco_sin;
     p.nco_cos = g_dev_tables[b->device].nco_cos;
+    p.nco_iq900 = g_dev_tables[b->device].nco_iq900;
+    p.nco_thr = g_dev_tables[b->device].nco_thr;
     static const int param_of_kind[5] = {-1, HRD_PARAM_AM_INDEX, HRD_PARAM_FM_DEV, HRD_PARAM_WBFM_DEV, -1};
     for (int k = 0; k < 5; k++) {
         if (!b->group_cnt[k]) continue;

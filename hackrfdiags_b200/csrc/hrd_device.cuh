@@ -88,13 +88,40 @@ __device__ __forceinline__ int f32_to_i16(float x)
 // Q15 tail: (int16_t)(acc >> 15), acc already holds the 1<<14 rounding constant
 __device__ __forceinline__ int q15(int acc) { return (int)(short)(acc >> 15); }
 
-// wrap a float phase difference into [-pi, pi]: double compares, double subtraction
-// narrowed to float (FmDemodulator.cc:511-519, WbFmDemodulator.cc:416-424)
+// ------------------------------------------------------------------------------------
+// phase wrapping without double arithmetic on the hot path
+// ------------------------------------------------------------------------------------
+// The reference wraps float phases with double constants: `while (x > M_PI) x -= 2*M_PI;`
+// i.e. compare (double)x with M_PI, subtract in double, narrow to float
+// (FmDemodulator.cc:511-519, WbFmDemodulator.cc:416-424, PhaseAccumulator.cc:165-177).
+// On sm_100a F2F.F64.F32 runs at 0.47 warp-instructions/clk/SM (tools/ubench/pipes.cu), so:
+//   * (double)x >  M_PI  <=>  x >=  HRD_PI_UP   (the float just above pi; the one below is < pi)
+//     (double)x < -M_PI  <=>  x <= -HRD_PI_UP
+//   * for |x| in [HRD_PI_UP, 12):  (float)((double)|x| - 2*M_PI) == (|x| - 2PI_HI) - 2PI_LO in
+//     fp32, where 2PI_HI = fl32(2*M_PI) and 2PI_LO = fl32(2*M_PI - 2PI_HI): the first
+//     subtraction is exact (Sterbenz), the second rounds once, and the rounding agrees with the
+//     double expression whenever | |x| - 2PI_HI | >= 2^-10.  Otherwise (4095 floats next to
+//     2*pi, or |x| >= 12) the double expression itself is evaluated.
+// tools/verify_fp_tricks.c checks both statements over every float in range (0 mismatches).
+#define HRD_PI_UP 3.14159274101257324219f
+#define HRD_2PI_HI 6.28318548202514648438f
+#define HRD_2PI_LO (-1.74845553146951715e-07f)
+
+// one wrap step toward zero of an x with |x| >= HRD_PI_UP: (float)((double)x -+ 2*M_PI)
+__device__ __forceinline__ float wrap_2pi_once(float x)
+{
+    const float s = fabsf(x);
+    const float t = __fsub_rn(s, HRD_2PI_HI);
+    float r = __fsub_rn(t, HRD_2PI_LO);
+    if (!(s < 12.0f) || fabsf(t) < 0x1p-10f) r = (float)((double)s - 2.0 * 3.14159265358979323846);
+    // x > 0: r;  x < 0: -(r)   (IEEE rounding is symmetric)
+    return __int_as_float(__float_as_int(r) ^ (__float_as_int(x) & (int)0x80000000));
+}
+
+// wrap a float phase (difference) into [-pi, pi] exactly as the reference's two while loops do
 __device__ __forceinline__ float wrap_pi(float d)
 {
-    const double pi = 3.14159265358979323846;
-    while ((double)d > pi) d = (float)((double)d - 2.0 * pi);
-    while ((double)d < -pi) d = (float)((double)d + 2.0 * pi);
+    while (fabsf(d) >= HRD_PI_UP) d = wrap_2pi_once(d);
     return d;
 }
 

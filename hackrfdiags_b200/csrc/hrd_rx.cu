@@ -74,18 +74,10 @@ struct SmemFm {
     int16_t d64[8 + BATCH256 / 4];
     int16_t a16[38 + BATCH256 / 16];
 };
-struct SmemWbfm {
-    float f256[BATCH256];
-    int16_t d256[4 + BATCH256];
-    int16_t d64[8 + BATCH256 / 4];
-    int16_t a16[38 + BATCH256 / 16];
-};
-
 template <int KIND> struct SmemOf;
 template <> struct SmemOf<K_NONE> { typedef SmemNone type; };
 template <> struct SmemOf<K_AM> { typedef SmemAm type; };
 template <> struct SmemOf<K_FM> { typedef SmemFm type; };
-template <> struct SmemOf<K_WBFM> { typedef SmemWbfm type; };
 
 // ------------------------------------------------------------------------------------
 // A. front end
@@ -208,18 +200,6 @@ __device__ __forceinline__ int dec_real(const int16_t *ring, const int32_t *taps
     return q15((int)acc);
 }
 
-// The serial part of IirFilter::filterData for a one-tap denominator
-// (Filters/IirFilter.cc:161-176): y[n] = fir[n] - a0*y[n-1], one lane, in place.
-__device__ __forceinline__ float iir_serial(float *f, int n, float a0, float y1)
-{
-    for (int i = 0; i < n; i++) {
-        float y = __fsub_rn(f[i], __fmul_rn(a0, y1));
-        f[i] = y;
-        y1 = y;
-    }
-    return y1;
-}
-
 template <typename T>
 __device__ __forceinline__ void ring_init(T *ring, const T *state, int hist, int lane, bool from_state)
 {
@@ -285,9 +265,9 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
     fk.a1 = c_tab.fe_a[1]; fk.b1 = c_tab.fe_b[1];
     fk.a2 = c_tab.fe_a[2]; fk.b2 = c_tab.fe_b[2];
     float gain = 0.f, scale = 0.f;
-    float x1 = 0.f, y1 = 0.f, th_keep = 0.f, v_keep = 0.f;
+    float x1 = 0.f;
     bool lsb = true;
-    if constexpr (KIND == K_FM || KIND == K_WBFM) gain = p.gain[sid];
+    if constexpr (KIND == K_FM) gain = p.gain[sid];
     if constexpr (KIND == K_AM) {
         const RxDec32 &d = ssb ? st.ssb : st.am;
         ring_init(sm.r256, d.r256, 2, lane, first);
@@ -306,17 +286,6 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
         ring_init(sm.a16, st.fm_a16, 38, lane, first);
         // FmDemodulator.cc:488-491
         scale = __fmul_rn(__fdiv_rn(gain, 15000.f), 32767.f);
-    }
-    if constexpr (KIND == K_WBFM) {
-        ring_init(sm.d256, st.wb_d256, 4, lane, first);
-        ring_init(sm.d64, st.wb_d64, 8, lane, first);
-        ring_init(sm.a16, st.wb_a16, 38, lane, first);
-        x1 = first ? st.wb_x1 : 0.f;
-        y1 = first ? st.wb_y1 : 0.f;
-        th_keep = first ? st.wb_prev_theta : 0.f;
-        v_keep = x1;
-        // WbFmDemodulator.cc:392-395
-        scale = __fmul_rn(__fdiv_rn(gain, 75000.f), 32767.f);
     }
     __syncwarp();
 
@@ -363,29 +332,8 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
                         __byte_perm(word, 0, 0x3120);
             } else if constexpr (KIND == K_AM) {
                 sm.r256[2 + widx] = word;
-            } else if constexpr (KIND == K_FM) {
+            } else {
                 sm.r256[14 + widx] = word;
-            } else { // K_WBFM: discriminator + the FIR half of the de-emphasis filter, in place
-                // uint8_t idx = (uint8_t)sample + 128  (WbFmDemodulator.cc:403-404)
-                uint32_t x = word ^ 0x80808080u;
-                uint32_t idx0 = __byte_perm(x, 0, 0x4420), idx1 = __byte_perm(x, 0, 0x4431);
-                float th0 = __ldg(p.atan2_lut + idx0), th1 = __ldg(p.atan2_lut + idx1);
-                // theta of the previous sample: previous lane's th1 (lane 0: kept from before)
-                float sel = (lane == 31) ? th_keep : th1;
-                float thp = __shfl_sync(HRD_FULL_MASK, sel, (lane + 31) & 31);
-                float d0 = wrap_pi(__fsub_rn(th0, thp));
-                float d1 = wrap_pi(__fsub_rn(th1, th0));
-                float v0 = __fmul_rn(scale, d0), v1 = __fmul_rn(scale, d1);
-                float selv = (lane == 31) ? v_keep : v1;
-                float vp = __shfl_sync(HRD_FULL_MASK, selv, (lane + 31) & 31);
-                th_keep = th1; // the state save reads them from the last live lane
-                v_keep = v1;
-                // FirFilter::filterData order: y = 0 + b0*x[n]; y = y + b1*x[n-1]
-                const float bb = 0.0253863f;
-                float f0 = __fadd_rn(__fmul_rn(bb, v0), __fmul_rn(bb, vp));
-                float f1 = __fadd_rn(__fmul_rn(bb, v1), __fmul_rn(bb, v0));
-                sm.f256[2 * widx] = f0;
-                sm.f256[2 * widx + 1] = f1;
             }
         };
         // Full batches have 16 iterations, a multiple of RX_DEPTH, so the buffers keep their
@@ -476,24 +424,6 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
             ring_shift(sm.a16, 38, n16, lane);
         }
 
-        if constexpr (KIND == K_WBFM) {
-            // the recursive half of the de-emphasis filter, serial at 256 kS/s
-            if (lane == 0) y1 = iir_serial(sm.f256, (int)nb, -0.9492274f, y1);
-            y1 = __shfl_sync(HRD_FULL_MASK, y1, 0);
-            __syncwarp();
-            // WbFmDemodulator.cc:460-500: (int16_t) cast, /4 (8) /4 (12) /2 (40)
-            for (int i = lane; i < (int)nb; i += 32) sm.d256[4 + i] = (int16_t)f32_to_i16(sm.f256[i]);
-            __syncwarp();
-            for (int j = lane; j < n64; j += 32) sm.d64[8 + j] = (int16_t)dec_real<8, 4>(sm.d256, c_tab.wbfm_post1, j);
-            __syncwarp();
-            for (int k = lane; k < n16; k += 32) sm.a16[38 + k] = (int16_t)dec_real<12, 4>(sm.d64, c_tab.fm_post, k);
-            __syncwarp();
-            if (emit && lane < n8) pcm_out[lane] = (int16_t)dec_real<40, 2>(sm.a16, c_tab.audio40, lane);
-            __syncwarp();
-            ring_shift(sm.d256, 4, (int)nb, lane);
-            ring_shift(sm.d64, 8, n64, lane);
-            ring_shift(sm.a16, 38, n16, lane);
-        }
         done256 += nb;
     }
 
@@ -529,16 +459,248 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
         ring_save_hist(sm.d64, so.fm_d64, 8, lane);
         ring_save_hist(sm.a16, so.fm_a16, 38, lane);
     }
-    if constexpr (KIND == K_WBFM) {
-        ring_save_hist(sm.d256, so.wb_d256, 4, lane);
-        ring_save_hist(sm.d64, so.wb_d64, 8, lane);
-        ring_save_hist(sm.a16, so.wb_a16, 38, lane);
+}
+
+// ------------------------------------------------------------------------------------
+// WBFM (WbFmDemodulator.cc:341-500)
+// ------------------------------------------------------------------------------------
+// The de-emphasis filter (WbFmDemodulator.cc:93-102, IirFilter.cc:161-176) is a float recurrence
+// at 256 kS/s, y[n] = fir[n] - (-0.9492274f * y[n-1]): a dependent FMUL+FSUB per sample that no
+// amount of lanes can shorten.  Run on one lane of the warp that owns the stream it idles the
+// other 31 (the first version of this kernel: 18 % of the HBM roofline, issue-bound on one-lane
+// instructions).  Here the recurrences of 31 items are TRANSPOSED onto the lanes of one warp:
+//
+//   CTA = 32 warps.  Warps 1..31 own one (stream, tile) item each and do everything that is
+//   parallel in time: front end, atan2 table, phase difference, wrap, gain, the FIR half of the
+//   de-emphasis filter (-> shared memory, floats), and after the recurrence the (int16_t)
+//   narrowing and the /4 /4 /2 decimators.  Warp 0 is the CHAIN warp: lane r walks item r's row
+//   of WB_STEP floats in place, 16 bytes at a time (row pitch 260 words: conflict-free LDS.128).
+//   Two row buffers make a two-stage pipeline with one __syncthreads per step: while the chain
+//   warp is on step t, every item warp narrows/decimates its step t-1 and then produces step t+1
+//   into the buffer it has just drained.
+//
+// The chain costs WB_STEP x ~10 cycles per step and runs beside ~31 x 4 warp-iterations of front
+// end, so it is hidden as long as the item warps have at least that much to do (they do: the
+// step is HBM- or issue-bound on them).  Results are bit-identical to the serial evaluation:
+// same operations, same order, per stream.
+constexpr int WB_ITEMS = 31;
+constexpr int WB_STEP = 256;            // 256 kS/s samples per pipeline step (4 warp iterations)
+constexpr int WB_PITCH = WB_STEP + 4;   // floats per row
+
+struct SmemWbItem {
+    int16_t d256[4 + WB_STEP];
+    int16_t d64[8 + WB_STEP / 4];
+    int16_t a16[38 + WB_STEP / 16];
+};
+struct SmemWb {
+    float f[2][32][WB_PITCH];
+    SmemWbItem item[WB_ITEMS];
+};
+
+template <int ENTRY>
+__global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
+{
+    typedef typename RawOf<ENTRY>::type Raw;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemWb &sm = *reinterpret_cast<SmemWb *>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const bool chain_warp = warp == 0;
+    const int n_items = p.n_streams * p.n_tiles;
+
+    // ---- this thread's item: the warp's (item warps) or the lane's (chain warp) ---------
+    const uint32_t tile_len = p.tile_batches * BATCH256;
+    const uint32_t halo = (uint32_t)HaloOf<K_WBFM>::value * BATCH256;
+    const int row = chain_warp ? lane : warp - 1;
+    const int item = blockIdx.x * WB_ITEMS + row;
+    const bool live = row < WB_ITEMS && item < n_items;
+    int tile = 0, sid = 0;
+    uint32_t start = 0, end = 0, emit_from = 0;
+    if (live) {
+        tile = item / p.n_streams;
+        sid = p.stream_ids[item - tile * p.n_streams];
+        emit_from = (uint32_t)tile * tile_len;
+        end = min(p.n256, emit_from + tile_len);
+        start = tile == 0 ? 0u : emit_from - halo;
+    }
+    const bool first = tile == 0, last = tile == p.n_tiles - 1;
+    // the same for every thread of the CTA: steps of the longest item
+    const uint32_t max_len = min(p.n256, tile_len + (p.n_tiles > 1 ? halo : 0u));
+    const uint32_t n_steps = (max_len + WB_STEP - 1) / WB_STEP;
+    const RxState &st = p.state_in[sid];
+
+    // ---- chain warp state ----------------------------------------------------------------
+    float y1 = 0.f;
+    if (chain_warp && live && first) y1 = st.wb_y1;
+
+    // ---- item warp state -----------------------------------------------------------------
+    SmemWbItem &it = sm.item[chain_warp ? 0 : warp - 1];
+    const int8_t *src = p.iq + (size_t)sid * p.iq_stride;
+    asm volatile("" : "+l"(src));
+    FeCarry fc;
+    fc.t = fc.v = fc.u = 0u;
+    FeTaps fk;
+    fk.a0 = c_tab.fe_a[0]; fk.b0 = c_tab.fe_b[0];
+    fk.a1 = c_tab.fe_a[1]; fk.b1 = c_tab.fe_b[1];
+    fk.a2 = c_tab.fe_a[2]; fk.b2 = c_tab.fe_b[2];
+    float scale = 0.f, th_keep = 0.f, v_keep = 0.f;
+    constexpr uint32_t BPS = ENTRY == 0 ? 16 : 2;
+    uint32_t pf = 0, pf_last = 0, last_active = 32;
+    Raw buf[RX_DEPTH];
+    if (!chain_warp && live) {
+        if (first) {
+            fc.t = st.fe_t; fc.v = st.fe_v; fc.u = st.fe_u;
+            th_keep = st.wb_prev_theta;
+            v_keep = st.wb_x1;
+        }
+        ring_init(it.d256, st.wb_d256, 4, lane, first);
+        ring_init(it.d64, st.wb_d64, 8, lane, first);
+        ring_init(it.a16, st.wb_a16, 38, lane, first);
+        // WbFmDemodulator.cc:392-395
+        scale = __fmul_rn(__fdiv_rn(p.gain[sid], 75000.f), 32767.f);
+        pf = (start + 2 * lane) * BPS;
+        pf_last = (end - 2) * BPS;
+#pragma unroll
+        for (int d = 0; d < RX_DEPTH; d++) {
+            buf[d] = load_raw<ENTRY>(src, pf, pf_last);
+            pf += IT_SAMPLES * BPS;
+        }
+    }
+    __syncwarp();
+
+    // one warp iteration: 64 samples at 256 kS/s -> 64 floats of the row (FIR half done)
+    auto iter = [&](Raw &b, float *dst) {
+        uint32_t word;
+        if constexpr (ENTRY == 0) {
+            uint32_t t[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) t[r] = __byte_perm(b.v[r], 0, 0x3120);
+            b = load_raw<ENTRY>(src, pf, pf_last);
+            word = front_end_iter(t, fc, fk, lane);
+        } else {
+            word = __byte_perm(b, 0, 0x3120);
+            b = load_raw<ENTRY>(src, pf, pf_last);
+        }
+        pf += IT_SAMPLES * BPS;
+        // uint8_t idx = (uint8_t)sample + 128  (WbFmDemodulator.cc:403-404)
+        const uint32_t x = word ^ 0x80808080u;
+        const uint32_t idx0 = __byte_perm(x, 0, 0x4420), idx1 = __byte_perm(x, 0, 0x4431);
+        const float th0 = __ldg(p.atan2_lut + idx0), th1 = __ldg(p.atan2_lut + idx1);
+        // theta of the previous sample: previous lane's th1 (lane 0: kept from before)
+        const float sel = (lane == 31) ? th_keep : th1;
+        const float thp = __shfl_sync(HRD_FULL_MASK, sel, (lane + 31) & 31);
+        const float d0 = wrap_pi(__fsub_rn(th0, thp));
+        const float d1 = wrap_pi(__fsub_rn(th1, th0));
+        const float v0 = __fmul_rn(scale, d0), v1 = __fmul_rn(scale, d1);
+        const float selv = (lane == 31) ? v_keep : v1;
+        const float vp = __shfl_sync(HRD_FULL_MASK, selv, (lane + 31) & 31);
+        th_keep = th1; // the state save reads them from the last live lane
+        v_keep = v1;
+        // FirFilter::filterData order: y = 0 + b0*x[n]; y = y + b1*x[n-1]   (FirFilter.cc:161-164)
+        const float bb = 0.0253863f;
+        const float m0 = __fmul_rn(bb, v0);
+        float2 o;
+        o.x = __fadd_rn(m0, __fmul_rn(bb, vp));
+        o.y = __fadd_rn(__fmul_rn(bb, v1), m0);
+        *reinterpret_cast<float2 *>(dst + 2 * lane) = o;
+    };
+
+    // step t of this item: samples [start + t*WB_STEP, ...) -> row of buffer t&1
+    auto produce = [&](uint32_t t) {
+        const uint32_t done = start + t * WB_STEP;
+        if (done >= end) return;
+        const uint32_t nb = min((uint32_t)WB_STEP, end - done);
+        const uint32_t n_it = (nb + IT_SAMPLES - 1) / IT_SAMPLES;
+        last_active = min(32u, (nb - (n_it - 1) * IT_SAMPLES) / 2);
+        float *dst = sm.f[t & 1][row];
+        uint32_t i = 0;
+        for (; i + RX_DEPTH <= n_it; i += RX_DEPTH) {
+#pragma unroll
+            for (int d = 0; d < RX_DEPTH; d++) iter(buf[d], dst + (i + d) * IT_SAMPLES);
+        }
+#pragma unroll
+        for (int d = 0; d < RX_DEPTH - 1; d++)
+            if (i + d < n_it) iter(buf[d], dst + (i + d) * IT_SAMPLES);
+        __syncwarp();
+    };
+
+    // WbFmDemodulator.cc:460-500 on step t: (int16_t) narrowing, /4 (8 taps) /4 (12) /2 (40)
+    auto consume = [&](uint32_t t) {
+        const uint32_t done = start + t * WB_STEP;
+        if (done >= end) return;
+        const int nb = (int)min((uint32_t)WB_STEP, end - done);
+        const int n64 = nb / 4, n16 = nb / 16, n8 = nb / 32;
+        const float *y = sm.f[t & 1][row];
+        for (int i = lane; i < nb; i += 32) it.d256[4 + i] = (int16_t)f32_to_i16(y[i]);
+        __syncwarp();
+        for (int j = lane; j < n64; j += 32) it.d64[8 + j] = (int16_t)dec_real<8, 4>(it.d256, c_tab.wbfm_post1, j);
+        __syncwarp();
+        if (lane < n16) it.a16[38 + lane] = (int16_t)dec_real<12, 4>(it.d64, c_tab.fm_post, lane);
+        __syncwarp();
+        if (done >= emit_from && lane < n8)
+            p.pcm[(size_t)sid * p.pcm_stride + done / 32 + lane] = (int16_t)dec_real<40, 2>(it.a16, c_tab.audio40, lane);
+        __syncwarp();
+        ring_shift(it.d256, 4, nb, lane);
+        ring_shift(it.d64, 8, n64, lane);
+        ring_shift(it.a16, 38, n16, lane);
+    };
+
+    // IirFilter.cc:161-176 with a = {-0.9492274f}: lane = item, in place, 32 samples per round
+    auto chain = [&](uint32_t t) {
+        const uint32_t done = start + t * WB_STEP;
+        if (done >= end) return;
+        const uint32_t nb = min((uint32_t)WB_STEP, end - done); // multiple of 32
+        float *r = sm.f[t & 1][lane];
+        for (uint32_t c = 0; c < nb; c += 32) {
+            float4 v[8];
+#pragma unroll
+            for (int g = 0; g < 8; g++) v[g] = *reinterpret_cast<float4 *>(r + c + 4 * g);
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+                v[g].x = y1 = __fsub_rn(v[g].x, __fmul_rn(-0.9492274f, y1));
+                v[g].y = y1 = __fsub_rn(v[g].y, __fmul_rn(-0.9492274f, y1));
+                v[g].z = y1 = __fsub_rn(v[g].z, __fmul_rn(-0.9492274f, y1));
+                v[g].w = y1 = __fsub_rn(v[g].w, __fmul_rn(-0.9492274f, y1));
+                *reinterpret_cast<float4 *>(r + c + 4 * g) = v[g];
+            }
+        }
+    };
+
+    if (!chain_warp && live) produce(0);
+    __syncthreads();
+    for (uint32_t t = 0; t < n_steps; t++) {
+        if (chain_warp) {
+            if (live) chain(t);
+        } else if (live) {
+            if (t >= 1) consume(t - 1);
+            if (t + 1 < n_steps) produce(t + 1);
+        }
+        __syncthreads();
+    }
+    if (!chain_warp && live) consume(n_steps - 1);
+
+    // ---- the last tile leaves the stream's state for the next call -----------------------
+    RxState &so = p.state_out[sid];
+    if (!chain_warp && live && last) {
+        const uint32_t *a = reinterpret_cast<const uint32_t *>(&st);
+        uint32_t *b = reinterpret_cast<uint32_t *>(&so);
+        for (int i = lane; i < (int)(sizeof(RxState) / 4); i += 32) b[i] = a[i];
+        __syncwarp();
+        ring_save_hist(it.d256, so.wb_d256, 4, lane);
+        ring_save_hist(it.d64, so.wb_d64, 8, lane);
+        ring_save_hist(it.a16, so.wb_a16, 38, lane);
         if (lane == (int)last_active - 1) {
+            if constexpr (ENTRY == 0) {
+                so.fe_t = fc.t;
+                so.fe_v = fc.v;
+                so.fe_u = fc.u;
+            }
             so.wb_prev_theta = th_keep;
             so.wb_x1 = v_keep;
         }
-        if (lane == 0) so.wb_y1 = y1;
     }
+    __syncthreads(); // the record copy above must land before the chain warp's y[n-1]
+    if (chain_warp && live && last) so.wb_y1 = y1;
 }
 
 // ------------------------------------------------------------------------------------
@@ -735,10 +897,12 @@ int resident_warps()
     return blocks * HRD_WARPS_PER_CTA;
 }
 
+// (stream, tile) items one SM works on at a time
 int rx_resident_warps_per_sm(int kind, int entry)
 {
     static int cache[5][2] = {};
     if (kind < 0 || kind > 4 || entry < 0 || entry > 1) return HRD_WARPS_PER_CTA;
+    if (kind == K_WBFM) return WB_ITEMS; // one 32-warp CTA per SM
     if (cache[kind][entry]) return cache[kind][entry];
     int w = HRD_WARPS_PER_CTA;
 #define HRD_RW(K, E) (w = resident_warps<K, E>())
@@ -746,11 +910,24 @@ int rx_resident_warps_per_sm(int kind, int entry)
     case K_NONE: entry == 0 ? HRD_RW(K_NONE, 0) : HRD_RW(K_NONE, 1); break;
     case K_AM: entry == 0 ? HRD_RW(K_AM, 0) : HRD_RW(K_AM, 1); break;
     case K_FM: entry == 0 ? HRD_RW(K_FM, 0) : HRD_RW(K_FM, 1); break;
-    case K_WBFM: entry == 0 ? HRD_RW(K_WBFM, 0) : HRD_RW(K_WBFM, 1); break;
     }
 #undef HRD_RW
     cache[kind][entry] = w;
     return w;
+}
+
+template <int ENTRY>
+int launch_wbfm(const RxParams &p, cudaStream_t s)
+{
+    static bool attr_set = false; // per template instance
+    if (!attr_set) {
+        cudaFuncSetAttribute(rx_wbfm_kernel<ENTRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemWb));
+        attr_set = true;
+    }
+    const long long items = (long long)p.n_streams * p.n_tiles;
+    const int grid = (int)((items + WB_ITEMS - 1) / WB_ITEMS);
+    rx_wbfm_kernel<ENTRY><<<grid, 1024, sizeof(SmemWb), s>>>(p);
+    return (int)cudaGetLastError();
 }
 
 // kind: K_NONE, K_AM (AM and SSB streams together), K_FM or K_WBFM
@@ -764,7 +941,8 @@ int launch_rx(int kind, int entry, const RxParams &p, cudaStream_t s)
         HRD_RX_CASE(K_NONE)
         HRD_RX_CASE(K_AM)
         HRD_RX_CASE(K_FM)
-        HRD_RX_CASE(K_WBFM)
+    case K_WBFM:
+        return entry == 0 ? launch_wbfm<0>(p, s) : launch_wbfm<1>(p, s);
     }
 #undef HRD_RX_CASE
     return (int)cudaErrorInvalidValue;

@@ -38,6 +38,8 @@ struct ConstTables {
     int32_t tx_hb8[8];      // stages 2,4,5
     int32_t tx_c3, tx_c7, tx_c8; // outer tap of stages 3&6 / 7 / 8 (8424 / 8249 / 8206)
     int32_t tx_m3, tx_m7, tx_m8; // their centre taps (16384 each after quantisation)
+    // 1 and 32768 as values the compiler cannot see (hrd_tx.cu: adds spelled as IMAD to balance pipes)
+    int32_t k_one, k_32768;
 };
 
 // ---------------------------------------------------------------- Rx per-stream state
@@ -144,6 +146,10 @@ struct TxParams {
     const float *param;        // AM index / FM deviation / WBFM deviation
     const uint8_t *lsb;
     const float *nco_sin, *nco_cos;
+    // WBFM: {(int16_t)(cos*900), (int16_t)(sin*900)} per NCO table entry, packed I = low half
+    // (WbFmModulator.cc:606-626 applied to Nco.cc's tables once, at table build)
+    const uint32_t *nco_iq900;
+    const float *nco_thr;      // [8194] Nco::runFast index thresholds (hrd_tx.cu nco_index)
 };
 
 enum { K_NONE = 0, K_AM = 1, K_FM = 2, K_WBFM = 3, K_SSB = 4 };

@@ -44,16 +44,6 @@ struct SmemTx {
     float ph[NB8];              // FM: NCO phases of the batch
 };
 
-struct SmemTxWb {
-    uint32_t s0[19 + NB8];
-    uint32_t s1[3 + 2 * NB8];
-    uint32_t s2[1 + 4 * NB8];
-    uint32_t s3[3 + 8 * NB8];
-    uint32_t s4[3 + 16 * NB8];
-    uint32_t s5[1 + 32 * NB8];  // stage 6 input @256k: first the real PCM, then I/Q pairs in place
-    float ph[32 * NB8];         // NCO phase per 256 kS/s sample
-};
-
 // ---- generic polyphase stages over rings of I/Q pairs ------------------------------------
 // stage 1: 40 taps, L = 2 (20 taps per branch); ring hist 19, input n at ring[19 + n]
 __device__ __forceinline__ void interp40(const uint32_t *in, int n, uint32_t &even, uint32_t &odd)
@@ -72,35 +62,65 @@ __device__ __forceinline__ void interp40(const uint32_t *in, int n, uint32_t &ev
     odd = pack16(q15((int)oi), q15((int)oq));
 }
 
-// stages 2,4,5: 8 taps, L = 2; ring hist 3, input n at ring[3 + n]
+// stages 2,4,5: 8 taps {a,0,b,16384,b,0,a,0}, L = 2; ring hist 3, input n at ring[3 + n]:
+// even = a*(x[n]+x[n-3]) + b*(x[n-1]+x[n-2]), odd = 16384*x[n-1]  (results fit int16, see hb4_*)
 __device__ __forceinline__ void interp8(const uint32_t *in, int n, uint32_t &even, uint32_t &odd)
 {
-    int ei = 1 << 14, eq = 1 << 14, oi = 1 << 14, oq = 1 << 14;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        uint32_t w = in[3 + n - k];
-        int xi = lo16(w), xq = hi16(w);
-        ei += c_tabtx.tx_hb8[2 * k] * xi;
-        eq += c_tabtx.tx_hb8[2 * k] * xq;
-        oi += c_tabtx.tx_hb8[2 * k + 1] * xi;
-        oq += c_tabtx.tx_hb8[2 * k + 1] * xq;
-    }
-    even = pack16(q15(ei), q15(eq));
-    odd = pack16(q15(oi), q15(oq));
+    const int ha = c_tabtx.tx_hb8[0], hb = c_tabtx.tx_hb8[2];
+    const uint32_t w0 = in[3 + n], w1 = in[2 + n], w2 = in[1 + n], w3 = in[n];
+    const int ei = ((1 << 14) + ha * (lo16(w0) + lo16(w3)) + hb * (lo16(w1) + lo16(w2))) >> 15;
+    const int eq = ((1 << 14) + ha * (hi16(w0) + hi16(w3)) + hb * (hi16(w1) + hi16(w2))) >> 15;
+    even = pack16(ei, eq);
+    odd = pack16((lo16(w1) + 1) >> 1, (hi16(w1) + 1) >> 1);
 }
 
-// stages 3,6,7,8: taps {c, m, c, 0}, L = 2:  even = c*(x[n]+x[n-1]), odd = m*x[n]
-__device__ __forceinline__ int hb4_even(int c, int x, int xm1) { return q15((1 << 14) + c * x + c * xm1); }
-__device__ __forceinline__ int hb4_odd(int m, int x) { return q15((1 << 14) + m * x); }
+// stages 3,6,7,8: taps {c, m, c, 0}, L = 2:  even = c*(x[n]+x[n-1]), odd = m*x[n].
+// The host asserts m == 16384 and 0 < c <= 16384 (hrd_api.cu build_tables), so for int16 inputs
+//   odd  = (16384 + 16384*x) >> 15 = (x + 1) >> 1                       (no multiply)
+//   even = (16384 + c*(x + xm1)) >> 15, |even| <= 16848                  (one multiply)
+// and neither can leave the int16 range: the reference's (int16_t) narrowing is the identity
+// here and is not spent on (Interpolator_int16.cc:398-418 evaluated with these taps).
+//
+// PIPE BALANCE.  These kernels are issue-bound, and on sm_100a the integer ALU pipe (IADD3, SHF,
+// LEA, PRMT, LOP3) and the FMA pipe (IMAD) each take one warp instruction every two cycles per
+// scheduler (profiles/: tx_kernel<SSB> ran the ALU pipe at 85 % with the FMA pipe at 25 %).  The
+// additions of the hot loop are therefore spelled as multiply-adds (mad.lo.s32 -> IMAD) so that
+// they issue on the FMA pipe; only the arithmetic right shifts and the byte packing stay on the
+// ALU pipe.
+__device__ __forceinline__ int imad(int a, int b, int c)
+{
+    int d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int hb4_even(int c, int x, int xm1) { return imad(c, x, imad(c, xm1, 1 << 14)) >> 15; }
+// `one` comes from constant memory (ConstTables::k_one) so that ptxas cannot fold x*1+1 back into
+// an ALU-pipe add
+__device__ __forceinline__ int hb4_odd(int x, int one) { return imad(x, one, one) >> 1; }
 
 // ---- PhaseAccumulator::run (Nco/PhaseAccumulator.cc:157-181) -------------------------------
+// acc += step, then the two while loops that wrap into [-pi, pi] (hrd_device.cuh wrap_pi: fp32
+// compares and an fp32 wrap that is bit-identical to the reference's double expression).
 __device__ __forceinline__ float phase_advance(float acc, float step)
 {
-    const double pi = 3.14159265358979323846;
-    acc = __fadd_rn(acc, step);
-    while ((double)acc > pi) acc = (float)((double)acc - 2.0 * pi);
-    while ((double)acc < -pi) acc = (float)((double)acc + 2.0 * pi);
-    return acc;
+    return wrap_pi(__fadd_rn(acc, step));
+}
+
+// The same, for the 256 kS/s chain of the WBFM modulator, where up to 31 lanes advance 31
+// independent accumulators in lock step and some lane wraps on almost every sample: the common
+// single wrap is evaluated branch-free on every lane (three dependent FADDs and a select), and
+// only the rare cases (hrd_device.cuh: next to 2*pi, |acc| >= 12, or a second wrap) branch.
+__device__ __forceinline__ float phase_advance_lockstep(float acc, float step)
+{
+    const float a = __fadd_rn(acc, step);
+    const float s = fabsf(a);
+    const float t = __fsub_rn(s, HRD_2PI_HI);
+    const float r = __fsub_rn(t, HRD_2PI_LO);
+    const float w = __int_as_float(__float_as_int(r) ^ (__float_as_int(a) & (int)0x80000000));
+    const bool wrap = s >= HRD_PI_UP;
+    float out = wrap ? w : a;
+    if (wrap && (!(s < 12.0f) || fabsf(t) < 0x1p-10f || fabsf(r) >= HRD_PI_UP)) out = wrap_pi(a);
+    return out;
 }
 
 // PhaseAccumulator::setFrequency (:95-107): (float)((2*M_PI*f)/fs) in double
@@ -111,38 +131,36 @@ __device__ __forceinline__ float phase_step(float f, double fs)
 
 // Stages 5..8 of one rail for one 128 kS/s input sample x (with its three predecessors):
 // 16 outputs as accumulators whose byte 2 is the (int8_t) value (doubled taps, see hrd_rx.cu).
+// Stage 5 is the 8-tap half-band {a,0,b,16384,b,0,a,0} (AmModulator.cc:57-67; structure asserted
+// on the host): its even branch is a*(x0+x3) + b*(x1+x2), its odd branch is 16384*x[n-1].
 __device__ __forceinline__ void tail4(int x0, int x1, int x2, int x3, int (&out)[16])
 {
-    const int *h = c_tabtx.tx_hb8;
-    // stage 5 (8 taps): even uses x[n..n-3], odd uses taps {q1,q3,q5,q7} on the same four
+    const int ha = c_tabtx.tx_hb8[0], hb = c_tabtx.tx_hb8[2];
+    const int one = c_tabtx.k_one, k15 = c_tabtx.k_32768;
     int y5[2], y5m1;
-    y5[0] = q15((1 << 14) + h[0] * x0 + h[2] * x1 + h[4] * x2 + h[6] * x3);
-    y5[1] = q15((1 << 14) + h[1] * x0 + h[3] * x1 + h[5] * x2 + h[7] * x3);
-    // previous odd output (input n-1): needs x[n-1..n-4]; q7 == 0 so x[n-4] drops out only
-    // if the tap is zero -- it is (AmModulator.cc:57-67), asserted on the host.
-    y5m1 = q15((1 << 14) + h[1] * x1 + h[3] * x2 + h[5] * x3);
-    const int c6 = c_tabtx.tx_c3, m6 = c_tabtx.tx_m3;
-    const int c7 = c_tabtx.tx_c7, m7 = c_tabtx.tx_m7;
-    const int c8 = c_tabtx.tx_c8, m8 = c_tabtx.tx_m8;
+    y5[0] = imad(ha, x0, imad(ha, x3, imad(hb, x1, imad(hb, x2, 1 << 14)))) >> 15; // |.| <= 21986: fits int16
+    y5[1] = (x1 + 1) >> 1;   // plain adds here: the FMA pipe is the fuller one after the re-balancing
+    y5m1 = (x2 + 1) >> 1;    // odd output of the previous input sample
+    const int c6 = c_tabtx.tx_c3, c7 = c_tabtx.tx_c7, c8d = 2 * c_tabtx.tx_c8;
     int y6[4], y6m1;
-    y6m1 = hb4_odd(m6, y5m1);
+    y6m1 = (y5m1 + 1) >> 1;
     y6[0] = hb4_even(c6, y5[0], y5m1);
-    y6[1] = hb4_odd(m6, y5[0]);
+    y6[1] = hb4_odd(y5[0], one);
     y6[2] = hb4_even(c6, y5[1], y5[0]);
-    y6[3] = hb4_odd(m6, y5[1]);
+    y6[3] = hb4_odd(y5[1], one);
     int y7[8], y7m1;
-    y7m1 = hb4_odd(m7, y6m1);
+    y7m1 = hb4_odd(y6m1, one);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         y7[2 * k] = hb4_even(c7, y6[k], k ? y6[k - 1] : y6m1);
-        y7[2 * k + 1] = hb4_odd(m7, y6[k]);
+        y7[2 * k + 1] = hb4_odd(y6[k], one);
     }
     // stage 8 with doubled taps: (int8_t)(acc>>15) == byte 2 of 2*acc
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         int left = k ? y7[k - 1] : y7m1;
-        out[2 * k] = (1 << 15) + 2 * c8 * (y7[k] + left);
-        out[2 * k + 1] = (1 << 15) + 2 * m8 * y7[k];
+        out[2 * k] = imad(c8d, y7[k] + left, 1 << 15);
+        out[2 * k + 1] = imad(y7[k], k15, k15);
     }
 }
 
@@ -152,25 +170,24 @@ __device__ __forceinline__ uint32_t merge16(uint32_t lo, uint32_t hi) { return _
 // ---- stages 6..8 only (WBFM: the NCO sits between stage 5 and stage 6) ----------------------
 __device__ __forceinline__ void tail3(int x0, int xm1, int (&out)[8])
 {
-    const int c6 = c_tabtx.tx_c3, m6 = c_tabtx.tx_m3;
-    const int c7 = c_tabtx.tx_c7, m7 = c_tabtx.tx_m7;
-    const int c8 = c_tabtx.tx_c8, m8 = c_tabtx.tx_m8;
+    const int c6 = c_tabtx.tx_c3, c7 = c_tabtx.tx_c7, c8d = 2 * c_tabtx.tx_c8;
+    const int one = c_tabtx.k_one, k15 = c_tabtx.k_32768;
     int y6[2], y6m1;
-    y6m1 = hb4_odd(m6, xm1);
+    y6m1 = hb4_odd(xm1, one);
     y6[0] = hb4_even(c6, x0, xm1);
-    y6[1] = hb4_odd(m6, x0);
+    y6[1] = hb4_odd(x0, one);
     int y7[4], y7m1;
-    y7m1 = hb4_odd(m7, y6m1);
+    y7m1 = hb4_odd(y6m1, one);
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         y7[2 * k] = hb4_even(c7, y6[k], k ? y6[k - 1] : y6m1);
-        y7[2 * k + 1] = hb4_odd(m7, y6[k]);
+        y7[2 * k + 1] = hb4_odd(y6[k], one);
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         int left = k ? y7[k - 1] : y7m1;
-        out[2 * k] = (1 << 15) + 2 * c8 * (y7[k] + left);
-        out[2 * k + 1] = (1 << 15) + 2 * m8 * y7[k];
+        out[2 * k] = imad(c8d, y7[k] + left, 1 << 15);
+        out[2 * k + 1] = imad(y7[k], k15, k15);
     }
 }
 
@@ -260,9 +277,9 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxPara
         __syncwarp();
         for (int n = lane; n < 4 * nb; n += 32) {
             uint32_t w = sm.s2[1 + n], wm = sm.s2[n];
-            const int c = c_tabtx.tx_c3, m = c_tabtx.tx_m3;
+            const int c = c_tabtx.tx_c3;
             sm.s3[3 + 2 * n] = pack16(hb4_even(c, lo16(w), lo16(wm)), hb4_even(c, hi16(w), hi16(wm)));
-            sm.s3[3 + 2 * n + 1] = pack16(hb4_odd(m, lo16(w)), hb4_odd(m, hi16(w)));
+            sm.s3[3 + 2 * n + 1] = pack16((lo16(w) + 1) >> 1, (hi16(w) + 1) >> 1);
         }
         __syncwarp();
         for (int n = lane; n < 8 * nb; n += 32) interp8(sm.s3, n, sm.s4[3 + 2 * n], sm.s4[3 + 2 * n + 1]);
@@ -272,18 +289,19 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxPara
         int8_t *out = dst + (size_t)done * 512;
         for (int n = lane; n < 16 * nb; n += 32) {
             uint32_t w0 = sm.s4[3 + n], w1 = sm.s4[2 + n], w2 = sm.s4[1 + n], w3 = sm.s4[n];
-            int oi[16], oq[16];
+            int oi[16];
             tail4(lo16(w0), lo16(w1), lo16(w2), lo16(w3), oi);
-            if constexpr (KIND == K_AM) {
-#pragma unroll
-                for (int k = 0; k < 16; k++) oq[k] = oi[k];
-            } else {
-                tail4(hi16(w0), hi16(w1), hi16(w2), hi16(w3), oq);
-            }
             u32x8 o;
+            if constexpr (KIND == K_AM) { // both rails carry the same samples (AmModulator.cc:601-602)
 #pragma unroll
-            for (int k = 0; k < 8; k++) // bytes {I[2k], Q[2k], I[2k+1], Q[2k+1]}
-                o.v[k] = merge16(pack_b2(oi[2 * k], oq[2 * k]), pack_b2(oi[2 * k + 1], oq[2 * k + 1]));
+                for (int k = 0; k < 8; k++) o.v[k] = __byte_perm((uint32_t)oi[2 * k], (uint32_t)oi[2 * k + 1], 0x6622);
+            } else {
+                int oq[16];
+                tail4(hi16(w0), hi16(w1), hi16(w2), hi16(w3), oq);
+#pragma unroll
+                for (int k = 0; k < 8; k++) // bytes {I[2k], Q[2k], I[2k+1], Q[2k+1]}
+                    o.v[k] = merge16(pack_b2(oi[2 * k], oq[2 * k]), pack_b2(oi[2 * k + 1], oq[2 * k + 1]));
+            }
             stg_stream_256(out + (size_t)n * 32, o);
         }
         __syncwarp();
@@ -309,111 +327,256 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxPara
 }
 
 // ------------------------------------------------------------------------------------
-// WBFM kernel: stages 1..5 on the real PCM, NCO at 256 kS/s, stages 6..8 on I and Q
+// WBFM (WbFmModulator.cc:347-632): stages 1..5 on the real PCM, NCO at 256 kS/s, stages 6..8
+// on I and Q.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_wbfm_kernel(const TxParams p)
+// The NCO phase (PhaseAccumulator.cc:157-181) is a float accumulation at 256 kS/s with no decay:
+// phase[n+1] = wrap(fl(phase[n] + step[n])).  It cannot be cut in time and it cannot be
+// re-associated, so it is evaluated serially per stream -- but TRANSPOSED, exactly like the
+// de-emphasis recurrence of the WBFM demodulator (hrd_rx.cu rx_wbfm_kernel):
+//   CTA = 32 warps.  Warps 1..31 own one stream each: PCM -> stages 1..5 -> phase step per
+//   256 kS/s sample (-> shared memory), and after the chain: table index -> (cos,sin)*900 as
+//   int16 -> stages 6..8 on both rails -> 32-byte stores.  Warp 0 is the chain warp: lane r
+//   walks stream r's row of TW_STEP phase steps in place, leaving the phase BEFORE each step.
+//   Two row buffers, one __syncthreads per step of 8 PCM samples.
+constexpr int TW_ITEMS = 31;
+constexpr int TW_STEP8 = 8;               // PCM samples per pipeline step
+constexpr int TW_STEP = TW_STEP8 * 32;    // 256 kS/s samples per step
+constexpr int TW_PITCH = TW_STEP + 4;     // floats per row: conflict-free LDS.128 by row
+
+struct SmemTwItem {                       // real samples, sign-extended
+    int32_t s0[19 + TW_STEP8];            // stage 1 input @8k
+    int32_t s1[3 + 2 * TW_STEP8];         // stage 2 input @16k
+    int32_t s2[1 + 4 * TW_STEP8];         // stage 3 input @32k
+    int32_t s3[3 + 8 * TW_STEP8];         // stage 4 input @64k
+    int32_t s4[3 + 16 * TW_STEP8];        // stage 5 input @128k
+};
+struct SmemTw {
+    float ph[2][32][TW_PITCH];
+    SmemTwItem item[TW_ITEMS];
+    alignas(16) uint32_t iq900[16384];    // {(int16_t)(cos*900), (int16_t)(sin*900)} per NCO entry
+    float thr[8194 + 2];                  // nco_index thresholds
+};
+
+__device__ __forceinline__ void load_real_hist(int32_t *ring, const uint32_t *state, int hist, int lane)
+{
+    for (int i = lane; i < hist; i += 32) ring[i] = lo16(state[i]);
+}
+__device__ __forceinline__ void save_real_hist(const int32_t *ring, uint32_t *state, int hist, int lane)
+{
+    for (int i = lane; i < hist; i += 32) state[i] = (uint32_t)ring[i] & 0xffffu;
+}
+
+// 8-tap half-band {a,0,b,16384,b,0,a,0} on a real ring (hist 3): input n -> outputs 2n, 2n+1
+__device__ __forceinline__ void interp8_real(const int32_t *in, int n, int &even, int &odd)
+{
+    const int ha = c_tabtx.tx_hb8[0], hb = c_tabtx.tx_hb8[2];
+    even = ((1 << 14) + ha * (in[3 + n] + in[n]) + hb * (in[2 + n] + in[1 + n])) >> 15;
+    odd = (in[2 + n] + 1) >> 1;
+}
+
+// fl32(fl64(a / 256000.0)) -- PhaseAccumulator::setFrequency's double division narrowed to
+// float -- without dividing in the common case.  r = a * (1/256000) is within 3 ulp64 of the
+// correctly rounded quotient; the two round to the same float unless a float rounding midpoint
+// (double mantissa bits 28..0 == 0x10000000) lies that close to r, or the result is not a
+// normal float.  Only then is the real division evaluated.
+__device__ __forceinline__ float div_256000_to_float(double a)
+{
+    double r = a * (1.0 / 256000.0);
+    const uint32_t lo = (uint32_t)__double2loint(r);
+    const uint32_t e = ((uint32_t)__double2hiint(r) >> 20) & 0x7ffu;
+    const bool risky = ((lo & 0x1fffffffu) - 0x0ffffff8u) <= 16u || (e - 898u) > 250u;
+    if (risky && a != 0.0) r = a / 256000.0;
+    return (float)r;
+}
+
+// Nco::runFast's table index (Nco.cc:231-248): (int16_t)((double)(phase*16384.0f)/(2*M_PI)) + 8192,
+// clamped to [0,16383].  The double division is replaced by a search in a table of thresholds built
+// on the host WITH that very expression: T[k] = the smallest float p >= 0 whose reference index is
+// >= k (hrd_api.cu; T[0] = 0, T[8193] = +inf).  An fp32 estimate lands within +-1 of the answer and
+// two comparisons settle it.  Truncation toward zero makes negative phases mirror images.
+// tools/verify_fp_tricks.c checks the search against the expression for every float in [0, pi].
+__device__ __forceinline__ int nco_index(float phase, const float *T)
+{
+    const float ap = fabsf(phase);
+    // round(ap * 16384/(2 pi)) by the 2^23 trick (no F2I: the XU pipe is 8x slower than FFMA)
+    int k = __float_as_int(__fmaf_rn(ap, 2607.59448f, 8388608.0f)) - 0x4b000000;
+    k = min(max(k, 0), 8192);
+    const float lo = T[k], hi = T[k + 1];
+    k += (ap >= hi) ? 1 : 0;
+    k -= (ap < lo) ? 1 : 0;
+    const int idx = 8192 + ((__float_as_int(phase) < 0) ? -k : k);
+    return min(idx, 16383);
+}
+
+__global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemTw &sm = *reinterpret_cast<SmemTw *>(smem_raw);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int slot = blockIdx.x * HRD_WARPS_PER_CTA + warp;
-    if (slot >= p.n_streams) return;
-    const int sid = p.stream_ids[slot];
-    SmemTxWb &sm = *reinterpret_cast<SmemTxWb *>(smem_raw + (size_t)warp * sizeof(SmemTxWb));
+    const bool chain_warp = warp == 0;
+    const int row = chain_warp ? lane : warp - 1;
+    const int slot = blockIdx.x * TW_ITEMS + row;
+    const bool live = row < TW_ITEMS && slot < p.n_streams;
+    const int sid = live ? p.stream_ids[slot] : 0;
     TxState &st = p.state[sid];
     TxRail8 &rs = st.wb;
+    SmemTwItem &it = sm.item[chain_warp ? 0 : warp - 1];
     const int16_t *src = p.pcm + (size_t)sid * p.pcm_stride;
     int8_t *dst = p.iq + (size_t)sid * p.iq_stride;
+    const uint32_t n_steps = (p.n8 + TW_STEP8 - 1) / TW_STEP8;
 
-    ring_load_hist(sm.s0, rs.s0, 19, lane);
-    ring_load_hist(sm.s1, rs.s1, 3, lane);
-    ring_load_hist(sm.s2, rs.s2, 1, lane);
-    ring_load_hist(sm.s3, rs.s3, 3, lane);
-    ring_load_hist(sm.s4, rs.s4, 3, lane);
-    ring_load_hist(sm.s5, rs.s5, 1, lane);
-    const float dev = p.param[sid];
-    float phase = st.wb_phase;
+    for (int i = threadIdx.x; i < 16384 / 4; i += 1024)
+        reinterpret_cast<uint4 *>(sm.iq900)[i] = __ldg(reinterpret_cast<const uint4 *>(p.nco_iq900) + i);
+    for (int i = threadIdx.x; i < 8194; i += 1024) sm.thr[i] = __ldg(p.nco_thr + i);
+    __syncthreads();
+
+    float phase = 0.f, dev = 0.f;
+    uint32_t iq_keep = 0; // the (cos,sin)*900 pair of the previous 256 kS/s sample (stage 6 history)
+    if (live) {
+        if (chain_warp) {
+            phase = st.wb_phase;
+        } else {
+            load_real_hist(it.s0, rs.s0, 19, lane);
+            load_real_hist(it.s1, rs.s1, 3, lane);
+            load_real_hist(it.s2, rs.s2, 1, lane);
+            load_real_hist(it.s3, rs.s3, 3, lane);
+            load_real_hist(it.s4, rs.s4, 3, lane);
+            iq_keep = rs.s5[0];
+            dev = p.param[sid];
+        }
+    }
     __syncwarp();
 
-    for (uint32_t done = 0; done < p.n8; done += NB8) {
-        const int nb = (int)min((uint32_t)NB8, p.n8 - done);
-        if (lane < nb) sm.s0[19 + lane] = (uint32_t)(int)src[done + lane] & 0xffffu;
+    // WbFmModulator.cc:389-441 + 596-604 on step t: PCM -> stages 1..5 -> phase steps
+    auto produce = [&](uint32_t t) {
+        const uint32_t done = t * TW_STEP8;
+        const int nb = (int)min((uint32_t)TW_STEP8, p.n8 - done);
+        if (lane < nb) it.s0[19 + lane] = (int)src[done + lane];
         __syncwarp();
-        // WbFmModulator.cc:389-441: stages 1..5 on the PCM (only the low halves are live)
-        for (int n = lane; n < nb; n += 32) interp40(sm.s0, n, sm.s1[3 + 2 * n], sm.s1[3 + 2 * n + 1]);
-        __syncwarp();
-        for (int n = lane; n < 2 * nb; n += 32) interp8(sm.s1, n, sm.s2[1 + 2 * n], sm.s2[1 + 2 * n + 1]);
-        __syncwarp();
-        for (int n = lane; n < 4 * nb; n += 32) {
-            uint32_t w = sm.s2[1 + n], wm = sm.s2[n];
-            sm.s3[3 + 2 * n] = pack16(hb4_even(c_tabtx.tx_c3, lo16(w), lo16(wm)), 0);
-            sm.s3[3 + 2 * n + 1] = pack16(hb4_odd(c_tabtx.tx_m3, lo16(w)), 0);
+        if (lane < nb) { // stage 1: 40 taps, L = 2 (the only stage whose output may wrap: keep q15)
+            unsigned e = 1u << 14, o = 1u << 14;
+#pragma unroll
+            for (int k = 0; k < 20; k++) {
+                const int x = it.s0[19 + lane - k];
+                e += (unsigned)(c_tabtx.audio40[2 * k] * x);
+                o += (unsigned)(c_tabtx.audio40[2 * k + 1] * x);
+            }
+            it.s1[3 + 2 * lane] = q15((int)e);
+            it.s1[3 + 2 * lane + 1] = q15((int)o);
         }
         __syncwarp();
-        for (int n = lane; n < 8 * nb; n += 32) interp8(sm.s3, n, sm.s4[3 + 2 * n], sm.s4[3 + 2 * n + 1]);
+        if (lane < 2 * nb) interp8_real(it.s1, lane, it.s2[1 + 2 * lane], it.s2[1 + 2 * lane + 1]);
         __syncwarp();
-        // stage 5 -> phase step per 256 kS/s sample (WbFmModulator.cc:596-604)
+        if (lane < 4 * nb) {
+            it.s3[3 + 2 * lane] = hb4_even(c_tabtx.tx_c3, it.s2[1 + lane], it.s2[lane]);
+            it.s3[3 + 2 * lane + 1] = (it.s2[1 + lane] + 1) >> 1;
+        }
+        __syncwarp();
+        for (int n = lane; n < 8 * nb; n += 32) interp8_real(it.s3, n, it.s4[3 + 2 * n], it.s4[3 + 2 * n + 1]);
+        __syncwarp();
+        float *out = sm.ph[t & 1][row];
         for (int n = lane; n < 16 * nb; n += 32) {
-            uint32_t e, o;
-            interp8(sm.s4, n, e, o);
-            float fe = __fdiv_rn(__fmul_rn(dev, (float)lo16(e)), 1024.f);
-            float fo = __fdiv_rn(__fmul_rn(dev, (float)lo16(o)), 1024.f);
-            sm.ph[2 * n] = phase_step(fe, 256000.0);
-            sm.ph[2 * n + 1] = phase_step(fo, 256000.0);
+            int e, o;
+            interp8_real(it.s4, n, e, o);
+            // ncoFrequency = frequencyDeviation * (float)pcm / 1024   (dividing by 2^10 is exact scaling)
+            const float fe = __fmul_rn(__fmul_rn(dev, (float)e), 0.0009765625f);
+            const float fo = __fmul_rn(__fmul_rn(dev, (float)o), 0.0009765625f);
+            // phaseStepSize = (2*M_PI*frequency)/sampleRate   (PhaseAccumulator.cc:103)
+            const double two_pi = 2.0 * 3.14159265358979323846;
+            float2 stp;
+            stp.x = div_256000_to_float(two_pi * (double)fe);
+            stp.y = div_256000_to_float(two_pi * (double)fo);
+            *reinterpret_cast<float2 *>(out + 2 * n) = stp;
         }
         __syncwarp();
-        // serial NCO phase recurrence at 256 kS/s: ph[n] <- phase before step n
-        if (lane == 0) {
-            for (int n = 0; n < 32 * nb; n++) {
-                float stp = sm.ph[n];
-                sm.ph[n] = phase;
-                phase = phase_advance(phase, stp);
+        ring_shift(it.s0, 19, nb, lane);
+        ring_shift(it.s1, 3, 2 * nb, lane);
+        ring_shift(it.s2, 1, 4 * nb, lane);
+        ring_shift(it.s3, 3, 8 * nb, lane);
+        ring_shift(it.s4, 3, 16 * nb, lane);
+    };
+
+    // PhaseAccumulator::run for every sample of step t: row[n] <- phase before step n
+    auto chain = [&](uint32_t t) {
+        const uint32_t nb = min((uint32_t)TW_STEP8, p.n8 - t * TW_STEP8) * 32;
+        float *r = sm.ph[t & 1][lane];
+        for (uint32_t c = 0; c < nb; c += 32) {
+            float4 v[8];
+#pragma unroll
+            for (int g = 0; g < 8; g++) v[g] = *reinterpret_cast<float4 *>(r + c + 4 * g);
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+                float s;
+                s = v[g].x; v[g].x = phase; phase = phase_advance_lockstep(phase, s);
+                s = v[g].y; v[g].y = phase; phase = phase_advance_lockstep(phase, s);
+                s = v[g].z; v[g].z = phase; phase = phase_advance_lockstep(phase, s);
+                s = v[g].w; v[g].w = phase; phase = phase_advance_lockstep(phase, s);
+                *reinterpret_cast<float4 *>(r + c + 4 * g) = v[g];
             }
         }
-        phase = __shfl_sync(HRD_FULL_MASK, phase, 0);
-        __syncwarp();
-        // Nco::runFast (Nco.cc:222-257) and the x900 scaling (WbFmModulator.cc:606-626)
-        for (int n = lane; n < 32 * nb; n += 32) {
-            float ph = sm.ph[n];
-            double t = (double)__fmul_rn(ph, 16384.f) / (2.0 * 3.14159265358979323846);
-            int v = __double2int_rz(t);
-            if (!(t > -2147483649.0 && t < 2147483648.0)) v = (int)0x80000000;
-            int idx = (int)(short)v + 8192;
-            idx = idx < 0 ? 0 : (idx > 16383 ? 16383 : idx);
-            int ci = f32_to_i16(__fmul_rn(__ldg(p.nco_cos + idx), 900.f));
-            int si = f32_to_i16(__fmul_rn(__ldg(p.nco_sin + idx), 900.f));
-            sm.s5[1 + n] = pack16(ci, si);
-        }
-        __syncwarp();
-        // stages 6..8: one 256 kS/s sample -> 8 output samples = 16 bytes per lane
+    };
+
+    // Nco::runFast + x900 (WbFmModulator.cc:606-626), stages 6..8 (:471-531): two 256 kS/s samples
+    // per lane -> 16 output samples = 32 bytes
+    auto consume = [&](uint32_t t) {
+        const uint32_t done = t * TW_STEP8;
+        const int nb = (int)min((uint32_t)TW_STEP8, p.n8 - done) * 32;
+        const float *ph = sm.ph[t & 1][row];
         int8_t *out = dst + (size_t)done * 512;
-        for (int n = lane; n < 32 * nb; n += 32) {
-            uint32_t w0 = sm.s5[1 + n], w1 = sm.s5[n];
+        for (int base = 0; base < nb; base += 64) { // warp-uniform trip count: shuffles inside
+            const int n = base + 2 * lane;
+            const bool valid = n < nb;               // a short last step leaves the upper lanes idle
+            const int last_lane = min(32, (nb - base) / 2) - 1;
+            const float2 pp = *reinterpret_cast<const float2 *>(ph + (valid ? n : 0));
+            const uint32_t w0 = sm.iq900[nco_index(pp.x, sm.thr)];
+            const uint32_t w1 = sm.iq900[nco_index(pp.y, sm.thr)];
+            // the sample before w0: previous lane's w1 (lane 0: kept from the previous round)
+            const uint32_t sel = (lane == 31) ? iq_keep : w1;
+            const uint32_t wm = __shfl_sync(HRD_FULL_MASK, sel, (lane + 31) & 31);
+            iq_keep = __shfl_sync(HRD_FULL_MASK, w1, last_lane);
+            if (!valid) continue;
             int oi[8], oq[8];
-            tail3(lo16(w0), lo16(w1), oi);
-            tail3(hi16(w0), hi16(w1), oq);
-            uint4 o;
-            o.x = merge16(pack_b2(oi[0], oq[0]), pack_b2(oi[1], oq[1]));
-            o.y = merge16(pack_b2(oi[2], oq[2]), pack_b2(oi[3], oq[3]));
-            o.z = merge16(pack_b2(oi[4], oq[4]), pack_b2(oi[5], oq[5]));
-            o.w = merge16(pack_b2(oi[6], oq[6]), pack_b2(oi[7], oq[7]));
-            __stcs(reinterpret_cast<uint4 *>(out + (size_t)n * 16), o);
+            u32x8 o;
+            tail3(lo16(w0), lo16(wm), oi);
+            tail3(hi16(w0), hi16(wm), oq);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                o.v[k] = merge16(pack_b2(oi[2 * k], oq[2 * k]), pack_b2(oi[2 * k + 1], oq[2 * k + 1]));
+            tail3(lo16(w1), lo16(w0), oi);
+            tail3(hi16(w1), hi16(w0), oq);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                o.v[4 + k] = merge16(pack_b2(oi[2 * k], oq[2 * k]), pack_b2(oi[2 * k + 1], oq[2 * k + 1]));
+            stg_stream_256(out + (size_t)n * 16, o);
         }
-        __syncwarp();
-        ring_shift(sm.s0, 19, nb, lane);
-        ring_shift(sm.s1, 3, 2 * nb, lane);
-        ring_shift(sm.s2, 1, 4 * nb, lane);
-        ring_shift(sm.s3, 3, 8 * nb, lane);
-        ring_shift(sm.s4, 3, 16 * nb, lane);
-        ring_shift(sm.s5, 1, 32 * nb, lane);
+    };
+
+    if (!chain_warp && live) produce(0);
+    __syncthreads();
+    for (uint32_t t = 0; t < n_steps; t++) {
+        if (chain_warp) {
+            if (live) chain(t);
+        } else if (live) {
+            if (t >= 1) consume(t - 1);
+            if (t + 1 < n_steps) produce(t + 1);
+        }
+        __syncthreads();
     }
-    ring_save_hist(sm.s0, rs.s0, 19, lane);
-    ring_save_hist(sm.s1, rs.s1, 3, lane);
-    ring_save_hist(sm.s2, rs.s2, 1, lane);
-    ring_save_hist(sm.s3, rs.s3, 3, lane);
-    ring_save_hist(sm.s4, rs.s4, 3, lane);
-    ring_save_hist(sm.s5, rs.s5, 1, lane);
-    if (lane == 0) st.wb_phase = phase;
+    if (live) {
+        if (chain_warp) {
+            st.wb_phase = phase;
+        } else {
+            consume(n_steps - 1);
+            save_real_hist(it.s0, rs.s0, 19, lane);
+            save_real_hist(it.s1, rs.s1, 3, lane);
+            save_real_hist(it.s2, rs.s2, 1, lane);
+            save_real_hist(it.s3, rs.s3, 3, lane);
+            save_real_hist(it.s4, rs.s4, 3, lane);
+            if (lane == 0) rs.s5[0] = iq_keep;
+        }
+    }
 }
 
 // mode NONE: BasebandDataProcessor.cc:689-694 fills the block with 64
@@ -447,14 +610,13 @@ int launch_tx(int kind, const TxParams &p, cudaStream_t s)
     case K_FM: return launch_one<K_FM>(p, s);
     case K_SSB: return launch_one<K_SSB>(p, s);
     case K_WBFM: {
-        const int grid = (p.n_streams + HRD_WARPS_PER_CTA - 1) / HRD_WARPS_PER_CTA;
-        const size_t smem = sizeof(SmemTxWb) * HRD_WARPS_PER_CTA;
+        const int grid = (p.n_streams + TW_ITEMS - 1) / TW_ITEMS;
         static bool attr_set = false;
         if (!attr_set) {
-            cudaFuncSetAttribute(tx_wbfm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(tx_wbfm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTw));
             attr_set = true;
         }
-        tx_wbfm_kernel<<<grid, HRD_WARPS_PER_CTA * 32, smem, s>>>(p);
+        tx_wbfm_kernel<<<grid, 1024, sizeof(SmemTw), s>>>(p);
         return (int)cudaGetLastError();
     }
     case K_NONE: {

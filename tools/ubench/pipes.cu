@@ -36,6 +36,14 @@ __global__ void __launch_bounds__(256) probe(int *out, int a0, int b0)
             }
             if (OP == 9) { float f = __int_as_float(acc[c]); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(__int_as_float(a)), "f"(__int_as_float(b))); acc[c] = __float_as_int(f); }
             if (OP == 10) asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+r"(acc[c]) : "r"(a & 31));
+            if (OP == 12) { // fp64 multiply (two chains share one 64-bit register pair)
+                if (c & 1) { double x = __hiloint2double(acc[c], acc[c - 1]); asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(x) : "d"(__hiloint2double(a, b))); acc[c] = __double2hiint(x); acc[c - 1] = __double2loint(x); }
+            }
+            if (OP == 13) { float f = __int_as_float(acc[c]); double x; asm volatile("cvt.f64.f32 %0, %1;" : "=d"(x) : "f"(f)); acc[c] ^= __double2hiint(x); }
+            if (OP == 14) { int v; asm volatile("cvt.rzi.s32.f32 %0, %1;" : "=r"(v) : "f"(__int_as_float(acc[c]))); acc[c] += v; }
+            if (OP == 15) { float f; asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(f) : "r"(acc[c])); acc[c] ^= __float_as_int(f); }
+            if (OP == 16) asm volatile("mul.hi.s32 %0, %0, %1;" : "+r"(acc[c]) : "r"(a));
+            if (OP == 17) { long long w; asm volatile("mad.wide.s32 %0, %1, %2, %3;" : "=l"(w) : "r"(acc[c]), "r"(a), "l"((long long)b)); acc[c] = (int)(w >> 32); }
             if (OP == 11) { // dp2a + imad alternating (both fma pipe?)
                 if (c & 1) asm volatile("mad.lo.s32 %0, %1, %2, %0;" : "+r"(acc[c]) : "r"(a), "r"(b));
                 else asm volatile("dp2a.lo.u32.s32 %0, %1, %2, %0;" : "+r"(acc[c]) : "r"(a), "r"(b));
@@ -95,5 +103,11 @@ int main()
     run<7>("dp2a+prmt 1:1", d, sms, clk);
     run<8>("imad+prmt 1:1", d, sms, clk);
     run<11>("dp2a+imad 1:1", d, sms, clk);
+    run<12>("mul.rn.f64 (x0.5: every other chain)", d, sms, clk);
+    run<13>("cvt.f64.f32 + xor", d, sms, clk);
+    run<14>("cvt.rzi.s32.f32 + add", d, sms, clk);
+    run<15>("cvt.rn.f32.s32 + xor", d, sms, clk);
+    run<16>("mul.hi.s32", d, sms, clk);
+    run<17>("mad.wide.s32 (hi word)", d, sms, clk);
     return 0;
 }
