@@ -107,19 +107,43 @@ __device__ __forceinline__ float phase_advance(float acc, float step)
 }
 
 // The same, for the 256 kS/s chain of the WBFM modulator, where up to 31 lanes advance 31
-// independent accumulators in lock step and some lane wraps on almost every sample: the common
-// single wrap is evaluated branch-free on every lane (three dependent FADDs and a select), and
-// only the rare cases (hrd_device.cuh: next to 2*pi, |acc| >= 12, or a second wrap) branch.
-__device__ __forceinline__ float phase_advance_lockstep(float acc, float step)
+// independent accumulators in lock step and some lane wraps on almost every sample.  A divergent
+// branch per sample costs > 100 cycles there (measured: the chain warp was the critical path of
+// the whole CTA), so the common single wrap is evaluated on every lane and SELECTED: one opaque
+// PTX block, five dependent operations per sample.  The cases the fp32 wrap does not cover
+// (hrd_device.cuh: next to 2*pi, |acc| >= 12, or a second wrap needed) only raise `rare`; the
+// caller then redoes its chunk with phase_advance, which handles everything.
+__device__ __forceinline__ float phase_advance_lockstep(float acc, float step, unsigned &rare)
 {
-    const float a = __fadd_rn(acc, step);
-    const float s = fabsf(a);
-    const float t = __fsub_rn(s, HRD_2PI_HI);
-    const float r = __fsub_rn(t, HRD_2PI_LO);
-    const float w = __int_as_float(__float_as_int(r) ^ (__float_as_int(a) & (int)0x80000000));
-    const bool wrap = s >= HRD_PI_UP;
-    float out = wrap ? w : a;
-    if (wrap && (!(s < 12.0f) || fabsf(t) < 0x1p-10f || fabsf(r) >= HRD_PI_UP)) out = wrap_pi(a);
+    float out;
+    unsigned flag;
+    asm("{\n\t"
+        ".reg .f32 a, s, t, r, w, m;\n\t"
+        ".reg .b32 ab, rb;\n\t"
+        ".reg .pred pw, p1, p2, p3;\n\t"
+        "add.rn.f32 a, %2, %3;\n\t"
+        "abs.f32 s, a;\n\t"
+        "add.rn.f32 t, s, 0fC0C90FDB;\n\t"        // |a| - 2PI_HI            (exact)
+        "add.rn.f32 r, t, 0f343BBD2E;\n\t"        // ... - 2PI_LO            (one rounding)
+        "mov.b32 ab, a;\n\t"
+        "mov.b32 rb, r;\n\t"
+        "lop3.b32 rb, rb, ab, 0x80000000, 0x78;\n\t" // rb ^ (ab & sign bit): back to a's side of zero
+        "mov.b32 w, rb;\n\t"
+        "setp.ge.f32 pw, s, 0f40490FDB;\n\t"      // (double)|a| > M_PI
+        "selp.f32 %0, w, a, pw;\n\t"
+        "abs.f32 m, t;\n\t"
+        "setp.lt.f32 p1, m, 0f3A800000;\n\t"      // |t| < 2^-10: fp32 wrap not proven exact
+        "setp.geu.f32 p2, s, 0f41400000;\n\t"     // !(|a| < 12)
+        "abs.f32 m, r;\n\t"
+        "setp.ge.f32 p3, m, 0f40490FDB;\n\t"      // still outside after one wrap
+        "or.pred p1, p1, p2;\n\t"
+        "or.pred p1, p1, p3;\n\t"
+        "and.pred p1, p1, pw;\n\t"
+        "selp.u32 %1, 1, 0, p1;\n\t"
+        "}"
+        : "=f"(out), "=r"(flag)
+        : "f"(acc), "f"(step));
+    rare |= flag;
     return out;
 }
 
@@ -506,14 +530,26 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
             float4 v[8];
 #pragma unroll
             for (int g = 0; g < 8; g++) v[g] = *reinterpret_cast<float4 *>(r + c + 4 * g);
+            const float phase0 = phase;
+            unsigned rare = 0;
 #pragma unroll
             for (int g = 0; g < 8; g++) {
                 float s;
-                s = v[g].x; v[g].x = phase; phase = phase_advance_lockstep(phase, s);
-                s = v[g].y; v[g].y = phase; phase = phase_advance_lockstep(phase, s);
-                s = v[g].z; v[g].z = phase; phase = phase_advance_lockstep(phase, s);
-                s = v[g].w; v[g].w = phase; phase = phase_advance_lockstep(phase, s);
-                *reinterpret_cast<float4 *>(r + c + 4 * g) = v[g];
+                s = v[g].x; v[g].x = phase; phase = phase_advance_lockstep(phase, s, rare);
+                s = v[g].y; v[g].y = phase; phase = phase_advance_lockstep(phase, s, rare);
+                s = v[g].z; v[g].z = phase; phase = phase_advance_lockstep(phase, s, rare);
+                s = v[g].w; v[g].w = phase; phase = phase_advance_lockstep(phase, s, rare);
+            }
+            if (rare) { // redo this lane's 32 samples with the reference's own loops (steps still in the row)
+                phase = phase0;
+                for (int i = 0; i < 32; i++) {
+                    const float s = r[c + i];
+                    r[c + i] = phase;
+                    phase = phase_advance(phase, s);
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < 8; g++) *reinterpret_cast<float4 *>(r + c + 4 * g) = v[g];
             }
         }
     };
