@@ -31,9 +31,21 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 FS = 2_048_000
 BYTES_PER_IN_SAMPLE_RX = 2.0 + 2.0 / 256.0
 BYTES_PER_OUT_SAMPLE_TX = 2.0 + 2.0 / 256.0
-# dram__bytes_read.sum + dram__bytes_write.sum of one rx_kernel<AM+SSB> launch of this workload, from the
-# committed ncu --set full capture (profiles/); None until one has been taken for the current kernel
-NCU_TRAFFIC_BYTES = None
+
+
+def ncu_traffic_bytes(streams, n_samples):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on this workload, from
+    the committed `ncu --set full` capture (profiles/ncu_traffic.json, written from the .ncu-rep by
+    tools/ncu_summary.py); None when no capture matches the workload."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)["rx_kernel<AM+SSB,2048k>"]
+        if t["streams"] == streams and t["samples_per_stream"] == n_samples:
+            return t["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
 METRIC = "aggregate input IQ MS/s (config 2: AM+SSB demod, 1024 streams/GPU, 2.048 MS/s entry)"
 UNIT = "MS/s"
 
@@ -268,14 +280,14 @@ def run_ours(args):
     achieved = dom_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "rx_kernel<AM+SSB, 2048k entry>",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
+                "traffic": ncu_traffic_bytes(args.streams, n_samples), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": round(kernel_ms, 4),
                 "tail_kernel": {"name": "rx_dc_iir_kernel", "avg_launch_ms": round(tail_ms, 4)}}
 
     out = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_max, 4), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int8 in / int32 accumulate (Q15) / f32 IIR", "data": "synthetic",
+        "vs_baseline": None, "dtype": "int32 (Q15 accumulate over int8/int16 samples) + f32 IIR tail", "data": "synthetic",
         "config": {"workload": "BASELINE configs[1]: 1024 streams/GPU = 512 AM + 256 LSB + 256 USB, "
                                f"{n_samples / FS:.3f} s of int8 IQ @2.048 MS/s each, IqDataProcessor entry",
                    "streams_per_gpu": args.streams, "input_bytes_per_step_per_gpu": 2 * in_samples_per_step,
@@ -289,13 +301,14 @@ def run_ours(args):
     del keep
     torch.cuda.empty_cache()
 
-    if rank == 0 and not args.quick:
-        out["e2e"] = run_e2e(torch, capi, device, args, groups, n_samples, world)
-        if world == 1:
+    # end to end through the C ABI with host buffers: every rank drives its own GPU at the same time
+    # (their PCIe links are independent); whole-job value = all ranks' samples / slowest rank's time
+    e2e = run_e2e(torch, capi, device, args, groups, n_samples, dist)
+    if rank == 0:
+        out["e2e"] = e2e
+        if world == 1 and not args.quick:
             out["modes"] = run_mode_sweep(torch, capi, device, args, peak)
             out["cpu_baseline"] = cpu_baseline(args, groups)
-    elif rank == 0:
-        out["e2e"] = run_e2e(torch, capi, device, args, groups, n_samples, world)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -303,8 +316,9 @@ def run_ours(args):
         print(json.dumps(out))
 
 
-def run_e2e(torch, capi, device, args, groups, n_samples, world):
-    """Same workload through the C ABI with pinned HOST buffers: H2D + kernels + D2H per step."""
+def run_e2e(torch, capi, device, args, groups, n_samples, dist):
+    """Same workload through the C ABI with pinned HOST buffers: H2D + kernels + D2H per step, on every rank."""
+    world = dist.get_world_size() if dist else 1
     steps = max(2, min(args.steps, 5))
     b, iq, pcm = make_rx_batch(torch, capi, device, groups, n_samples, 99)
     host_iq = torch.empty(iq.shape, dtype=torch.int8, pin_memory=True)
@@ -317,14 +331,21 @@ def run_e2e(torch, capi, device, args, groups, n_samples, world):
         b.rx_host_ptr(host_iq.data_ptr(), host_iq.shape[1], host_iq.stride(0), host_pcm.data_ptr(), host_pcm.stride(0))
 
     step()
+    if dist:
+        dist.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    value = args.streams * n_samples / dt / 1e6
-    return {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": host_iq.numel(),
-            "d2h_bytes_per_step": host_pcm.numel() * 2, "ms_per_step": round(dt * 1e3, 3), "steps": steps,
-            "note": "hrd_rx_process(HRD_MEM_HOST) on pinned buffers, per GPU; this rank only"}
+    t = torch.tensor([dt], device=device, dtype=torch.float64)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    value = world * args.streams * n_samples / dt / 1e6
+    return {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": host_iq.numel() * world,
+            "d2h_bytes_per_step": host_pcm.numel() * 2 * world, "ms_per_step": round(dt * 1e3, 3), "steps": steps,
+            "note": "hrd_rx_process(HRD_MEM_HOST) on pinned host buffers, one call per step per GPU, copies inside "
+                    "the call; whole job = all ranks, slowest rank's wall time; bound by PCIe H2D (2 B per IQ sample)"}
 
 
 def run_mode_sweep(torch, capi, device, args, peak):

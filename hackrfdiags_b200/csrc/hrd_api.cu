@@ -504,7 +504,7 @@ int hrd_set_param(hrd_batch_t *b, int stream, int param, float value)
         case HRD_PARAM_FM_DEV: // FmModulator.cc:336-346: the guard reads the member, not the argument
             if (cur >= 0 && cur <= 3500) cur = value;
             break;
-        case HRD_PARAM_WBFM_DEV: // WbFmModulator.cc:318-328
+        case HRD_PARAM_WBFM_DEV: // WbFmModulator.cc:310-328
             if (cur >= 0 && cur <= 112000) cur = value;
             break;
         default:
@@ -555,7 +555,7 @@ int hrd_reset(hrd_batch_t *b, int stream, int unit)
         switch (unit) {
         case HRD_UNIT_AM: rc = zero_state(b, stream, RANGE(RxState, am, fm_r256)); break;
         case HRD_UNIT_FM: rc = zero_state(b, stream, RANGE(RxState, fm_r256, wb_prev_theta)); break;
-        case HRD_UNIT_WBFM: // WbFmDemodulator.cc:284-298: decimators and previousTheta, not the IIR
+        case HRD_UNIT_WBFM: // WbFmDemodulator.cc:265-297: decimators and previousTheta, not the IIR
             rc = zero_state(b, stream, RANGE(RxState, wb_prev_theta, wb_x1));
             if (!rc) rc = zero_state(b, stream, RANGE(RxState, wb_d256, ssb));
             break;

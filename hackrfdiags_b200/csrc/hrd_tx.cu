@@ -1,8 +1,8 @@
 // hrd_tx.cu -- transmit chains: int16 PCM at 8 kS/s -> int8 I,Q at 2.048 MS/s.
 //
 // Replaces, per stream (reference paths relative to radioDiags/):
-//   AmModulator/AmModulator.cc:366-607, FmModulator/FmModulator.cc:353-622,
-//   WbFmModulator/WbFmModulator.cc:347-632, SsbModulator/SsbModulator.cc:430-707
+//   AmModulator/AmModulator.cc:366-607, FmModulator/FmModulator.cc:373-622,
+//   WbFmModulator/WbFmModulator.cc:347-632, SsbModulator/SsbModulator.cc:455-707
 // and underneath them Filters/Int16/{Interpolator,FirFilter}_int16.cc and
 // Nco/{Nco,PhaseAccumulator}.cc.
 //

@@ -9,14 +9,14 @@
 // What each member replaces (reference paths relative to radioDiags/):
 //   <X>Demodulator::acceptIqData      AmDemodulator.cc:297-315, FmDemodulator.cc:353-371,
 //                                     WbFmDemodulator.cc:341-356, SsbDemodulator.cc:420-438
-//   <X>Demodulator::resetDemodulator  AmDemodulator.cc:249-263, FmDemodulator.cc:296-308,
-//                                     WbFmDemodulator.cc:284-298, SsbDemodulator.cc:297-313
-//   <X>Demodulator::setDemodulatorGain  AmDemodulator.cc:281, FmDemodulator.cc:326, ...
-//   <X>Modulator::acceptData          AmModulator.cc:366-381, FmModulator.cc:353-368,
-//                                     WbFmModulator.cc:347-365, SsbModulator.cc:430-445
+//   <X>Demodulator::resetDemodulator  AmDemodulator.cc:232-265, FmDemodulator.cc:290-321,
+//                                     WbFmDemodulator.cc:265-297, SsbDemodulator.cc:297-331
+//   <X>Demodulator::setDemodulatorGain  AmDemodulator.cc:267, FmDemodulator.cc:323, WbFmDemodulator.cc:299, SsbDemodulator.cc:390
+//   <X>Modulator::acceptData          AmModulator.cc:366-381, FmModulator.cc:373-388,
+//                                     WbFmModulator.cc:347-365, SsbModulator.cc:455-470
 //   setModulationIndex / setFrequencyDeviation / set{Lsb,Usb}ModulationMode and their guards
 //                                     AmModulator.cc:329-339, FmModulator.cc:336-346,
-//                                     WbFmModulator.cc:318-328, SsbModulator.cc:379-411
+//                                     WbFmModulator.cc:310-328, SsbModulator.cc:392-446
 // The objects keep the reference's threading rule: one data thread per object;
 // setters may arrive from another thread and take effect at the next call.
 //

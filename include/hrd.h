@@ -53,13 +53,13 @@ enum {
 
 /* per-stream scalar parameters and the reference setter each one replaces */
 enum {
-    HRD_PARAM_AM_GAIN = 0,   /* AmDemodulator::setDemodulatorGain   (AmDemodulator.cc:281)   default 300        */
-    HRD_PARAM_FM_GAIN = 1,   /* FmDemodulator::setDemodulatorGain   (FmDemodulator.cc:326)   default 64000/2pi  */
-    HRD_PARAM_WBFM_GAIN = 2, /* WbFmDemodulator::setDemodulatorGain (WbFmDemodulator.cc:316) default 256000/2pi */
-    HRD_PARAM_SSB_GAIN = 3,  /* SsbDemodulator::setDemodulatorGain  (SsbDemodulator.cc:393)  default 300        */
+    HRD_PARAM_AM_GAIN = 0,   /* AmDemodulator::setDemodulatorGain   (AmDemodulator.cc:267)   default 300        */
+    HRD_PARAM_FM_GAIN = 1,   /* FmDemodulator::setDemodulatorGain   (FmDemodulator.cc:323)   default 64000/2pi  */
+    HRD_PARAM_WBFM_GAIN = 2, /* WbFmDemodulator::setDemodulatorGain (WbFmDemodulator.cc:299) default 256000/2pi */
+    HRD_PARAM_SSB_GAIN = 3,  /* SsbDemodulator::setDemodulatorGain  (SsbDemodulator.cc:390)  default 300        */
     HRD_PARAM_AM_INDEX = 4,  /* AmModulator::setModulationIndex     (AmModulator.cc:329)  accepted iff 0<=m<=1, default 0.8 */
     HRD_PARAM_FM_DEV = 5,    /* FmModulator::setFrequencyDeviation  (FmModulator.cc:336)  guard tests the OLD value vs 0..3500   */
-    HRD_PARAM_WBFM_DEV = 6,  /* WbFmModulator::setFrequencyDeviation(WbFmModulator.cc:318) guard tests the OLD value vs 0..112000 */
+    HRD_PARAM_WBFM_DEV = 6,  /* WbFmModulator::setFrequencyDeviation(WbFmModulator.cc:310) guard tests the OLD value vs 0..112000 */
     HRD_PARAM_COUNT = 7
 };
 

@@ -446,7 +446,7 @@ void hro_rx_reset_demod(hro_rx *rx, int demod)
         dec16_reset(&rx->fm_audio);
         firf_reset(&rx->fm_diff);
         break;
-    case HRO_DEMOD_WBFM: /* WbFmDemodulator.cc:284-298: the de-emphasis filter is NOT reset */
+    case HRO_DEMOD_WBFM: /* WbFmDemodulator.cc:265-297: the de-emphasis filter is NOT reset */
         dec16_reset(&rx->wb_post1);
         dec16_reset(&rx->wb_post2);
         dec16_reset(&rx->wb_audio);

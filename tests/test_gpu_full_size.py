@@ -1,0 +1,126 @@
+"""Parity at BASELINE.json's full sizes (configs 2, 3, 4), through the C ABI on device buffers.
+
+The oracle cannot chew through 4-17 GB in a test, so full size is covered by size-independent properties:
+  * a sample of streams, whole length, bit for bit against the CPU oracle (FM Tx: <= 1 LSB int8);
+  * streams fed identical inputs give identical outputs wherever they sit in the batch (independence);
+  * automatic time tiling == one tile per stream (the serial order);
+  * one long call == the same signal in several calls (state carry-over);
+Inputs are generated on the device (bench.py's generators: 32 distinct rows per mode, tiled)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FS = 2_048_000
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    import bench
+    from hackrfdiags_b200 import capi
+    assert torch.cuda.is_available()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    return torch, bench, capi, dev
+
+
+def _rx_call(capi, b, iq, pcm, lo=0, hi=None, stream=0):
+    hi = iq.shape[1] if hi is None else hi
+    b.rx_device(iq.data_ptr() + lo, hi - lo, iq.stride(0), pcm.data_ptr() + (lo // 512) * 2, pcm.stride(0),
+                capi.ENTRY_2048K, stream)
+
+
+def _check_sample_vs_oracle(torch, oracle, iq, pcm, modes, picks):
+    worst = 0
+    for s in picks:
+        want = oracle.run_rx(modes[s], iq[s].cpu().numpy())
+        got = pcm[s].cpu().numpy()
+        assert got.shape == want.shape
+        d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        worst = max(worst, int(d.max()))
+        assert worst == 0, f"stream {s} (mode {modes[s]}): max abs err {d.max()}, {(d != 0).sum()} of {d.size} differ"
+    return worst
+
+
+def test_config2_am_ssb_1024_streams(env, oracle):
+    torch, bench, capi, dev = env
+    n_samples = FS  # 1 s per stream: 4.19 GB of IQ
+    groups = [(capi.MODE_AM, 512), (capi.MODE_LSB, 256), (capi.MODE_USB, 256)]
+    b, iq, pcm = bench.make_rx_batch(torch, capi, dev, groups, n_samples, seed=21)
+    modes = [m for m, c in groups for _ in range(c)]
+    _rx_call(capi, b, iq, pcm)
+    torch.cuda.synchronize()
+    # (1) a sample of streams against the oracle, whole second
+    _check_sample_vs_oracle(torch, oracle, iq, pcm, modes, [0, 3, 31, 511, 512, 530, 767, 768, 1000, 1023])
+    # (2) independence: rows repeat with period 32 inside each mode group
+    assert torch.equal(pcm[0:32], pcm[32:64]) and torch.equal(pcm[0:32], pcm[480:512])
+    assert torch.equal(pcm[512:544], pcm[736:768]) and torch.equal(pcm[768:800], pcm[992:1024])
+    assert not torch.equal(pcm[512:544], pcm[768:800])  # LSB vs USB of mirrored signals differ
+    # (3) automatic tiling == a single tile per stream
+    b2 = capi.Batch(1024, capi.RX, 0)
+    for s, m in enumerate(modes):
+        b2.set_mode(m, s)
+    b2.set_option(capi.OPT_RX_TILE_BATCHES, n_samples // 8192)
+    pcm2 = torch.zeros_like(pcm)
+    _rx_call(capi, b2, iq, pcm2)
+    torch.cuda.synchronize()
+    assert torch.equal(pcm, pcm2)
+    # (4) one call == four calls
+    b3 = capi.Batch(1024, capi.RX, 0)
+    for s, m in enumerate(modes):
+        b3.set_mode(m, s)
+    pcm3 = torch.zeros_like(pcm)
+    q = iq.shape[1] // 4
+    for k in range(4):
+        _rx_call(capi, b3, iq, pcm3, k * q, (k + 1) * q)
+    torch.cuda.synchronize()
+    assert torch.equal(pcm, pcm3)
+
+
+def test_config3_wbfm_4096_streams(env, oracle):
+    torch, bench, capi, dev = env
+    n_samples = FS // 2 // 8192 * 8192  # 0.5 s per stream: 8.4 GB of IQ
+    b, iq, pcm = bench.make_rx_batch(torch, capi, dev, [(capi.MODE_WBFM, 4096)], n_samples, seed=22)
+    _rx_call(capi, b, iq, pcm)
+    torch.cuda.synchronize()
+    _check_sample_vs_oracle(torch, oracle, iq, pcm, [capi.MODE_WBFM] * 4096, [0, 5, 30, 31, 2048, 4095])
+    assert torch.equal(pcm[0:32], pcm[32:64]) and torch.equal(pcm[0:32], pcm[4064:4096])
+    # one call == three uneven calls (the de-emphasis recurrence and the FIR histories carry over)
+    b2 = capi.Batch(4096, capi.RX, 0)
+    b2.set_mode(capi.MODE_WBFM)
+    pcm2 = torch.zeros_like(pcm)
+    cuts = [0, 8192 * 2 * 7, 8192 * 2 * 40, iq.shape[1]]
+    for k in range(3):
+        _rx_call(capi, b2, iq, pcm2, cuts[k], cuts[k + 1])
+    torch.cuda.synchronize()
+    assert torch.equal(pcm, pcm2)
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5])
+def test_config4_tx_4096_streams(env, oracle, mode):
+    torch, bench, capi, dev = env
+    n_pcm = 2000  # 0.25 s per stream -> 4.19 GB of IQ out
+    distinct = bench.make_tx_pcm_device(torch, 32, n_pcm, dev, seed=23)
+    pcm = bench.tile_rows(torch, distinct, 4096)
+    iq = torch.empty((4096, n_pcm * 512), dtype=torch.int8, device=dev)
+    b = capi.Batch(4096, capi.TX, 0)
+    b.set_mode(mode)
+    b.tx_device(pcm.data_ptr(), n_pcm, pcm.stride(0), iq.data_ptr(), iq.stride(0), 0)
+    torch.cuda.synchronize()
+    tol = 1 if mode == capi.MODE_FM else 0
+    for s in (0, 1, 2, 31, 4095):
+        want = oracle.run_tx(mode, pcm[s].cpu().numpy())
+        got = iq[s].cpu().numpy()
+        err = np.abs(got.astype(np.int32) - want.astype(np.int32)).max()
+        assert err <= tol, f"mode {mode} stream {s}: max abs err {err}"
+    assert torch.equal(iq[0:32], iq[32:64]) and torch.equal(iq[0:32], iq[4064:4096])
+    # one call == two calls (interpolator histories and NCO phase carry over)
+    b2 = capi.Batch(4096, capi.TX, 0)
+    b2.set_mode(mode)
+    iq2 = torch.empty_like(iq)
+    cut = 777
+    b2.tx_device(pcm.data_ptr(), cut, pcm.stride(0), iq2.data_ptr(), iq2.stride(0), 0)
+    b2.tx_device(pcm.data_ptr() + 2 * cut, n_pcm - cut, pcm.stride(0), iq2.data_ptr() + cut * 512, iq2.stride(0), 0)
+    torch.cuda.synchronize()
+    assert torch.equal(iq, iq2)
