@@ -164,6 +164,15 @@ int ensure_tables(int device)
     std::vector<float> lut(65536);
     for (int x = 0; x < 256; x++)
         for (int y = 0; y < 256; y++) lut[(size_t)y * 256 + x] = (float)atan2((double)y - 128, (double)x - 128);
+    // rx_wbfm_kernel keeps only the rows q >= 0 on chip and mirrors the rest: that needs the table
+    // to be odd in q bit for bit (glibc's atan2 is; anything else is refused, not approximated)
+    for (int q = 1; q < 128; q++)
+        for (int x = 0; x < 256; x++) {
+            const float up = lut[(size_t)(128 + q) * 256 + x], dn = lut[(size_t)(128 - q) * 256 + x];
+            const float mirrored = -dn;
+            if (memcmp(&up, &mirrored, sizeof up) != 0)
+                return fail(HRD_EINVAL, "host atan2 table is not odd-symmetric at q=%d: unsupported libm", q);
+        }
     // NCO tables (Nco.cc:45-61): the angle is accumulated in float, sinf/cosf of it
     std::vector<float> s(16384), c(16384);
     float inc = (float)(2 * M_PI / 16384);

@@ -78,10 +78,12 @@ __device__ __forceinline__ void stg_stream_256(void *p, const u32x8 &r)
 // (int16_t)someFloat on x86-64: cvttss2si (0x80000000 when out of range / NaN), then the
 // low 16 bits.  CUDA's cvt.rzi.s32.f32 saturates instead, so the out-of-range case is
 // patched by hand (e.g. FmDemodulator.cc:565).
+// F2I saturates; of the values it can return only +overflow (0x7fffffff, low half 0xffff) differs
+// in the low 16 bits from cvttss2si's 0x80000000, and NaN gives 0 on both: one compare suffices.
 __device__ __forceinline__ int f32_to_i16(float x)
 {
     int v = __float2int_rz(x);
-    if (!(x >= -2147483648.0f && x < 2147483648.0f)) v = (int)0x80000000;
+    if (!(x < 2147483648.0f)) v = 0;
     return (int)(short)v;
 }
 
@@ -123,6 +125,23 @@ __device__ __forceinline__ float wrap_pi(float d)
 {
     while (fabsf(d) >= HRD_PI_UP) d = wrap_2pi_once(d);
     return d;
+}
+
+// The same for the discriminators, whose argument is a difference of two atan2 TABLE values.
+// The table holds atan2(q, i) for integer q, i in [-128, 127]: its largest entry is +pi (q = 0,
+// i < 0) and its smallest is atan2(-1, -128) = -3.13378 (q is never -0.0), so
+//   |d| <= pi + 3.13378 = 6.27537 < 2*pi - 2^-10 :
+// one wrap at most, the fp32 wrap is always the exact one (hrd_device.cuh above) and no fallback
+// is needed (tests/test_capi_host.py checks the bound on the table itself).  Loops and divergent
+// branches cost more than the arithmetic here, so the wrap is computed on all lanes and selected:
+// two FADDs, a LOP3, a compare and a select.
+__device__ __forceinline__ float wrap_pi_select(float d)
+{
+    const float s = fabsf(d);
+    const float t = __fsub_rn(s, HRD_2PI_HI);
+    const float r = __fsub_rn(t, HRD_2PI_LO);
+    const float w = __int_as_float(__float_as_int(r) ^ (__float_as_int(d) & (int)0x80000000));
+    return (s >= HRD_PI_UP) ? w : d;
 }
 
 // ------------------------------------------------------------------------------------

@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
             __syncwarp();
             // FmDemodulator.cc:479-529: FirFilter with taps {0,0,1,0,-1,0,0} = th[n-2]-th[n-4]
             for (int j = lane; j < n64; j += 32) {
-                float d = wrap_pi(__fsub_rn(sm.th[4 + j - 2], sm.th[4 + j - 4]));
+                float d = wrap_pi_select(__fsub_rn(sm.th[4 + j - 2], sm.th[4 + j - 4]));
                 sm.d64[8 + j] = (int16_t)f32_to_i16(__fmul_rn(scale, d));
             }
             __syncwarp();
@@ -495,6 +495,14 @@ struct SmemWbItem {
 struct SmemWb {
     float f[2][32][WB_PITCH];
     SmemWbItem item[WB_ITEMS];
+    int32_t audio40[40];   // copy of c_tab.audio40 for lane-dependent tap indices (see consume)
+    // Upper half of the atan2 table, rows q = 0..128 (row 128 = minus the table's q = -128 row).
+    // atan2 is odd in q and the table is the host libm's (double, narrowed to float), which is odd
+    // bit for bit -- checked when the table is built (hrd_api.cu ensure_tables) -- so
+    // theta(q, i) = sign(q) * lut[|q|][i + 128].  132 KB: the whole table (256 KB) fits neither
+    // shared memory nor L1, and at two scattered 4-byte gathers per lane per iteration the L1
+    // tag stage, not HBM, was the limiter of this kernel (profiles/: L1 hit rate 52 %).
+    float lut[129 * 256];
 };
 
 template <int ENTRY>
@@ -582,15 +590,21 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
             b = load_raw<ENTRY>(src, pf, pf_last);
         }
         pf += IT_SAMPLES * BPS;
-        // uint8_t idx = (uint8_t)sample + 128  (WbFmDemodulator.cc:403-404)
-        const uint32_t x = word ^ 0x80808080u;
-        const uint32_t idx0 = __byte_perm(x, 0, 0x4420), idx1 = __byte_perm(x, 0, 0x4431);
-        const float th0 = __ldg(p.atan2_lut + idx0), th1 = __ldg(p.atan2_lut + idx1);
+        // theta = atan2LookupTable[(uint8_t)Q + 128][(uint8_t)I + 128]  (WbFmDemodulator.cc:403-406)
+        // word = {I0, I1, Q0, Q1}: sign-extend Q, fold the table on |Q|, put the sign back
+        int q0, q1; // prmt with the sign-replicate bit (8) set in three selector nibbles: one-instruction sext of a byte
+        asm("prmt.b32 %0, %1, 0, 0xaaa2;" : "=r"(q0) : "r"(word));
+        asm("prmt.b32 %0, %1, 0, 0xbbb3;" : "=r"(q1) : "r"(word));
+        const uint32_t x = word ^ 0x00008080u;
+        const float a0 = sm.lut[abs(q0) * 256 + (int)(x & 0xffu)];
+        const float a1 = sm.lut[abs(q1) * 256 + (int)__byte_perm(x, 0, 0x4441)];
+        const float th0 = __int_as_float(__float_as_int(a0) ^ (q0 & (int)0x80000000));
+        const float th1 = __int_as_float(__float_as_int(a1) ^ (q1 & (int)0x80000000));
         // theta of the previous sample: previous lane's th1 (lane 0: kept from before)
         const float sel = (lane == 31) ? th_keep : th1;
         const float thp = __shfl_sync(HRD_FULL_MASK, sel, (lane + 31) & 31);
-        const float d0 = wrap_pi(__fsub_rn(th0, thp));
-        const float d1 = wrap_pi(__fsub_rn(th1, th0));
+        const float d0 = wrap_pi_select(__fsub_rn(th0, thp));
+        const float d1 = wrap_pi_select(__fsub_rn(th1, th0));
         const float v0 = __fmul_rn(scale, d0), v1 = __fmul_rn(scale, d1);
         const float selv = (lane == 31) ? v_keep : v1;
         const float vp = __shfl_sync(HRD_FULL_MASK, selv, (lane + 31) & 31);
@@ -637,8 +651,23 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
         __syncwarp();
         if (lane < n16) it.a16[38 + lane] = (int16_t)dec_real<12, 4>(it.d64, c_tab.fm_post, lane);
         __syncwarp();
-        if (done >= emit_from && lane < n8)
-            p.pcm[(size_t)sid * p.pcm_stride + done / 32 + lane] = (int16_t)dec_real<40, 2>(it.a16, c_tab.audio40, lane);
+        {
+            // audio decimator: only n8 <= 8 outputs per step but 40 taps each, so four lanes share an
+            // output (10 taps each; the int32 accumulation wraps, so the order of the sum is free)
+            const int k = lane >> 2, part = lane & 3;
+            unsigned acc = part == 0 ? (1u << 14) : 0u;
+            if (k < n8) {
+#pragma unroll
+                for (int t = 0; t < 10; t++) {
+                    const int tt = part * 10 + t;
+                    acc += (unsigned)(sm.audio40[tt] * (int)it.a16[2 * k + 39 - tt]);
+                }
+            }
+            acc += __shfl_xor_sync(HRD_FULL_MASK, acc, 1);
+            acc += __shfl_xor_sync(HRD_FULL_MASK, acc, 2);
+            if (done >= emit_from && part == 0 && k < n8)
+                p.pcm[(size_t)sid * p.pcm_stride + done / 32 + k] = (int16_t)q15((int)acc);
+        }
         __syncwarp();
         ring_shift(it.d256, 4, nb, lane);
         ring_shift(it.d64, 8, n64, lane);
@@ -666,6 +695,10 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
         }
     };
 
+    if (threadIdx.x < 40) sm.audio40[threadIdx.x] = c_tab.audio40[threadIdx.x];
+    for (int i = threadIdx.x; i < 129 * 256; i += 1024) // table rows q = 0..127 are rows 128..255; row 128 = -row 0
+        sm.lut[i] = i < 128 * 256 ? __ldg(p.atan2_lut + 128 * 256 + i) : -__ldg(p.atan2_lut + (i - 128 * 256));
+    __syncthreads(); // the tables are complete before any warp looks an angle up
     if (!chain_warp && live) produce(0);
     __syncthreads();
     for (uint32_t t = 0; t < n_steps; t++) {

@@ -96,3 +96,10 @@ def test_product_does_not_import_the_oracle():
                     if re.search(r"liboracle|#include.*hrd_oracle|libhrd_ref|cpu_checkers|\bhro_[a-z_]+\(", text):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_atan2_table_bound_behind_the_branch_free_wrap(oracle):
+    """hrd_device.cuh wrap_pi_select relies on |theta_a - theta_b| < 2*pi - 2^-10 for any two table entries."""
+    t = oracle.atan2_table().astype(np.float64)
+    assert t.max() <= np.float32(np.pi) and t.min() > -3.1338
+    assert t.max() - t.min() < 2 * np.pi - 2.0 ** -10
