@@ -695,6 +695,7 @@ static int rx_common(hrd_batch_t *b, const int8_t *iq, size_t bytes, size_t iq_s
     p.state_out = (hrd::RxState *)b->d_state[b->cur ^ 1];
     p.lsb = b->d_lsb;
     p.atan2_lut = g_dev_tables[b->device].atan2_lut;
+    p.sm_count = b->sm_count;
     const uint32_t n_batches = (uint32_t)((n256 + 1023) / 1024);
     if (front_end_only) {
         p.out256 = d_o256;
@@ -840,6 +841,7 @@ int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size
     p.nco_cos = g_dev_tables[b->device].nco_cos;
     p.nco_iq900 = g_dev_tables[b->device].nco_iq900;
     p.nco_thr = g_dev_tables[b->device].nco_thr;
+    p.sm_count = b->sm_count;
     static const int param_of_kind[5] = {-1, HRD_PARAM_AM_INDEX, HRD_PARAM_FM_DEV, HRD_PARAM_WBFM_DEV, -1};
     for (int k = 0; k < 5; k++) {
         if (!b->group_cnt[k]) continue;

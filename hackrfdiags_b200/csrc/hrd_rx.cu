@@ -520,8 +520,8 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
     const uint32_t tile_len = p.tile_batches * BATCH256;
     const uint32_t halo = (uint32_t)HaloOf<K_WBFM>::value * BATCH256;
     const int row = chain_warp ? lane : warp - 1;
-    const int item = blockIdx.x * WB_ITEMS + row;
-    const bool live = row < WB_ITEMS && item < n_items;
+    const int item = blockIdx.x * p.items_per_cta + row;
+    const bool live = row < p.items_per_cta && item < n_items;
     int tile = 0, sid = 0;
     uint32_t start = 0, end = 0, emit_from = 0;
     if (live) {
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
     };
 
     if (threadIdx.x < 40) sm.audio40[threadIdx.x] = c_tab.audio40[threadIdx.x];
-    for (int i = threadIdx.x; i < 129 * 256; i += 1024) // table rows q = 0..127 are rows 128..255; row 128 = -row 0
+    for (int i = threadIdx.x; i < 129 * 256; i += blockDim.x) // table rows q = 0..127 are rows 128..255; row 128 = -row 0
         sm.lut[i] = i < 128 * 256 ? __ldg(p.atan2_lut + 128 * 256 + i) : -__ldg(p.atan2_lut + (i - 128 * 256));
     __syncthreads(); // the tables are complete before any warp looks an angle up
     if (!chain_warp && live) produce(0);
@@ -958,8 +958,10 @@ int launch_wbfm(const RxParams &p, cudaStream_t s)
         attr_set = true;
     }
     const long long items = (long long)p.n_streams * p.n_tiles;
-    const int grid = (int)((items + WB_ITEMS - 1) / WB_ITEMS);
-    rx_wbfm_kernel<ENTRY><<<grid, 1024, sizeof(SmemWb), s>>>(p);
+    RxParams q = p;
+    q.items_per_cta = balanced_items_per_cta(items, p.sm_count, WB_ITEMS);
+    const int grid = (int)((items + q.items_per_cta - 1) / q.items_per_cta);
+    rx_wbfm_kernel<ENTRY><<<grid, (q.items_per_cta + 1) * 32, sizeof(SmemWb), s>>>(q);
     return (int)cudaGetLastError();
 }
 

@@ -127,11 +127,15 @@ struct RxParams {
     // histories by running HALO batches ahead of their first output.
     int32_t n_tiles;
     uint32_t tile_batches;
+    int32_t sm_count;          // multiprocessors of the device (grid sizing)
     // AM / SSB: the FIR half of the DC-removal filter, fir[n] = x[n] - x[n-1] as floats, one per
     // PCM sample.  The recurrence itself is serial per stream and runs in rx_dc_iir_kernel
     // afterwards.
     float *pre_iir;
     size_t pre_stride;         // elements between streams (multiple of 8)
+    // rx_wbfm_kernel: (stream, tile) items per CTA, <= 31; chosen by the launcher so that the grid
+    // fills whole waves of SMs (4096 items: 147 CTAs of 28 instead of 133 of 31)
+    int32_t items_per_cta;
 };
 
 struct TxParams {
@@ -150,9 +154,23 @@ struct TxParams {
     // (WbFmModulator.cc:606-626 applied to Nco.cc's tables once, at table build)
     const uint32_t *nco_iq900;
     const float *nco_thr;      // [8194] Nco::runFast index thresholds (hrd_tx.cu nco_index)
+    int32_t items_per_cta;     // tx_wbfm_kernel: streams per CTA, <= 31 (see RxParams)
+    int32_t sm_count;
 };
 
 enum { K_NONE = 0, K_AM = 1, K_FM = 2, K_WBFM = 3, K_SSB = 4 };
+
+// Items per CTA for the chain-warp kernels (at most `cap`): the smallest count that still needs no
+// more waves of CTAs than `cap` per CTA would, so that the last wave is as full as the others.
+static inline int balanced_items_per_cta(long long items, int sms, int cap)
+{
+    if (items <= 0 || sms <= 0) return cap;
+    const long long waves = (items + (long long)cap * sms - 1) / ((long long)cap * sms);
+    long long ipc = (items + waves * sms - 1) / (waves * sms);
+    if (ipc < 1) ipc = 1;
+    if (ipc > cap) ipc = cap;
+    return (int)ipc;
+}
 
 void upload_tables(const ConstTables &t);            // hrd_rx.cu (owns the __constant__ copy)
 void upload_tables_tx(const ConstTables &t);         // hrd_tx.cu

@@ -404,13 +404,17 @@ __device__ __forceinline__ void interp8_real(const int32_t *in, int n, int &even
 // correctly rounded quotient; the two round to the same float unless a float rounding midpoint
 // (double mantissa bits 28..0 == 0x10000000) lies that close to r, or the result is not a
 // normal float.  Only then is the real division evaluated.
+// out of line on purpose: inlined, the compiler hoists most of the division sequence above the
+// `risky` test and every lane pays for it (it was 10 % of the kernel's instructions)
+__device__ __noinline__ float div_256000_exact(double a) { return (float)(a / 256000.0); }
+
 __device__ __forceinline__ float div_256000_to_float(double a)
 {
     double r = a * (1.0 / 256000.0);
     const uint32_t lo = (uint32_t)__double2loint(r);
     const uint32_t e = ((uint32_t)__double2hiint(r) >> 20) & 0x7ffu;
     const bool risky = ((lo & 0x1fffffffu) - 0x0ffffff8u) <= 16u || (e - 898u) > 250u;
-    if (risky && a != 0.0) r = a / 256000.0;
+    if (risky && a != 0.0) return div_256000_exact(a);
     return (float)r;
 }
 
@@ -441,8 +445,8 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
     const int warp = threadIdx.x >> 5;
     const bool chain_warp = warp == 0;
     const int row = chain_warp ? lane : warp - 1;
-    const int slot = blockIdx.x * TW_ITEMS + row;
-    const bool live = row < TW_ITEMS && slot < p.n_streams;
+    const int slot = blockIdx.x * p.items_per_cta + row;
+    const bool live = row < p.items_per_cta && slot < p.n_streams;
     const int sid = live ? p.stream_ids[slot] : 0;
     TxState &st = p.state[sid];
     TxRail8 &rs = st.wb;
@@ -451,9 +455,9 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
     int8_t *dst = p.iq + (size_t)sid * p.iq_stride;
     const uint32_t n_steps = (p.n8 + TW_STEP8 - 1) / TW_STEP8;
 
-    for (int i = threadIdx.x; i < 16384 / 4; i += 1024)
+    for (int i = threadIdx.x; i < 16384 / 4; i += blockDim.x)
         reinterpret_cast<uint4 *>(sm.iq900)[i] = __ldg(reinterpret_cast<const uint4 *>(p.nco_iq900) + i);
-    for (int i = threadIdx.x; i < 8194; i += 1024) sm.thr[i] = __ldg(p.nco_thr + i);
+    for (int i = threadIdx.x; i < 8194; i += blockDim.x) sm.thr[i] = __ldg(p.nco_thr + i);
     __syncthreads();
 
     float phase = 0.f, dev = 0.f;
@@ -646,13 +650,15 @@ int launch_tx(int kind, const TxParams &p, cudaStream_t s)
     case K_FM: return launch_one<K_FM>(p, s);
     case K_SSB: return launch_one<K_SSB>(p, s);
     case K_WBFM: {
-        const int grid = (p.n_streams + TW_ITEMS - 1) / TW_ITEMS;
+        TxParams q = p;
+        q.items_per_cta = balanced_items_per_cta(p.n_streams, p.sm_count, TW_ITEMS);
+        const int grid = (p.n_streams + q.items_per_cta - 1) / q.items_per_cta;
         static bool attr_set = false;
         if (!attr_set) {
             cudaFuncSetAttribute(tx_wbfm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTw));
             attr_set = true;
         }
-        tx_wbfm_kernel<<<grid, 1024, sizeof(SmemTw), s>>>(p);
+        tx_wbfm_kernel<<<grid, (q.items_per_cta + 1) * 32, sizeof(SmemTw), s>>>(q);
         return (int)cudaGetLastError();
     }
     case K_NONE: {
