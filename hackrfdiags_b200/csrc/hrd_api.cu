@@ -111,7 +111,6 @@ int build_tables(hrd::ConstTables &t)
     for (int i = 0; i < 31; i++) t.hilbert[i] = quantise(k_hilbert31[i]);
     for (int i = 0; i < 16; i++) t.delay[i] = quantise(k_delay16[i]);
     for (int i = 0; i < 8; i++) t.tx_hb8[i] = quantise(k_tx_hb8[i]);
-    t.k_one = 1;
     t.k_32768 = 32768;
     t.tx_c3 = quantise(k_fe3[0]);
     t.tx_m3 = quantise(k_fe3[1]);

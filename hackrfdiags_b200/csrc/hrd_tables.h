@@ -38,8 +38,7 @@ struct ConstTables {
     int32_t tx_hb8[8];      // stages 2,4,5
     int32_t tx_c3, tx_c7, tx_c8; // outer tap of stages 3&6 / 7 / 8 (8424 / 8249 / 8206)
     int32_t tx_m3, tx_m7, tx_m8; // their centre taps (16384 each after quantisation)
-    // 1 and 32768 as values the compiler cannot see (hrd_tx.cu: adds spelled as IMAD to balance pipes)
-    int32_t k_one, k_32768;
+    int32_t k_32768;             // 32768 as a value ptxas cannot see (hrd_tx.cu PIPE BALANCE)
 };
 
 // ---------------------------------------------------------------- Rx per-stream state

@@ -81,22 +81,16 @@ __device__ __forceinline__ void interp8(const uint32_t *in, int n, uint32_t &eve
 // and neither can leave the int16 range: the reference's (int16_t) narrowing is the identity
 // here and is not spent on (Interpolator_int16.cc:398-418 evaluated with these taps).
 //
-// PIPE BALANCE.  These kernels are issue-bound, and on sm_100a the integer ALU pipe (IADD3, SHF,
-// LEA, PRMT, LOP3) and the FMA pipe (IMAD) each take one warp instruction every two cycles per
-// scheduler (profiles/: tx_kernel<SSB> ran the ALU pipe at 85 % with the FMA pipe at 25 %).  The
-// additions of the hot loop are therefore spelled as multiply-adds (mad.lo.s32 -> IMAD) so that
-// they issue on the FMA pipe; only the arithmetic right shifts and the byte packing stay on the
-// ALU pipe.
-__device__ __forceinline__ int imad(int a, int b, int c)
-{
-    int d;
-    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ int hb4_even(int c, int x, int xm1) { return imad(c, x, imad(c, xm1, 1 << 14)) >> 15; }
-// `one` comes from constant memory (ConstTables::k_one) so that ptxas cannot fold x*1+1 back into
-// an ALU-pipe add
-__device__ __forceinline__ int hb4_odd(int x, int one) { return imad(x, one, one) >> 1; }
+// PIPE BALANCE.  These kernels are issue-bound.  On sm_100a (tools/ubench/pipes.cu, profiles/):
+// IMAD (FMA pipe) and SHF / LEA / PRMT / LOP3 (ALU pipe) each sustain 2 warp-instructions/clk/SM,
+// plain adds 4 (ptxas spreads them over both pipes).  Left alone, the compiler turns the stage-8
+// odd outputs, (y << 15) + 32768, into LEAs and the ALU pipe ends up at 85 % with the FMA pipe at
+// 25 % (tx_kernel<SSB>).  Those 16 operations per iteration are therefore spelled as
+// y * K + K with K = 32768 read from constant memory, which ptxas cannot strength-reduce: they
+// issue as IMADs.  Measured on tx_kernel<SSB>, 4096 x 0.5 s: 2.15 ms -> 1.98 ms.  (Pinning the
+// "+1" adds of the odd phases onto the FMA pipe as well was tried and was slower: 2.07 ms.)
+__device__ __forceinline__ int hb4_even(int c, int x, int xm1) { return ((1 << 14) + c * (x + xm1)) >> 15; }
+__device__ __forceinline__ int hb4_odd(int x) { return (x + 1) >> 1; }
 
 // ---- PhaseAccumulator::run (Nco/PhaseAccumulator.cc:157-181) -------------------------------
 // acc += step, then the two while loops that wrap into [-pi, pi] (hrd_device.cuh wrap_pi: fp32
@@ -160,31 +154,31 @@ __device__ __forceinline__ float phase_step(float f, double fs)
 __device__ __forceinline__ void tail4(int x0, int x1, int x2, int x3, int (&out)[16])
 {
     const int ha = c_tabtx.tx_hb8[0], hb = c_tabtx.tx_hb8[2];
-    const int one = c_tabtx.k_one, k15 = c_tabtx.k_32768;
     int y5[2], y5m1;
-    y5[0] = imad(ha, x0, imad(ha, x3, imad(hb, x1, imad(hb, x2, 1 << 14)))) >> 15; // |.| <= 21986: fits int16
-    y5[1] = (x1 + 1) >> 1;   // plain adds here: the FMA pipe is the fuller one after the re-balancing
+    y5[0] = ((1 << 14) + ha * (x0 + x3) + hb * (x1 + x2)) >> 15; // |.| <= 21986: fits int16
+    y5[1] = (x1 + 1) >> 1;
     y5m1 = (x2 + 1) >> 1;    // odd output of the previous input sample
     const int c6 = c_tabtx.tx_c3, c7 = c_tabtx.tx_c7, c8d = 2 * c_tabtx.tx_c8;
+    const int k15 = c_tabtx.k_32768;
     int y6[4], y6m1;
     y6m1 = (y5m1 + 1) >> 1;
     y6[0] = hb4_even(c6, y5[0], y5m1);
-    y6[1] = hb4_odd(y5[0], one);
+    y6[1] = hb4_odd(y5[0]);
     y6[2] = hb4_even(c6, y5[1], y5[0]);
-    y6[3] = hb4_odd(y5[1], one);
+    y6[3] = hb4_odd(y5[1]);
     int y7[8], y7m1;
-    y7m1 = hb4_odd(y6m1, one);
+    y7m1 = hb4_odd(y6m1);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         y7[2 * k] = hb4_even(c7, y6[k], k ? y6[k - 1] : y6m1);
-        y7[2 * k + 1] = hb4_odd(y6[k], one);
+        y7[2 * k + 1] = hb4_odd(y6[k]);
     }
     // stage 8 with doubled taps: (int8_t)(acc>>15) == byte 2 of 2*acc
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         int left = k ? y7[k - 1] : y7m1;
-        out[2 * k] = imad(c8d, y7[k] + left, 1 << 15);
-        out[2 * k + 1] = imad(y7[k], k15, k15);
+        out[2 * k] = (1 << 15) + c8d * (y7[k] + left);
+        out[2 * k + 1] = y7[k] * k15 + k15;
     }
 }
 
@@ -195,23 +189,23 @@ __device__ __forceinline__ uint32_t merge16(uint32_t lo, uint32_t hi) { return _
 __device__ __forceinline__ void tail3(int x0, int xm1, int (&out)[8])
 {
     const int c6 = c_tabtx.tx_c3, c7 = c_tabtx.tx_c7, c8d = 2 * c_tabtx.tx_c8;
-    const int one = c_tabtx.k_one, k15 = c_tabtx.k_32768;
+    const int k15 = c_tabtx.k_32768;
     int y6[2], y6m1;
-    y6m1 = hb4_odd(xm1, one);
+    y6m1 = hb4_odd(xm1);
     y6[0] = hb4_even(c6, x0, xm1);
-    y6[1] = hb4_odd(x0, one);
+    y6[1] = hb4_odd(x0);
     int y7[4], y7m1;
-    y7m1 = hb4_odd(y6m1, one);
+    y7m1 = hb4_odd(y6m1);
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         y7[2 * k] = hb4_even(c7, y6[k], k ? y6[k - 1] : y6m1);
-        y7[2 * k + 1] = hb4_odd(y6[k], one);
+        y7[2 * k + 1] = hb4_odd(y6[k]);
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         int left = k ? y7[k - 1] : y7m1;
-        out[2 * k] = imad(c8d, y7[k] + left, 1 << 15);
-        out[2 * k + 1] = imad(y7[k], k15, k15);
+        out[2 * k] = (1 << 15) + c8d * (y7[k] + left);
+        out[2 * k + 1] = y7[k] * k15 + k15;
     }
 }
 
