@@ -308,6 +308,7 @@ def run_ours(args):
         out["e2e"] = e2e
         if world == 1 and not args.quick:
             out["modes"] = run_mode_sweep(torch, capi, device, args, peak)
+            out["mixed_mode_stream_sweep"] = run_stream_sweep(torch, capi, device, args, peak)
             out["cpu_baseline"] = cpu_baseline(args, groups)
     if dist:
         dist.barrier()
@@ -354,7 +355,7 @@ def run_mode_sweep(torch, capi, device, args, peak):
     n_streams = args.sweep_streams
     n_samples = int(args.sweep_seconds * FS) // 8192 * 8192
     for mode in (1, 2, 3, 4):
-        ms, kms, tms, _, keep = bench_rx_modes(torch, capi, device, [(mode, n_streams)], n_samples, 3, 2, seed=7)
+        ms, kms, tms, _, keep = bench_rx_modes(torch, capi, device, [(mode, n_streams)], n_samples, 5, 3, seed=7)
         del keep
         torch.cuda.empty_cache()
         sps = n_streams * n_samples / (ms * 1e-3)
@@ -363,11 +364,31 @@ def run_mode_sweep(torch, capi, device, args, peak):
                                          "kernel_ms": round(kms, 3), "tail_ms": round(tms, 3)}
     n_pcm = n_samples // 256
     for mode in (1, 2, 3, 4):
-        ms = bench_tx_mode(torch, capi, device, mode, n_streams, n_pcm, 3, 2, seed=11)
+        ms = bench_tx_mode(torch, capi, device, mode, n_streams, n_pcm, 5, 3, seed=11)
         torch.cuda.empty_cache()
         sps = n_streams * n_pcm * 256 / (ms * 1e-3)
         res[f"tx_{MODE_NAMES[mode]}"] = {"streams": n_streams, "MS/s": round(sps / 1e6, 1), "ms": round(ms, 3),
                                          "hbm_frac": round(sps * BYTES_PER_OUT_SAMPLE_TX / 1e9 / peak, 4)}
+    return res
+
+
+def run_stream_sweep(torch, capi, device, args, peak):
+    """BASELINE configs[4] on one GPU: mixed-mode batches (1/4 each AM, NBFM, WBFM, SSB) from 1k to 64k streams,
+    the same total signal per point (so only the stream count changes)."""
+    from hackrfdiags_b200 import shard
+    res = {}
+    total_samples = 4096 * (int(0.5 * FS) // 8192 * 8192)
+    for n_streams in (1024, 4096, 16384, 65536):
+        n_samples = max(8192, total_samples // n_streams // 8192 * 8192)
+        modes = shard.mixed_mode_plan(n_streams, {1: 0.25, 2: 0.25, 3: 0.25, 4: 0.125, 5: 0.125})
+        groups = shard.mode_groups(sorted(enumerate(modes), key=lambda sm: sm[1]))
+        ms, kms, tms, launches, keep = bench_rx_modes(torch, capi, device, groups, n_samples, 5, 3, seed=13)
+        del keep
+        torch.cuda.empty_cache()
+        sps = n_streams * n_samples / (ms * 1e-3)
+        res[str(n_streams)] = {"seconds_per_stream": round(n_samples / FS, 4), "MS/s": round(sps / 1e6, 1), "ms": round(ms, 3),
+                               "hbm_frac": round(sps * BYTES_PER_IN_SAMPLE_RX / 1e9 / peak, 4),
+                               "launches_per_step": launches // 5 if launches else None}
     return res
 
 

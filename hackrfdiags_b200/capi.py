@@ -22,13 +22,13 @@ UNIT_AM, UNIT_FM, UNIT_WBFM, UNIT_SSB, UNIT_FRONT_END, UNIT_ALL = range(6)
 ENTRY_2048K, ENTRY_256K = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 ALL_STREAMS = -1
-OPT_RX_TILE_BATCHES, OPT_RX_WBFM_TILING, OPT_TX_TILE_SAMPLES, OPT_PROFILE = range(4)
+OPT_RX_TILE_BATCHES, OPT_RX_WBFM_TILING, OPT_TX_TILE_SAMPLES, OPT_PROFILE, OPT_DEBUG_WBFM_FORCE_RERUN = range(5)
 
 # every symbol include/hrd.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "hrd_abi_version", "hrd_create", "hrd_destroy", "hrd_last_error", "hrd_set_mode", "hrd_get_mode",
     "hrd_set_param", "hrd_get_param", "hrd_reset", "hrd_set_option", "hrd_get_option", "hrd_rx_process", "hrd_rx_front_end", "hrd_tx_process",
-    "hrd_synchronize", "hrd_launch_count", "hrd_kernel_ms", "hrd_get_table", "hrd_get_taps", "hrd_state_bytes_per_stream",
+    "hrd_synchronize", "hrd_launch_count", "hrd_wbfm_fallback_count", "hrd_kernel_ms", "hrd_get_table", "hrd_get_taps", "hrd_state_bytes_per_stream",
 ]
 
 
@@ -65,6 +65,7 @@ def load():
     lib.hrd_synchronize.argtypes = [vp]
     lib.hrd_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.hrd_kernel_ms.argtypes = [vp, i, i, C.POINTER(C.c_float)]
+    lib.hrd_wbfm_fallback_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.hrd_get_table.argtypes = [vp, i, vp, sz]
     lib.hrd_get_taps.argtypes = [i, vp, i]
     lib.hrd_state_bytes_per_stream.argtypes = [i]
@@ -141,6 +142,11 @@ class Batch:
     def launch_count(self) -> int:
         c = C.c_uint64()
         _check(self.lib.hrd_launch_count(self.h, C.byref(c)))
+        return c.value
+
+    def wbfm_fallback_count(self) -> int:
+        c = C.c_uint64()
+        _check(self.lib.hrd_wbfm_fallback_count(self.h, C.byref(c)))
         return c.value
 
     def kernel_ms(self, which: int = 0, age: int = 0) -> float:

@@ -242,6 +242,10 @@ struct hrd_batch {
     int sm_count = 148;
     int opt[HRD_OPT_COUNT] = {};
     float *d_pre = nullptr;                // Rx AM/SSB: IIR input scratch, [n][pre_stride]
+    void *d_wbv = nullptr;                 // Rx WBFM: verification pairs, [n][n_tiles] float2
+    size_t d_wbv_cap = 0;
+    uint32_t *d_wbflag = nullptr;          // [0] = streams to re-run in this call; +2 words: 64-bit total
+    int32_t *d_wbrerun = nullptr;          // their ids, [n]
     size_t d_pre_cap = 0, pre_stride = 0;
     int32_t *d_ids = nullptr; // streams grouped by kernel kind
     int32_t *d_all = nullptr; // 0..n-1
@@ -355,7 +359,13 @@ void choose_tiles(hrd_batch *b, int kind, int entry, int n_streams, uint32_t n_b
                 const uint32_t tiles = (n_batches + cand - 1) / cand;
                 const double items = (double)tiles * n_streams;
                 const double waves = ceil(items / slots);
-                const double fill = items / (waves * slots);
+                double fill = items / (waves * slots);
+                if (kind == hrd::K_WBFM) {
+                    // one CTA per SM whose size is balanced over the waves (hrd_rx.cu launch_wbfm); an SM needs
+                    // about 16 item warps to stay busy (measured: 7 items per CTA run at 0.45 of the rate of 28)
+                    const int ipc = hrd::balanced_items_per_cta((long long)items, b->sm_count, hrd::rx_resident_warps_per_sm(kind, entry));
+                    fill = ceil(items / ipc) / (waves * b->sm_count) * (ipc >= 16 ? 1.0 : ipc / 16.0);
+                }
                 const double useful = (double)cand / (double)(cand + (tiles > 1 ? halo : 0));
                 const double score = fill * useful;
                 if (score > best + 1e-9) {
@@ -430,6 +440,10 @@ int hrd_create(int device, int n_streams, int kind, hrd_batch_t **out)
         if (e == cudaSuccess) e = cudaMalloc(&b->d_state[h], ssz);
         if (e == cudaSuccess) e = cudaMemset(b->d_state[h], 0, ssz);
     }
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_wbflag, 16);
+    if (e == cudaSuccess) e = cudaMemset(b->d_wbflag, 0, 16);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_wbrerun, (size_t)n_streams * sizeof(int32_t));
+    b->opt[HRD_OPT_RX_WBFM_TILING] = 1;
     if (e == cudaSuccess) e = cudaMalloc(&b->d_ids, (size_t)n_streams * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_all, (size_t)n_streams * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_lsb, (size_t)n_streams);
@@ -457,6 +471,9 @@ int hrd_destroy(hrd_batch_t *b)
     cudaFree(b->d_state[0]);
     cudaFree(b->d_state[1]);
     cudaFree(b->d_pre);
+    cudaFree(b->d_wbv);
+    cudaFree(b->d_wbflag);
+    cudaFree(b->d_wbrerun);
     cudaFree(b->d_ids);
     cudaFree(b->d_all);
     cudaFree(b->d_lsb);
@@ -608,6 +625,17 @@ int hrd_launch_count(hrd_batch_t *b, uint64_t *count)
     return HRD_OK;
 }
 
+int hrd_wbfm_fallback_count(hrd_batch_t *b, uint64_t *count)
+{
+    if (!b || !count) return fail(HRD_EINVAL, "null argument");
+    DeviceGuard guard(b->device);
+    unsigned long long v = 0;
+    HRD_CUDA(cudaDeviceSynchronize());
+    HRD_CUDA(cudaMemcpy(&v, b->d_wbflag + 2, sizeof v, cudaMemcpyDeviceToHost));
+    *count = (uint64_t)v;
+    return HRD_OK;
+}
+
 int hrd_kernel_ms(hrd_batch_t *b, int which, int age, float *ms)
 {
     if (!b || !ms) return fail(HRD_EINVAL, "null argument");
@@ -744,9 +772,31 @@ static int rx_common(hrd_batch_t *b, const int8_t *iq, size_t bytes, size_t iq_s
             p.n_streams = cnt;
             p.gain = k ? b->d_param[gain_of_kind[k]] : nullptr;
             choose_tiles(b, k, entry, p.n_streams, n_batches, &p.n_tiles, &p.tile_batches);
+            const bool speculate = k == hrd::K_WBFM && p.n_tiles > 1;
+            if (speculate) { // verified speculation (hrd_rx.cu): pairs to compare, this call's flag
+                rc = ensure_cap(&b->d_wbv, &b->d_wbv_cap, sizeof(float2) * (size_t)p.n_streams * (size_t)p.n_tiles);
+                if (rc) return rc;
+                p.wb_verify = (float2 *)b->d_wbv;
+                HRD_CUDA(cudaMemsetAsync(b->d_wbflag, 0, sizeof(uint32_t), s));
+            }
             int e = hrd::launch_rx(k, entry, p, s);
             if (e) return fail(HRD_ECUDA, "rx launch (kind %d) failed: %s", k, cudaGetErrorString((cudaError_t)e));
             b->launches++;
+            if (speculate) {
+                e = hrd::launch_rx_wbfm_verify(p, b->d_wbflag, b->d_wbrerun, (unsigned long long *)(b->d_wbflag + 2),
+                                               b->opt[HRD_OPT_DEBUG_WBFM_FORCE_RERUN], s);
+                if (e) return fail(HRD_ECUDA, "wbfm verify launch failed: %s", cudaGetErrorString((cudaError_t)e));
+                hrd::RxParams again = p; // the exact untiled run, from the untouched state_in; runs only if flagged
+                again.n_tiles = 1;
+                again.tile_batches = n_batches;
+                again.wb_verify = nullptr;
+                again.run_if = b->d_wbflag;
+                again.rerun_ids = b->d_wbrerun;
+                e = hrd::launch_rx(k, entry, again, s);
+                if (e) return fail(HRD_ECUDA, "wbfm re-run launch failed: %s", cudaGetErrorString((cudaError_t)e));
+                b->launches += 2;
+                p.wb_verify = nullptr;
+            }
             if (k == hrd::K_AM) {
                 iir_p = p;
                 iir = true;

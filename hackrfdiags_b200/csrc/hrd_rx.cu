@@ -20,10 +20,8 @@
 // The two float recurrences are the exception: the AM/SSB DC-removal IIR (8 kS/s) has no finite
 // look-back, so the tile kernel stops at the IIR's INPUT (one int32 per PCM sample) and
 // rx_dc_iir_kernel runs the recurrence afterwards, one thread per stream, serially, exactly as
-// the reference does.  The WBFM de-emphasis IIR (256 kS/s) runs inside the tile kernel on one
-// lane; WBFM calls are therefore only tiled when the caller opts in (the warm-started
-// recurrence converges to the serial one within the halo, but that is a numerical argument,
-// not an identity).
+// the reference does.  The WBFM de-emphasis IIR (256 kS/s) has its own kernel (rx_wbfm_kernel
+// below: recurrences transposed onto a chain warp, time tiles by verified speculation).
 //
 // Inside a batch:
 //   A. front end, 16 iterations: every lane takes 32 input bytes (16 I,Q samples, one
@@ -479,6 +477,21 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
 //   warp is on step t, every item warp narrows/decimates its step t-1 and then produces step t+1
 //   into the buffer it has just drained.
 //
+// VERIFIED SPECULATION (time tiles).  The recurrence has no finite look-back, so a tile after the
+// first cannot rebuild it exactly from a halo the way the FIR stages do.  It does not have to
+// be exact to be CHECKED: a tile k >= 1 starts two batches (2048 samples) early from y = 0; after
+// the first 1024 samples the pole (0.949^1024 ~ 1e-23) has long forgotten the start value, and in
+// practice y is bit-identical to the serial one -- but that is a numerical argument, not an
+// identity.  So the tile records y at sample emit_from-1025 (the end of its first halo batch,
+// "speculated"), the tile before it records its own y at the same sample ("true": by induction
+// from tile 0, which starts from the saved state), and rx_wbfm_verify_kernel compares the pairs
+// bit for bit.  Equal at that sample and fed the same inputs, the two recurrences are identical
+// from there on, so the second halo batch (1024 samples, more than the 704-sample look-back of
+// the /4 /4 /2 decimators behind the filter) rebuilds the FIR histories from EXACT values and the
+// tile's output is the serial output.  Streams with a differing pair are run again untiled from
+// the untouched state_in (run_if / rerun_ids), so the result is bit-exact in every case; the
+// re-run costs one empty launch when it is not needed.
+//
 // The chain costs WB_STEP x ~10 cycles per step and runs beside ~31 x 4 warp-iterations of front
 // end, so it is hidden as long as the item warps have at least that much to do (they do: the
 // step is HBM- or issue-bound on them).  Results are bit-identical to the serial evaluation:
@@ -505,16 +518,21 @@ struct SmemWb {
     float lut[129 * 256];
 };
 
-template <int ENTRY>
+// TILED: the call is cut into time tiles (n_tiles > 1); only that instance carries the verification stores
+template <int ENTRY, bool TILED>
 __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
 {
     typedef typename RawOf<ENTRY>::type Raw;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // the exact re-run after a failed verification: only the streams the verifier listed
+    const int n_streams = p.run_if ? (int)*p.run_if : p.n_streams;
+    const int32_t *stream_ids = p.run_if ? p.rerun_ids : p.stream_ids;
+    if ((int)blockIdx.x * p.items_per_cta >= n_streams * p.n_tiles) return; // uniform over the CTA
     SmemWb &sm = *reinterpret_cast<SmemWb *>(smem_raw);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const bool chain_warp = warp == 0;
-    const int n_items = p.n_streams * p.n_tiles;
+    const int n_items = n_streams * p.n_tiles;
 
     // ---- this thread's item: the warp's (item warps) or the lane's (chain warp) ---------
     const uint32_t tile_len = p.tile_batches * BATCH256;
@@ -522,11 +540,12 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
     const int row = chain_warp ? lane : warp - 1;
     const int item = blockIdx.x * p.items_per_cta + row;
     const bool live = row < p.items_per_cta && item < n_items;
-    int tile = 0, sid = 0;
+    int tile = 0, sid = 0, slot = 0;
     uint32_t start = 0, end = 0, emit_from = 0;
     if (live) {
-        tile = item / p.n_streams;
-        sid = p.stream_ids[item - tile * p.n_streams];
+        tile = item / n_streams;
+        slot = item - tile * n_streams;
+        sid = stream_ids[slot];
         emit_from = (uint32_t)tile * tile_len;
         end = min(p.n256, emit_from + tile_len);
         start = tile == 0 ? 0u : emit_from - halo;
@@ -693,6 +712,12 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
                 *reinterpret_cast<float4 *>(r + c + 4 * g) = v[g];
             }
         }
+        // verified speculation: y at the two check points of this tile (see the kernel's header)
+        if constexpr (TILED) {
+            const uint32_t pos = done + nb;
+            if (tile >= 1 && pos == start + BATCH256) p.wb_verify[(size_t)slot * p.n_tiles + tile].x = y1;
+            if (tile + 1 < p.n_tiles && pos == end - BATCH256) p.wb_verify[(size_t)slot * p.n_tiles + tile + 1].y = y1;
+        }
     };
 
     if (threadIdx.x < 40) sm.audio40[threadIdx.x] = c_tab.audio40[threadIdx.x];
@@ -736,6 +761,26 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
     if (chain_warp && live && last) so.wb_y1 = y1;
 }
 
+// One thread per stream: speculated vs true recurrence value of every tile >= 1, bit for bit.  A stream with
+// any difference is appended to the re-run list.  (Differences are not an error: a stream whose
+// discriminator output is exactly zero for long stretches -- constant input -- leaves the filter in a
+// slowly decaying denormal tail that a warm-up from zero cannot reproduce bit for bit.)
+__global__ void rx_wbfm_verify_kernel(const float2 *pairs, const int32_t *stream_ids, int n_streams, int n_tiles,
+                                      uint32_t *count, int32_t *rerun_ids, unsigned long long *fallbacks, int force)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_streams) return;
+    bool bad = force != 0;
+    for (int t = 1; t < n_tiles; t++) {
+        const float2 v = pairs[(size_t)slot * n_tiles + t];
+        bad |= __float_as_uint(v.x) != __float_as_uint(v.y);
+    }
+    if (bad) {
+        rerun_ids[atomicAdd(count, 1u)] = stream_ids[slot];
+        atomicAdd(fallbacks, 1ull);
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // AM / SSB DC-removal IIR (AmDemodulator.cc:67-68,460-465, SsbDemodulator.cc:104-105,586-592;
 // Filters/IirFilter.cc:161-176): one thread per stream walks the call's PCM samples in order,
@@ -746,16 +791,17 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
 // ------------------------------------------------------------------------------------
 // One CTA runs 32 streams.  The recurrence is a dependent FMUL+FSUB per sample, so the time of
 // a call is (samples per stream) x (chain latency) no matter how many streams there are; what
-// can be done is to keep everything else OFF the warp that walks the chain.  Four warps form a
+// can be done is to keep everything else OFF the warp that walks the chain.  Six warps form a
 // software pipeline over chunks of 64 samples per stream, one __syncthreads per step:
 //   warp 0   loader: cp.async brings chunk t+3 in ([32 rows][64 floats], coalesced);
 //   warp 1   chain: lane r walks row r of chunk t in place, y = fir - (-0.95f * y1), reading
 //            and writing shared memory 16 bytes at a time (pitch 68 words: conflict-free);
-//   warps 2,3 post: chunk t-1, element-parallel: pcm = (int16_t)(gain * y), 16-byte stores.
+//   warps 2..5 post: chunk t-1, element-parallel: pcm = (int16_t)(gain * y), 16-byte stores.
 constexpr int IIR_CHUNK = 64;   // samples per stream per pipeline step
 constexpr int IIR_AHEAD = 3;    // chunks in flight ahead of the chain
 constexpr int IIR_STAGES = IIR_AHEAD + 2;
 constexpr int IIR_PITCH = 68;   // words per staged row (16-byte aligned, 17 x 4: conflict-free LDS.128)
+constexpr int IIR_POST_THREADS = 128; // warps 2..5: the narrowing/store stage must not outlast the chain warp
 
 struct SmemIir {
     float f[IIR_STAGES][32][IIR_PITCH];
@@ -771,7 +817,7 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(128) rx_dc_iir_kernel(const RxParams p)
+__global__ void __launch_bounds__(64 + IIR_POST_THREADS) rx_dc_iir_kernel(const RxParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemIir &sm = *reinterpret_cast<SmemIir *>(smem_raw);
@@ -854,10 +900,10 @@ __global__ void __launch_bounds__(128) rx_dc_iir_kernel(const RxParams p)
                 const uint32_t c = t - 1;
                 const float(*src)[IIR_PITCH] = sm.f[c % IIR_STAGES];
                 const uint32_t base = c * IIR_CHUNK;
-                const int pl = threadIdx.x - 64; // 0..63: 4 x (row, 8 samples) each
+                const int pl = threadIdx.x - 64; // 0..IIR_POST_THREADS-1: (row, 8 samples) items, 256 per chunk
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int r = 8 * i + (pl >> 3), part = pl & 7;
+                for (int i = 0; i < 256 / IIR_POST_THREADS; i++) {
+                    const int r = (IIR_POST_THREADS / 8) * i + (pl >> 3), part = pl & 7;
                     const uint32_t at = base + part * 8;
                     if (r < rows_live && at < n) {
                         const float g = sm.gain[r];
@@ -949,20 +995,27 @@ int rx_resident_warps_per_sm(int kind, int entry)
     return w;
 }
 
-template <int ENTRY>
-int launch_wbfm(const RxParams &p, cudaStream_t s)
+template <int ENTRY, bool TILED>
+int launch_wbfm_as(const RxParams &q, int grid, cudaStream_t s)
 {
     static bool attr_set = false; // per template instance
     if (!attr_set) {
-        cudaFuncSetAttribute(rx_wbfm_kernel<ENTRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemWb));
+        cudaFuncSetAttribute(rx_wbfm_kernel<ENTRY, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemWb));
         attr_set = true;
     }
+    rx_wbfm_kernel<ENTRY, TILED><<<grid, (q.items_per_cta + 1) * 32, sizeof(SmemWb), s>>>(q);
+    return (int)cudaGetLastError();
+}
+
+template <int ENTRY>
+int launch_wbfm(const RxParams &p, cudaStream_t s)
+{
     const long long items = (long long)p.n_streams * p.n_tiles;
     RxParams q = p;
-    q.items_per_cta = balanced_items_per_cta(items, p.sm_count, WB_ITEMS);
+    // (the re-run's stream count is only known on the device: small CTAs, surplus ones exit at once)
+    q.items_per_cta = p.run_if ? 4 : balanced_items_per_cta(items, p.sm_count, WB_ITEMS);
     const int grid = (int)((items + q.items_per_cta - 1) / q.items_per_cta);
-    rx_wbfm_kernel<ENTRY><<<grid, (q.items_per_cta + 1) * 32, sizeof(SmemWb), s>>>(q);
-    return (int)cudaGetLastError();
+    return p.n_tiles > 1 ? launch_wbfm_as<ENTRY, true>(q, grid, s) : launch_wbfm_as<ENTRY, false>(q, grid, s);
 }
 
 // kind: K_NONE, K_AM (AM and SSB streams together), K_FM or K_WBFM
@@ -983,6 +1036,14 @@ int launch_rx(int kind, int entry, const RxParams &p, cudaStream_t s)
     return (int)cudaErrorInvalidValue;
 }
 
+int launch_rx_wbfm_verify(const RxParams &p, uint32_t *count, int32_t *rerun_ids, unsigned long long *fallbacks, int force,
+                          cudaStream_t s)
+{
+    rx_wbfm_verify_kernel<<<(p.n_streams + 127) / 128, 128, 0, s>>>(p.wb_verify, p.stream_ids, p.n_streams, p.n_tiles, count,
+                                                                     rerun_ids, fallbacks, force);
+    return (int)cudaGetLastError();
+}
+
 int launch_rx_dc_iir(const RxParams &p, cudaStream_t s)
 {
     if (p.n_streams <= 0 || p.n256 == 0) return 0;
@@ -992,7 +1053,7 @@ int launch_rx_dc_iir(const RxParams &p, cudaStream_t s)
         cudaFuncSetAttribute(rx_dc_iir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemIir));
         attr_set = true;
     }
-    rx_dc_iir_kernel<<<grid, 128, sizeof(SmemIir), s>>>(p);
+    rx_dc_iir_kernel<<<grid, 64 + IIR_POST_THREADS, sizeof(SmemIir), s>>>(p);
     return (int)cudaGetLastError();
 }
 

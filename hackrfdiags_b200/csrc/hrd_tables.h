@@ -135,6 +135,12 @@ struct RxParams {
     // rx_wbfm_kernel: (stream, tile) items per CTA, <= 31; chosen by the launcher so that the grid
     // fills whole waves of SMs (4096 items: 147 CTAs of 28 instead of 133 of 31)
     int32_t items_per_cta;
+    // rx_wbfm_kernel, time-tiled calls: one {speculated, true} pair of de-emphasis outputs per
+    // (stream slot, tile); see "verified speculation" in hrd_rx.cu.  run_if: when non-null the
+    // kernel runs only if *run_if != 0 (the exact untiled re-run after a failed verification).
+    float2 *wb_verify;
+    const uint32_t *run_if;    // [0] = number of streams to re-run
+    const int32_t *rerun_ids;  // their stream ids (replaces stream_ids / n_streams in the re-run)
 };
 
 struct TxParams {
@@ -175,6 +181,10 @@ void upload_tables(const ConstTables &t);            // hrd_rx.cu (owns the __co
 void upload_tables_tx(const ConstTables &t);         // hrd_tx.cu
 int launch_rx(int kind, int entry, const RxParams &p, cudaStream_t s);
 int launch_rx_dc_iir(const RxParams &p, cudaStream_t s);  // AM + SSB streams, after their launch_rx
+// WBFM, tiled call: compare every tile's speculated recurrence value with the true one; streams with any
+// difference are appended to rerun_ids (*count of them) and added to *fallbacks (or always, when force is set: test hook)
+int launch_rx_wbfm_verify(const RxParams &p, uint32_t *count, int32_t *rerun_ids, unsigned long long *fallbacks, int force,
+                          cudaStream_t s);
 int rx_halo_batches(int kind);                            // batches a tile > 0 runs ahead
 int rx_resident_warps_per_sm(int kind, int entry);        // occupancy of that kernel (cached)
 int launch_tx(int kind, const TxParams &p, cudaStream_t s);

@@ -85,17 +85,20 @@ enum {
     /* Rx: batches (of 8192 input samples = 32 PCM samples) per time tile; one warp owns one
      * (stream, tile).  0 = choose from the stream count and the SM count. */
     HRD_OPT_RX_TILE_BATCHES = 0,
-    /* Rx WBFM: allow time tiling.  Off (default): a WBFM stream's call is one tile and the
-     * 256 kS/s de-emphasis recurrence is evaluated serially from the saved state, bit-exact.
-     * On: tiles after the first warm the recurrence up over >= 1024 samples from zero, which
-     * converges to the serial value (pole 0.949) but is not an identity: <= 1 LSB of PCM. */
+    /* Rx WBFM: time tiling by verified speculation.  1 (default): tiles after the first warm the
+     * 256 kS/s de-emphasis recurrence up from zero, every tile's warmed-up value is compared bit
+     * for bit with the true one, and streams where any differs are re-run untiled -- the result is
+     * bit-exact either way (hrd_wbfm_fallback_count tells how often the re-run was needed).
+     * 0: never tile WBFM calls. */
     HRD_OPT_RX_WBFM_TILING = 1,
     /* Tx: PCM samples per time tile (multiple of 32).  0 = choose automatically. */
     HRD_OPT_TX_TILE_SAMPLES = 2,
     /* record CUDA events around the kernels of every process call (bench.py's roofline):
      * hrd_kernel_ms() then reports the main and tail kernel times of the latest calls */
     HRD_OPT_PROFILE = 3,
-    HRD_OPT_COUNT = 4
+    /* test hook: make the WBFM verification fail, so that the exact re-run path is exercised */
+    HRD_OPT_DEBUG_WBFM_FORCE_RERUN = 4,
+    HRD_OPT_COUNT = 5
 };
 
 #define HRD_ALL_STREAMS (-1)
@@ -175,6 +178,9 @@ int hrd_synchronize(hrd_batch_t *b);
 int hrd_kernel_ms(hrd_batch_t *b, int which, int age, float *ms);
 /* kernels this batch has launched so far (bench.py's gpu_launches) */
 int hrd_launch_count(hrd_batch_t *b, uint64_t *count);
+/* Rx WBFM: how many stream-calls failed the tile verification and were re-run untiled so far
+ * (HRD_OPT_RX_WBFM_TILING); waits for the batch's queued work */
+int hrd_wbfm_fallback_count(hrd_batch_t *b, uint64_t *count);
 /* copy a device table back: 0 = atan2 LUT (65536 floats), 1 = NCO sin,
  * 2 = NCO cos (16384 floats each) */
 int hrd_get_table(hrd_batch_t *b, int which, float *out, size_t n);

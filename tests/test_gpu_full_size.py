@@ -43,6 +43,22 @@ def _check_sample_vs_oracle(torch, oracle, iq, pcm, modes, picks):
     return worst
 
 
+def test_config1_single_stream_nbfm_10s(env, oracle):
+    """BASELINE configs[0]: one NBFM stream, 10 s at 2.048 MS/s, fed in the reference's 262144-byte blocks
+    (IqDataProcessor::acceptIqData block size) through the host-memory entry; 79 872 + 128 PCM samples."""
+    torch, bench, capi, dev = env
+    from hackrfdiags_b200 import synth
+    n = 10 * FS
+    iq = synth.rx_stream(capi.MODE_FM, n, stream=0, config=1)
+    b = capi.Batch(1, capi.RX, 0)
+    b.set_mode(capi.MODE_FM)
+    parts = [b.rx(iq[None, off:off + 262144].copy()) for off in range(0, iq.size, 262144)]
+    got = np.concatenate(parts, axis=1)[0]
+    want = oracle.run_rx(capi.MODE_FM, iq)
+    assert got.size == want.size == n // 256
+    assert np.array_equal(got, want), f"{(got != want).sum()} of {want.size} PCM samples differ"
+
+
 def test_config2_am_ssb_1024_streams(env, oracle):
     torch, bench, capi, dev = env
     n_samples = FS  # 1 s per stream: 4.19 GB of IQ
