@@ -237,12 +237,14 @@ struct hrd_batch {
     std::vector<uint8_t> lsb;
     std::vector<float> param[HRD_PARAM_COUNT];
     bool dirty = true;
-    void *d_state[2] = {nullptr, nullptr}; // Rx: double-buffered, see hrd::RxParams; Tx uses [0] only
+    void *d_state[2] = {nullptr, nullptr}; // double-buffered, see hrd::RxParams / hrd::TxParams
     int cur = 0;                           // the half the next call reads
     int sm_count = 148;
     int opt[HRD_OPT_COUNT] = {};
     float *d_pre = nullptr;                // Rx AM/SSB: IIR input scratch, [n][pre_stride]
     void *d_wbv = nullptr;                 // Rx WBFM: verification pairs, [n][n_tiles] float2
+    void *d_fmph = nullptr;                // Tx FM: NCO phase per PCM sample, [n_fm][n8]
+    size_t d_fmph_cap = 0;
     size_t d_wbv_cap = 0;
     uint32_t *d_wbflag = nullptr;          // [0] = streams to re-run in this call; +2 words: 64-bit total
     int32_t *d_wbrerun = nullptr;          // their ids, [n]
@@ -329,7 +331,7 @@ int check_stream_arg(hrd_batch *b, int stream)
 int zero_state(hrd_batch *b, int stream, size_t off, size_t len)
 {
     const size_t pitch = state_size(b->kind);
-    char *base = (char *)b->d_state[b->kind == HRD_RX ? b->cur : 0] + off;
+    char *base = (char *)b->d_state[b->cur] + off;
     if (stream == HRD_ALL_STREAMS)
         HRD_CUDA(cudaMemset2DAsync(base, pitch, 0, len, (size_t)b->n, b->own));
     else
@@ -377,6 +379,42 @@ void choose_tiles(hrd_batch *b, int kind, int entry, int n_streams, uint32_t n_b
         if (tb > n_batches) tb = n_batches;
     }
     *tile_batches = tb;
+    *n_tiles = (int32_t)((n_batches + tb - 1) / tb);
+    if (*n_tiles < 1) *n_tiles = 1;
+}
+
+// Tx: tiles of whole 32-sample batches; same trade-off as choose_tiles (fill of the last wave of
+// resident warps against the halo every tile after the first recomputes)
+void choose_tx_tiles(hrd_batch *b, int kind, int n_streams, uint32_t n8, int32_t *n_tiles, uint32_t *tile_len8)
+{
+    const uint32_t n_batches = (n8 + 31) / 32;
+    const uint32_t halo = (uint32_t)hrd::tx_halo_samples(kind) / 32;
+    uint32_t tb = n_batches ? n_batches : 1;
+    if (n_batches > 1) {
+        if (b->opt[HRD_OPT_TX_TILE_SAMPLES] > 0) {
+            tb = ((uint32_t)b->opt[HRD_OPT_TX_TILE_SAMPLES] + 31) / 32;
+            if (tb < halo) tb = halo;
+        } else {
+            const double slots = (double)b->sm_count * hrd::tx_resident_warps_per_sm(kind);
+            double best = -1.0;
+            for (uint32_t t = 1; t <= 512 && t <= n_batches; t++) {
+                const uint32_t cand = (n_batches + t - 1) / t;
+                if (t > 1 && cand < 4 * halo) break; // keep the halo below a fifth of the work
+                const uint32_t tiles = (n_batches + cand - 1) / cand;
+                const double items = (double)tiles * n_streams;
+                const double waves = ceil(items / slots);
+                const double fill = items / (waves * slots);
+                const double useful = (double)cand / (double)(cand + (tiles > 1 ? halo : 0));
+                const double score = fill * useful;
+                if (score > best + 1e-9) {
+                    best = score;
+                    tb = cand;
+                }
+            }
+        }
+        if (tb > n_batches) tb = n_batches;
+    }
+    *tile_len8 = tb * 32;
     *n_tiles = (int32_t)((n_batches + tb - 1) / tb);
     if (*n_tiles < 1) *n_tiles = 1;
 }
@@ -436,7 +474,7 @@ int hrd_create(int device, int n_streams, int kind, hrd_batch_t **out)
     const size_t ssz = state_size(kind) * (size_t)n_streams;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->own, cudaStreamNonBlocking);
     b->sm_count = prop.multiProcessorCount;
-    for (int h = 0; h < (kind == HRD_RX ? 2 : 1); h++) {
+    for (int h = 0; h < 2; h++) {
         if (e == cudaSuccess) e = cudaMalloc(&b->d_state[h], ssz);
         if (e == cudaSuccess) e = cudaMemset(b->d_state[h], 0, ssz);
     }
@@ -472,6 +510,7 @@ int hrd_destroy(hrd_batch_t *b)
     cudaFree(b->d_state[1]);
     cudaFree(b->d_pre);
     cudaFree(b->d_wbv);
+    cudaFree(b->d_fmph);
     cudaFree(b->d_wbflag);
     cudaFree(b->d_wbrerun);
     cudaFree(b->d_ids);
@@ -884,7 +923,11 @@ int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size
     p.n8 = (uint32_t)n_per_stream;
     p.iq = d_iq;
     p.iq_stride = d_iq_stride;
-    p.state = (hrd::TxState *)b->d_state[0];
+    p.state = (const hrd::TxState *)b->d_state[b->cur];
+    p.state_out = (hrd::TxState *)b->d_state[b->cur ^ 1];
+    // every record is carried over first; the kernels then write only what their modulator owns
+    HRD_CUDA(cudaMemcpyAsync(b->d_state[b->cur ^ 1], b->d_state[b->cur], sizeof(hrd::TxState) * (size_t)b->n,
+                             cudaMemcpyDeviceToDevice, s));
     p.lsb = b->d_lsb;
     p.nco_sin = g_dev_tables[b->device].nco_sin;
     p.nco_cos = g_dev_tables[b->device].nco_cos;
@@ -897,10 +940,22 @@ int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size
         p.stream_ids = b->d_ids + b->group_off[k];
         p.n_streams = b->group_cnt[k];
         p.param = param_of_kind[k] >= 0 ? b->d_param[param_of_kind[k]] : nullptr;
+        p.n_tiles = 1;
+        p.tile_len8 = (uint32_t)((n_per_stream + 31) & ~(size_t)31);
+        if (k == hrd::K_AM || k == hrd::K_FM || k == hrd::K_SSB) choose_tx_tiles(b, k, p.n_streams, (uint32_t)n_per_stream, &p.n_tiles, &p.tile_len8);
+        if (k == hrd::K_FM) { // the serial NCO phase pass first (hrd_tx.cu tx_fm_phase_kernel)
+            rc = ensure_cap(&b->d_fmph, &b->d_fmph_cap, sizeof(float) * (size_t)p.n_streams * n_per_stream);
+            if (rc) return rc;
+            p.fm_phase = (float *)b->d_fmph;
+            int e = hrd::launch_tx_fm_phase(p, s);
+            if (e) return fail(HRD_ECUDA, "tx FM phase launch failed: %s", cudaGetErrorString((cudaError_t)e));
+            b->launches++;
+        }
         int e = hrd::launch_tx(k, p, s);
         if (e) return fail(HRD_ECUDA, "tx launch (kind %d) failed: %s", k, cudaGetErrorString((cudaError_t)e));
         b->launches++;
     }
+    b->cur ^= 1; // what this call wrote is what the next one reads
     if (mem == HRD_MEM_HOST) {
         HRD_CUDA(cudaMemcpy2DAsync(iq, iq_stride, b->d_out, d_iq_stride, out_row, (size_t)b->n,
                                    cudaMemcpyDeviceToHost, s));

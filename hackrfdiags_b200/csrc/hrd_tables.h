@@ -149,7 +149,16 @@ struct TxParams {
     uint32_t n8;               // PCM samples per stream in this call
     int8_t *iq;
     size_t iq_stride;
-    TxState *state;
+    // Per-stream state is double-buffered like the receive side's: a call reads `state` and writes
+    // `state_out` (the host copies the records over first, so kernels only write what they own).
+    const TxState *state;
+    TxState *state_out;
+    // Time tiles (AM / FM / SSB; hrd_tx.cu): every stream's call is cut into n_tiles tiles of
+    // tile_len8 PCM samples (a multiple of 32); one warp owns one (stream, tile).
+    int32_t n_tiles;
+    uint32_t tile_len8;
+    // FM: NCO phase BEFORE each PCM sample's step, [slot of this launch][n8] (tx_fm_phase_kernel)
+    float *fm_phase;
     const int32_t *stream_ids;
     int32_t n_streams;
     const float *param;        // AM index / FM deviation / WBFM deviation
@@ -188,5 +197,8 @@ int launch_rx_wbfm_verify(const RxParams &p, uint32_t *count, int32_t *rerun_ids
 int rx_halo_batches(int kind);                            // batches a tile > 0 runs ahead
 int rx_resident_warps_per_sm(int kind, int entry);        // occupancy of that kernel (cached)
 int launch_tx(int kind, const TxParams &p, cudaStream_t s);
+int launch_tx_fm_phase(const TxParams &p, cudaStream_t s);   // FM streams, before their launch_tx
+int tx_resident_warps_per_sm(int kind);                      // occupancy of tx_kernel<kind> (cached)
+int tx_halo_samples(int kind);                               // PCM samples a tile > 0 runs ahead
 
 } // namespace hrd

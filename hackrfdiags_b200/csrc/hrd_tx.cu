@@ -6,7 +6,13 @@
 // and underneath them Filters/Int16/{Interpolator,FirFilter}_int16.cc and
 // Nco/{Nco,PhaseAccumulator}.cc.
 //
-// One warp owns one stream.  A batch is 32 PCM samples (8192 output I,Q samples, 16 KiB):
+// One warp owns one (stream, time tile).  Everything behind the modulator heads is an FIR, so a tile
+// after the first starts HALO PCM samples early from all-zero histories (32 samples for AM / FM: the
+// 40-tap stage 1 looks back 19 and the later stages less than 2 more; 64 for SSB, whose 31-tap
+// Hilbert FIR sits in front) and simply does not store what the halo produces: bit-exact for any
+// tile size.  The FM head's NCO phase is the one recurrence; tx_fm_phase_kernel walks it first
+// (serially per stream, as the reference does) and leaves the phase before every PCM sample.
+// A batch is 32 PCM samples (8192 output I,Q samples, 16 KiB):
 //   1. the modulator head at 8 kS/s, one PCM sample per lane (the NCO phase recurrence is
 //      the only serial piece);
 //   2. interpolator stages 1..4 lane-parallel through small shared-memory rings;
@@ -212,34 +218,52 @@ __device__ __forceinline__ void tail3(int x0, int xm1, int (&out)[8])
 // ------------------------------------------------------------------------------------
 // AM / FM / SSB kernel
 // ------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void ring_init(T *ring, const T *state, int hist, int lane, bool from_state)
+{
+    for (int i = lane; i < hist; i += 32) ring[i] = from_state ? state[i] : T();
+}
+
+template <int KIND> struct TxHaloOf { static constexpr uint32_t value = 32; };
+template <> struct TxHaloOf<K_SSB> { static constexpr uint32_t value = 64; };
+
 template <int KIND>
 __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int slot = blockIdx.x * HRD_WARPS_PER_CTA + warp;
-    if (slot >= p.n_streams) return;
+    const int item = blockIdx.x * HRD_WARPS_PER_CTA + warp;
+    if (item >= p.n_streams * p.n_tiles) return;
+    const int tile = item / p.n_streams;
+    const int slot = item - tile * p.n_streams;
     const int sid = p.stream_ids[slot];
+    const bool first = tile == 0, last = tile == p.n_tiles - 1;
     SmemTx &sm = *reinterpret_cast<SmemTx *>(smem_raw + (size_t)warp * sizeof(SmemTx));
-    TxState &st = p.state[sid];
-    TxRail8 &rs = KIND == K_AM ? st.am : (KIND == K_FM ? st.fm : st.ssb);
+    const TxState &st = p.state[sid];
+    const TxRail8 &rs = KIND == K_AM ? st.am : (KIND == K_FM ? st.fm : st.ssb);
     const int16_t *src = p.pcm + (size_t)sid * p.pcm_stride;
     int8_t *dst = p.iq + (size_t)sid * p.iq_stride;
 
-    ring_load_hist(sm.s0, rs.s0, 19, lane);
-    ring_load_hist(sm.s1, rs.s1, 3, lane);
-    ring_load_hist(sm.s2, rs.s2, 1, lane);
-    ring_load_hist(sm.s3, rs.s3, 3, lane);
-    ring_load_hist(sm.s4, rs.s4, 3, lane);
-    if constexpr (KIND == K_SSB) ring_load_hist(sm.h8, st.ssb_h8, 30, lane);
+    // this tile's range in PCM samples; a later tile rebuilds the FIR histories from zero in its halo
+    const uint32_t emit_from = (uint32_t)tile * p.tile_len8;
+    const uint32_t end = min(p.n8, emit_from + p.tile_len8);
+    const uint32_t start = first ? 0u : emit_from - TxHaloOf<KIND>::value;
+
+    ring_init(sm.s0, rs.s0, 19, lane, first);
+    ring_init(sm.s1, rs.s1, 3, lane, first);
+    ring_init(sm.s2, rs.s2, 1, lane, first);
+    ring_init(sm.s3, rs.s3, 3, lane, first);
+    ring_init(sm.s4, rs.s4, 3, lane, first);
+    if constexpr (KIND == K_SSB) ring_init(sm.h8, st.ssb_h8, 30, lane, first);
     const float prm = (KIND == K_SSB) ? 0.f : p.param[sid];
     const bool lsb = (KIND == K_SSB) ? (p.lsb[sid] != 0) : true;
-    float phase = (KIND == K_FM) ? st.fm_phase : 0.f;
+    const float *fm_phase = (KIND == K_FM) ? p.fm_phase + (size_t)slot * p.n8 : nullptr;
     __syncwarp();
 
-    for (uint32_t done = 0; done < p.n8; done += NB8) {
-        const int nb = (int)min((uint32_t)NB8, p.n8 - done);
+    for (uint32_t done = start; done < end; done += NB8) {
+        const int nb = (int)min((uint32_t)NB8, end - done);
+        const bool emit = done >= emit_from; // halo batches compute, they do not store
         // ---- 1. modulator head, one PCM sample per lane ---------------------------------
         const int x = (lane < nb) ? (int)src[done + lane] : 0;
         uint32_t head = 0;
@@ -253,16 +277,9 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxPara
             head = pack16(m, m);
         }
         if constexpr (KIND == K_FM) {
-            // FmModulator.cc:596-617: frequency -> phase step, NCO at 8 kS/s
-            float f = __fdiv_rn(__fmul_rn(prm, (float)x), 32768.f);
-            float step = phase_step(f, 8000.0);
-            // serial phase recurrence: lane n needs the phase BEFORE step n is added
-            float my_phase = 0.f;
-            for (int n = 0; n < nb; n++) {
-                float sn = __shfl_sync(HRD_FULL_MASK, step, n);
-                if (lane == n) my_phase = phase;
-                phase = phase_advance(phase, sn);
-            }
+            // FmModulator.cc:596-617: the NCO phase before this sample's step (tx_fm_phase_kernel walked
+            // PhaseAccumulator::run for the whole call already)
+            const float my_phase = (lane < nb) ? fm_phase[done + lane] : 0.f;
             // Nco::run (Nco.cc:186-199): cosf/sinf of the float phase.  Evaluated in double
             // and rounded to float (see DESIGN.md "float tolerance").
             double sd, cd;
@@ -320,7 +337,7 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxPara
                 for (int k = 0; k < 8; k++) // bytes {I[2k], Q[2k], I[2k+1], Q[2k+1]}
                     o.v[k] = merge16(pack_b2(oi[2 * k], oq[2 * k]), pack_b2(oi[2 * k + 1], oq[2 * k + 1]));
             }
-            stg_stream_256(out + (size_t)n * 32, o);
+            if (emit) stg_stream_256(out + (size_t)n * 32, o);
         }
         __syncwarp();
         ring_shift(sm.s0, 19, nb, lane);
@@ -331,15 +348,17 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxPara
         if constexpr (KIND == K_SSB) ring_shift(sm.h8, 30, nb, lane);
     }
 
-    ring_save_hist(sm.s0, rs.s0, 19, lane);
-    ring_save_hist(sm.s1, rs.s1, 3, lane);
-    ring_save_hist(sm.s2, rs.s2, 1, lane);
-    ring_save_hist(sm.s3, rs.s3, 3, lane);
-    ring_save_hist(sm.s4, rs.s4, 3, lane);
-    if constexpr (KIND == K_SSB) ring_save_hist(sm.h8, st.ssb_h8, 30, lane);
-    if constexpr (KIND == K_FM) {
-        if (lane == 0) st.fm_phase = phase;
-    }
+    if (!last) return;
+    // the last tile leaves the interpolator histories for the next call (the rest of the record was
+    // copied over by the host; the FM phase is tx_fm_phase_kernel's)
+    TxState &so = p.state_out[sid];
+    TxRail8 &ro = KIND == K_AM ? so.am : (KIND == K_FM ? so.fm : so.ssb);
+    ring_save_hist(sm.s0, ro.s0, 19, lane);
+    ring_save_hist(sm.s1, ro.s1, 3, lane);
+    ring_save_hist(sm.s2, ro.s2, 1, lane);
+    ring_save_hist(sm.s3, ro.s3, 3, lane);
+    ring_save_hist(sm.s4, ro.s4, 3, lane);
+    if constexpr (KIND == K_SSB) ring_save_hist(sm.h8, so.ssb_h8, 30, lane);
     // stages 6,7,8 keep one input sample each; it is always the last output of the stage
     // before, which tail4 recomputes from s4's history, so nothing more needs saving.
 }
@@ -352,9 +371,9 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxPara
 // phase[n+1] = wrap(fl(phase[n] + step[n])).  It cannot be cut in time and it cannot be
 // re-associated, so it is evaluated serially per stream -- but TRANSPOSED, exactly like the
 // de-emphasis recurrence of the WBFM demodulator (hrd_rx.cu rx_wbfm_kernel):
-//   CTA = 32 warps.  Warps 1..31 own one stream each: PCM -> stages 1..5 -> phase step per
+//   CTA = up to 32 warps.  All but the last own one stream each: PCM -> stages 1..5 -> phase step per
 //   256 kS/s sample (-> shared memory), and after the chain: table index -> (cos,sin)*900 as
-//   int16 -> stages 6..8 on both rails -> 32-byte stores.  Warp 0 is the chain warp: lane r
+//   int16 -> stages 6..8 on both rails -> 32-byte stores.  The last warp is the chain warp: lane r
 //   walks stream r's row of TW_STEP phase steps in place, leaving the phase BEFORE each step.
 //   Two row buffers, one __syncthreads per step of 8 PCM samples.
 constexpr int TW_ITEMS = 31;
@@ -437,14 +456,16 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
     SmemTw &sm = *reinterpret_cast<SmemTw *>(smem_raw);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const bool chain_warp = warp == 0;
-    const int row = chain_warp ? lane : warp - 1;
+    // the chain warp is the LAST warp of the CTA: the warp scheduler favours the highest warp id among
+    // eligible warps, and the chain (two dependent instructions per sample) is the CTA's critical path
+    const bool chain_warp = warp == p.items_per_cta;
+    const int row = chain_warp ? lane : warp;
     const int slot = blockIdx.x * p.items_per_cta + row;
     const bool live = row < p.items_per_cta && slot < p.n_streams;
     const int sid = live ? p.stream_ids[slot] : 0;
-    TxState &st = p.state[sid];
+    TxState &st = p.state_out[sid]; // == state[sid]: the host copied the records over before the launch
     TxRail8 &rs = st.wb;
-    SmemTwItem &it = sm.item[chain_warp ? 0 : warp - 1];
+    SmemTwItem &it = sm.item[chain_warp ? 0 : warp];
     const int16_t *src = p.pcm + (size_t)sid * p.pcm_stride;
     int8_t *dst = p.iq + (size_t)sid * p.iq_stride;
     const uint32_t n_steps = (p.n8 + TW_STEP8 - 1) / TW_STEP8;
@@ -613,6 +634,49 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
     }
 }
 
+// ------------------------------------------------------------------------------------
+// FM: the NCO phase recurrence at 8 kS/s (FmModulator.cc:596-604, PhaseAccumulator.cc:95-181)
+// ------------------------------------------------------------------------------------
+// One warp per FM stream.  Per 32 PCM samples every lane turns its sample into a phase step
+// (frequency = deviation * pcm / 32768; step = (float)((2*M_PI*frequency)/8000.0), the double
+// division included), then the warp walks the 32 accumulations in order -- the same operations in
+// the same order as PhaseAccumulator::run -- and stores the phase BEFORE each step.  tx_kernel<FM>
+// reads them, which lets it cut the call into time tiles like the other modes.
+__global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_fm_phase_kernel(const TxParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * HRD_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (slot >= p.n_streams) return;
+    const int sid = p.stream_ids[slot];
+    const int16_t *src = p.pcm + (size_t)sid * p.pcm_stride;
+    float *out = p.fm_phase + (size_t)slot * p.n8;
+    const float dev = p.param[sid];
+    float phase = p.state[sid].fm_phase;
+    for (uint32_t done = 0; done < p.n8; done += NB8) {
+        const int nb = (int)min((uint32_t)NB8, p.n8 - done);
+        const int x = (lane < nb) ? (int)src[done + lane] : 0;
+        const float f = __fdiv_rn(__fmul_rn(dev, (float)x), 32768.f);
+        const float step = phase_step(f, 8000.0);
+        float my_phase = 0.f;
+        if (nb == NB8) { // the common case, unrolled: no loop counter, constant shuffle lanes
+#pragma unroll
+            for (int n = 0; n < NB8; n++) {
+                const float sn = __shfl_sync(HRD_FULL_MASK, step, n);
+                my_phase = (lane == n) ? phase : my_phase;
+                phase = phase_advance(phase, sn);
+            }
+        } else {
+            for (int n = 0; n < nb; n++) {
+                const float sn = __shfl_sync(HRD_FULL_MASK, step, n);
+                if (lane == n) my_phase = phase;
+                phase = phase_advance(phase, sn);
+            }
+        }
+        if (lane < nb) out[done + lane] = my_phase;
+    }
+    if (lane == 0) p.state_out[sid].fm_phase = phase;
+}
+
 // mode NONE: BasebandDataProcessor.cc:689-694 fills the block with 64
 __global__ void tx_idle_kernel(const TxParams p)
 {
@@ -628,13 +692,42 @@ __global__ void tx_idle_kernel(const TxParams p)
 template <int KIND>
 int launch_one(const TxParams &p, cudaStream_t s)
 {
-    const int grid = (p.n_streams + HRD_WARPS_PER_CTA - 1) / HRD_WARPS_PER_CTA;
+    const long long items = (long long)p.n_streams * p.n_tiles;
+    const int grid = (int)((items + HRD_WARPS_PER_CTA - 1) / HRD_WARPS_PER_CTA);
     const size_t smem = sizeof(SmemTx) * HRD_WARPS_PER_CTA;
     tx_kernel<KIND><<<grid, HRD_WARPS_PER_CTA * 32, smem, s>>>(p);
     return (int)cudaGetLastError();
 }
 
+template <int KIND>
+int tx_resident_warps()
+{
+    int blocks = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, tx_kernel<KIND>, HRD_WARPS_PER_CTA * 32,
+                                                      sizeof(SmemTx) * HRD_WARPS_PER_CTA) != cudaSuccess || blocks < 1)
+        blocks = 1;
+    return blocks * HRD_WARPS_PER_CTA;
+}
+
 } // namespace
+
+int tx_halo_samples(int kind) { return kind == K_SSB ? (int)TxHaloOf<K_SSB>::value : (int)TxHaloOf<K_AM>::value; }
+
+int tx_resident_warps_per_sm(int kind)
+{
+    static int cache[5] = {};
+    if (kind != K_AM && kind != K_FM && kind != K_SSB) return HRD_WARPS_PER_CTA;
+    if (!cache[kind]) cache[kind] = kind == K_AM ? tx_resident_warps<K_AM>() : kind == K_FM ? tx_resident_warps<K_FM>() : tx_resident_warps<K_SSB>();
+    return cache[kind];
+}
+
+int launch_tx_fm_phase(const TxParams &p, cudaStream_t s)
+{
+    if (p.n_streams <= 0 || p.n8 == 0) return 0;
+    const int grid = (p.n_streams + HRD_WARPS_PER_CTA - 1) / HRD_WARPS_PER_CTA;
+    tx_fm_phase_kernel<<<grid, HRD_WARPS_PER_CTA * 32, 0, s>>>(p);
+    return (int)cudaGetLastError();
+}
 
 int launch_tx(int kind, const TxParams &p, cudaStream_t s)
 {

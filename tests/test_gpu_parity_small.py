@@ -118,6 +118,47 @@ def test_tx_streaming_state(oracle, mode):
         assert mx <= tol, f"{NAMES[mode]} stream {s}: max abs err {mx}, {cnt} mismatches"
 
 
+@pytest.mark.parametrize("mode", [capi.MODE_AM, capi.MODE_FM, capi.MODE_LSB, capi.MODE_USB])
+@pytest.mark.parametrize("tile_samples", [32, 64, 96, 160])
+def test_tx_time_tiles(oracle, mode, tile_samples):
+    """Tx tiles of 1..5 batches (halo 32 or 64 PCM samples), ragged last tile, three calls in a row; FM reads the
+    NCO phases of the serial pre-pass.  Same bits as one tile (FM: <= 1 LSB, libm sinf/cosf in the reference)."""
+    n_streams = 7
+    sizes = [32 * 11 + 5, 32 * 4, 77]
+    pcm = synth.tx_batch(n_streams, sum(sizes), config=12)
+    b = capi.Batch(n_streams, capi.TX)
+    b.set_mode(mode)
+    b.set_option(capi.OPT_TX_TILE_SAMPLES, tile_samples)
+    parts, off = [], 0
+    for sz in sizes:
+        parts.append(b.tx(np.ascontiguousarray(pcm[:, off:off + sz])))
+        off += sz
+    got = np.concatenate(parts, axis=1)
+    tol = 1 if mode == capi.MODE_FM else 0
+    for s in range(n_streams):
+        want = oracle.run_tx(mode, pcm[s])
+        mx, cnt = _diff(got[s], want)
+        assert mx <= tol, f"{NAMES[mode]} tile={tile_samples} stream {s}: max abs err {mx}, {cnt} mismatches"
+
+
+def test_tx_mixed_modes_one_batch(oracle):
+    """All modulators plus the idle carrier in one batch, two calls; automatic tiling."""
+    modes = [capi.MODE_AM, capi.MODE_FM, capi.MODE_WBFM, capi.MODE_LSB, capi.MODE_USB, capi.MODE_NONE] * 2
+    n = 32 * 40 + 9
+    pcm = synth.tx_batch(len(modes), n, config=13)
+    b = capi.Batch(len(modes), capi.TX)
+    for i, m in enumerate(modes):
+        b.set_mode(m, i)
+    got = np.concatenate([b.tx(np.ascontiguousarray(pcm[:, :700])), b.tx(np.ascontiguousarray(pcm[:, 700:]))], axis=1)
+    for i, m in enumerate(modes):
+        if m == capi.MODE_NONE:
+            assert (got[i] == 64).all()  # BasebandDataProcessor.cc:689-694
+            continue
+        want = oracle.run_tx(m, pcm[i])
+        err = np.abs(got[i].astype(np.int32) - want.astype(np.int32)).max()
+        assert err <= (1 if m == capi.MODE_FM else 0), f"stream {i} mode {m}: max abs err {err}"
+
+
 # ---- time tiling: every tile size must give what one tile (= the serial order) gives -----
 @pytest.mark.parametrize("mode", [capi.MODE_AM, capi.MODE_FM, capi.MODE_LSB, capi.MODE_USB])
 @pytest.mark.parametrize("tile_batches", [1, 2, 3, 5])
