@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhrd_b200.so")
+# HRD_LIB: timing experiments load a variant build (tools/exp_build.sh); the product is libhrd_b200.so
+LIB_PATH = os.environ.get("HRD_LIB") or os.path.join(_HERE, "libhrd_b200.so")
 
 RX, TX = 0, 1
 MODE_NONE, MODE_AM, MODE_FM, MODE_WBFM, MODE_LSB, MODE_USB = range(6)

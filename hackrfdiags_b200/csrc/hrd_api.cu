@@ -79,6 +79,16 @@ const int k_n_tapsets = (int)(sizeof k_tapsets / sizeof k_tapsets[0]);
 
 // (int16_t)round(c*32768) evaluated in float; the narrowing keeps the low 16 bits, so
 // 1.0 -> 32768 -> -32768 exactly as the reference build does
+// taps of an N-tap decimator for mac_pair (hrd_tables.h): word w = {tl(q[N-1-2w]), tl(q[N-2-2w]), th(..), th(..)}
+void split_taps(const int32_t *q, int n, uint32_t *out)
+{
+    for (int w = 0; w < n / 2; w++) {
+        const int q0 = q[n - 1 - 2 * w], q1 = q[n - 2 - 2 * w];
+        out[w] = (uint32_t)(q0 & 0xff) | (uint32_t)(q1 & 0xff) << 8 | (uint32_t)((q0 >> 8) & 0xff) << 16 |
+                 (uint32_t)((q1 >> 8) & 0xff) << 24;
+    }
+}
+
 int16_t quantise(float c)
 {
     float scaled = c * 32768;
@@ -108,6 +118,9 @@ int build_tables(hrd::ConstTables &t)
     for (int i = 0; i < 12; i++) t.fm_post[i] = quantise(k_fm_post[i]);
     for (int i = 0; i < 40; i++) t.audio40[i] = quantise(k_audio40[i]);
     for (int i = 0; i < 8; i++) t.wbfm_post1[i] = quantise(k_wbfm_post1[i]);
+    split_taps(t.wbfm_post1, 8, t.wb1_sp);
+    split_taps(t.fm_post, 12, t.fm_post_sp);
+    split_taps(t.audio40, 40, t.audio40_sp);
     for (int i = 0; i < 31; i++) t.hilbert[i] = quantise(k_hilbert31[i]);
     for (int i = 0; i < 16; i++) t.delay[i] = quantise(k_delay16[i]);
     for (int i = 0; i < 8; i++) t.tx_hb8[i] = quantise(k_tx_hb8[i]);

@@ -65,11 +65,74 @@ __device__ __forceinline__ u32x8 ldg_stream_256(const void *p)
     return r;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void stg_stream_256(void *p, const u32x8 &r)
 {
     asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.v[0]),
                  "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
                  : "memory");
+}
+
+// cp.async (LDGSTS): global -> shared copies that need no registers and complete in order per thread,
+// so wait_group N is exact ("all but the N newest groups have landed").
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Bulk asynchronous copy (the TMA engine, 1-D form): ONE instruction moves a whole chunk global -> shared
+// and signals an mbarrier with the byte count; no registers, no per-lane requests, and every waiter sees
+// the data once its try_wait on the barrier's phase succeeds.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 "HRD_WAIT:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra HRD_DONE;\n\t"
+                 "bra HRD_WAIT;\n\t"
+                 "HRD_DONE:\n\t"
+                 "}" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+
+// Named barriers (bar.sync / bar.arrive with an id and a thread count): the producer / consumer
+// hand-over of the chain-warp kernels.  Threads that ARRIVE do not wait; shared-memory writes made
+// before the arrive are visible to the threads the barrier releases.  Id 0 is __syncthreads.
+#define HRD_BAR_PRODUCED 1 // and 2: item warps -> chain warp, by step parity
+#define HRD_BAR_CHAINED 3  // and 4: chain warp -> item warps
+// (the id is an immediate chosen by the step's parity: a register id makes ptxas reserve all 16 barriers)
+__device__ __forceinline__ void named_bar_sync(int base, uint32_t parity, int threads)
+{
+    if (parity & 1)
+        asm volatile("bar.sync %0, %1;" ::"r"(base + 1), "r"(threads) : "memory");
+    else
+        asm volatile("bar.sync %0, %1;" ::"r"(base), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int base, uint32_t parity, int threads)
+{
+    if (parity & 1)
+        asm volatile("bar.arrive %0, %1;" ::"r"(base + 1), "r"(threads) : "memory");
+    else
+        asm volatile("bar.arrive %0, %1;" ::"r"(base), "r"(threads) : "memory");
 }
 
 // ------------------------------------------------------------------------------------

@@ -36,6 +36,10 @@
 // (-fmad=false) and IEEE division.
 #include "hrd_device.cuh"
 
+#ifndef HRD_EXP
+#define HRD_EXP 0 // timing experiments only (tools/exp_build.sh): bits switch parts of a kernel off
+#endif
+
 namespace hrd {
 
 __constant__ ConstTables c_tab;
@@ -47,6 +51,7 @@ namespace {
 constexpr int BATCH256 = 1024; // 256 kS/s samples per batch
 constexpr int IT_SAMPLES = 64; // 256 kS/s samples per warp iteration
 constexpr int RX_DEPTH = 2;    // input iterations in flight per warp (software prefetch)
+constexpr uint32_t RX_L2_AHEAD = 4; // ... and this many more pulled into L2 ahead of them (load_raw)
 
 // batches a tile > 0 runs ahead of its first stored output.  Look-back of each cascade in PCM
 // periods (one batch = 32): AM 10, FM 23, SSB 40 (the 31-tap Hilbert FIR at 8 kS/s),
@@ -198,6 +203,17 @@ __device__ __forceinline__ int dec_real(const int16_t *ring, const int32_t *taps
     return q15((int)acc);
 }
 
+// Two int16 samples {x[2w], x[2w+1]} against their two taps in ONE pair of dp2a: the taps are split
+// tap = th*256 + tl (th signed, tl unsigned byte) and packed {tl0, tl1, th0, th1} on the host
+// (hrd_api.cu split_taps), so  acc_l += x0*tl0 + x1*tl1,  acc_h += x0*th0 + x1*th1  and the Q15
+// accumulator is acc_l + 256*acc_h (mod 2^32, like the reference's int32).  Half the instructions of
+// the unpack-and-IMAD form, and the samples stay packed from narrowing to the last decimator.
+__device__ __forceinline__ void mac_pair(uint32_t x, uint32_t taps, int &acc_l, int &acc_h)
+{
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %0;" : "+r"(acc_l) : "r"(x), "r"(taps));
+    asm("dp2a.hi.s32.s32 %0, %1, %2, %0;" : "+r"(acc_h) : "r"(x), "r"(taps));
+}
+
 template <typename T>
 __device__ __forceinline__ void ring_init(T *ring, const T *state, int hist, int lane, bool from_state)
 {
@@ -216,8 +232,15 @@ template <int ENTRY>
 __device__ __forceinline__ typename RawOf<ENTRY>::type load_raw(const int8_t *src, uint32_t off, uint32_t off_last)
 {
     const uint32_t o = min(off, off_last);
-    if constexpr (ENTRY == 0)
+    if constexpr (ENTRY == 0) {
+        // ptxas puts every global load of the loop on ONE counting scoreboard (tools/sass_ctl.py), so the
+        // consumer of an older prefetch also waits for the load issued just before it: the register
+        // prefetch alone hides about half an iteration, not RX_DEPTH.  An L2 prefetch needs no register and
+        // no scoreboard: it pulls the lines RX_L2_AHEAD iterations further on from DRAM, and the LDG that
+        // follows hits in L2 (a few hundred cycles instead of a DRAM round trip under load).
+        prefetch_l2(src + min(off + RX_L2_AHEAD * IT_SAMPLES * 16, off_last));
         return ldg_stream_256(src + o);
+    }
     else
         return __ldg(reinterpret_cast<const uint32_t *>(src + o));
 }
@@ -425,6 +448,7 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
         done256 += nb;
     }
 
+
     // ---- the last tile leaves the stream's state for the next call -----------------------
     if (!last) return;
     RxState &so = p.state_out[sid];
@@ -500,22 +524,27 @@ constexpr int WB_ITEMS = 31;
 constexpr int WB_STEP = 256;            // 256 kS/s samples per pipeline step (4 warp iterations)
 constexpr int WB_PITCH = WB_STEP + 4;   // floats per row
 
-struct SmemWbItem {
-    int16_t d256[4 + WB_STEP];
-    int16_t d64[8 + WB_STEP / 4];
-    int16_t a16[38 + WB_STEP / 16];
+struct SmemWbItem {                    // int16 samples, two per word {x[2w], x[2w+1]} (mac_pair's operand)
+    uint32_t d64[4 + WB_STEP / 8];     // @64k: 8 samples of history + 64 new per step
+    uint32_t a16[19 + WB_STEP / 32];   // @16k: 38 samples of history + 16 new per step
 };
 struct SmemWb {
     float f[2][32][WB_PITCH];
     SmemWbItem item[WB_ITEMS];
-    int32_t audio40[40];   // copy of c_tab.audio40 for lane-dependent tap indices (see consume)
+    // split taps of the 12-tap and the 40-tap decimator, by the lane's share of the taps (see consume)
+    alignas(16) uint32_t t12[2][4];
+    alignas(16) uint32_t t40[4][8];
     // Upper half of the atan2 table, rows q = 0..128 (row 128 = minus the table's q = -128 row).
     // atan2 is odd in q and the table is the host libm's (double, narrowed to float), which is odd
     // bit for bit -- checked when the table is built (hrd_api.cu ensure_tables) -- so
     // theta(q, i) = sign(q) * lut[|q|][i + 128].  132 KB: the whole table (256 KB) fits neither
     // shared memory nor L1, and at two scattered 4-byte gathers per lane per iteration the L1
     // tag stage, not HBM, was the limiter of this kernel (profiles/: L1 hit rate 52 %).
+#if HRD_EXP & 8
+    float lut[256];
+#else
     float lut[129 * 256];
+#endif
 };
 
 // TILED: the call is cut into time tiles (n_tiles > 1); only that instance carries the verification stores
@@ -572,7 +601,10 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
     fk.a0 = c_tab.fe_a[0]; fk.b0 = c_tab.fe_b[0];
     fk.a1 = c_tab.fe_a[1]; fk.b1 = c_tab.fe_b[1];
     fk.a2 = c_tab.fe_a[2]; fk.b2 = c_tab.fe_b[2];
-    float scale = 0.f, th_keep = 0.f, v_keep = 0.f;
+    float scale = 0.f, th_keep = 0.f, v_keep = 0.f, m_keep = 0.f;
+    uint32_t keep2 = 0u, keep3 = 0u; // the last four narrowed samples @256k (history of the /4 decimator)
+    int last_nl = 32;                // lanes that were live in the most recent consume
+    bool narrow_fast = false;
     constexpr uint32_t BPS = ENTRY == 0 ? 16 : 2;
     uint32_t pf = 0, pf_last = 0, last_active = 32;
     Raw buf[RX_DEPTH];
@@ -582,11 +614,19 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
             th_keep = st.wb_prev_theta;
             v_keep = st.wb_x1;
         }
-        ring_init(it.d256, st.wb_d256, 4, lane, first);
-        ring_init(it.d64, st.wb_d64, 8, lane, first);
-        ring_init(it.a16, st.wb_a16, 38, lane, first);
+        if (first) {
+            keep2 = reinterpret_cast<const uint32_t *>(st.wb_d256)[0];
+            keep3 = reinterpret_cast<const uint32_t *>(st.wb_d256)[1];
+        }
+        ring_init(it.d64, reinterpret_cast<const uint32_t *>(st.wb_d64), 4, lane, first);
+        ring_init(it.a16, reinterpret_cast<const uint32_t *>(st.wb_a16), 19, lane, first);
         // WbFmDemodulator.cc:392-395
         scale = __fmul_rn(__fdiv_rn(p.gain[sid], 75000.f), 32767.f);
+        m_keep = __fmul_rn(0.0253863f, v_keep);
+        // |y| <= max(|y[-1]|, pi * scale * (1 + 1e-6)): the de-emphasis filter has unit DC gain and a
+        // positive impulse response, and |x| <= pi * scale.  Below 2^31 the (int16_t) narrowing needs no
+        // out-of-range patch (f32_to_i16).  NaN gains fail the test and take the patched path.
+        narrow_fast = scale < 0x1p27f && fabsf(first ? st.wb_y1 : 0.f) < 0x1p30f;
         pf = (start + 2 * lane) * BPS;
         pf_last = (end - 2) * BPS;
 #pragma unroll
@@ -611,6 +651,10 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
             b = load_raw<ENTRY>(src, pf, pf_last);
         }
         pf += IT_SAMPLES * BPS;
+#if HRD_EXP & 4
+        *reinterpret_cast<float2 *>(dst + 2 * lane) = make_float2(__int_as_float(word), 0.f);
+        return;
+#endif
         // theta = atan2LookupTable[(uint8_t)Q + 128][(uint8_t)I + 128]  (WbFmDemodulator.cc:403-406)
         // word = {I0, I1, Q0, Q1}: sign-extend Q, fold the table on |Q|, put the sign back
         int q0, q1; // prmt with the sign-replicate bit (8) set in three selector nibbles: one-instruction sext of a byte
@@ -627,16 +671,18 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
         const float d0 = wrap_pi_select(__fsub_rn(th0, thp));
         const float d1 = wrap_pi_select(__fsub_rn(th1, th0));
         const float v0 = __fmul_rn(scale, d0), v1 = __fmul_rn(scale, d1);
-        const float selv = (lane == 31) ? v_keep : v1;
-        const float vp = __shfl_sync(HRD_FULL_MASK, selv, (lane + 31) & 31);
+        // FirFilter::filterData order: y = 0 + b0*x[n]; y = y + b1*x[n-1]   (FirFilter.cc:161-164).
+        // b0 == b1, so b1*x[n-1] is the previous sample's b0*x[n]: the product crosses lanes, not x.
+        const float bb = 0.0253863f;
+        const float m0 = __fmul_rn(bb, v0), m1 = __fmul_rn(bb, v1);
+        const float selm = (lane == 31) ? m_keep : m1;
+        const float mp = __shfl_sync(HRD_FULL_MASK, selm, (lane + 31) & 31);
         th_keep = th1; // the state save reads them from the last live lane
         v_keep = v1;
-        // FirFilter::filterData order: y = 0 + b0*x[n]; y = y + b1*x[n-1]   (FirFilter.cc:161-164)
-        const float bb = 0.0253863f;
-        const float m0 = __fmul_rn(bb, v0);
+        m_keep = m1;
         float2 o;
-        o.x = __fadd_rn(m0, __fmul_rn(bb, vp));
-        o.y = __fadd_rn(__fmul_rn(bb, v1), m0);
+        o.x = __fadd_rn(m0, mp);
+        o.y = __fadd_rn(m1, m0);
         *reinterpret_cast<float2 *>(dst + 2 * lane) = o;
     };
 
@@ -659,40 +705,82 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
         __syncwarp();
     };
 
-    // WbFmDemodulator.cc:460-500 on step t: (int16_t) narrowing, /4 (8 taps) /4 (12) /2 (40)
+    // WbFmDemodulator.cc:460-500 on step t: (int16_t) narrowing, /4 (8 taps) /4 (12) /2 (40).
+    // Register-blocked: lane L owns samples 8L..8L+7 of the step, narrows them, packs them two per word
+    // and feeds the decimators with mac_pair (two taps per instruction pair, no unpacking).
     auto consume = [&](uint32_t t) {
         const uint32_t done = start + t * WB_STEP;
         if (done >= end) return;
-        const int nb = (int)min((uint32_t)WB_STEP, end - done);
-        const int n64 = nb / 4, n16 = nb / 16, n8 = nb / 32;
-        const float *y = sm.f[t & 1][row];
-        for (int i = lane; i < nb; i += 32) it.d256[4 + i] = (int16_t)f32_to_i16(y[i]);
-        __syncwarp();
-        for (int j = lane; j < n64; j += 32) it.d64[8 + j] = (int16_t)dec_real<8, 4>(it.d256, c_tab.wbfm_post1, j);
-        __syncwarp();
-        if (lane < n16) it.a16[38 + lane] = (int16_t)dec_real<12, 4>(it.d64, c_tab.fm_post, lane);
+        const int nb = (int)min((uint32_t)WB_STEP, end - done); // multiple of 32
+        const int nl = nb >> 3;                                   // live lanes, a multiple of 4
+        last_nl = nl;
+        const float *y = sm.f[t & 1][row] + 8 * lane;             // lanes >= nl read stale floats and store nothing
+        const float4 ya = *reinterpret_cast<const float4 *>(y), yb = *reinterpret_cast<const float4 *>(y + 4);
+        const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+        int v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = __float2int_rz(yv[i]);
+        if (!narrow_fast) { // (int16_t)float of an out-of-range value (hrd_device.cuh f32_to_i16)
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (!(yv[i] < 2147483648.0f)) v[i] = 0;
+        }
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) w[i] = merge16((uint32_t)v[2 * i], (uint32_t)v[2 * i + 1]);
+        // /4, 8 taps: output j reads samples 4j-4 .. 4j+3; this lane has outputs 2L (half from the lane
+        // before) and 2L+1
+        const uint32_t l2 = from_left(w[2], keep2, lane), l3 = from_left(w[3], keep3, lane);
+        int al = 1 << 14, ah = 0;
+        mac_pair(l2, c_tab.wb1_sp[0], al, ah);
+        mac_pair(l3, c_tab.wb1_sp[1], al, ah);
+        mac_pair(w[0], c_tab.wb1_sp[2], al, ah);
+        mac_pair(w[1], c_tab.wb1_sp[3], al, ah);
+        const int e0 = (al + (ah << 8)) >> 15;
+        al = 1 << 14, ah = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) mac_pair(w[i], c_tab.wb1_sp[i], al, ah);
+        const int e1 = (al + (ah << 8)) >> 15;
+        if (lane < nl) it.d64[4 + lane] = merge16((uint32_t)e0, (uint32_t)e1);
         __syncwarp();
         {
-            // audio decimator: only n8 <= 8 outputs per step but 40 taps each, so four lanes share an
-            // output (10 taps each; the int32 accumulation wraps, so the order of the sum is free)
-            const int k = lane >> 2, part = lane & 3;
-            unsigned acc = part == 0 ? (1u << 14) : 0u;
-            if (k < n8) {
-#pragma unroll
-                for (int t = 0; t < 10; t++) {
-                    const int tt = part * 10 + t;
-                    acc += (unsigned)(sm.audio40[tt] * (int)it.a16[2 * k + 39 - tt]);
-                }
-            }
+            // /4, 12 taps: output k reads ring words 2k .. 2k+5; two lanes share an output (the int32
+            // accumulation wraps, so the order of the sum is free)
+            const int k = lane >> 1, h = lane & 1;
+            const uint4 b = *reinterpret_cast<const uint4 *>(sm.t12[h]);
+            const uint32_t *r = it.d64 + 2 * k + 3 * h;
+            al = h ? 0 : (1 << 14), ah = 0;
+            mac_pair(r[0], b.x, al, ah);
+            mac_pair(r[1], b.y, al, ah);
+            mac_pair(r[2], b.z, al, ah);
+            int acc = al + (ah << 8);
             acc += __shfl_xor_sync(HRD_FULL_MASK, acc, 1);
-            acc += __shfl_xor_sync(HRD_FULL_MASK, acc, 2);
-            if (done >= emit_from && part == 0 && k < n8)
-                p.pcm[(size_t)sid * p.pcm_stride + done / 32 + k] = (int16_t)q15((int)acc);
+            const int o = acc >> 15;
+            const int o_next = __shfl_down_sync(HRD_FULL_MASK, o, 2);
+            if ((lane & 3) == 0 && lane < nl) it.a16[19 + (lane >> 2)] = merge16((uint32_t)o, (uint32_t)o_next);
         }
         __syncwarp();
-        ring_shift(it.d256, 4, nb, lane);
-        ring_shift(it.d64, 8, n64, lane);
-        ring_shift(it.a16, 38, n16, lane);
+        {
+            // audio decimator /2, 40 taps: output k reads ring words k .. k+19; four lanes share an output
+            const int k = lane >> 2, part = lane & 3;
+            const uint4 b = *reinterpret_cast<const uint4 *>(sm.t40[part]);
+            const uint32_t b4 = sm.t40[part][4];
+            const uint32_t *r = it.a16 + k + 5 * part;
+            al = part ? 0 : (1 << 14), ah = 0;
+            mac_pair(r[0], b.x, al, ah);
+            mac_pair(r[1], b.y, al, ah);
+            mac_pair(r[2], b.z, al, ah);
+            mac_pair(r[3], b.w, al, ah);
+            mac_pair(r[4], b4, al, ah);
+            int acc = al + (ah << 8);
+            acc += __shfl_xor_sync(HRD_FULL_MASK, acc, 1);
+            acc += __shfl_xor_sync(HRD_FULL_MASK, acc, 2);
+            if (done >= emit_from && part == 0 && lane < nl)
+                p.pcm[(size_t)sid * p.pcm_stride + done / 32 + k] = (int16_t)q15(acc);
+        }
+        __syncwarp();
+        ring_shift(it.d64, 4, nl, lane);
+        ring_shift(it.a16, 19, nb / 32, lane);
     };
 
     // IirFilter.cc:161-176 with a = {-0.9492274f}: lane = item, in place, 32 samples per round
@@ -722,22 +810,39 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
         }
     };
 
-    if (threadIdx.x < 40) sm.audio40[threadIdx.x] = c_tab.audio40[threadIdx.x];
-    for (int i = threadIdx.x; i < 129 * 256; i += blockDim.x) // table rows q = 0..127 are rows 128..255; row 128 = -row 0
+    if (threadIdx.x < 6) sm.t12[threadIdx.x / 3][threadIdx.x % 3] = c_tab.fm_post_sp[threadIdx.x];
+    if (threadIdx.x < 20) sm.t40[threadIdx.x / 5][threadIdx.x % 5] = c_tab.audio40_sp[threadIdx.x];
+    for (int i = threadIdx.x; i < (int)(sizeof(sm.lut) / 4); i += blockDim.x) // table rows q = 0..127 are rows 128..255; row 128 = -row 0
         sm.lut[i] = i < 128 * 256 ? __ldg(p.atan2_lut + 128 * 256 + i) : -__ldg(p.atan2_lut + (i - 128 * 256));
     __syncthreads(); // the tables are complete before any warp looks an angle up
-    if (!chain_warp && live) produce(0);
-    __syncthreads();
-    for (uint32_t t = 0; t < n_steps; t++) {
-        if (chain_warp) {
+    // Hand-over between the item warps and the chain warp: two pairs of named barriers (by step parity)
+    // instead of one __syncthreads per step.  Item warps ARRIVE on "produced" and go on; only the chain
+    // warp waits there.  The chain warp arrives on "chained" after its step; item warps wait there before
+    // they narrow that step.  No item warp ever waits for another item warp's consume, so a slow warp
+    // costs the CTA nothing as long as it keeps within a step of the others.
+    const int bar_threads = (int)blockDim.x;
+    if (chain_warp) {
+        for (uint32_t t = 0; t < n_steps; t++) {
+            named_bar_sync(HRD_BAR_PRODUCED, t, bar_threads);
+#if !(HRD_EXP & 1)
             if (live) chain(t);
-        } else if (live) {
-            if (t >= 1) consume(t - 1);
-            if (t + 1 < n_steps) produce(t + 1);
+#endif
+            named_bar_arrive(HRD_BAR_CHAINED, t, bar_threads);
         }
-        __syncthreads();
+    } else {
+        if (live) produce(0);
+        named_bar_arrive(HRD_BAR_PRODUCED, 0, bar_threads);
+        for (uint32_t t = 0; t < n_steps; t++) {
+            if (t + 1 < n_steps) {
+                if (live) produce(t + 1); // into the buffer this warp drained in consume(t - 1)
+                named_bar_arrive(HRD_BAR_PRODUCED, t + 1, bar_threads);
+            }
+            named_bar_sync(HRD_BAR_CHAINED, t, bar_threads);
+#if !(HRD_EXP & 2)
+            if (live) consume(t);
+#endif
+        }
     }
-    if (!chain_warp && live) consume(n_steps - 1);
 
     // ---- the last tile leaves the stream's state for the next call -----------------------
     RxState &so = p.state_out[sid];
@@ -746,9 +851,12 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
         uint32_t *b = reinterpret_cast<uint32_t *>(&so);
         for (int i = lane; i < (int)(sizeof(RxState) / 4); i += 32) b[i] = a[i];
         __syncwarp();
-        ring_save_hist(it.d256, so.wb_d256, 4, lane);
-        ring_save_hist(it.d64, so.wb_d64, 8, lane);
-        ring_save_hist(it.a16, so.wb_a16, 38, lane);
+        ring_save_hist(it.d64, reinterpret_cast<uint32_t *>(so.wb_d64), 4, lane);
+        ring_save_hist(it.a16, reinterpret_cast<uint32_t *>(so.wb_a16), 19, lane);
+        if (lane == last_nl - 1) { // from_left left every lane's own last two words in keep2/keep3
+            reinterpret_cast<uint32_t *>(so.wb_d256)[0] = keep2;
+            reinterpret_cast<uint32_t *>(so.wb_d256)[1] = keep3;
+        }
         if (lane == (int)last_active - 1) {
             if constexpr (ENTRY == 0) {
                 so.fe_t = fc.t;
@@ -811,13 +919,6 @@ struct SmemIir {
     float gain[32];
 };
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
-{
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(64 + IIR_POST_THREADS) rx_dc_iir_kernel(const RxParams p)
 {
@@ -948,9 +1049,9 @@ __global__ void __launch_bounds__(64 + IIR_POST_THREADS) rx_dc_iir_kernel(const 
 template <int KIND, int ENTRY>
 int launch_one(const RxParams &p, cudaStream_t s)
 {
-    typedef typename SmemOf<KIND>::type Smem;
     const long long items = (long long)p.n_streams * p.n_tiles;
     const int grid = (int)((items + HRD_WARPS_PER_CTA - 1) / HRD_WARPS_PER_CTA);
+    typedef typename SmemOf<KIND>::type Smem;
     const size_t smem = sizeof(Smem) * HRD_WARPS_PER_CTA;
     rx_kernel<KIND, ENTRY><<<grid, HRD_WARPS_PER_CTA * 32, smem, s>>>(p);
     return (int)cudaGetLastError();
@@ -970,10 +1071,9 @@ int rx_halo_batches(int kind)
 template <int KIND, int ENTRY>
 int resident_warps()
 {
-    typedef typename SmemOf<KIND>::type Smem;
     int blocks = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, rx_kernel<KIND, ENTRY>, HRD_WARPS_PER_CTA * 32,
-                                                      sizeof(Smem) * HRD_WARPS_PER_CTA) != cudaSuccess || blocks < 1)
+                                                      sizeof(typename SmemOf<KIND>::type) * HRD_WARPS_PER_CTA) != cudaSuccess || blocks < 1)
         blocks = 1;
     return blocks * HRD_WARPS_PER_CTA;
 }

@@ -26,6 +26,10 @@
 // (Interpolator_int16.cc:398-418).
 #include "hrd_device.cuh"
 
+#ifndef HRD_EXP
+#define HRD_EXP 0 // timing experiments only (tools/exp_build.sh)
+#endif
+
 namespace hrd {
 
 __constant__ ConstTables c_tabtx;
@@ -47,7 +51,6 @@ struct SmemTx {
     uint32_t s3[3 + 8 * NB8];   // stage 4 input  @64k
     uint32_t s4[3 + 16 * NB8];  // stage 5 input  @128k
     uint32_t h8[30 + NB8];      // SSB: PCM/2 history for delay line / Hilbert
-    float ph[NB8];              // FM: NCO phases of the batch
 };
 
 // ---- generic polyphase stages over rings of I/Q pairs ------------------------------------
@@ -281,7 +284,8 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxPara
             // PhaseAccumulator::run for the whole call already)
             const float my_phase = (lane < nb) ? fm_phase[done + lane] : 0.f;
             // Nco::run (Nco.cc:186-199): cosf/sinf of the float phase.  Evaluated in double
-            // and rounded to float (see DESIGN.md "float tolerance").
+            // and rounded to float (see DESIGN.md "float tolerance").  (Measured: moving the sincos into
+            // tx_fm_phase_kernel makes that kernel FP64-pipe-bound and the pair slower, 2.28 -> 2.36 ms.)
             double sd, cd;
             sincos((double)my_phase, &sd, &cd);
             int ci = f32_to_i16(__fmul_rn((float)cd, 16000.f));
@@ -391,6 +395,7 @@ struct SmemTwItem {                       // real samples, sign-extended
 struct SmemTw {
     float ph[2][32][TW_PITCH];
     SmemTwItem item[TW_ITEMS];
+    uint32_t big[2][32];                  // per row and step: some |phase step| >= 3 (the chain's slow path)
     alignas(16) uint32_t iq900[16384];    // {(int16_t)(cos*900), (int16_t)(sin*900)} per NCO entry
     float thr[8194 + 2];                  // nco_index thresholds
 };
@@ -520,6 +525,7 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
         for (int n = lane; n < 8 * nb; n += 32) interp8_real(it.s3, n, it.s4[3 + 2 * n], it.s4[3 + 2 * n + 1]);
         __syncwarp();
         float *out = sm.ph[t & 1][row];
+        bool big = false;
         for (int n = lane; n < 16 * nb; n += 32) {
             int e, o;
             interp8_real(it.s4, n, e, o);
@@ -532,7 +538,10 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
             stp.x = div_256000_to_float(two_pi * (double)fe);
             stp.y = div_256000_to_float(two_pi * (double)fo);
             *reinterpret_cast<float2 *>(out + 2 * n) = stp;
+            big |= !(fabsf(stp.x) < 3.0f) | !(fabsf(stp.y) < 3.0f);
         }
+        big = __any_sync(HRD_FULL_MASK, big);
+        if (lane == 0) sm.big[t & 1][row] = big;
         __syncwarp();
         ring_shift(it.s0, 19, nb, lane);
         ring_shift(it.s1, 3, 2 * nb, lane);
@@ -541,10 +550,34 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
         ring_shift(it.s4, 3, 16 * nb, lane);
     };
 
-    // PhaseAccumulator::run for every sample of step t: row[n] <- phase before step n
+    // PhaseAccumulator::run for every sample of step t: row[n] <- phase before step n.
+    // The item warps flag rows with a step of 3 rad or more (a deviation setting beyond the reference's
+    // limits, or NaN).  Without one, |phase + step| < pi + 3 < 2*pi - 2^-10, so a single fp32 wrap is the
+    // exact one (hrd_device.cuh wrap_pi_select) and the chain is six operations per sample with no
+    // bookkeeping; with one, the lock-step version with its exact per-chunk redo runs instead.
     auto chain = [&](uint32_t t) {
         const uint32_t nb = min((uint32_t)TW_STEP8, p.n8 - t * TW_STEP8) * 32;
         float *r = sm.ph[t & 1][lane];
+        // (every lane of the chain warp votes; lanes without a stream then leave)
+        const bool slow = __any_sync(HRD_FULL_MASK, live && (sm.big[t & 1][lane] != 0 || !(fabsf(phase) < HRD_PI_UP)));
+        if (!live) return;
+        if (!slow) {
+            for (uint32_t c = 0; c < nb; c += 32) {
+                float4 v[8];
+#pragma unroll
+                for (int g = 0; g < 8; g++) v[g] = *reinterpret_cast<float4 *>(r + c + 4 * g);
+#pragma unroll
+                for (int g = 0; g < 8; g++) {
+                    float s;
+                    s = v[g].x; v[g].x = phase; phase = wrap_pi_select(__fadd_rn(phase, s));
+                    s = v[g].y; v[g].y = phase; phase = wrap_pi_select(__fadd_rn(phase, s));
+                    s = v[g].z; v[g].z = phase; phase = wrap_pi_select(__fadd_rn(phase, s));
+                    s = v[g].w; v[g].w = phase; phase = wrap_pi_select(__fadd_rn(phase, s));
+                    *reinterpret_cast<float4 *>(r + c + 4 * g) = v[g];
+                }
+            }
+            return;
+        }
         for (uint32_t c = 0; c < nb; c += 32) {
             float4 v[8];
 #pragma unroll
@@ -608,22 +641,53 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
         }
     };
 
+    // hand-over by named barriers, as in rx_wbfm_kernel (hrd_rx.cu): item warps arrive on "produced"
+    // and wait on "chained"; the chain warp does the opposite
+    const int bar_threads = (int)blockDim.x;
+#if HRD_EXP & 128
     if (!chain_warp && live) produce(0);
     __syncthreads();
     for (uint32_t t = 0; t < n_steps; t++) {
         if (chain_warp) {
-            if (live) chain(t);
+#if !(HRD_EXP & 16)
+            chain(t);
+#endif
         } else if (live) {
             if (t >= 1) consume(t - 1);
             if (t + 1 < n_steps) produce(t + 1);
         }
         __syncthreads();
     }
+    if (!chain_warp && live) consume(n_steps - 1);
+#else
+    if (chain_warp) {
+        for (uint32_t t = 0; t < n_steps; t++) {
+            named_bar_sync(HRD_BAR_PRODUCED, t, bar_threads);
+#if !(HRD_EXP & 16)
+            chain(t);
+#endif
+            named_bar_arrive(HRD_BAR_CHAINED, t, bar_threads);
+        }
+    } else {
+        if (live) produce(0);
+        named_bar_arrive(HRD_BAR_PRODUCED, 0, bar_threads);
+        for (uint32_t t = 0; t < n_steps; t++) {
+            if (t + 1 < n_steps) {
+                if (live) produce(t + 1);
+                named_bar_arrive(HRD_BAR_PRODUCED, t + 1, bar_threads);
+            }
+            named_bar_sync(HRD_BAR_CHAINED, t, bar_threads);
+#if !(HRD_EXP & 32)
+            if (live) consume(t);
+#endif
+        }
+    }
+#endif
+    __syncthreads();
     if (live) {
         if (chain_warp) {
             st.wb_phase = phase;
         } else {
-            consume(n_steps - 1);
             save_real_hist(it.s0, rs.s0, 19, lane);
             save_real_hist(it.s1, rs.s1, 3, lane);
             save_real_hist(it.s2, rs.s2, 1, lane);
