@@ -18,17 +18,17 @@ LIB_PATH = os.environ.get("HRD_LIB") or os.path.join(_HERE, "libhrd_b200.so")
 RX, TX = 0, 1
 MODE_NONE, MODE_AM, MODE_FM, MODE_WBFM, MODE_LSB, MODE_USB = range(6)
 (PARAM_AM_GAIN, PARAM_FM_GAIN, PARAM_WBFM_GAIN, PARAM_SSB_GAIN,
- PARAM_AM_INDEX, PARAM_FM_DEV, PARAM_WBFM_DEV) = range(7)
+ PARAM_AM_INDEX, PARAM_FM_DEV, PARAM_WBFM_DEV, PARAM_SQUELCH_THRESHOLD, PARAM_RX_GAIN_DB) = range(9)
 UNIT_AM, UNIT_FM, UNIT_WBFM, UNIT_SSB, UNIT_FRONT_END, UNIT_ALL = range(6)
 ENTRY_2048K, ENTRY_256K = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 ALL_STREAMS = -1
-OPT_RX_TILE_BATCHES, OPT_RX_WBFM_TILING, OPT_TX_TILE_SAMPLES, OPT_PROFILE, OPT_DEBUG_WBFM_FORCE_RERUN = range(5)
+OPT_RX_TILE_BATCHES, OPT_RX_WBFM_TILING, OPT_TX_TILE_SAMPLES, OPT_PROFILE, OPT_DEBUG_WBFM_FORCE_RERUN, OPT_RX_SQUELCH = range(6)
 
 # every symbol include/hrd.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "hrd_abi_version", "hrd_create", "hrd_destroy", "hrd_last_error", "hrd_set_mode", "hrd_get_mode",
-    "hrd_set_param", "hrd_get_param", "hrd_reset", "hrd_set_option", "hrd_get_option", "hrd_rx_process", "hrd_rx_front_end", "hrd_tx_process",
+    "hrd_set_param", "hrd_get_param", "hrd_reset", "hrd_set_option", "hrd_get_option", "hrd_rx_process", "hrd_rx_front_end", "hrd_rx_squelch_report", "hrd_tx_process",
     "hrd_synchronize", "hrd_launch_count", "hrd_wbfm_fallback_count", "hrd_kernel_ms", "hrd_get_table", "hrd_get_taps", "hrd_state_bytes_per_stream",
 ]
 
@@ -63,6 +63,7 @@ def load():
     lib.hrd_rx_process.argtypes = [vp, vp, sz, sz, i, vp, sz, vp, i, vp]
     lib.hrd_rx_front_end.argtypes = [vp, vp, sz, sz, vp, sz, i, vp]
     lib.hrd_tx_process.argtypes = [vp, vp, sz, sz, vp, sz, i, vp]
+    lib.hrd_rx_squelch_report.argtypes = [vp, vp, vp, sz, C.POINTER(C.c_uint32)]
     lib.hrd_synchronize.argtypes = [vp]
     lib.hrd_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.hrd_kernel_ms.argtypes = [vp, i, i, C.POINTER(C.c_float)]
@@ -173,6 +174,15 @@ class Batch:
                                        pcm.shape[1], counts.ctypes.data, MEM_HOST, None))
         self.last_counts = counts
         return pcm[:, :npcm]
+
+    def squelch_report(self):
+        """(magnitudes[n_streams, n_blocks] uint32, allowed[n_streams, n_blocks] uint8) of the latest squelched rx call."""
+        nb = C.c_uint32(0)
+        _check(self.lib.hrd_rx_squelch_report(self.h, None, None, 0, C.byref(nb)))
+        mags = np.zeros((self.n, max(nb.value, 1)), dtype=np.uint32)
+        allowed = np.zeros((self.n, max(nb.value, 1)), dtype=np.uint8)
+        _check(self.lib.hrd_rx_squelch_report(self.h, mags.ctypes.data, allowed.ctypes.data, mags.shape[1], C.byref(nb)))
+        return mags[:, :nb.value], allowed[:, :nb.value]
 
     def rx_front_end(self, iq: np.ndarray) -> np.ndarray:
         assert iq.dtype == np.int8 and iq.ndim == 2 and iq.shape[0] == self.n and iq.strides[1] == 1

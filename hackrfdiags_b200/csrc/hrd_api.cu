@@ -171,6 +171,17 @@ int ensure_tables(int device)
     if (rc) return rc;
     hrd::upload_tables(t);
     hrd::upload_tables_tx(t);
+    {
+        // DbfsCalculator::DbfsCalculator (DbfsCalculator.cc:56-65): (int32_t)(20 * log10((float)i)), the float
+        // overload of log10 as the C++ reference resolves it; entry 0 repeats entry 1
+        int32_t db[257];
+        for (int i = 1; i <= 256; i++) {
+            volatile float level = 20 * log10f((float)i);
+            db[i] = (int32_t)level;
+        }
+        db[0] = db[1];
+        hrd::upload_db_table(db);
+    }
     HRD_CUDA(cudaGetLastError());
     // atan2 table (FmDemodulator.cc:158-170): double atan2 narrowed to float, [q+128][i+128]
     std::vector<float> lut(65536);
@@ -270,6 +281,15 @@ struct hrd_batch {
     int group_off[5] = {}, group_cnt[5] = {};
     void *d_in = nullptr, *d_out = nullptr;
     size_t d_in_cap = 0, d_out_cap = 0;
+    // squelch gate (hrd_squelch.cu): the 256 kS/s stream of the call, per-(stream, block) magnitudes,
+    // decisions and output offsets, one block of PCM, per-block stream lists, tracker state
+    void *d_sq256 = nullptr, *d_sq_mag = nullptr, *d_sq_open = nullptr, *d_sq_at = nullptr, *d_sq_pcm = nullptr, *d_sq_ids = nullptr;
+    size_t d_sq256_cap = 0, d_sq_mag_cap = 0, d_sq_open_cap = 0, d_sq_at_cap = 0, d_sq_pcm_cap = 0, d_sq_ids_cap = 0;
+    uint8_t *d_sq_track = nullptr;
+    std::vector<uint8_t> h_kind;           // kernel kind of every stream (host copy of d_kind)
+    std::vector<uint32_t> sq_mag;          // latest squelched call: [n][sq_blocks]
+    std::vector<uint8_t> sq_open;
+    uint32_t sq_blocks = 0;
     cudaStream_t own = nullptr;
     uint64_t launches = 0;
     // HRD_OPT_PROFILE: events around the hot kernel(s) of the latest call and around its tail kernel
@@ -299,6 +319,7 @@ int regroup(hrd_batch *b)
             if (kinds[(size_t)s] == k) ids.push_back(s);
         b->group_cnt[k] = (int)ids.size() - b->group_off[k];
     }
+    b->h_kind = kinds;
     HRD_CUDA(cudaMemcpy(b->d_kind, kinds.data(), (size_t)b->n, cudaMemcpyHostToDevice));
     HRD_CUDA(cudaMemcpy(b->d_ids, ids.data(), (size_t)b->n * sizeof(int32_t), cudaMemcpyHostToDevice));
     HRD_CUDA(cudaMemcpy(b->d_lsb, b->lsb.data(), (size_t)b->n, cudaMemcpyHostToDevice));
@@ -481,7 +502,9 @@ int hrd_create(int device, int n_streams, int kind, hrd_batch_t **out)
                                              300.f,                              // SsbDemodulator.cc:146
                                              0.8f,                               // AmModulator.cc:218
                                              3500.f,                             // FmModulator.cc:218
-                                             70000.f};                           // WbFmModulator.cc:204
+                                             70000.f,                            // WbFmModulator.cc:204
+                                             -200.f,                             // IqDataProcessor.cc:120-124
+                                             16.f};                              // Radio.cc:413
     for (int p = 0; p < HRD_PARAM_COUNT; p++) b->param[p].assign((size_t)n_streams, defaults[p]);
     cudaError_t e = cudaSuccess;
     const size_t ssz = state_size(kind) * (size_t)n_streams;
@@ -499,6 +522,8 @@ int hrd_create(int device, int n_streams, int kind, hrd_batch_t **out)
     if (e == cudaSuccess) e = cudaMalloc(&b->d_all, (size_t)n_streams * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_lsb, (size_t)n_streams);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_kind, (size_t)n_streams);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_sq_track, (size_t)n_streams);
+    if (e == cudaSuccess) e = cudaMemset(b->d_sq_track, 0, (size_t)n_streams); // SignalTracker: NoSignal
     for (int p = 0; p < HRD_PARAM_COUNT && e == cudaSuccess; p++)
         e = cudaMalloc(&b->d_param[p], (size_t)n_streams * sizeof(float));
     if (e == cudaSuccess) {
@@ -533,6 +558,13 @@ int hrd_destroy(hrd_batch_t *b)
     for (int p = 0; p < HRD_PARAM_COUNT; p++) cudaFree(b->d_param[p]);
     cudaFree(b->d_in);
     cudaFree(b->d_out);
+    cudaFree(b->d_sq256);
+    cudaFree(b->d_sq_mag);
+    cudaFree(b->d_sq_open);
+    cudaFree(b->d_sq_at);
+    cudaFree(b->d_sq_pcm);
+    cudaFree(b->d_sq_ids);
+    cudaFree(b->d_sq_track);
     for (int r = 0; r < HRD_PROFILE_RING; r++)
         for (int i = 0; i < 3; i++)
             if (b->ev[r][i]) cudaEventDestroy(b->ev[r][i]);
@@ -583,6 +615,12 @@ int hrd_set_param(hrd_batch_t *b, int stream, int param, float value)
             break;
         case HRD_PARAM_WBFM_DEV: // WbFmModulator.cc:310-328
             if (cur >= 0 && cur <= 112000) cur = value;
+            break;
+        case HRD_PARAM_SQUELCH_THRESHOLD: // an int32_t in the reference
+        case HRD_PARAM_RX_GAIN_DB:        // a uint32_t
+            if (!(value >= -2147483000.f && value <= 2147483000.f) || (param == HRD_PARAM_RX_GAIN_DB && value < 0))
+                return fail(HRD_EINVAL, "param %d: %g is not representable in the reference's integer", param, (double)value);
+            cur = truncf(value);
             break;
         default:
             cur = value;
@@ -640,7 +678,16 @@ int hrd_reset(hrd_batch_t *b, int stream, int unit)
             rc = zero_state(b, stream, offsetof(RxState, ssb), sizeof(RxState) - offsetof(RxState, ssb));
             break;
         case HRD_UNIT_FRONT_END: rc = zero_state(b, stream, RANGE(RxState, fe_t, am)); break;
-        case HRD_UNIT_ALL: rc = zero_state(b, stream, 0, sizeof(RxState)); break;
+        case HRD_UNIT_ALL:
+            rc = zero_state(b, stream, 0, sizeof(RxState));
+            // a freshly constructed IqDataProcessor also has a fresh SignalTracker (state NoSignal)
+            if (!rc) {
+                if (stream == HRD_ALL_STREAMS)
+                    HRD_CUDA(cudaMemsetAsync(b->d_sq_track, 0, (size_t)b->n, b->own));
+                else
+                    HRD_CUDA(cudaMemsetAsync(b->d_sq_track + stream, 0, 1, b->own));
+            }
+            break;
         default: return fail(HRD_EINVAL, "bad unit %d", unit);
         }
     } else {
@@ -713,6 +760,184 @@ int hrd_get_table(hrd_batch_t *b, int which, float *out, size_t n)
     return HRD_OK;
 }
 
+// The demodulator launches of one call (or, with the squelch armed, of one block): one tile-kernel launch
+// per kernel kind over the given stream lists, then the AM/SSB recurrence pass.  after_tiles, when set, is
+// recorded between the two (HRD_OPT_PROFILE).
+static int run_demods(hrd_batch_t *b, hrd::RxParams &p, int entry, uint32_t n_batches, const int32_t *const ids_of[4],
+                      const int cnt_of[4], cudaStream_t s, cudaEvent_t after_tiles)
+{
+    static const int gain_of_kind[5] = {-1, HRD_PARAM_AM_GAIN, HRD_PARAM_FM_GAIN, HRD_PARAM_WBFM_GAIN, HRD_PARAM_SSB_GAIN};
+    int rc;
+    hrd::RxParams iir_p;
+    bool iir = false;
+    for (int k = 0; k < 4; k++) {
+        const int cnt = cnt_of[k];
+        if (!cnt) continue;
+        if (k == hrd::K_NONE && entry == HRD_ENTRY_256K) continue;
+        p.stream_ids = ids_of[k];
+        p.n_streams = cnt;
+        p.gain = k ? b->d_param[gain_of_kind[k]] : nullptr;
+        choose_tiles(b, k, entry, p.n_streams, n_batches, &p.n_tiles, &p.tile_batches);
+        const bool speculate = k == hrd::K_WBFM && p.n_tiles > 1;
+        if (speculate) { // verified speculation (hrd_rx.cu): pairs to compare, this call's flag
+            rc = ensure_cap(&b->d_wbv, &b->d_wbv_cap, sizeof(float2) * (size_t)p.n_streams * (size_t)p.n_tiles);
+            if (rc) return rc;
+            p.wb_verify = (float2 *)b->d_wbv;
+            HRD_CUDA(cudaMemsetAsync(b->d_wbflag, 0, sizeof(uint32_t), s));
+        }
+        int e = hrd::launch_rx(k, entry, p, s);
+        if (e) return fail(HRD_ECUDA, "rx launch (kind %d) failed: %s", k, cudaGetErrorString((cudaError_t)e));
+        b->launches++;
+        if (speculate) {
+            e = hrd::launch_rx_wbfm_verify(p, b->d_wbflag, b->d_wbrerun, (unsigned long long *)(b->d_wbflag + 2),
+                                           b->opt[HRD_OPT_DEBUG_WBFM_FORCE_RERUN], s);
+            if (e) return fail(HRD_ECUDA, "wbfm verify launch failed: %s", cudaGetErrorString((cudaError_t)e));
+            hrd::RxParams again = p; // the exact untiled run, from the untouched state_in; runs only if flagged
+            again.n_tiles = 1;
+            again.tile_batches = n_batches;
+            again.wb_verify = nullptr;
+            again.run_if = b->d_wbflag;
+            again.rerun_ids = b->d_wbrerun;
+            e = hrd::launch_rx(k, entry, again, s);
+            if (e) return fail(HRD_ECUDA, "wbfm re-run launch failed: %s", cudaGetErrorString((cudaError_t)e));
+            b->launches += 2;
+            p.wb_verify = nullptr;
+        }
+        if (k == hrd::K_AM) {
+            iir_p = p;
+            iir = true;
+        }
+    }
+    if (after_tiles) HRD_CUDA(cudaEventRecord(after_tiles, s));
+    if (iir) { // the serial 8 kS/s recurrence of the AM/SSB streams, after every tile kernel
+        int e = hrd::launch_rx_dc_iir(iir_p, s);
+        if (e) return fail(HRD_ECUDA, "rx IIR launch failed: %s", cudaGetErrorString((cudaError_t)e));
+        b->launches++;
+    }
+    return HRD_OK;
+}
+
+// The squelched receive call (include/hrd.h "Squelch"; hrd_squelch.cu): front end for every stream into a
+// 256 kS/s scratch, per-block magnitudes and tracker decisions, then block by block the demodulators of the
+// streams the gate lets through (256 kS/s entry kernels on the scratch, state carried for the others) and a
+// scatter of their PCM to the caller's rows.  p arrives with iq / state / tables set for the whole call.
+static int rx_squelched(hrd_batch_t *b, hrd::RxParams p, size_t n256, int16_t *d_pcm, size_t d_pcm_stride,
+                        uint32_t *pcm_counts, cudaStream_t s)
+{
+    const size_t blk256 = 16384; // 262144 bytes at 2.048 MS/s = one reference call (hackRf/hackrf.c:101)
+    const int n_blocks = (int)((n256 + blk256 - 1) / blk256);
+    const size_t n = (size_t)b->n, cells = n * (size_t)n_blocks;
+    const size_t row256 = (n256 * 2 + 31) & ~(size_t)31;
+    int rc = ensure_cap(&b->d_sq256, &b->d_sq256_cap, row256 * n);
+    if (!rc) rc = ensure_cap(&b->d_sq_mag, &b->d_sq_mag_cap, cells * sizeof(uint32_t));
+    if (!rc) rc = ensure_cap(&b->d_sq_open, &b->d_sq_open_cap, cells);
+    if (!rc) rc = ensure_cap(&b->d_sq_at, &b->d_sq_at_cap, cells * sizeof(uint32_t));
+    if (!rc) rc = ensure_cap(&b->d_sq_pcm, &b->d_sq_pcm_cap, n * 512 * sizeof(int16_t));
+    if (!rc) rc = ensure_cap(&b->d_sq_ids, &b->d_sq_ids_cap, cells * sizeof(int32_t));
+    if (rc) return rc;
+
+    // 1. IqDataProcessor::reduceSampleRate + upconvertByFsOver4 for every stream, gated or not (:937-946)
+    {
+        hrd::RxParams fe = p;
+        fe.out256 = (int8_t *)b->d_sq256;
+        fe.out_stride = row256;
+        fe.stream_ids = b->d_all;
+        fe.n_streams = b->n;
+        choose_tiles(b, hrd::K_NONE, HRD_ENTRY_2048K, b->n, (uint32_t)((n256 + 1023) / 1024), &fe.n_tiles, &fe.tile_batches);
+        if (hrd::launch_rx(hrd::K_NONE, HRD_ENTRY_2048K, fe, s))
+            return fail(HRD_ECUDA, "front-end launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        b->launches++;
+        b->cur ^= 1;
+    }
+    // 2. Squelch::run per block, in order (the tracker state lives across calls)
+    if (hrd::launch_squelch_magnitude((const int8_t *)b->d_sq256, row256, (uint32_t)(blk256 * 2), (uint32_t)(n256 * 2), b->n,
+                                      n_blocks, (uint32_t *)b->d_sq_mag, s) ||
+        hrd::launch_squelch_track((const uint32_t *)b->d_sq_mag, b->n, n_blocks, b->d_param[HRD_PARAM_SQUELCH_THRESHOLD],
+                                  b->d_param[HRD_PARAM_RX_GAIN_DB], b->d_sq_track, (uint8_t *)b->d_sq_open, s))
+        return fail(HRD_ECUDA, "squelch launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    b->launches += 2;
+    b->sq_mag.resize(cells);
+    b->sq_open.resize(cells);
+    b->sq_blocks = (uint32_t)n_blocks;
+    HRD_CUDA(cudaMemcpyAsync(b->sq_mag.data(), b->d_sq_mag, cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    HRD_CUDA(cudaMemcpyAsync(b->sq_open.data(), b->d_sq_open, cells, cudaMemcpyDeviceToHost, s));
+    HRD_CUDA(cudaStreamSynchronize(s)); // the decisions shape the launches below
+    // 3. where every open block's PCM goes, and who runs in which block
+    std::vector<uint32_t> at(cells);
+    std::vector<int32_t> ids(cells);
+    std::vector<int> cnt((size_t)n_blocks * 4, 0), off((size_t)n_blocks * 4, 0);
+    for (size_t st = 0; st < n; st++) {
+        uint32_t o = 0;
+        const bool demod = b->h_kind[st] != hrd::K_NONE;
+        for (int k = 0; k < n_blocks; k++) {
+            at[st * n_blocks + k] = o;
+            const size_t len = std::min(blk256, n256 - (size_t)k * blk256);
+            if (demod && b->sq_open[st * n_blocks + k]) o += (uint32_t)(len / 32);
+        }
+        if (pcm_counts) pcm_counts[st] = o;
+    }
+    static const int list_of_kind[5] = {hrd::K_NONE, hrd::K_AM, hrd::K_FM, hrd::K_WBFM, hrd::K_AM}; // SSB rides with AM
+    size_t fill = 0;
+    for (int k = 0; k < n_blocks; k++)
+        for (int list = 1; list < 4; list++) {
+            off[(size_t)k * 4 + list] = (int)fill;
+            for (size_t st = 0; st < n; st++)
+                if (list_of_kind[b->h_kind[st]] == list && b->sq_open[st * n_blocks + k]) ids[fill++] = (int32_t)st;
+            cnt[(size_t)k * 4 + list] = (int)fill - off[(size_t)k * 4 + list];
+        }
+    HRD_CUDA(cudaMemcpyAsync(b->d_sq_at, at.data(), cells * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    if (fill) HRD_CUDA(cudaMemcpyAsync(b->d_sq_ids, ids.data(), fill * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    HRD_CUDA(cudaStreamSynchronize(s)); // at / ids are stack-lived host vectors
+    // 4. the demodulators, one reference call (block) at a time
+    if (b->pre_stride < 512) {
+        rc = ensure_cap((void **)&b->d_pre, &b->d_pre_cap, 512 * sizeof(float) * n);
+        if (rc) return rc;
+        b->pre_stride = 512;
+    }
+    for (int k = 0; k < n_blocks; k++) {
+        const size_t len = std::min(blk256, n256 - (size_t)k * blk256);
+        if (!(cnt[(size_t)k * 4 + 1] + cnt[(size_t)k * 4 + 2] + cnt[(size_t)k * 4 + 3])) continue; // gate closed everywhere
+        hrd::RxParams q = p;
+        q.iq = (const int8_t *)b->d_sq256 + (size_t)k * blk256 * 2;
+        q.iq_stride = row256;
+        q.n256 = (uint32_t)len;
+        q.pcm = (int16_t *)b->d_sq_pcm;
+        q.pcm_stride = 512;
+        q.state_in = (const hrd::RxState *)b->d_state[b->cur];
+        q.state_out = (hrd::RxState *)b->d_state[b->cur ^ 1];
+        q.pre_iir = b->d_pre;
+        q.pre_stride = b->pre_stride;
+        q.kind_of = b->d_kind;
+        q.gain_ssb = b->d_param[HRD_PARAM_SSB_GAIN];
+        // streams that do not run in this block keep their record
+        HRD_CUDA(cudaMemcpyAsync(b->d_state[b->cur ^ 1], b->d_state[b->cur], sizeof(hrd::RxState) * n, cudaMemcpyDeviceToDevice, s));
+        const int32_t *ids_of[4];
+        int cnt_of[4];
+        for (int list = 0; list < 4; list++) {
+            ids_of[list] = (const int32_t *)b->d_sq_ids + off[(size_t)k * 4 + list];
+            cnt_of[list] = list ? cnt[(size_t)k * 4 + list] : 0;
+        }
+        rc = run_demods(b, q, HRD_ENTRY_256K, (uint32_t)((len + 1023) / 1024), ids_of, cnt_of, s, nullptr);
+        if (rc) return rc;
+        if (hrd::launch_squelch_scatter((const int16_t *)b->d_sq_pcm, 512, d_pcm, d_pcm_stride, (const uint32_t *)b->d_sq_at,
+                                        (const uint8_t *)b->d_sq_open, b->d_kind, b->n, n_blocks, k, (uint32_t)(len / 32), s))
+            return fail(HRD_ECUDA, "squelch scatter launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        b->launches++;
+        b->cur ^= 1;
+    }
+    return HRD_OK;
+}
+
+// can the gate of any stream close?  dBFS >= dbTable[0] - 42 - gain = -42 - gain (DbfsCalculator.cc, SignalDetector.cc:263)
+static bool squelch_armed(const hrd_batch_t *b)
+{
+    if (b->opt[HRD_OPT_RX_SQUELCH]) return true;
+    for (int i = 0; i < b->n; i++)
+        if ((double)b->param[HRD_PARAM_SQUELCH_THRESHOLD][(size_t)i] > -42.0 - (double)b->param[HRD_PARAM_RX_GAIN_DB][(size_t)i])
+            return true;
+    return false;
+}
+
 static int rx_common(hrd_batch_t *b, const int8_t *iq, size_t bytes, size_t iq_stride, int entry, int16_t *pcm,
                      size_t pcm_stride, int8_t *out256, size_t out_stride, uint32_t *pcm_counts, int mem,
                      void *cuda_stream, bool front_end_only)
@@ -776,7 +1001,12 @@ static int rx_common(hrd_batch_t *b, const int8_t *iq, size_t bytes, size_t iq_s
     p.atan2_lut = g_dev_tables[b->device].atan2_lut;
     p.sm_count = b->sm_count;
     const uint32_t n_batches = (uint32_t)((n256 + 1023) / 1024);
-    if (front_end_only) {
+    b->sq_blocks = 0;
+    if (!front_end_only && entry == HRD_ENTRY_2048K && squelch_armed(b)) {
+        if (mem == HRD_MEM_HOST) HRD_CUDA(cudaMemsetAsync(b->d_out, 0, d_pcm_stride * sizeof(int16_t) * (size_t)b->n, s));
+        rc = rx_squelched(b, p, n256, d_pcm, d_pcm_stride, pcm_counts, s);
+        if (rc) return rc;
+    } else if (front_end_only) {
         p.out256 = d_o256;
         p.out_stride = d_o_stride;
         p.stream_ids = b->d_all;
@@ -785,8 +1015,6 @@ static int rx_common(hrd_batch_t *b, const int8_t *iq, size_t bytes, size_t iq_s
         if (hrd::launch_rx(hrd::K_NONE, HRD_ENTRY_2048K, p, s)) return fail(HRD_ECUDA, "front-end launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         b->launches++;
     } else {
-        static const int gain_of_kind[5] = {-1, HRD_PARAM_AM_GAIN, HRD_PARAM_FM_GAIN, HRD_PARAM_WBFM_GAIN,
-                                            HRD_PARAM_SSB_GAIN};
         if (b->group_cnt[hrd::K_AM] || b->group_cnt[hrd::K_SSB]) {
             // the DC-removal IIR's input, one float per PCM sample (rows 32-byte aligned)
             const size_t stride = (npcm + 7) & ~(size_t)7;
@@ -813,59 +1041,20 @@ static int rx_common(hrd_batch_t *b, const int8_t *iq, size_t bytes, size_t iq_s
                 if (!ev[i]) HRD_CUDA(cudaEventCreate(&ev[i]));
             HRD_CUDA(cudaEventRecord(ev[0], s));
         }
-        hrd::RxParams iir_p;
-        bool iir = false;
-        for (int k = 0; k < 4; k++) { // K_NONE, K_AM (+ K_SSB), K_FM, K_WBFM
-            int cnt = b->group_cnt[k];
-            if (k == hrd::K_AM) cnt += b->group_cnt[hrd::K_SSB]; // adjacent in d_ids, one launch
-            if (!cnt) continue;
-            if (k == hrd::K_NONE && entry == HRD_ENTRY_256K) continue;
-            p.stream_ids = b->d_ids + b->group_off[k];
-            p.n_streams = cnt;
-            p.gain = k ? b->d_param[gain_of_kind[k]] : nullptr;
-            choose_tiles(b, k, entry, p.n_streams, n_batches, &p.n_tiles, &p.tile_batches);
-            const bool speculate = k == hrd::K_WBFM && p.n_tiles > 1;
-            if (speculate) { // verified speculation (hrd_rx.cu): pairs to compare, this call's flag
-                rc = ensure_cap(&b->d_wbv, &b->d_wbv_cap, sizeof(float2) * (size_t)p.n_streams * (size_t)p.n_tiles);
-                if (rc) return rc;
-                p.wb_verify = (float2 *)b->d_wbv;
-                HRD_CUDA(cudaMemsetAsync(b->d_wbflag, 0, sizeof(uint32_t), s));
-            }
-            int e = hrd::launch_rx(k, entry, p, s);
-            if (e) return fail(HRD_ECUDA, "rx launch (kind %d) failed: %s", k, cudaGetErrorString((cudaError_t)e));
-            b->launches++;
-            if (speculate) {
-                e = hrd::launch_rx_wbfm_verify(p, b->d_wbflag, b->d_wbrerun, (unsigned long long *)(b->d_wbflag + 2),
-                                               b->opt[HRD_OPT_DEBUG_WBFM_FORCE_RERUN], s);
-                if (e) return fail(HRD_ECUDA, "wbfm verify launch failed: %s", cudaGetErrorString((cudaError_t)e));
-                hrd::RxParams again = p; // the exact untiled run, from the untouched state_in; runs only if flagged
-                again.n_tiles = 1;
-                again.tile_batches = n_batches;
-                again.wb_verify = nullptr;
-                again.run_if = b->d_wbflag;
-                again.rerun_ids = b->d_wbrerun;
-                e = hrd::launch_rx(k, entry, again, s);
-                if (e) return fail(HRD_ECUDA, "wbfm re-run launch failed: %s", cudaGetErrorString((cudaError_t)e));
-                b->launches += 2;
-                p.wb_verify = nullptr;
-            }
-            if (k == hrd::K_AM) {
-                iir_p = p;
-                iir = true;
-            }
+        const int32_t *ids_of[4];
+        int cnt_of[4];
+        for (int k = 0; k < 4; k++) { // K_NONE, K_AM (+ K_SSB: adjacent in d_ids, one launch), K_FM, K_WBFM
+            ids_of[k] = b->d_ids + b->group_off[k];
+            cnt_of[k] = b->group_cnt[k] + (k == hrd::K_AM ? b->group_cnt[hrd::K_SSB] : 0);
         }
-        if (prof) HRD_CUDA(cudaEventRecord(ev[1], s));
-        if (iir) { // the serial 8 kS/s recurrence of the AM/SSB streams, after every tile kernel
-            int e = hrd::launch_rx_dc_iir(iir_p, s);
-            if (e) return fail(HRD_ECUDA, "rx IIR launch failed: %s", cudaGetErrorString((cudaError_t)e));
-            b->launches++;
-        }
+        rc = run_demods(b, p, entry, n_batches, ids_of, cnt_of, s, prof ? ev[1] : nullptr);
+        if (rc) return rc;
         if (prof) {
             HRD_CUDA(cudaEventRecord(ev[2], s));
             b->ev_calls++;
         }
     }
-    b->cur ^= 1; // what this call wrote is what the next one reads
+    if (!b->sq_blocks) b->cur ^= 1; // what this call wrote is what the next one reads (rx_squelched swaps per block)
     if (mem == HRD_MEM_HOST) {
         if (front_end_only)
             HRD_CUDA(cudaMemcpy2DAsync(out256, out_stride, b->d_out, d_o_stride, out_row, (size_t)b->n,
@@ -892,6 +1081,19 @@ int hrd_rx_front_end(hrd_batch_t *b, const int8_t *iq, size_t bytes_per_stream, 
     if (out_stride < bytes_per_stream / 8) return fail(HRD_EINVAL, "out_stride too small");
     return rx_common(b, iq, bytes_per_stream, iq_stride, HRD_ENTRY_2048K, nullptr, 0, out256k, out_stride, nullptr,
                      mem, cuda_stream, true);
+}
+
+int hrd_rx_squelch_report(hrd_batch_t *b, uint32_t *magnitudes, uint8_t *allowed, size_t blocks_cap, uint32_t *n_blocks)
+{
+    if (!b || b->kind != HRD_RX) return fail(HRD_EINVAL, "not an Rx batch");
+    if (n_blocks) *n_blocks = b->sq_blocks;
+    if (b->sq_blocks > blocks_cap && (magnitudes || allowed)) return fail(HRD_EINVAL, "blocks_cap %zu < %u blocks", blocks_cap, b->sq_blocks);
+    for (size_t st = 0; st < (size_t)b->n; st++)
+        for (uint32_t k = 0; k < b->sq_blocks; k++) {
+            if (magnitudes) magnitudes[st * blocks_cap + k] = b->sq_mag[st * b->sq_blocks + k];
+            if (allowed) allowed[st * blocks_cap + k] = b->sq_open[st * b->sq_blocks + k];
+        }
+    return HRD_OK;
 }
 
 int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size_t pcm_stride, int8_t *iq,

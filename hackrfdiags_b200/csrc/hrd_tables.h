@@ -199,6 +199,15 @@ int launch_rx_wbfm_verify(const RxParams &p, uint32_t *count, int32_t *rerun_ids
                           cudaStream_t s);
 int rx_halo_batches(int kind);                            // batches a tile > 0 runs ahead
 int rx_resident_warps_per_sm(int kind, int entry);        // occupancy of that kernel (cached)
+// squelch gate (hrd_squelch.cu)
+void upload_db_table(const int32_t *table257);
+int launch_squelch_magnitude(const int8_t *iq256, size_t stride, uint32_t block_bytes, uint32_t total_bytes, int n_streams,
+                             int n_blocks, uint32_t *magnitude, cudaStream_t s);
+int launch_squelch_track(const uint32_t *magnitude, int n_streams, int n_blocks, const float *threshold, const float *gain_db,
+                         uint8_t *tracking, uint8_t *allowed, cudaStream_t s);
+int launch_squelch_scatter(const int16_t *scratch, size_t scratch_stride, int16_t *pcm, size_t pcm_stride, const uint32_t *out_at,
+                           const uint8_t *allowed, const uint8_t *kind_of, int n_streams, int n_blocks, int blk, uint32_t n,
+                           cudaStream_t s);
 int launch_tx(int kind, const TxParams &p, cudaStream_t s);
 int launch_tx_fm_phase(const TxParams &p, cudaStream_t s);   // FM streams, before their launch_tx
 int tx_resident_warps_per_sm(int kind);                      // occupancy of tx_kernel<kind> (cached)

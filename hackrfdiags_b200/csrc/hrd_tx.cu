@@ -425,16 +425,21 @@ __device__ __forceinline__ void interp8_real(const int32_t *in, int n, int &even
 // out of line on purpose: inlined, the compiler hoists most of the division sequence above the
 // `risky` test and every lane pays for it (it was 10 % of the kernel's instructions)
 __device__ __noinline__ float div_256000_exact(double a) { return (float)(a / 256000.0); }
+__device__ __noinline__ float div_8000_exact(double a) { return (float)(a / 8000.0); }
 
-__device__ __forceinline__ float div_256000_to_float(double a)
+// (the argument holds for any divisor: r is a * fl(1/D), two roundings away from the exact quotient)
+template <int D>
+__device__ __forceinline__ float div_const_to_float(double a)
 {
-    double r = a * (1.0 / 256000.0);
+    static_assert(D == 256000 || D == 8000, "one out-of-line exact division per divisor");
+    double r = a * (1.0 / (double)D);
     const uint32_t lo = (uint32_t)__double2loint(r);
     const uint32_t e = ((uint32_t)__double2hiint(r) >> 20) & 0x7ffu;
     const bool risky = ((lo & 0x1fffffffu) - 0x0ffffff8u) <= 16u || (e - 898u) > 250u;
-    if (risky && a != 0.0) return div_256000_exact(a);
+    if (risky && a != 0.0) return D == 256000 ? div_256000_exact(a) : div_8000_exact(a);
     return (float)r;
 }
+__device__ __forceinline__ float div_256000_to_float(double a) { return div_const_to_float<256000>(a); }
 
 // Nco::runFast's table index (Nco.cc:231-248): (int16_t)((double)(phase*16384.0f)/(2*M_PI)) + 8192,
 // clamped to [0,16383].  The double division is replaced by a search in a table of thresholds built
@@ -701,44 +706,135 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
 // ------------------------------------------------------------------------------------
 // FM: the NCO phase recurrence at 8 kS/s (FmModulator.cc:596-604, PhaseAccumulator.cc:95-181)
 // ------------------------------------------------------------------------------------
-// One warp per FM stream.  Per 32 PCM samples every lane turns its sample into a phase step
-// (frequency = deviation * pcm / 32768; step = (float)((2*M_PI*frequency)/8000.0), the double
-// division included), then the warp walks the 32 accumulations in order -- the same operations in
-// the same order as PhaseAccumulator::run -- and stores the phase BEFORE each step.  tx_kernel<FM>
-// reads them, which lets it cut the call into time tiles like the other modes.
-__global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_fm_phase_kernel(const TxParams p)
+// phase[n+1] = wrap(fl(phase[n] + step[n])) has no decay and cannot be cut in time, so every stream's
+// call is one dependent chain of n8 additions (about 22 cycles each).  The first version gave a warp to
+// every stream and broadcast the steps by shuffle: 10 warp instructions per sample, 0.34 ms for 4096
+// streams x 0.5 s, 15 % of the FM modulator's time (profiles/).  Here the recurrences of 32 streams
+// are transposed onto the lanes of ONE chain warp, as in the WBFM kernels: a CTA owns 32 streams; worker
+// warps turn PCM into phase steps, lane-parallel and coalesced (frequency = deviation * pcm / 32768,
+// step = (float)((2*M_PI*frequency)/8000.0), the double division included), into a shared-memory tile;
+// the chain warp's lane r walks row r in place, leaving the phase BEFORE each step; worker warps write
+// the finished tile out, coalesced.  Three tiles rotate through the three roles, one __syncthreads per
+// chunk.  Same operations in the same order per stream as PhaseAccumulator::run.  tx_kernel<FM> reads the
+// phases, which lets it cut the call into time tiles like the other modes.
+constexpr int FP_ROWS = 32;              // streams per CTA
+constexpr int FP_CH = 64;                // PCM samples per chunk
+constexpr int FP_PITCH = FP_CH + 1;      // floats per row: lane r, sample n -> bank (r + n) % 32
+constexpr int FP_WORKERS = 16;           // worker warps; warp FP_WORKERS is the chain warp
+constexpr int FP_RPW = FP_ROWS / FP_WORKERS; // rows per worker warp
+
+struct SmemFp {
+    float t[3][FP_ROWS][FP_PITCH];
+    uint32_t big[3][FP_ROWS];            // per row and chunk: some |step| >= 3 (see tx_wbfm_kernel's chain)
+};
+
+__global__ void __launch_bounds__((FP_WORKERS + 1) * 32) tx_fm_phase_kernel(const TxParams p)
 {
+    __shared__ SmemFp sm;
     const int lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * HRD_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (slot >= p.n_streams) return;
-    const int sid = p.stream_ids[slot];
-    const int16_t *src = p.pcm + (size_t)sid * p.pcm_stride;
-    float *out = p.fm_phase + (size_t)slot * p.n8;
-    const float dev = p.param[sid];
-    float phase = p.state[sid].fm_phase;
-    for (uint32_t done = 0; done < p.n8; done += NB8) {
-        const int nb = (int)min((uint32_t)NB8, p.n8 - done);
-        const int x = (lane < nb) ? (int)src[done + lane] : 0;
-        const float f = __fdiv_rn(__fmul_rn(dev, (float)x), 32768.f);
-        const float step = phase_step(f, 8000.0);
-        float my_phase = 0.f;
-        if (nb == NB8) { // the common case, unrolled: no loop counter, constant shuffle lanes
+    const int warp = threadIdx.x >> 5;
+    const bool chain_warp = warp == FP_WORKERS;
+    const int row0 = blockIdx.x * FP_ROWS;
+    const int rows_live = min(FP_ROWS, p.n_streams - row0);
+    const uint32_t n_chunks = (p.n8 + FP_CH - 1) / FP_CH;
+
+    float phase = 0.f;
+    int sid_chain = 0;
+    const bool live = lane < rows_live; // chain warp: this lane has a stream
+    if (chain_warp && live) {
+        sid_chain = p.stream_ids[row0 + lane];
+        phase = p.state[sid_chain].fm_phase;
+    }
+
+    // workers: PCM of chunk c -> phase steps, rows warp, warp + FP_WORKERS, ...  All loads first (the rows
+    // are in different streams: four independent DRAM round trips instead of four in a row), and the
+    // double division by the multiply-and-check of div_const_to_float.
+    int w_sid[FP_RPW];
+    float w_dev[FP_RPW];
 #pragma unroll
-            for (int n = 0; n < NB8; n++) {
-                const float sn = __shfl_sync(HRD_FULL_MASK, step, n);
-                my_phase = (lane == n) ? phase : my_phase;
-                phase = phase_advance(phase, sn);
+    for (int i = 0; i < FP_RPW; i++) {
+        const int r = warp + i * FP_WORKERS;
+        w_sid[i] = (!chain_warp && r < rows_live) ? p.stream_ids[row0 + r] : -1;
+        w_dev[i] = w_sid[i] >= 0 ? p.param[w_sid[i]] : 0.f;
+    }
+    auto produce = [&](uint32_t c) {
+        int x[FP_RPW][FP_CH / 32];
+#pragma unroll
+        for (int i = 0; i < FP_RPW; i++) {
+            const int16_t *src = p.pcm + (size_t)max(w_sid[i], 0) * p.pcm_stride;
+#pragma unroll
+            for (int j = 0; j < FP_CH / 32; j++) {
+                const uint32_t at = c * FP_CH + lane + 32 * j;
+                x[i][j] = (w_sid[i] >= 0 && at < p.n8) ? (int)src[at] : 0;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < FP_RPW; i++) {
+            const int r = warp + i * FP_WORKERS;
+            if (w_sid[i] < 0) continue; // warp-uniform
+            bool big = false;
+#pragma unroll
+            for (int j = 0; j < FP_CH / 32; j++) {
+                const float f = __fdiv_rn(__fmul_rn(w_dev[i], (float)x[i][j]), 32768.f);
+                // PhaseAccumulator::setFrequency (:95-107): (float)((2*M_PI*f)/8000.0) in double
+                const float step = div_const_to_float<8000>(2.0 * 3.14159265358979323846 * (double)f);
+                sm.t[c % 3][r][lane + 32 * j] = step;
+                big |= !(fabsf(step) < 3.0f);
+            }
+            big = __any_sync(HRD_FULL_MASK, big);
+            if (lane == 0) sm.big[c % 3][r] = big;
+        }
+    };
+    // chain warp: PhaseAccumulator::run over chunk c of row `lane`, in place
+    auto walk = [&](uint32_t c) {
+        const int nb = (int)min((uint32_t)FP_CH, p.n8 - c * FP_CH);
+        float *row = sm.t[c % 3][lane];
+        const bool slow = __any_sync(HRD_FULL_MASK, live && (sm.big[c % 3][lane] != 0 || !(fabsf(phase) < HRD_PI_UP)));
+        if (!live) return;
+        if (!slow && nb == FP_CH) {
+            // |phase + step| < pi + 3 < 2*pi - 2^-10: one fp32 wrap is the exact one (wrap_pi_select)
+#pragma unroll 16
+            for (int n = 0; n < FP_CH; n++) {
+                const float s = row[n];
+                row[n] = phase;
+                phase = wrap_pi_select(__fadd_rn(phase, s));
             }
         } else {
             for (int n = 0; n < nb; n++) {
-                const float sn = __shfl_sync(HRD_FULL_MASK, step, n);
-                if (lane == n) my_phase = phase;
-                phase = phase_advance(phase, sn);
+                const float s = row[n];
+                row[n] = phase;
+                phase = phase_advance(phase, s);
             }
         }
-        if (lane < nb) out[done + lane] = my_phase;
+    };
+    // workers: phases of chunk c -> global, coalesced
+    auto flush = [&](uint32_t c) {
+#pragma unroll
+        for (int i = 0; i < FP_RPW; i++) {
+            const int r = warp + i * FP_WORKERS;
+            if (w_sid[i] < 0) continue;
+            float *out = p.fm_phase + (size_t)(row0 + r) * p.n8;
+#pragma unroll
+            for (int n = lane; n < FP_CH; n += 32) {
+                const uint32_t at = c * FP_CH + n;
+                if (at < p.n8) out[at] = sm.t[c % 3][r][n];
+            }
+        }
+    };
+
+    if (!chain_warp) produce(0);
+    __syncthreads();
+    for (uint32_t t = 0; t < n_chunks; t++) {
+        if (chain_warp) {
+            walk(t);
+        } else {
+            if (t >= 1) flush(t - 1);
+            if (t + 1 < n_chunks) produce(t + 1);
+        }
+        __syncthreads();
     }
-    if (lane == 0) p.state_out[sid].fm_phase = phase;
+    if (!chain_warp) flush(n_chunks - 1);
+    if (chain_warp && live) p.state_out[sid_chain].fm_phase = phase;
 }
 
 // mode NONE: BasebandDataProcessor.cc:689-694 fills the block with 64
@@ -788,8 +884,8 @@ int tx_resident_warps_per_sm(int kind)
 int launch_tx_fm_phase(const TxParams &p, cudaStream_t s)
 {
     if (p.n_streams <= 0 || p.n8 == 0) return 0;
-    const int grid = (p.n_streams + HRD_WARPS_PER_CTA - 1) / HRD_WARPS_PER_CTA;
-    tx_fm_phase_kernel<<<grid, HRD_WARPS_PER_CTA * 32, 0, s>>>(p);
+    const int grid = (p.n_streams + FP_ROWS - 1) / FP_ROWS;
+    tx_fm_phase_kernel<<<grid, (FP_WORKERS + 1) * 32, 0, s>>>(p);
     return (int)cudaGetLastError();
 }
 

@@ -119,3 +119,20 @@ def tx_batch(n_streams: int, n_samples: int, config: int = 0) -> np.ndarray:
     for s in range(n_streams):
         out[s] = tx_stream(n_samples, s, config)
     return out
+
+
+def rx_bursty_stream(mode: int, n_blocks: int, stream: int = 0, config: int = 7,
+                     levels=(100, 2, 2, 60, 60, 1, 20, 127, 0, 0, 40, 3)) -> np.ndarray:
+    """Squelch test input at the 2.048 MS/s entry: ``n_blocks`` blocks of 131072 IQ samples (one reference
+    call each) whose carrier amplitude changes from block to block (cycling through ``levels``, rotated by the
+    stream number), so that a squelch threshold opens, holds for its one-block tail and closes again."""
+    rng = np.random.default_rng(stream_seed(config, stream))
+    n_blk = 131072
+    n = n_blocks * n_blk
+    t = np.arange(n, dtype=np.float64) / FS_RX
+    amp = np.repeat(np.array([levels[(b + stream) % len(levels)] for b in range(n_blocks)], dtype=np.float64), n_blk)
+    z = amp * _baseband(mode, t) * np.exp(2j * np.pi * -64000.0 * t)
+    out = np.empty(2 * n, dtype=np.int8)
+    out[0::2] = np.clip(np.rint(z.real + rng.normal(0.0, 1.0, n)), -128, 127).astype(np.int8)
+    out[1::2] = np.clip(np.rint(z.imag + rng.normal(0.0, 1.0, n)), -128, 127).astype(np.int8)
+    return out

@@ -60,7 +60,12 @@ enum {
     HRD_PARAM_AM_INDEX = 4,  /* AmModulator::setModulationIndex     (AmModulator.cc:329)  accepted iff 0<=m<=1, default 0.8 */
     HRD_PARAM_FM_DEV = 5,    /* FmModulator::setFrequencyDeviation  (FmModulator.cc:336)  guard tests the OLD value vs 0..3500   */
     HRD_PARAM_WBFM_DEV = 6,  /* WbFmModulator::setFrequencyDeviation(WbFmModulator.cc:310) guard tests the OLD value vs 0..112000 */
-    HRD_PARAM_COUNT = 7
+    /* the squelch gate of IqDataProcessor::acceptIqData (2.048 MS/s entry only; see hrd_rx_process) */
+    HRD_PARAM_SQUELCH_THRESHOLD = 7, /* IqDataProcessor::setSignalDetectThreshold (IqDataProcessor.cc:392-405), dBFS as an
+                                        integer value, default -200 = always open (IqDataProcessor.cc:120-124) */
+    HRD_PARAM_RX_GAIN_DB = 8,        /* radio_adjustableReceiveGainInDb, the gain Squelch::run refers the level to
+                                        (IqDataProcessor.cc:961; Radio.cc:413 default 16) */
+    HRD_PARAM_COUNT = 9
 };
 
 /* which object hrd_reset addresses */
@@ -98,7 +103,11 @@ enum {
     HRD_OPT_PROFILE = 3,
     /* test hook: make the WBFM verification fail, so that the exact re-run path is exercised */
     HRD_OPT_DEBUG_WBFM_FORCE_RERUN = 4,
-    HRD_OPT_COUNT = 5
+    /* Rx, 2.048 MS/s entry: 1 = take the squelched path (per-block magnitudes and decisions, see
+     * hrd_rx_squelch_report) even when no stream's threshold can close the gate.  The path is taken
+     * automatically as soon as one stream's threshold can (threshold > -42 - gain dB). */
+    HRD_OPT_RX_SQUELCH = 5,
+    HRD_OPT_COUNT = 6
 };
 
 #define HRD_ALL_STREAMS (-1)
@@ -141,6 +150,15 @@ int hrd_get_option(hrd_batch_t *b, int option, int *value);
  * pcm       int16 out; stream s starts at pcm + s*pcm_stride samples; gets
  *           bytes_per_stream/512 (resp. /64) samples, 0 when the mode is NONE
  * pcm_counts  optional, host memory, n_streams entries
+ *
+ * Squelch (entry 2048K; Squelch.cc:227-273, SignalDetector.cc:205-273, SignalTracker.cc:104-145,
+ * DbfsCalculator.cc): the reference takes one squelch decision per acceptIqData call, i.e. per
+ * 262144-byte transfer block (hackRf/hackrf.c:101).  A call here is cut into blocks of 262144 bytes (a
+ * shorter last block counts as its own call); a block the gate closes is not demodulated: the
+ * demodulator state does not move and the stream's PCM is shorter by that block (pcm_counts tells).
+ * With every threshold at its default (-200 dBFS) the gate cannot close and the call runs fused as one
+ * pass; otherwise it runs block by block and waits once for the decisions (the call synchronises
+ * cuda_stream once even with HRD_MEM_DEVICE).
  * mem       HRD_MEM_HOST: pointers are host memory, copied through pinned
  *           staging inside the call (the call returns when pcm is ready);
  *           HRD_MEM_DEVICE: device pointers, work is queued on cuda_stream
@@ -158,6 +176,11 @@ int hrd_rx_process(hrd_batch_t *b, const int8_t *iq, size_t bytes_per_stream, si
 int hrd_rx_front_end(hrd_batch_t *b, const int8_t *iq, size_t bytes_per_stream, size_t iq_stride,
                      int8_t *out256k, size_t out_stride, int mem, void *cuda_stream);
 
+/* What the reference reports through registerSignalMagnitudeCallback / registerSignalStateCallback
+ * (IqDataProcessor.cc:961-988), for every stream and block of the latest squelched hrd_rx_process call:
+ * magnitudes[s * blocks_cap + b] = Squelch::getSignalMagnitude(), allowed[...] = Squelch::run()'s result.
+ * Either array may be NULL.  *n_blocks gets the number of blocks of that call (0 if it was not squelched). */
+int hrd_rx_squelch_report(hrd_batch_t *b, uint32_t *magnitudes, uint8_t *allowed, size_t blocks_cap, uint32_t *n_blocks);
 /* ---- transmit -------------------------------------------------------- */
 /*
  * One call = <mode's modulator>::acceptData(pcm, n_per_stream, iq, &len) on

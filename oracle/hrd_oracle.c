@@ -360,6 +360,12 @@ struct hro_rx {
     fir16 ssb_delay, ssb_hilbert;
     iirf ssb_dc;
     float ssb_gain;
+    /* Squelch (Squelch.cc, SignalDetector.cc, SignalTracker.cc, DbfsCalculator.cc) */
+    int32_t sq_threshold;     /* IqDataProcessor::signalDetectThreshold, dBFS */
+    uint32_t sq_gain_db;      /* radio_adjustableReceiveGainInDb (Radio.cc:413) */
+    int sq_tracking;          /* SignalTracker::state == Tracking */
+    uint32_t sq_magnitude;    /* SignalDetector::signalMagnitude of the latest block */
+    int sq_allowed;           /* what Squelch::run returned for the latest block */
     /* scratch for the 256 kS/s stream */
     int8_t *scratch;
     size_t scratch_cap;
@@ -375,6 +381,10 @@ hro_rx *hro_rx_new(void)
     /* FmDemodulator.cc:116-125: "-1/16" and "1/16" are integer divisions */
     static const float diff[7] = {-1 / 16, 0, 1, 0, -1, 0, 1 / 16};
     rx->mode = HRO_NONE;   /* IqDataProcessor.cc:70 */
+    rx->sq_threshold = -200; /* IqDataProcessor.cc:120-124 */
+    rx->sq_gain_db = 16;     /* Radio.cc:413 */
+    rx->sq_tracking = 0;     /* SignalTracker.cc: state = NoSignal */
+    rx->sq_allowed = 1;
     rx->ssb_lsb = 1;       /* SsbDemodulator.cc:143 */
     for (int r = 0; r < 2; r++) {
         dec16_init(&rx->fe[r][0], k_fe1, 3, 2);
@@ -634,6 +644,62 @@ size_t hro_rx_accept_256k(hro_rx *rx, const int8_t *iq, size_t nbytes, int16_t *
     }
 }
 
+/* ---- squelch ------------------------------------------------------- */
+
+/* DbfsCalculator::DbfsCalculator(7) + convertMagnitudeToDbFs (DbfsCalculator.cc:36-68, 111-147):
+ * fullScaleValue = 127, fullScaleValueInDb = (uint32_t)(20*log10(127.0)) = 42,
+ * dbTable[i] = (int32_t)(20 * log10((float)i)) for i = 1..256, dbTable[0] = dbTable[1]. */
+static int32_t dbfs_of_magnitude(uint32_t magnitude)
+{
+    static int32_t table[257];
+    static int ready = 0;
+    if (!ready) {
+        for (int i = 1; i <= 256; i++) {
+            float level = 20 * log10f((float)i); /* C++ log10(float) is the float overload */
+            table[i] = (int32_t)level;
+        }
+        table[0] = table[1];
+        ready = 1;
+    }
+    int32_t decibels = 0;
+    if (magnitude > 127) magnitude = 127; /* clip to fullScaleValue (:121-125) */
+    while (magnitude > 256) {             /* never taken after the clip; kept as in :127-134 */
+        magnitude /= 2;
+        decibels += 6;
+    }
+    return table[magnitude] + decibels - (int32_t)(uint32_t)(20 * log10((double)127));
+}
+
+/* SignalDetector::detectSignal (SignalDetector.cc:205-273) on nbytes of 256 kS/s int8 I,Q,
+ * SignalTracker::run (SignalTracker.cc:104-145) and Squelch::run (Squelch.cc:227-273) */
+static int squelch_run(hro_rx *rx, const int8_t *iq256, size_t nbytes)
+{
+    uint32_t magnitude = 0;
+    const uint32_t count = (uint32_t)(nbytes / 2);
+    for (size_t i = 0; i < nbytes; i += 2) {
+        uint8_t im = (uint8_t)abs(iq256[i]), qm = (uint8_t)abs(iq256[i + 1]);
+        uint8_t m = im > qm ? (uint8_t)(im + (qm >> 1)) : (uint8_t)(qm + (im >> 1));
+        magnitude += m;
+    }
+    magnitude /= count;
+    int32_t dbfs = dbfs_of_magnitude(magnitude);
+    dbfs -= rx->sq_gain_db; /* int32 -= uint32, as the reference writes it */
+    const int present = dbfs >= rx->sq_threshold;
+    rx->sq_magnitude = magnitude;
+    /* NoSignal: present -> Tracking/START (allowed), else NOISE (not allowed);
+     * Tracking: present -> SIGNALPRESENT (allowed), else -> NoSignal/ENDOFSIGNAL (allowed: the tail) */
+    const int allowed = rx->sq_tracking ? 1 : present;
+    rx->sq_tracking = present;
+    rx->sq_allowed = allowed;
+    return allowed;
+}
+
+void hro_rx_set_squelch_threshold(hro_rx *rx, int32_t threshold_dbfs) { rx->sq_threshold = threshold_dbfs; }
+void hro_rx_set_rx_gain_db(hro_rx *rx, uint32_t gain_db) { rx->sq_gain_db = gain_db; }
+uint32_t hro_rx_signal_magnitude(const hro_rx *rx) { return rx->sq_magnitude; }
+int hro_rx_signal_allowed(const hro_rx *rx) { return rx->sq_allowed; }
+
+/* IqDataProcessor::acceptIqData (IqDataProcessor.cc:926-1038): front end, squelch, gated demodulator */
 size_t hro_rx_accept_2048k(hro_rx *rx, const int8_t *iq, size_t nbytes, int16_t *pcm)
 {
     size_t need = nbytes / 8 + 16;
@@ -643,6 +709,8 @@ size_t hro_rx_accept_2048k(hro_rx *rx, const int8_t *iq, size_t nbytes, int16_t 
         rx->scratch_cap = need;
     }
     size_t nb = hro_rx_front_end(rx, iq, nbytes, rx->scratch);
+    if (nb == 0) return 0;
+    if (!squelch_run(rx, rx->scratch, nb)) return 0; /* :991: the demodulator is not called */
     return hro_rx_accept_256k(rx, rx->scratch, nb, pcm);
 }
 

@@ -169,6 +169,41 @@ size_t ref_rx_accept_256k(void *h, const int8_t *iq, size_t nbytes, int16_t *pcm
     return sink.count;
 }
 
+/* IqDataProcessor::setSignalDetectThreshold (IqDataProcessor.cc:392-405) */
+void ref_rx_set_squelch_threshold(void *h, int32_t threshold) { ((RefRx *)h)->iqdp->setSignalDetectThreshold(threshold); }
+/* the global Squelch::run is given (Radio.cc:413 sets 16); shared by every IqDataProcessor of the process */
+void ref_set_rx_gain_db(uint32_t gain_db) { radio_adjustableReceiveGainInDb = gain_db; }
+
+static void magnitude_cb(uint32_t magnitude, void *ctx) { *(uint32_t *)ctx = magnitude; }
+static void state_cb(bool present, void *ctx) { *(uint8_t *)ctx = present ? 1 : 0; }
+
+/* like ref_rx_run_2048k, and reports per block what the reference's own notification callbacks deliver:
+ * the average magnitude (registerSignalMagnitudeCallback) and the squelch decision
+ * (registerSignalStateCallback) of IqDataProcessor.cc:961-988 */
+size_t ref_rx_run_2048k_squelch(void *h, const int8_t *iq, size_t nbytes, size_t block, int16_t *pcm,
+                                uint32_t *magnitudes, uint8_t *allowed)
+{
+    RefRx *rx = (RefRx *)h;
+    uint32_t mag = 0;
+    uint8_t open = 0;
+    rx->iqdp->registerSignalMagnitudeCallback(magnitude_cb, &mag);
+    rx->iqdp->registerSignalStateCallback(state_cb, &open);
+    rx->iqdp->enableSignalMagnitudeNotification();
+    rx->iqdp->enableSignalNotification();
+    size_t total = 0, b = 0;
+    for (size_t off = 0; off < nbytes; off += block, b++) {
+        size_t n = nbytes - off < block ? nbytes - off : block;
+        total += ref_rx_accept_2048k(h, iq + off, n, pcm + total);
+        magnitudes[b] = mag;
+        allowed[b] = open;
+    }
+    rx->iqdp->disableSignalMagnitudeNotification();
+    rx->iqdp->disableSignalNotification();
+    rx->iqdp->registerSignalMagnitudeCallback(NULL, NULL);
+    rx->iqdp->registerSignalStateCallback(NULL, NULL);
+    return total;
+}
+
 /* stream a long buffer through in reference-sized blocks */
 size_t ref_rx_run_2048k(void *h, const int8_t *iq, size_t nbytes, size_t block, int16_t *pcm)
 {

@@ -151,6 +151,7 @@ def _declare(lib, prefix):
         "rx_front_end": (C.c_size_t, [vp, _i8p, C.c_size_t, _i8p]),
         "rx_accept_2048k": (C.c_size_t, [vp, _i8p, C.c_size_t, _i16p]),
         "rx_accept_256k": (C.c_size_t, [vp, _i8p, C.c_size_t, _i16p]),
+        "rx_set_squelch_threshold": (None, [vp, C.c_int32]),
         "tx_new": (vp, []),
         "tx_free": (None, [vp]),
         "tx_set_am_index": (None, [vp, C.c_float]),
@@ -177,6 +178,33 @@ class Oracle(_Base):
         self.lib.hro_taps.argtypes = [C.c_int, _i16p, C.c_int]
         self.lib.hro_atan2_table.argtypes = [_f32p]
         self.lib.hro_nco_tables.argtypes = [_f32p, _f32p]
+        self.lib.hro_rx_set_rx_gain_db.argtypes = [C.c_void_p, C.c_uint32]
+        self.lib.hro_rx_signal_magnitude.restype = C.c_uint32
+        self.lib.hro_rx_signal_magnitude.argtypes = [C.c_void_p]
+        self.lib.hro_rx_signal_allowed.restype = C.c_int
+        self.lib.hro_rx_signal_allowed.argtypes = [C.c_void_p]
+
+    def run_rx_squelch(self, mode, iq, threshold, gain_db=16, block=262144, demod_gain=None):
+        """IqDataProcessor::acceptIqData block by block with a squelch threshold: returns
+        (pcm, per-block average magnitude, per-block squelch decision)."""
+        iq = np.ascontiguousarray(iq, dtype=np.int8)
+        h = self.rx_new()
+        try:
+            self.rx_set_mode(h, mode)
+            if demod_gain is not None:
+                self.rx_set_gain(h, {1: 0, 2: 1, 3: 2, 4: 3, 5: 3}[mode], demod_gain)
+            self.lib.hro_rx_set_squelch_threshold(h, int(threshold))
+            self.lib.hro_rx_set_rx_gain_db(h, int(gain_db))
+            pcm = np.zeros(iq.size // 512 + 1024, dtype=np.int16)
+            mags, opens, total = [], [], 0
+            for off in range(0, iq.size, block):
+                chunk = iq[off:off + block]
+                total += self.lib.hro_rx_accept_2048k(h, _ptr(chunk, _i8p), chunk.size, _ptr(pcm[total:], _i16p))
+                mags.append(self.lib.hro_rx_signal_magnitude(h))
+                opens.append(self.lib.hro_rx_signal_allowed(h))
+            return pcm[:total].copy(), np.array(mags, dtype=np.uint32), np.array(opens, dtype=np.uint8)
+        finally:
+            self.rx_free(h)
 
     def taps(self, which: int) -> np.ndarray:
         out = np.zeros(64, dtype=np.int16)
@@ -207,12 +235,38 @@ class Ref(_Base):
         self.lib.ref_taps.restype = C.c_int
         self.lib.ref_taps.argtypes = [vp, vp, C.c_int, _i16p, C.c_int]
         self.lib.ref_nco_tables.argtypes = [vp, _f32p, _f32p]
+        self.lib.ref_set_rx_gain_db.argtypes = [C.c_uint32]
+        self.lib.ref_rx_run_2048k_squelch.restype = C.c_size_t
+        self.lib.ref_rx_run_2048k_squelch.argtypes = [vp, _i8p, C.c_size_t, C.c_size_t, _i16p,
+                                                      C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)]
         self.lib.ref_bench_rx.restype = C.c_double
         self.lib.ref_bench_rx.argtypes = [C.c_int, _i8p, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
                                           _i16p, C.c_size_t]
         self.lib.ref_bench_tx.restype = C.c_double
         self.lib.ref_bench_tx.argtypes = [C.c_int, _i16p, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
                                           _i8p, C.c_size_t]
+
+    def run_rx_squelch(self, mode, iq, threshold, gain_db=16, block=262144, demod_gain=None):
+        """The unmodified IqDataProcessor with its own notification callbacks reporting per block."""
+        iq = np.ascontiguousarray(iq, dtype=np.int8)
+        h = self.rx_new()
+        try:
+            self.rx_set_mode(h, mode)
+            if demod_gain is not None:
+                self.rx_set_gain(h, {1: 0, 2: 1, 3: 2, 4: 3, 5: 3}[mode], demod_gain)
+            self.lib.ref_rx_set_squelch_threshold(h, int(threshold))
+            self.lib.ref_set_rx_gain_db(int(gain_db))
+            n_blocks = (iq.size + block - 1) // block
+            pcm = np.zeros(iq.size // 512 + 1024, dtype=np.int16)
+            mags = np.zeros(n_blocks, dtype=np.uint32)
+            opens = np.zeros(n_blocks, dtype=np.uint8)
+            total = self.lib.ref_rx_run_2048k_squelch(h, _ptr(iq, _i8p), iq.size, block, _ptr(pcm, _i16p),
+                                                      mags.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                      opens.ctypes.data_as(C.POINTER(C.c_uint8)))
+            return pcm[:total].copy(), mags, opens
+        finally:
+            self.lib.ref_set_rx_gain_db(16)
+            self.rx_free(h)
 
     def taps(self, which: int) -> np.ndarray:
         rx, tx = self.rx_new(), self.tx_new()

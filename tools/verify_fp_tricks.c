@@ -8,7 +8,7 @@
  * 1. wrap:   (float)((double)x - 2*M_PI) for x in [PI_UP, 12)   vs   (x - 2PI_HI) - 2PI_LO in fp32,
  *            with the kernels' fallback rule (|x - 2PI_HI| < 2^-10 -> use the double expression)
  *            (FmDemodulator.cc:511-519, WbFmDemodulator.cc:416-424, PhaseAccumulator.cc:165-177)
- * 2. step:   (float)((2*M_PI*(double)f)/256000.0) for every finite float f   vs   multiply by the
+ * 2. step:   (float)((2*M_PI*(double)f)/fs) for fs = 256000 (WBFM NCO) and 8000 (FM NCO), every finite float f   vs   multiply by the
  *            reciprocal with the kernels' "risky -> divide" rule (PhaseAccumulator.cc:103)
  * 3. index:  (int16_t)((double)(p*16384.0f)/(2*M_PI)) for every float p in [0, PI_UP]   vs   the
  *            threshold-table search the Tx WBFM kernel uses (Nco.cc:231-233)
@@ -49,33 +49,33 @@ static long check_wrap(void)
     return bad;
 }
 
-static float step_fast(float f, int *slow)
+static float step_fast(float f, int *slow, double fs)
 {
     const double a = (2 * M_PI) * (double)f;
-    double r = a * (1.0 / 256000.0);
+    double r = a * (1.0 / fs);
     const uint64_t b = d2u(r);
     const uint32_t lo = (uint32_t)b, e = (uint32_t)(b >> 52) & 0x7ffu;
     const int risky = ((lo & 0x1fffffffu) - 0x0ffffff8u) <= 16u || (e - 898u) > 250u;
-    if (risky && a != 0.0) { r = a / 256000.0; (*slow)++; }
+    if (risky && a != 0.0) { r = a / fs; (*slow)++; }
     return (float)r;
 }
 
-static long check_step(void)
+static long check_step(double fs)
 {
     long bad = 0, slow_total = 0, n = 0;
 #pragma omp parallel for reduction(+ : bad, slow_total, n)
     for (uint64_t u = 0; u < 0x7f800000ull; u++) { /* every non-negative finite float; negatives mirror */
         const float f = u2f((uint32_t)u);
         int slow = 0;
-        const float want = (float)((2 * M_PI * (double)f) / 256000.0);
-        const float got = step_fast(f, &slow);
+        const float want = (float)((2 * M_PI * (double)f) / fs);
+        const float got = step_fast(f, &slow, fs);
         if (f2u(got) != f2u(want)) bad++;
-        const float gn = step_fast(-f, &slow);
-        if (f2u(gn) != f2u((float)((2 * M_PI * (double)(-f)) / 256000.0))) bad++;
+        const float gn = step_fast(-f, &slow, fs);
+        if (f2u(gn) != f2u((float)((2 * M_PI * (double)(-f)) / fs))) bad++;
         slow_total += slow;
         n += 2;
     }
-    printf("step : %ld floats, %ld through the division fallback, %ld mismatches\n", n, slow_total, bad);
+    printf("step / %.0f: %ld floats, %ld through the division fallback, %ld mismatches\n", fs, n, slow_total, bad);
     return bad;
 }
 
@@ -111,7 +111,7 @@ static long check_index(void)
 
 int main(void)
 {
-    long bad = check_wrap() + check_index() + check_step();
+    long bad = check_wrap() + check_index() + check_step(256000.0) + check_step(8000.0);
     printf(bad ? "FAILED\n" : "all identities hold\n");
     return bad != 0;
 }
