@@ -291,6 +291,9 @@ struct hrd_batch {
     std::vector<uint8_t> sq_open;
     uint32_t sq_blocks = 0;
     cudaStream_t own = nullptr;
+    // mixed-mode batches: the tile kernels of the different modes run side by side (run_demods)
+    cudaStream_t aux[4] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[4] = {};
     uint64_t launches = 0;
     // HRD_OPT_PROFILE: events around the hot kernel(s) of the latest call and around its tail kernel
     // (a ring of the last HRD_PROFILE_RING calls, so back-to-back timed steps can all be read)
@@ -509,6 +512,11 @@ int hrd_create(int device, int n_streams, int kind, hrd_batch_t **out)
     cudaError_t e = cudaSuccess;
     const size_t ssz = state_size(kind) * (size_t)n_streams;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->own, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; i++) {
+        e = cudaStreamCreateWithFlags(&b->aux[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming);
     b->sm_count = prop.multiProcessorCount;
     for (int h = 0; h < 2; h++) {
         if (e == cudaSuccess) e = cudaMalloc(&b->d_state[h], ssz);
@@ -568,6 +576,11 @@ int hrd_destroy(hrd_batch_t *b)
     for (int r = 0; r < HRD_PROFILE_RING; r++)
         for (int i = 0; i < 3; i++)
             if (b->ev[r][i]) cudaEventDestroy(b->ev[r][i]);
+    for (int i = 0; i < 4; i++) {
+        if (b->aux[i]) cudaStreamSynchronize(b->aux[i]), cudaStreamDestroy(b->aux[i]);
+        if (b->ev_join[i]) cudaEventDestroy(b->ev_join[i]);
+    }
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->own) cudaStreamDestroy(b->own);
     delete b;
     return HRD_OK;
@@ -645,6 +658,8 @@ int hrd_set_option(hrd_batch_t *b, int option, int value)
     if (!b) return fail(HRD_EINVAL, "null batch");
     if (option < 0 || option >= HRD_OPT_COUNT) return fail(HRD_EINVAL, "bad option %d", option);
     if (value < 0) return fail(HRD_EINVAL, "option values are non-negative");
+    if (option == HRD_OPT_RX_SQUELCH_BLOCK && value % 512)
+        return fail(HRD_EINVAL, "squelch block of %d bytes is not a whole number of PCM samples (512 bytes)", value);
     b->opt[option] = value;
     return HRD_OK;
 }
@@ -763,6 +778,10 @@ int hrd_get_table(hrd_batch_t *b, int which, float *out, size_t n)
 // The demodulator launches of one call (or, with the squelch armed, of one block): one tile-kernel launch
 // per kernel kind over the given stream lists, then the AM/SSB recurrence pass.  after_tiles, when set, is
 // recorded between the two (HRD_OPT_PROFILE).
+// A batch that holds several kinds (BASELINE config 5, mixed-mode sweeps) FANS OUT: every kind's launches go
+// to a stream of their own between a fork and a join event on the caller's stream, so the kernels fill each
+// other's last waves and the latency-bound recurrence pass of the AM/SSB streams runs beside the other
+// modes' tile kernels.  The kinds touch disjoint streams' records and disjoint scratch buffers.
 static int run_demods(hrd_batch_t *b, hrd::RxParams &p, int entry, uint32_t n_batches, const int32_t *const ids_of[4],
                       const int cnt_of[4], cudaStream_t s, cudaEvent_t after_tiles)
 {
@@ -770,10 +789,20 @@ static int run_demods(hrd_batch_t *b, hrd::RxParams &p, int entry, uint32_t n_ba
     int rc;
     hrd::RxParams iir_p;
     bool iir = false;
+    int kinds = 0;
+    for (int k = 0; k < 4; k++) kinds += cnt_of[k] && !(k == hrd::K_NONE && entry == HRD_ENTRY_256K);
+    const bool fan = kinds >= 2;
+    if (fan) HRD_CUDA(cudaEventRecord(b->ev_fork, s));
+    int lane = 0;
     for (int k = 0; k < 4; k++) {
         const int cnt = cnt_of[k];
         if (!cnt) continue;
         if (k == hrd::K_NONE && entry == HRD_ENTRY_256K) continue;
+        cudaStream_t ks = s;
+        if (fan) {
+            ks = b->aux[lane];
+            HRD_CUDA(cudaStreamWaitEvent(ks, b->ev_fork, 0));
+        }
         p.stream_ids = ids_of[k];
         p.n_streams = cnt;
         p.gain = k ? b->d_param[gain_of_kind[k]] : nullptr;
@@ -783,14 +812,14 @@ static int run_demods(hrd_batch_t *b, hrd::RxParams &p, int entry, uint32_t n_ba
             rc = ensure_cap(&b->d_wbv, &b->d_wbv_cap, sizeof(float2) * (size_t)p.n_streams * (size_t)p.n_tiles);
             if (rc) return rc;
             p.wb_verify = (float2 *)b->d_wbv;
-            HRD_CUDA(cudaMemsetAsync(b->d_wbflag, 0, sizeof(uint32_t), s));
+            HRD_CUDA(cudaMemsetAsync(b->d_wbflag, 0, sizeof(uint32_t), ks));
         }
-        int e = hrd::launch_rx(k, entry, p, s);
+        int e = hrd::launch_rx(k, entry, p, ks);
         if (e) return fail(HRD_ECUDA, "rx launch (kind %d) failed: %s", k, cudaGetErrorString((cudaError_t)e));
         b->launches++;
         if (speculate) {
             e = hrd::launch_rx_wbfm_verify(p, b->d_wbflag, b->d_wbrerun, (unsigned long long *)(b->d_wbflag + 2),
-                                           b->opt[HRD_OPT_DEBUG_WBFM_FORCE_RERUN], s);
+                                           b->opt[HRD_OPT_DEBUG_WBFM_FORCE_RERUN], ks);
             if (e) return fail(HRD_ECUDA, "wbfm verify launch failed: %s", cudaGetErrorString((cudaError_t)e));
             hrd::RxParams again = p; // the exact untiled run, from the untouched state_in; runs only if flagged
             again.n_tiles = 1;
@@ -798,7 +827,7 @@ static int run_demods(hrd_batch_t *b, hrd::RxParams &p, int entry, uint32_t n_ba
             again.wb_verify = nullptr;
             again.run_if = b->d_wbflag;
             again.rerun_ids = b->d_wbrerun;
-            e = hrd::launch_rx(k, entry, again, s);
+            e = hrd::launch_rx(k, entry, again, ks);
             if (e) return fail(HRD_ECUDA, "wbfm re-run launch failed: %s", cudaGetErrorString((cudaError_t)e));
             b->launches += 2;
             p.wb_verify = nullptr;
@@ -806,6 +835,17 @@ static int run_demods(hrd_batch_t *b, hrd::RxParams &p, int entry, uint32_t n_ba
         if (k == hrd::K_AM) {
             iir_p = p;
             iir = true;
+            if (fan) { // the recurrence pass follows its tile kernel on the same stream, beside the other kinds
+                e = hrd::launch_rx_dc_iir(iir_p, ks);
+                if (e) return fail(HRD_ECUDA, "rx IIR launch failed: %s", cudaGetErrorString((cudaError_t)e));
+                b->launches++;
+                iir = false;
+            }
+        }
+        if (fan) {
+            HRD_CUDA(cudaEventRecord(b->ev_join[lane], ks));
+            HRD_CUDA(cudaStreamWaitEvent(s, b->ev_join[lane], 0));
+            lane++;
         }
     }
     if (after_tiles) HRD_CUDA(cudaEventRecord(after_tiles, s));
@@ -824,7 +864,9 @@ static int run_demods(hrd_batch_t *b, hrd::RxParams &p, int entry, uint32_t n_ba
 static int rx_squelched(hrd_batch_t *b, hrd::RxParams p, size_t n256, int16_t *d_pcm, size_t d_pcm_stride,
                         uint32_t *pcm_counts, cudaStream_t s)
 {
-    const size_t blk256 = 16384; // 262144 bytes at 2.048 MS/s = one reference call (hackRf/hackrf.c:101)
+    // one reference call: 262144 bytes at 2.048 MS/s (hackRf/hackrf.c:101) = 16384 samples at 256 kS/s
+    const size_t blk256 = b->opt[HRD_OPT_RX_SQUELCH_BLOCK] > 0 ? (size_t)b->opt[HRD_OPT_RX_SQUELCH_BLOCK] / 16 : 16384;
+    const size_t blk_pcm = blk256 / 32;
     const int n_blocks = (int)((n256 + blk256 - 1) / blk256);
     const size_t n = (size_t)b->n, cells = n * (size_t)n_blocks;
     const size_t row256 = (n256 * 2 + 31) & ~(size_t)31;
@@ -832,7 +874,7 @@ static int rx_squelched(hrd_batch_t *b, hrd::RxParams p, size_t n256, int16_t *d
     if (!rc) rc = ensure_cap(&b->d_sq_mag, &b->d_sq_mag_cap, cells * sizeof(uint32_t));
     if (!rc) rc = ensure_cap(&b->d_sq_open, &b->d_sq_open_cap, cells);
     if (!rc) rc = ensure_cap(&b->d_sq_at, &b->d_sq_at_cap, cells * sizeof(uint32_t));
-    if (!rc) rc = ensure_cap(&b->d_sq_pcm, &b->d_sq_pcm_cap, n * 512 * sizeof(int16_t));
+    if (!rc) rc = ensure_cap(&b->d_sq_pcm, &b->d_sq_pcm_cap, n * blk_pcm * sizeof(int16_t));
     if (!rc) rc = ensure_cap(&b->d_sq_ids, &b->d_sq_ids_cap, cells * sizeof(int32_t));
     if (rc) return rc;
 
@@ -889,10 +931,11 @@ static int rx_squelched(hrd_batch_t *b, hrd::RxParams p, size_t n256, int16_t *d
     if (fill) HRD_CUDA(cudaMemcpyAsync(b->d_sq_ids, ids.data(), fill * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     HRD_CUDA(cudaStreamSynchronize(s)); // at / ids are stack-lived host vectors
     // 4. the demodulators, one reference call (block) at a time
-    if (b->pre_stride < 512) {
-        rc = ensure_cap((void **)&b->d_pre, &b->d_pre_cap, 512 * sizeof(float) * n);
+    const size_t pre_need = (blk_pcm + 7) & ~(size_t)7;
+    if (b->pre_stride < pre_need) {
+        rc = ensure_cap((void **)&b->d_pre, &b->d_pre_cap, pre_need * sizeof(float) * n);
         if (rc) return rc;
-        b->pre_stride = 512;
+        b->pre_stride = pre_need;
     }
     for (int k = 0; k < n_blocks; k++) {
         const size_t len = std::min(blk256, n256 - (size_t)k * blk256);
@@ -902,7 +945,7 @@ static int rx_squelched(hrd_batch_t *b, hrd::RxParams p, size_t n256, int16_t *d
         q.iq_stride = row256;
         q.n256 = (uint32_t)len;
         q.pcm = (int16_t *)b->d_sq_pcm;
-        q.pcm_stride = 512;
+        q.pcm_stride = blk_pcm;
         q.state_in = (const hrd::RxState *)b->d_state[b->cur];
         q.state_out = (hrd::RxState *)b->d_state[b->cur ^ 1];
         q.pre_iir = b->d_pre;
@@ -919,7 +962,7 @@ static int rx_squelched(hrd_batch_t *b, hrd::RxParams p, size_t n256, int16_t *d
         }
         rc = run_demods(b, q, HRD_ENTRY_256K, (uint32_t)((len + 1023) / 1024), ids_of, cnt_of, s, nullptr);
         if (rc) return rc;
-        if (hrd::launch_squelch_scatter((const int16_t *)b->d_sq_pcm, 512, d_pcm, d_pcm_stride, (const uint32_t *)b->d_sq_at,
+        if (hrd::launch_squelch_scatter((const int16_t *)b->d_sq_pcm, blk_pcm, d_pcm, d_pcm_stride, (const uint32_t *)b->d_sq_at,
                                         (const uint8_t *)b->d_sq_open, b->d_kind, b->n, n_blocks, k, (uint32_t)(len / 32), s))
             return fail(HRD_ECUDA, "squelch scatter launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         b->launches++;

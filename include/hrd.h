@@ -107,7 +107,10 @@ enum {
      * hrd_rx_squelch_report) even when no stream's threshold can close the gate.  The path is taken
      * automatically as soon as one stream's threshold can (threshold > -42 - gain dB). */
     HRD_OPT_RX_SQUELCH = 5,
-    HRD_OPT_COUNT = 6
+    /* Rx, 2.048 MS/s entry: input bytes per squelch decision, i.e. the size of the reference call being
+     * modelled (a multiple of 512).  0 (default) = 262144, the HackRF transfer block. */
+    HRD_OPT_RX_SQUELCH_BLOCK = 6,
+    HRD_OPT_COUNT = 7
 };
 
 #define HRD_ALL_STREAMS (-1)

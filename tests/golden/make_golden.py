@@ -13,6 +13,8 @@ depend on numpy's random generator staying stable.  Reference calls made per vec
   rx256k_<mode>    <X>Demodulator::acceptIqData, two calls
   fe               IqDataProcessor::reduceSampleRate + upconvertByFsOver4
   tx_<mode>        <X>Modulator::acceptData, two calls (64 + 32 PCM samples)
+  squelch_<mode>   IqDataProcessor::setSignalDetectThreshold(-40) + acceptIqData in 12 calls of 8192 bytes whose
+                   level crosses the threshold; PCM plus what the reference's magnitude / state callbacks reported
   tables           quantised taps as the constructors built them, sha256 of the NCO tables
 """
 import hashlib
@@ -85,6 +87,25 @@ def main():
             ref.tx_free(h)
             out[f"tx_{name}_{kind}_pcm"] = pcm
             out[f"tx_{name}_{kind}_iq"] = iq
+
+    # ---- squelch gate: short reference calls whose level crosses the threshold -------------
+    for name in ("am", "fm", "usb"):
+        mode, blk = MODES[name], 8192
+        rng = np.random.default_rng(synth.stream_seed(CONFIG, 40 + mode))
+        levels = [90, 2, 2, 50, 50, 1, 20, 120, 0, 0, 40, 3]
+        n = 12 * blk // 2
+        t = np.arange(n) / 2.048e6
+        amp = np.repeat(np.array(levels, dtype=np.float64), blk // 2)
+        z = amp * np.exp(2j * np.pi * (-64000.0 * t + 0.4 * np.sin(2 * np.pi * 1000 * t)))
+        iq = np.empty(2 * n, dtype=np.int8)
+        iq[0::2] = np.clip(np.rint(z.real + rng.normal(0, 1, n)), -128, 127).astype(np.int8)
+        iq[1::2] = np.clip(np.rint(z.imag + rng.normal(0, 1, n)), -128, 127).astype(np.int8)
+        pcm, mags, opens = ref.run_rx_squelch(mode, iq, -40, 16, block=blk)
+        assert 0 < opens.sum() < 12
+        out[f"squelch_{name}_iq"] = iq
+        out[f"squelch_{name}_pcm"] = pcm
+        out[f"squelch_{name}_mag"] = mags
+        out[f"squelch_{name}_open"] = opens
 
     # ---- tables -------------------------------------------------------------------------
     for i, name in enumerate(TAPS):

@@ -25,6 +25,15 @@ def golden():
 # ------------------------------------------------------------------------------------------
 # oracle vs golden (CPU)
 # ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["am", "fm", "usb"])
+def test_oracle_squelch(oracle, golden, name):
+    """Squelch gate: 12 reference calls of 8192 bytes, threshold -40 dBFS."""
+    pcm, mags, opens = oracle.run_rx_squelch(MODES[name], golden[f"squelch_{name}_iq"], -40, 16, block=8192)
+    assert np.array_equal(mags, golden[f"squelch_{name}_mag"])
+    assert np.array_equal(opens, golden[f"squelch_{name}_open"])
+    assert np.array_equal(pcm, golden[f"squelch_{name}_pcm"])
+
+
 @pytest.mark.parametrize("name", list(MODES))
 @pytest.mark.parametrize("tag", ["sig", "noise"])
 def test_oracle_rx_2048k(oracle, golden, name, tag):
@@ -137,3 +146,19 @@ def test_cuda_tables(golden):
     b = capi.Batch(1, capi.TX)
     assert hashlib.sha256(b.get_table(1).tobytes()).digest() == golden["nco_sin_sha256"].tobytes()
     assert hashlib.sha256(b.get_table(2).tobytes()).digest() == golden["nco_cos_sha256"].tobytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["am", "fm", "usb"])
+def test_cuda_squelch(golden, name):
+    from hackrfdiags_b200 import capi
+    b = capi.Batch(1, capi.RX, 0)
+    b.set_mode(MODES[name])
+    b.set_param(capi.PARAM_SQUELCH_THRESHOLD, -40)
+    b.set_option(capi.OPT_RX_SQUELCH_BLOCK, 8192)
+    got = b.rx(golden[f"squelch_{name}_iq"][None, :].copy())
+    mags, opens = b.squelch_report()
+    want = golden[f"squelch_{name}_pcm"]
+    assert np.array_equal(mags[0], golden[f"squelch_{name}_mag"])
+    assert np.array_equal(opens[0], golden[f"squelch_{name}_open"])
+    assert b.last_counts[0] == want.size and np.array_equal(got[0, :want.size], want)
