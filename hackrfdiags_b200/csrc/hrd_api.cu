@@ -1193,8 +1193,19 @@ int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size
     p.nco_thr = g_dev_tables[b->device].nco_thr;
     p.sm_count = b->sm_count;
     static const int param_of_kind[5] = {-1, HRD_PARAM_AM_INDEX, HRD_PARAM_FM_DEV, HRD_PARAM_WBFM_DEV, -1};
+    // a batch holding several kinds fans out like the receive side's (run_demods): one stream per kind
+    int kinds = 0;
+    for (int k = 0; k < 5; k++) kinds += b->group_cnt[k] != 0;
+    const bool fan = kinds >= 2;
+    if (fan) HRD_CUDA(cudaEventRecord(b->ev_fork, s));
+    int lane = 0;
     for (int k = 0; k < 5; k++) {
         if (!b->group_cnt[k]) continue;
+        cudaStream_t ks = s;
+        if (fan) {
+            ks = b->aux[lane & 3];
+            HRD_CUDA(cudaStreamWaitEvent(ks, b->ev_fork, 0));
+        }
         p.stream_ids = b->d_ids + b->group_off[k];
         p.n_streams = b->group_cnt[k];
         p.param = param_of_kind[k] >= 0 ? b->d_param[param_of_kind[k]] : nullptr;
@@ -1205,13 +1216,18 @@ int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size
             rc = ensure_cap(&b->d_fmph, &b->d_fmph_cap, sizeof(float) * (size_t)p.n_streams * n_per_stream);
             if (rc) return rc;
             p.fm_phase = (float *)b->d_fmph;
-            int e = hrd::launch_tx_fm_phase(p, s);
+            int e = hrd::launch_tx_fm_phase(p, ks);
             if (e) return fail(HRD_ECUDA, "tx FM phase launch failed: %s", cudaGetErrorString((cudaError_t)e));
             b->launches++;
         }
-        int e = hrd::launch_tx(k, p, s);
+        int e = hrd::launch_tx(k, p, ks);
         if (e) return fail(HRD_ECUDA, "tx launch (kind %d) failed: %s", k, cudaGetErrorString((cudaError_t)e));
         b->launches++;
+        if (fan) { // five kinds share four side streams: the fifth queues behind the first
+            HRD_CUDA(cudaEventRecord(b->ev_join[lane & 3], ks));
+            HRD_CUDA(cudaStreamWaitEvent(s, b->ev_join[lane & 3], 0));
+            lane++;
+        }
     }
     b->cur ^= 1; // what this call wrote is what the next one reads
     if (mem == HRD_MEM_HOST) {
