@@ -17,9 +17,10 @@ LIB_PATH = os.environ.get("HRD_LIB") or os.path.join(_HERE, "libhrd_b200.so")
 
 RX, TX = 0, 1
 MODE_NONE, MODE_AM, MODE_FM, MODE_WBFM, MODE_LSB, MODE_USB = range(6)
+MODE_IQ8K, MODE_DSB, MODE_PM, MODE_AM_PROTO = 6, 7, 8, 9  # Tx only: the tool chain of signals/
 (PARAM_AM_GAIN, PARAM_FM_GAIN, PARAM_WBFM_GAIN, PARAM_SSB_GAIN,
  PARAM_AM_INDEX, PARAM_FM_DEV, PARAM_WBFM_DEV, PARAM_SQUELCH_THRESHOLD, PARAM_RX_GAIN_DB) = range(9)
-UNIT_AM, UNIT_FM, UNIT_WBFM, UNIT_SSB, UNIT_FRONT_END, UNIT_ALL = range(6)
+UNIT_AM, UNIT_FM, UNIT_WBFM, UNIT_SSB, UNIT_FRONT_END, UNIT_ALL, UNIT_SIGNALS = range(7)
 ENTRY_2048K, ENTRY_256K = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 ALL_STREAMS = -1
@@ -192,10 +193,11 @@ class Batch:
                                          out.shape[1], MEM_HOST, None))
         return out[:, :nbytes // 8]
 
-    def tx(self, pcm: np.ndarray) -> np.ndarray:
-        """pcm[n_streams, n] int16 -> iq[n_streams, n*512] int8."""
+    def tx(self, pcm: np.ndarray, n: int | None = None) -> np.ndarray:
+        """pcm[n_streams, n] int16 -> iq[n_streams, n*512] int8.  With HRD_MODE_IQ8K streams in the batch the rows
+        hold 2*n int16 (I,Q pairs for those streams, PCM in the first n for the others): pass n."""
         assert pcm.dtype == np.int16 and pcm.ndim == 2 and pcm.shape[0] == self.n and pcm.strides[1] == 2
-        n = pcm.shape[1]
+        n = pcm.shape[1] if n is None else n
         iq = np.zeros((self.n, max(n * 512, 32)), dtype=np.int8)
         _check(self.lib.hrd_tx_process(self.h, pcm.ctypes.data, n, pcm.strides[0] // 2, iq.ctypes.data,
                                        iq.shape[1], MEM_HOST, None))

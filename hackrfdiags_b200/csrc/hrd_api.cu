@@ -58,6 +58,14 @@ const float k_audio40[40] = {
     -0.0862280f, -0.0497761f, 0.1793543f,  0.4145808f,  0.4145808f,  0.1793543f,  -0.0497761f, -0.0862280f,
     0.0070312f,  0.0550219f,  0.0091343f,  -0.0363745f, -0.0161248f, 0.0230891f,  0.0184489f,  -0.0133345f,
     -0.0183409f, 0.0065495f,  0.0180618f,  -0.0023190f, -0.0265610f, -0.0270501f, -0.0111080f, 0.0015969f};
+// signals/interpolateSignal.cc:30-72
+const float k_sig40[40] = {
+    -0.0011405f, 0.0183372f,  0.0030542f,  -0.0100052f, -0.0059350f, 0.0115377f,  0.0109293f,
+    -0.0120883f, -0.0175779f, 0.0110390f,  0.0262645f,  -0.0074772f, -0.0377408f, -0.0003152f,
+    0.0541009f,  0.0165897f,  -0.0829085f, 0.0587608f,  0.1736804f,  0.4222137f,  0.4222137f,
+    0.1736804f,  -0.0587608f, -0.0829085f, 0.0165897f,  0.0541009f,  -0.0003152f, -0.0377408f,
+    -0.0074772f, 0.0262645f,  0.0110390f,  -0.0175779f, -0.0120883f, 0.0109293f,  0.0115377f,
+    -0.0059350f, -0.0100052f, 0.0030542f,  0.0183372f,  -0.0011405f};
 const float k_wbfm_post1[8] = {0.0243699f, 0.0769537f, 0.1463572f, 0.1967096f,
                                0.1967096f, 0.1463572f, 0.0769537f, 0.0243699f};
 const float k_delay16[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1};
@@ -117,6 +125,7 @@ int build_tables(hrd::ConstTables &t)
     for (int i = 0; i < 16; i++) t.am3[i] = quantise(k_am3[i]);
     for (int i = 0; i < 12; i++) t.fm_post[i] = quantise(k_fm_post[i]);
     for (int i = 0; i < 40; i++) t.audio40[i] = quantise(k_audio40[i]);
+    for (int i = 0; i < 40; i++) t.sig40[i] = quantise(k_sig40[i]);
     for (int i = 0; i < 8; i++) t.wbfm_post1[i] = quantise(k_wbfm_post1[i]);
     split_taps(t.wbfm_post1, 8, t.wb1_sp);
     split_taps(t.fm_post, 12, t.fm_post_sp);
@@ -247,6 +256,10 @@ int kernel_kind_of_mode(int mode)
     case HRD_MODE_WBFM: return hrd::K_WBFM;
     case HRD_MODE_LSB:
     case HRD_MODE_USB: return hrd::K_SSB;
+    case HRD_MODE_IQ8K:
+    case HRD_MODE_DSB:
+    case HRD_MODE_PM:
+    case HRD_MODE_AM_PROTO: return hrd::K_IQ;
     default: return hrd::K_NONE;
     }
 }
@@ -278,7 +291,8 @@ struct hrd_batch {
     uint8_t *d_lsb = nullptr;
     uint8_t *d_kind = nullptr; // kernel kind (hrd::K_*) of every stream
     float *d_param[HRD_PARAM_COUNT] = {};
-    int group_off[5] = {}, group_cnt[5] = {};
+    int group_off[hrd::K_COUNT] = {}, group_cnt[hrd::K_COUNT] = {};
+    int32_t *d_mode = nullptr; // HRD_MODE_* of every stream
     void *d_in = nullptr, *d_out = nullptr;
     size_t d_in_cap = 0, d_out_cap = 0;
     // squelch gate (hrd_squelch.cu): the 256 kS/s stream of the call, per-(stream, block) magnitudes,
@@ -314,8 +328,8 @@ int regroup(hrd_batch *b)
     std::vector<uint8_t> kinds((size_t)b->n);
     for (int s = 0; s < b->n; s++) kinds[(size_t)s] = (uint8_t)kernel_kind_of_mode(b->mode[(size_t)s]);
     // AM and SSB streams sit next to each other: on Rx one launch runs both
-    static const int order[5] = {hrd::K_NONE, hrd::K_FM, hrd::K_WBFM, hrd::K_AM, hrd::K_SSB};
-    for (int o = 0; o < 5; o++) {
+    static const int order[hrd::K_COUNT] = {hrd::K_NONE, hrd::K_FM, hrd::K_WBFM, hrd::K_AM, hrd::K_SSB, hrd::K_IQ};
+    for (int o = 0; o < hrd::K_COUNT; o++) {
         const int k = order[o];
         b->group_off[k] = (int)ids.size();
         for (int s = 0; s < b->n; s++)
@@ -326,6 +340,7 @@ int regroup(hrd_batch *b)
     HRD_CUDA(cudaMemcpy(b->d_kind, kinds.data(), (size_t)b->n, cudaMemcpyHostToDevice));
     HRD_CUDA(cudaMemcpy(b->d_ids, ids.data(), (size_t)b->n * sizeof(int32_t), cudaMemcpyHostToDevice));
     HRD_CUDA(cudaMemcpy(b->d_lsb, b->lsb.data(), (size_t)b->n, cudaMemcpyHostToDevice));
+    HRD_CUDA(cudaMemcpy(b->d_mode, b->mode.data(), (size_t)b->n * sizeof(int32_t), cudaMemcpyHostToDevice));
     for (int p = 0; p < HRD_PARAM_COUNT; p++)
         HRD_CUDA(cudaMemcpy(b->d_param[p], b->param[p].data(), (size_t)b->n * sizeof(float), cudaMemcpyHostToDevice));
     b->dirty = false;
@@ -529,6 +544,7 @@ int hrd_create(int device, int n_streams, int kind, hrd_batch_t **out)
     if (e == cudaSuccess) e = cudaMalloc(&b->d_ids, (size_t)n_streams * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_all, (size_t)n_streams * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_lsb, (size_t)n_streams);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_mode, (size_t)n_streams * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_kind, (size_t)n_streams);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_sq_track, (size_t)n_streams);
     if (e == cudaSuccess) e = cudaMemset(b->d_sq_track, 0, (size_t)n_streams); // SignalTracker: NoSignal
@@ -562,6 +578,7 @@ int hrd_destroy(hrd_batch_t *b)
     cudaFree(b->d_ids);
     cudaFree(b->d_all);
     cudaFree(b->d_lsb);
+    cudaFree(b->d_mode);
     cudaFree(b->d_kind);
     for (int p = 0; p < HRD_PARAM_COUNT; p++) cudaFree(b->d_param[p]);
     cudaFree(b->d_in);
@@ -590,7 +607,8 @@ int hrd_set_mode(hrd_batch_t *b, int stream, int mode)
 {
     int rc = check_stream_arg(b, stream);
     if (rc) return rc;
-    if (mode < HRD_MODE_NONE || mode > HRD_MODE_USB) return fail(HRD_EINVAL, "bad mode %d", mode);
+    if (mode < HRD_MODE_NONE || mode > (b->kind == HRD_TX ? HRD_MODE_AM_PROTO : HRD_MODE_USB))
+        return fail(HRD_EINVAL, "bad mode %d", mode);
     const int lo = stream == HRD_ALL_STREAMS ? 0 : stream, hi = stream == HRD_ALL_STREAMS ? b->n : stream + 1;
     for (int s = lo; s < hi; s++) {
         b->mode[(size_t)s] = mode;
@@ -714,6 +732,7 @@ int hrd_reset(hrd_batch_t *b, int stream, int unit)
             if (!rc) rc = zero_state(b, stream, RANGE(TxState, ssb_h8, pad));
             break;
         case HRD_UNIT_WBFM: rc = zero_state(b, stream, RANGE(TxState, wb, fm_phase)); break; // phase kept
+        case HRD_UNIT_SIGNALS: rc = zero_state(b, stream, offsetof(TxState, sig), sizeof(hrd::TxRail8)); break;
         case HRD_UNIT_ALL: rc = zero_state(b, stream, 0, sizeof(TxState)); break;
         default: return fail(HRD_EINVAL, "bad unit %d", unit);
         }
@@ -1147,6 +1166,11 @@ int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size
     if (mem != HRD_MEM_HOST && mem != HRD_MEM_DEVICE) return fail(HRD_EINVAL, "bad mem %d", mem);
     if (n_per_stream > 0x7fffffu) return fail(HRD_EINVAL, "call too long");
     if (pcm_stride < n_per_stream) return fail(HRD_EINVAL, "pcm_stride too small");
+    bool pairs = false; // a stream of int16 I,Q pairs (HRD_MODE_IQ8K) doubles the row
+    for (int i = 0; i < b->n; i++) pairs |= b->mode[(size_t)i] == HRD_MODE_IQ8K;
+    const size_t in_elems = pairs ? 2 * n_per_stream : n_per_stream;
+    if (pairs && (pcm_stride < in_elems || (pcm_stride & 1) || ((uintptr_t)pcm & 3)))
+        return fail(HRD_EINVAL, "HRD_MODE_IQ8K rows hold %zu int16: pcm_stride must be even and at least that, pcm 4-byte aligned", in_elems);
     const size_t out_row = n_per_stream * 512;
     if (iq_stride < out_row) return fail(HRD_EINVAL, "iq_stride too small");
     DeviceGuard guard(b->device);
@@ -1159,11 +1183,11 @@ int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size
     int8_t *d_iq = iq;
     size_t d_pcm_stride = pcm_stride, d_iq_stride = iq_stride;
     if (mem == HRD_MEM_HOST) {
-        const size_t in_row = (n_per_stream * sizeof(int16_t) + 31) & ~(size_t)31;
+        const size_t in_row = (in_elems * sizeof(int16_t) + 31) & ~(size_t)31;
         rc = ensure_cap(&b->d_in, &b->d_in_cap, in_row * (size_t)b->n);
         if (!rc) rc = ensure_cap(&b->d_out, &b->d_out_cap, out_row * (size_t)b->n);
         if (rc) return rc;
-        HRD_CUDA(cudaMemcpy2DAsync(b->d_in, in_row, pcm, pcm_stride * sizeof(int16_t), n_per_stream * sizeof(int16_t),
+        HRD_CUDA(cudaMemcpy2DAsync(b->d_in, in_row, pcm, pcm_stride * sizeof(int16_t), in_elems * sizeof(int16_t),
                                    (size_t)b->n, cudaMemcpyHostToDevice, s));
         d_pcm = (const int16_t *)b->d_in;
         d_pcm_stride = in_row / sizeof(int16_t);
@@ -1187,19 +1211,20 @@ int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size
     HRD_CUDA(cudaMemcpyAsync(b->d_state[b->cur ^ 1], b->d_state[b->cur], sizeof(hrd::TxState) * (size_t)b->n,
                              cudaMemcpyDeviceToDevice, s));
     p.lsb = b->d_lsb;
+    p.mode_of = b->d_mode;
     p.nco_sin = g_dev_tables[b->device].nco_sin;
     p.nco_cos = g_dev_tables[b->device].nco_cos;
     p.nco_iq900 = g_dev_tables[b->device].nco_iq900;
     p.nco_thr = g_dev_tables[b->device].nco_thr;
     p.sm_count = b->sm_count;
-    static const int param_of_kind[5] = {-1, HRD_PARAM_AM_INDEX, HRD_PARAM_FM_DEV, HRD_PARAM_WBFM_DEV, -1};
+    static const int param_of_kind[hrd::K_COUNT] = {-1, HRD_PARAM_AM_INDEX, HRD_PARAM_FM_DEV, HRD_PARAM_WBFM_DEV, -1, -1};
     // a batch holding several kinds fans out like the receive side's (run_demods): one stream per kind
     int kinds = 0;
-    for (int k = 0; k < 5; k++) kinds += b->group_cnt[k] != 0;
+    for (int k = 0; k < hrd::K_COUNT; k++) kinds += b->group_cnt[k] != 0;
     const bool fan = kinds >= 2;
     if (fan) HRD_CUDA(cudaEventRecord(b->ev_fork, s));
     int lane = 0;
-    for (int k = 0; k < 5; k++) {
+    for (int k = 0; k < hrd::K_COUNT; k++) {
         if (!b->group_cnt[k]) continue;
         cudaStream_t ks = s;
         if (fan) {
@@ -1211,7 +1236,7 @@ int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size
         p.param = param_of_kind[k] >= 0 ? b->d_param[param_of_kind[k]] : nullptr;
         p.n_tiles = 1;
         p.tile_len8 = (uint32_t)((n_per_stream + 31) & ~(size_t)31);
-        if (k == hrd::K_AM || k == hrd::K_FM || k == hrd::K_SSB) choose_tx_tiles(b, k, p.n_streams, (uint32_t)n_per_stream, &p.n_tiles, &p.tile_len8);
+        if (k == hrd::K_AM || k == hrd::K_FM || k == hrd::K_SSB || k == hrd::K_IQ) choose_tx_tiles(b, k, p.n_streams, (uint32_t)n_per_stream, &p.n_tiles, &p.tile_len8);
         if (k == hrd::K_FM) { // the serial NCO phase pass first (hrd_tx.cu tx_fm_phase_kernel)
             rc = ensure_cap(&b->d_fmph, &b->d_fmph_cap, sizeof(float) * (size_t)p.n_streams * n_per_stream);
             if (rc) return rc;

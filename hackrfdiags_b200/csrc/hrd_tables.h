@@ -31,6 +31,7 @@ struct ConstTables {
     int32_t am3[16];        // AmDemodulator.cc:44-62    /2
     int32_t fm_post[12];    // FmDemodulator.cc:54-68    /4 (also WBFM post-demod 2)
     int32_t audio40[40];    // FmDemodulator.cc:71-113   /2 (also WBFM audio, Tx stage 1)
+    int32_t sig40[40];      // signals/interpolateSignal.cc:30-72: the stand-alone interpolator's own stage 1
     int32_t wbfm_post1[8];  // WbFmDemodulator.cc:17-27  /4
     // The same taps for mac_pair (hrd_rx.cu): word w serves ring samples 2w (low half) and 2w+1, i.e.
     // taps q[N-1-2w] and q[N-2-2w], each split q = th*256 + tl and packed {tl0, tl1, th0, th1}
@@ -100,6 +101,7 @@ struct TxState {
     float wb_phase;        // ... of the WBFM NCO (256 kS/s)
     uint32_t ssb_h8[30];   // PCM/2 history for the delay line / Hilbert FIR
     uint32_t pad[2];
+    TxRail8 sig;           // signals/interpolateSignal.cc: its I and Q interpolator trees
 };
 
 // ---------------------------------------------------------------- kernel parameters
@@ -164,6 +166,7 @@ struct TxParams {
     float *fm_phase;
     const int32_t *stream_ids;
     int32_t n_streams;
+    const int32_t *mode_of;    // [n_streams_total] HRD_MODE_* of every stream (the signals/ launch picks its head by it)
     const float *param;        // AM index / FM deviation / WBFM deviation
     const uint8_t *lsb;
     const float *nco_sin, *nco_cos;
@@ -175,7 +178,10 @@ struct TxParams {
     int32_t sm_count;
 };
 
-enum { K_NONE = 0, K_AM = 1, K_FM = 2, K_WBFM = 3, K_SSB = 4 };
+enum { K_NONE = 0, K_AM = 1, K_FM = 2, K_WBFM = 3, K_SSB = 4,
+       K_IQ = 5 /* Tx only: the tool chain of signals/ (heads + interpolateSignal) */, K_COUNT = 6 };
+// HRD_MODE_* values of the signals/ heads (include/hrd.h), as the kernel sees them
+enum { SIG_MODE_IQ8K = 6, SIG_MODE_DSB = 7, SIG_MODE_PM = 8, SIG_MODE_AM_PROTO = 9 };
 
 // Items per CTA for the chain-warp kernels (at most `cap`): the smallest count that still needs no
 // more waves of CTAs than `cap` per CTA would, so that the last wave is as full as the others.

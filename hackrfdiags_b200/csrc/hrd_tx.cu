@@ -55,17 +55,17 @@ struct SmemTx {
 
 // ---- generic polyphase stages over rings of I/Q pairs ------------------------------------
 // stage 1: 40 taps, L = 2 (20 taps per branch); ring hist 19, input n at ring[19 + n]
-__device__ __forceinline__ void interp40(const uint32_t *in, int n, uint32_t &even, uint32_t &odd)
+__device__ __forceinline__ void interp40(const uint32_t *in, const int32_t *taps, int n, uint32_t &even, uint32_t &odd)
 {
     unsigned ei = 1u << 14, eq = 1u << 14, oi = 1u << 14, oq = 1u << 14;
 #pragma unroll
     for (int k = 0; k < 20; k++) {
         uint32_t w = in[19 + n - k];
         int xi = lo16(w), xq = hi16(w);
-        ei += (unsigned)(c_tabtx.audio40[2 * k] * xi);
-        eq += (unsigned)(c_tabtx.audio40[2 * k] * xq);
-        oi += (unsigned)(c_tabtx.audio40[2 * k + 1] * xi);
-        oq += (unsigned)(c_tabtx.audio40[2 * k + 1] * xq);
+        ei += (unsigned)(taps[2 * k] * xi);
+        eq += (unsigned)(taps[2 * k] * xq);
+        oi += (unsigned)(taps[2 * k + 1] * xi);
+        oq += (unsigned)(taps[2 * k + 1] * xq);
     }
     even = pack16(q15((int)ei), q15((int)eq));
     odd = pack16(q15((int)oi), q15((int)oq));
@@ -244,7 +244,10 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxPara
     const bool first = tile == 0, last = tile == p.n_tiles - 1;
     SmemTx &sm = *reinterpret_cast<SmemTx *>(smem_raw + (size_t)warp * sizeof(SmemTx));
     const TxState &st = p.state[sid];
-    const TxRail8 &rs = KIND == K_AM ? st.am : (KIND == K_FM ? st.fm : st.ssb);
+    const TxRail8 &rs = KIND == K_AM ? st.am : (KIND == K_FM ? st.fm : (KIND == K_IQ ? st.sig : st.ssb));
+    // signals/interpolateSignal.cc has its own stage-1 prototype (:30-72); stages 2..8 are the modulators'
+    const int32_t *taps40 = KIND == K_IQ ? c_tabtx.sig40 : c_tabtx.audio40;
+    const int sub = KIND == K_IQ ? p.mode_of[sid] : 0;
     const int16_t *src = p.pcm + (size_t)sid * p.pcm_stride;
     int8_t *dst = p.iq + (size_t)sid * p.iq_stride;
 
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxPara
     ring_init(sm.s3, rs.s3, 3, lane, first);
     ring_init(sm.s4, rs.s4, 3, lane, first);
     if constexpr (KIND == K_SSB) ring_init(sm.h8, st.ssb_h8, 30, lane, first);
-    const float prm = (KIND == K_SSB) ? 0.f : p.param[sid];
+    const float prm = (KIND == K_SSB || KIND == K_IQ) ? 0.f : p.param[sid];
     const bool lsb = (KIND == K_SSB) ? (p.lsb[sid] != 0) : true;
     const float *fm_phase = (KIND == K_FM) ? p.fm_phase + (size_t)slot * p.n8 : nullptr;
     __syncwarp();
@@ -268,8 +271,28 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxPara
         const int nb = (int)min((uint32_t)NB8, end - done);
         const bool emit = done >= emit_from; // halo batches compute, they do not store
         // ---- 1. modulator head, one PCM sample per lane ---------------------------------
-        const int x = (lane < nb) ? (int)src[done + lane] : 0;
+        const int x = (lane < nb && !(KIND == K_IQ && sub == SIG_MODE_IQ8K)) ? (int)src[done + lane] : 0;
         uint32_t head = 0;
+        if constexpr (KIND == K_IQ) {
+            // the tool chain of signals/ (generateBaseband.sh): one of the prototype heads, or raw I,Q pairs
+            if (sub == SIG_MODE_IQ8K) { // interpolateSignal.cc:266-340 reads int16 I,Q pairs
+                head = (lane < nb) ? reinterpret_cast<const uint32_t *>(src)[done + lane] : 0u;
+            } else if (sub == SIG_MODE_DSB) { // dsb.cc:38-47
+                const int v = f32_to_i16(__fdiv_rn((float)x, 4.f));
+                head = pack16(v, v);
+            } else if (sub == SIG_MODE_AM_PROTO) { // am.cc:38-50: "scaledSample *= 0.8" is a double multiply
+                float s = (float)((double)(float)x * 0.8);
+                s = __fdiv_rn(__fadd_rn(s, 65536.f), 4.f);
+                const int v = f32_to_i16(s);
+                head = pack16(v, v);
+            } else { // pm.cc:39-55: angle = x / 60000 * M_PI (double multiply), cosf/sinf, * 16000
+                float a = __fdiv_rn((float)x, 60000.f);
+                a = (float)((double)a * 3.14159265358979323846);
+                double sd, cd;
+                sincos((double)a, &sd, &cd); // evaluated in double and rounded (DESIGN.md "the one tolerance")
+                head = pack16(f32_to_i16(__fmul_rn((float)cd, 16000.f)), f32_to_i16(__fmul_rn((float)sd, 16000.f)));
+            }
+        }
         if constexpr (KIND == K_AM) {
             // AmModulator.cc:583-602
             float s = __fdiv_rn((float)x, 32768.f);
@@ -310,7 +333,7 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxPara
         __syncwarp();
 
         // ---- 2. stages 1..4 ---------------------------------------------------------------
-        for (int n = lane; n < nb; n += 32) interp40(sm.s0, n, sm.s1[3 + 2 * n], sm.s1[3 + 2 * n + 1]);
+        for (int n = lane; n < nb; n += 32) interp40(sm.s0, taps40, n, sm.s1[3 + 2 * n], sm.s1[3 + 2 * n + 1]);
         __syncwarp();
         for (int n = lane; n < 2 * nb; n += 32) interp8(sm.s1, n, sm.s2[1 + 2 * n], sm.s2[1 + 2 * n + 1]);
         __syncwarp();
@@ -356,7 +379,7 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxPara
     // the last tile leaves the interpolator histories for the next call (the rest of the record was
     // copied over by the host; the FM phase is tx_fm_phase_kernel's)
     TxState &so = p.state_out[sid];
-    TxRail8 &ro = KIND == K_AM ? so.am : (KIND == K_FM ? so.fm : so.ssb);
+    TxRail8 &ro = KIND == K_AM ? so.am : (KIND == K_FM ? so.fm : (KIND == K_IQ ? so.sig : so.ssb));
     ring_save_hist(sm.s0, ro.s0, 19, lane);
     ring_save_hist(sm.s1, ro.s1, 3, lane);
     ring_save_hist(sm.s2, ro.s2, 1, lane);
@@ -875,9 +898,11 @@ int tx_halo_samples(int kind) { return kind == K_SSB ? (int)TxHaloOf<K_SSB>::val
 
 int tx_resident_warps_per_sm(int kind)
 {
-    static int cache[5] = {};
-    if (kind != K_AM && kind != K_FM && kind != K_SSB) return HRD_WARPS_PER_CTA;
-    if (!cache[kind]) cache[kind] = kind == K_AM ? tx_resident_warps<K_AM>() : kind == K_FM ? tx_resident_warps<K_FM>() : tx_resident_warps<K_SSB>();
+    static int cache[K_COUNT] = {};
+    if (kind != K_AM && kind != K_FM && kind != K_SSB && kind != K_IQ) return HRD_WARPS_PER_CTA;
+    if (!cache[kind])
+        cache[kind] = kind == K_AM ? tx_resident_warps<K_AM>() : kind == K_FM ? tx_resident_warps<K_FM>()
+                      : kind == K_IQ ? tx_resident_warps<K_IQ>() : tx_resident_warps<K_SSB>();
     return cache[kind];
 }
 
@@ -896,6 +921,7 @@ int launch_tx(int kind, const TxParams &p, cudaStream_t s)
     case K_AM: return launch_one<K_AM>(p, s);
     case K_FM: return launch_one<K_FM>(p, s);
     case K_SSB: return launch_one<K_SSB>(p, s);
+    case K_IQ: return launch_one<K_IQ>(p, s);
     case K_WBFM: {
         TxParams q = p;
         q.items_per_cta = balanced_items_per_cta(p.n_streams, p.sm_count, TW_ITEMS);

@@ -48,7 +48,13 @@ enum {
     HRD_MODE_FM = 2,
     HRD_MODE_WBFM = 3,
     HRD_MODE_LSB = 4,
-    HRD_MODE_USB = 5
+    HRD_MODE_USB = 5,
+    /* Tx batches only: the stand-alone tool chain of signals/ (generateBaseband.sh: <head> < pcm | interpolateSignal),
+     * i.e. signals/interpolateSignal.cc's eight-stage interpolator with ITS stage-1 taps (:30-72) behind ... */
+    HRD_MODE_IQ8K = 6,     /* nothing: the input rows are int16 I,Q PAIRS at 8 kS/s (interpolateSignal.cc:266-340) */
+    HRD_MODE_DSB = 7,      /* signals/dsb.cc:38-47  x/4 on both rails                                            */
+    HRD_MODE_PM = 8,       /* signals/pm.cc:39-55   (cos, sin)(x/60000*pi) * 16000 (libm: <= 1 LSB, like FM Tx)  */
+    HRD_MODE_AM_PROTO = 9  /* signals/am.cc:38-50   (x*0.8 + 65536)/4 on both rails                              */
 };
 
 /* per-stream scalar parameters and the reference setter each one replaces */
@@ -75,7 +81,8 @@ enum {
     HRD_UNIT_WBFM = 2, /* WbFm... (demodulator: the de-emphasis filter is NOT reset)        */
     HRD_UNIT_SSB = 3,  /* Ssb...                                                            */
     HRD_UNIT_FRONT_END = 4, /* (ours) IqDataProcessor's three half-band decimators          */
-    HRD_UNIT_ALL = 5        /* (ours) everything, i.e. freshly constructed objects          */
+    HRD_UNIT_ALL = 5,       /* (ours) everything, i.e. freshly constructed objects          */
+    HRD_UNIT_SIGNALS = 6    /* (ours) Tx: the interpolator trees of the signals/ tool chain (a fresh process) */
 };
 
 enum { HRD_ENTRY_2048K = 0, /* IqDataProcessor::acceptIqData  (IqDataProcessor.cc:926)  */
@@ -192,6 +199,8 @@ int hrd_rx_squelch_report(hrd_batch_t *b, uint32_t *magnitudes, uint8_t *allowed
  * int8 I,Q at 2.048 MS/s at iq + s*iq_stride bytes (32-byte aligned starts).
  * Mode NONE writes the idle carrier BasebandDataProcessor uses: every byte
  * 64 (BasebandDataProcessor.cc:689-694).  No 512-sample ceiling.
+ * A stream in mode HRD_MODE_IQ8K reads n_per_stream int16 I,Q PAIRS from its row (4-byte aligned, so
+ * pcm_stride must be even and at least 2*n_per_stream when the batch holds one).
  */
 int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size_t pcm_stride,
                    int8_t *iq, size_t iq_stride, int mem, void *cuda_stream);

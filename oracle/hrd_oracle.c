@@ -104,6 +104,15 @@ static const float k_audio40[40] = {
     0.1793543f,  -0.0497761f, -0.0862280f, 0.0070312f,  0.0550219f,  0.0091343f,  -0.0363745f,
     -0.0161248f, 0.0230891f,  0.0184489f,  -0.0133345f, -0.0183409f, 0.0065495f,  0.0180618f,
     -0.0023190f, -0.0265610f, -0.0270501f, -0.0111080f, 0.0015969f};
+/* signals/interpolateSignal.cc:30-72: the stand-alone interpolator's OWN stage-1 prototype (stages 2..8 carry the
+ * same numbers as the modulator classes, interpolateSignal.cc:74-140 vs AmModulator.cc:57-123) */
+static const float k_sig40[40] = {
+    -0.0011405f, 0.0183372f,  0.0030542f,  -0.0100052f, -0.0059350f, 0.0115377f,  0.0109293f,
+    -0.0120883f, -0.0175779f, 0.0110390f,  0.0262645f,  -0.0074772f, -0.0377408f, -0.0003152f,
+    0.0541009f,  0.0165897f,  -0.0829085f, 0.0587608f,  0.1736804f,  0.4222137f,  0.4222137f,
+    0.1736804f,  -0.0587608f, -0.0829085f, 0.0165897f,  0.0541009f,  -0.0003152f, -0.0377408f,
+    -0.0074772f, 0.0262645f,  0.0110390f,  -0.0175779f, -0.0120883f, 0.0109293f,  0.0115377f,
+    -0.0059350f, -0.0100052f, 0.0030542f,  0.0183372f,  -0.0011405f};
 static const float k_wbfm_post1[8] = {0.0243699f, 0.0769537f, 0.1463572f, 0.1967096f,
                                       0.1967096f, 0.1463572f, 0.0769537f, 0.0243699f};
 static const float k_delay16[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1};
@@ -765,6 +774,8 @@ struct hro_tx {
     /* SsbModulator */
     tx_rail ssb[2];
     fir16 ssb_delay, ssb_hilbert;
+    /* signals/interpolateSignal.cc: the stand-alone I and Q interpolator trees */
+    tx_rail sig[2];
 };
 
 hro_tx *hro_tx_new(void)
@@ -779,6 +790,10 @@ hro_tx *hro_tx_new(void)
         tx_rail_init(&tx->ssb[r]);
     }
     tx_rail_init(&tx->wb_pcm);
+    for (int r = 0; r < 2; r++) {
+        tx_rail_init(&tx->sig[r]);
+        int16i_init(&tx->sig[r].st[0], k_sig40, 40, 2); /* interpolateSignal.cc:30-72, 206-208 */
+    }
     tx->am_index = 0.8f;        /* AmModulator.cc:218 */
     tx->fm_dev = 3500;          /* FmModulator.cc:218 */
     tx->fm_phase.fs = 8000;     /* FmModulator.cc:221 */
@@ -832,6 +847,55 @@ static void emit_iq(const int16_t *i8, const int16_t *q8, int n, int8_t *out)
         out[2 * k] = (int8_t)(uint8_t)((uint16_t)i8[k] & 0xff);
         out[2 * k + 1] = (int8_t)(uint8_t)((uint16_t)q8[k] & 0xff);
     }
+}
+
+/* The tool chain of signals/ (generateBaseband.sh:  <head> < pcm | interpolateSignal > x.iq).
+ * head HRO_SIG_IQ:  in = n int16 I,Q pairs at 8 kS/s, straight into interpolateSignal (interpolateSignal.cc:266-340)
+ *      HRO_SIG_DSB: signals/dsb.cc:38-47   x/4 on both rails
+ *      HRO_SIG_AM:  signals/am.cc:38-50    (x*0.8 + 65536)/4 on both rails (the *0.8 is a double multiply)
+ *      HRO_SIG_PM:  signals/pm.cc:39-55    angle = x/60000*pi (double multiply), (cos, sin)*16000
+ * Output: n*512 bytes of int8 I,Q at 2.048 MS/s. */
+size_t hro_tx_signals(hro_tx *tx, int head, const int16_t *in, size_t n, int8_t *iq)
+{
+    int16_t ibuf[256], qbuf[256];
+    for (size_t j = 0; j < n; j++) {
+        int16_t i16, q16;
+        switch (head) {
+        case HRO_SIG_IQ:
+            i16 = in[2 * j];
+            q16 = in[2 * j + 1];
+            break;
+        case HRO_SIG_DSB: {
+            volatile float s = (float)in[j];
+            s = s / 4;
+            i16 = q16 = f32_to_i16(s);
+            break;
+        }
+        case HRO_SIG_AM: {
+            volatile float s = (float)in[j];
+            s = (float)((double)s * 0.8);
+            s = s + 65536;
+            s = s / 4;
+            i16 = q16 = f32_to_i16(s);
+            break;
+        }
+        case HRO_SIG_PM: {
+            volatile float s = (float)in[j];
+            s = s / 60000;
+            s = (float)((double)s * M_PI);
+            /* C++ <math.h>: cos(float) is the float overload */
+            volatile float c = cosf(s) * 16000, q = sinf(s) * 16000;
+            i16 = f32_to_i16(c);
+            q16 = f32_to_i16(q);
+            break;
+        }
+        default: return 0;
+        }
+        tx_rail_run(&tx->sig[0], 0, 7, i16, ibuf);
+        tx_rail_run(&tx->sig[1], 0, 7, q16, qbuf);
+        emit_iq(ibuf, qbuf, 256, iq + j * 512);
+    }
+    return n * 512;
 }
 
 size_t hro_tx_accept(hro_tx *tx, int mode, const int16_t *pcm, size_t n, int8_t *iq)

@@ -178,11 +178,30 @@ class Oracle(_Base):
         self.lib.hro_taps.argtypes = [C.c_int, _i16p, C.c_int]
         self.lib.hro_atan2_table.argtypes = [_f32p]
         self.lib.hro_nco_tables.argtypes = [_f32p, _f32p]
+        self.lib.hro_tx_signals.restype = C.c_size_t
+        self.lib.hro_tx_signals.argtypes = [C.c_void_p, C.c_int, _i16p, C.c_size_t, _i8p]
         self.lib.hro_rx_set_rx_gain_db.argtypes = [C.c_void_p, C.c_uint32]
         self.lib.hro_rx_signal_magnitude.restype = C.c_uint32
         self.lib.hro_rx_signal_magnitude.argtypes = [C.c_void_p]
         self.lib.hro_rx_signal_allowed.restype = C.c_int
         self.lib.hro_rx_signal_allowed.argtypes = [C.c_void_p]
+
+    def run_tx_signals(self, head, samples, chunks=None) -> np.ndarray:
+        """signals/ tool chain (hro_tx_signals): head 0 = int16 I,Q pairs, 1 dsb, 2 am, 3 pm."""
+        samples = np.ascontiguousarray(samples, dtype=np.int16)
+        n = samples.size // 2 if head == 0 else samples.size
+        out = np.zeros(n * 512, dtype=np.int8)
+        h = self.tx_new()
+        try:
+            at = 0
+            for c in (chunks or [n]):
+                part = samples[2 * at:2 * (at + c)] if head == 0 else samples[at:at + c]
+                self.lib.hro_tx_signals(h, head, _ptr(part, _i16p), c, _ptr(out[at * 512:], _i8p))
+                at += c
+            assert at == n
+        finally:
+            self.tx_free(h)
+        return out
 
     def run_rx_squelch(self, mode, iq, threshold, gain_db=16, block=262144, demod_gain=None):
         """IqDataProcessor::acceptIqData block by block with a squelch threshold: returns

@@ -15,6 +15,7 @@ depend on numpy's random generator staying stable.  Reference calls made per vec
   tx_<mode>        <X>Modulator::acceptData, two calls (64 + 32 PCM samples)
   squelch_<mode>   IqDataProcessor::setSignalDetectThreshold(-40) + acceptIqData in 12 calls of 8192 bytes whose
                    level crosses the threshold; PCM plus what the reference's magnitude / state callbacks reported
+  sig_<head>       signals/<head> < pcm | signals/interpolateSignal (the programs themselves, oracle/_ref/)
   tables           quantised taps as the constructors built them, sha256 of the NCO tables
 """
 import hashlib
@@ -106,6 +107,26 @@ def main():
         out[f"squelch_{name}_pcm"] = pcm
         out[f"squelch_{name}_mag"] = mags
         out[f"squelch_{name}_open"] = opens
+
+    # ---- the stand-alone tools of signals/: heads piped into interpolateSignal, as generateBaseband.sh does ----
+    import subprocess
+    refdir = os.path.join(ROOT, "oracle", "_ref")
+
+    def pipe(data, *programs):
+        buf = data.tobytes()
+        for prog in programs:
+            buf = subprocess.run([os.path.join(refdir, prog)], input=buf, capture_output=True, check=True).stdout
+        return np.frombuffer(buf, dtype=np.int8).copy()
+
+    pcm = synth.tx_stream(96, stream=51, config=CONFIG, kind="sine")
+    pcm2 = synth.tx_stream(96, stream=52, config=CONFIG, kind="noise")
+    pairs = np.empty(192, dtype=np.int16)
+    pairs[0::2], pairs[1::2] = pcm, pcm2
+    out["sig_pcm"] = pcm2
+    out["sig_pairs"] = pairs
+    out["sig_iq8k_iq"] = pipe(pairs, "interpolateSignal")
+    for head in ("dsb", "am", "pm"):
+        out[f"sig_{head}_iq"] = pipe(pcm2, f"sig_{head}", "interpolateSignal")
 
     # ---- tables -------------------------------------------------------------------------
     for i, name in enumerate(TAPS):

@@ -25,6 +25,17 @@ def golden():
 # ------------------------------------------------------------------------------------------
 # oracle vs golden (CPU)
 # ------------------------------------------------------------------------------------------
+SIG_HEADS = {"iq8k": 0, "dsb": 1, "am": 2, "pm": 3}
+
+
+@pytest.mark.parametrize("head", list(SIG_HEADS))
+def test_oracle_signals_chain(oracle, golden, head):
+    """signals/ tool chain: <head> | interpolateSignal, two calls (state carries)."""
+    data = golden["sig_pairs"] if head == "iq8k" else golden["sig_pcm"]
+    got = oracle.run_tx_signals(SIG_HEADS[head], data, chunks=[64, 32])
+    assert np.array_equal(got, golden[f"sig_{head}_iq"])
+
+
 @pytest.mark.parametrize("name", ["am", "fm", "usb"])
 def test_oracle_squelch(oracle, golden, name):
     """Squelch gate: 12 reference calls of 8192 bytes, threshold -40 dBFS."""
@@ -162,3 +173,20 @@ def test_cuda_squelch(golden, name):
     assert np.array_equal(mags[0], golden[f"squelch_{name}_mag"])
     assert np.array_equal(opens[0], golden[f"squelch_{name}_open"])
     assert b.last_counts[0] == want.size and np.array_equal(got[0, :want.size], want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("head", list(SIG_HEADS))
+def test_cuda_signals_chain(golden, head):
+    from hackrfdiags_b200 import capi
+    mode = {"iq8k": capi.MODE_IQ8K, "dsb": capi.MODE_DSB, "am": capi.MODE_AM_PROTO, "pm": capi.MODE_PM}[head]
+    b = capi.Batch(1, capi.TX, 0)
+    b.set_mode(mode)
+    if head == "iq8k":
+        pairs = golden["sig_pairs"]
+        got = np.concatenate([b.tx(pairs[None, :128].copy(), n=64)[0], b.tx(pairs[None, 128:].copy(), n=32)[0]])
+    else:
+        pcm = golden["sig_pcm"]
+        got = np.concatenate([b.tx(pcm[None, :64].copy())[0], b.tx(pcm[None, 64:].copy())[0]])
+    err = np.abs(got.astype(np.int32) - golden[f"sig_{head}_iq"].astype(np.int32)).max()
+    assert err <= (1 if head == "pm" else 0), f"{head}: max abs err {err}"
