@@ -369,6 +369,43 @@ def run_mode_sweep(torch, capi, device, args, peak):
         sps = n_streams * n_pcm * 256 / (ms * 1e-3)
         res[f"tx_{MODE_NAMES[mode]}"] = {"streams": n_streams, "MS/s": round(sps / 1e6, 1), "ms": round(ms, 3),
                                          "hbm_frac": round(sps * BYTES_PER_OUT_SAMPLE_TX / 1e9 / peak, 4)}
+    res.update(run_next_rows(torch, capi, device, args, peak))
+    return res
+
+
+def run_next_rows(torch, capi, device, args, peak):
+    """SURVEY 8f rows built so far, measured like the chains above (4096 streams x 0.5 s, device-resident):
+    the squelched receive call (AM streams whose level closes the gate on every other pair of 64 ms blocks:
+    front end for every block, demodulator for the open ones) and the signals/ tool chain on the transmit side."""
+    res = {}
+    n_streams = args.sweep_streams
+    n_samples = int(args.sweep_seconds * FS) // 131072 * 131072
+    stream = torch.cuda.current_stream().cuda_stream
+    # squelch: bursty level (loud, loud, quiet, quiet, ...) so that the tracker opens, holds its tail and closes
+    b, iq, pcm = make_rx_batch(torch, capi, device, [(1, n_streams)], n_samples, seed=17)
+    blocks = n_samples // 131072
+    for k in range(blocks):
+        if (k // 2) % 2 == 1:
+            iq[:, k * 262144:(k + 1) * 262144].div_(32, rounding_mode="floor")
+    b.set_param(capi.PARAM_SQUELCH_THRESHOLD, -40.0)
+    call = lambda: b.rx_device(iq.data_ptr(), iq.shape[1], iq.stride(0), pcm.data_ptr(), pcm.stride(0), capi.ENTRY_2048K, stream)
+    ms, _ = time_calls(torch, [call], 5, 3)
+    _, allowed = b.squelch_report()
+    sps = n_streams * n_samples / (ms * 1e-3)
+    res["rx_am_squelched"] = {"streams": n_streams, "MS/s": round(sps / 1e6, 1), "ms": round(ms, 3),
+                              "hbm_frac": round(sps * BYTES_PER_IN_SAMPLE_RX / 1e9 / peak, 4),
+                              "blocks_per_call": int(blocks), "open_fraction": round(float(allowed.mean()), 3),
+                              "note": "gated path: front end + magnitudes for every block, one host read of the decisions, "
+                                      "demodulators block by block for the open ones"}
+    del b, iq, pcm
+    torch.cuda.empty_cache()
+    n_pcm = n_samples // 256
+    for name, mode in (("tx_sig_pm", capi.MODE_PM), ("tx_sig_dsb", capi.MODE_DSB)):
+        ms = bench_tx_mode(torch, capi, device, mode, n_streams, n_pcm, 5, 3, seed=19)
+        torch.cuda.empty_cache()
+        sps = n_streams * n_pcm * 256 / (ms * 1e-3)
+        res[name] = {"streams": n_streams, "MS/s": round(sps / 1e6, 1), "ms": round(ms, 3),
+                     "hbm_frac": round(sps * BYTES_PER_OUT_SAMPLE_TX / 1e9 / peak, 4)}
     return res
 
 
