@@ -252,6 +252,10 @@ def run_ours(args):
     torch.cuda.set_device(device)
     dist = None
     if world > 1:
+        # NCCL_DEBUG=VERSION makes NCCL print its version on STDOUT, in front of the one JSON line the
+        # contract asks for; keep warnings, drop the banner (INFO and above are left as the caller set them)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     peak, peak_src = measured_peak_gbs()
