@@ -50,8 +50,13 @@ namespace {
 
 constexpr int BATCH256 = 1024; // 256 kS/s samples per batch
 constexpr int IT_SAMPLES = 64; // 256 kS/s samples per warp iteration
-constexpr int RX_DEPTH = 2;    // input iterations in flight per warp (software prefetch)
-constexpr uint32_t RX_L2_AHEAD = 4; // ... and this many more pulled into L2 ahead of them (load_raw)
+// Register prefetch depth, in warp iterations.  ONE, on purpose: ptxas puts every global load of the loop on one
+// counting scoreboard (tools/sass_ctl.py), so with two buffers the consumer of the older load also waits for
+// the younger one and the second buffer buys nothing but register pressure (measured: depth 1 is 1-4 % faster
+// than depth 2 in all three kernels).  The distance comes from the L2 prefetch below instead.
+constexpr int RX_DEPTH = 1;
+constexpr int WB_DEPTH = 1;    // the same in rx_wbfm_kernel
+constexpr uint32_t RX_L2_AHEAD = 4; // ... and a 4 KiB chunk pulled into L2 this many iterations ahead (prefetch_chunk)
 
 // batches a tile > 0 runs ahead of its first stored output.  Look-back of each cascade in PCM
 // periods (one batch = 32): AM 10, FM 23, SSB 40 (the 31-tap Hilbert FIR at 8 kS/s),
@@ -122,6 +127,21 @@ __device__ __forceinline__ void halfband_stage(const uint32_t (&in)[N], uint32_t
     }
 }
 
+// The same stage on separate I-pair and Q-pair words {x_e, x_o, -, -}; `left` is the merged {I,I,Q,Q} word of
+// the lane before.
+template <int N>
+__device__ __forceinline__ void halfband_split(const uint32_t (&ini)[N], const uint32_t (&inq)[N], uint32_t left, uint32_t a,
+                                               uint32_t b, int (&pi)[N], int (&pq)[N])
+{
+    pi[0] = dp2a_lo_us(a, ini[0], dp2a_lo_us(b, left, 32768));
+    pq[0] = dp2a_lo_us(a, inq[0], dp2a_hi_us(b, left, 32768));
+#pragma unroll
+    for (int r = 1; r < N; r++) {
+        pi[r] = dp2a_lo_us(a, ini[r], dp2a_lo_us(b, ini[r - 1], 32768));
+        pq[r] = dp2a_lo_us(a, inq[r], dp2a_lo_us(b, inq[r - 1], 32768));
+    }
+}
+
 // 16 input samples (8 raw words {I,Q,I,Q}) -> one ring word {I0,I1,Q0,Q1} at 256 kS/s,
 // rotated by +Fs/4 (IqDataProcessor.cc:771-815) and narrowed like (int8_t) does.
 // t[] is the raw input already transposed to {I_e, I_o, Q_e, Q_o} (the caller does that first
@@ -130,18 +150,25 @@ __device__ __forceinline__ uint32_t front_end_iter(const uint32_t (&t)[8], FeCar
 {
     int pi8[8], pq8[8];
     halfband_stage<8>(t, from_left(t[7], c.t, lane), k.a0, k.b0, pi8, pq8);
-    uint32_t v[4];
+    // Stages 2 and 3 keep the I pairs and the Q pairs in separate words (pack_b2 puts a pair into bytes 0,1,
+    // which is all dp2a.lo reads): merging them into {I,I,Q,Q} words first would cost a third PRMT per word.
+    // Only the word that crosses to the next lane is merged, so the carried state keeps its layout.
+    uint32_t vi[4], vq[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++)
-        v[j] = merge16(pack_b2(pi8[2 * j], pi8[2 * j + 1]), pack_b2(pq8[2 * j], pq8[2 * j + 1]));
+    for (int j = 0; j < 4; j++) {
+        vi[j] = pack_b2(pi8[2 * j], pi8[2 * j + 1]);
+        vq[j] = pack_b2(pq8[2 * j], pq8[2 * j + 1]);
+    }
     int pi4[4], pq4[4];
-    halfband_stage<4>(v, from_left(v[3], c.v, lane), k.a1, k.b1, pi4, pq4);
-    uint32_t u[2];
+    halfband_split<4>(vi, vq, from_left(merge16(vi[3], vq[3]), c.v, lane), k.a1, k.b1, pi4, pq4);
+    uint32_t ui[2], uq[2];
 #pragma unroll
-    for (int j = 0; j < 2; j++)
-        u[j] = merge16(pack_b2(pi4[2 * j], pi4[2 * j + 1]), pack_b2(pq4[2 * j], pq4[2 * j + 1]));
+    for (int j = 0; j < 2; j++) {
+        ui[j] = pack_b2(pi4[2 * j], pi4[2 * j + 1]);
+        uq[j] = pack_b2(pq4[2 * j], pq4[2 * j + 1]);
+    }
     int pi2[2], pq2[2];
-    halfband_stage<2>(u, from_left(u[1], c.u, lane), k.a2, k.b2, pi2, pq2);
+    halfband_split<2>(ui, uq, from_left(merge16(ui[1], uq[1]), c.u, lane), k.a2, k.b2, pi2, pq2);
     // rotation: this lane's samples are number 2*lane and 2*lane+1 of the iteration, so
     // their phases are {0,1} on even lanes and {2,3} on odd lanes:
     //   0:(x,y) 1:(-y,x) 2:(-x,-y) 3:(y,-x).  Negating "acc>>16" is (65535-acc)>>16.
@@ -233,16 +260,19 @@ __device__ __forceinline__ typename RawOf<ENTRY>::type load_raw(const int8_t *sr
 {
     const uint32_t o = min(off, off_last);
     if constexpr (ENTRY == 0) {
-        // ptxas puts every global load of the loop on ONE counting scoreboard (tools/sass_ctl.py), so the
-        // consumer of an older prefetch also waits for the load issued just before it: the register
-        // prefetch alone hides about half an iteration, not RX_DEPTH.  An L2 prefetch needs no register and
-        // no scoreboard: it pulls the lines RX_L2_AHEAD iterations further on from DRAM, and the LDG that
-        // follows hits in L2 (a few hundred cycles instead of a DRAM round trip under load).
-        prefetch_l2(src + min(off + RX_L2_AHEAD * IT_SAMPLES * 16, off_last));
         return ldg_stream_256(src + o);
     }
     else
         return __ldg(reinterpret_cast<const uint32_t *>(src + o));
+}
+
+// An L2 prefetch needs no register and no scoreboard: once every four iterations the warp pulls the 4 KiB it
+// will read RX_L2_AHEAD iterations from now out of DRAM (lane l takes the 128-byte line l), and the LDG that
+// follows later hits in L2 (a few hundred cycles instead of a DRAM round trip under load).
+// pf is the lane's own next load offset (warp base + 32 * lane).
+__device__ __forceinline__ void prefetch_chunk(const int8_t *src, uint32_t pf, uint32_t pf_last, int lane)
+{
+    prefetch_l2(src + min(pf + 96u * (uint32_t)lane + RX_L2_AHEAD * IT_SAMPLES * 16, pf_last));
 }
 
 // ------------------------------------------------------------------------------------
@@ -338,6 +368,7 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
 #pragma unroll
                 for (int r = 0; r < 8; r++) t[r] = __byte_perm(b.v[r], 0, 0x3120);
                 b = load_raw<ENTRY>(src, pf, pf_last); // in place: b is dead now
+                if ((it & 3) == 0) prefetch_chunk(src, pf, pf_last, lane);
                 word = front_end_iter(t, fc, fk, lane);
             } else {
                 word = __byte_perm(b, 0, 0x3120);
@@ -357,16 +388,8 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
                 sm.r256[14 + widx] = word;
             }
         };
-        // Full batches have 16 iterations, a multiple of RX_DEPTH, so the buffers keep their
-        // roles from batch to batch; only the tile's last batch can leave a remainder.
-        uint32_t it = 0;
-        for (; it + RX_DEPTH <= n_it; it += RX_DEPTH) {
-#pragma unroll
-            for (int d = 0; d < RX_DEPTH; d++) step(buf[d], it + d);
-        }
-#pragma unroll
-        for (int d = 0; d < RX_DEPTH - 1; d++)
-            if (it + d < n_it) step(buf[d], it + d);
+#pragma unroll 2
+        for (uint32_t it = 0; it < n_it; it++) step(buf[0], it);
         __syncwarp();
 
         const int n64 = nb / 4, n16 = nb / 16, n8 = nb / 32;
@@ -607,7 +630,7 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
     bool narrow_fast = false;
     constexpr uint32_t BPS = ENTRY == 0 ? 16 : 2;
     uint32_t pf = 0, pf_last = 0, last_active = 32;
-    Raw buf[RX_DEPTH];
+    Raw buf[WB_DEPTH];
     if (!chain_warp && live) {
         if (first) {
             fc.t = st.fe_t; fc.v = st.fe_v; fc.u = st.fe_u;
@@ -630,7 +653,7 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
         pf = (start + 2 * lane) * BPS;
         pf_last = (end - 2) * BPS;
 #pragma unroll
-        for (int d = 0; d < RX_DEPTH; d++) {
+        for (int d = 0; d < WB_DEPTH; d++) {
             buf[d] = load_raw<ENTRY>(src, pf, pf_last);
             pf += IT_SAMPLES * BPS;
         }
@@ -693,15 +716,14 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
         const uint32_t nb = min((uint32_t)WB_STEP, end - done);
         const uint32_t n_it = (nb + IT_SAMPLES - 1) / IT_SAMPLES;
         last_active = min(32u, (nb - (n_it - 1) * IT_SAMPLES) / 2);
+        if constexpr (ENTRY == 0) prefetch_chunk(src, pf, pf_last, lane); // a step is four iterations = 4 KiB
         float *dst = sm.f[t & 1][row];
-        uint32_t i = 0;
-        for (; i + RX_DEPTH <= n_it; i += RX_DEPTH) {
+        if (n_it == WB_STEP / IT_SAMPLES) { // a full step, unrolled: the in-place refill of buf needs no register moves
 #pragma unroll
-            for (int d = 0; d < RX_DEPTH; d++) iter(buf[d], dst + (i + d) * IT_SAMPLES);
+            for (uint32_t i = 0; i < WB_STEP / IT_SAMPLES; i++) iter(buf[0], dst + i * IT_SAMPLES);
+        } else {
+            for (uint32_t i = 0; i < n_it; i++) iter(buf[0], dst + i * IT_SAMPLES);
         }
-#pragma unroll
-        for (int d = 0; d < RX_DEPTH - 1; d++)
-            if (i + d < n_it) iter(buf[d], dst + (i + d) * IT_SAMPLES);
         __syncwarp();
     };
 

@@ -1,3 +1,6 @@
 #!/bin/bash
-# tools/exp_run.sh -- on the GPU box: time the variant builds (see exp_build.sh); every run under `timeout`
-for n in 16 128 144; do echo "exp $n:"; HRD_LIB=build/exp/libhrd_b200_$n.so timeout 60 python tools/prof_run.py tx wbfm 4096 0.5 6 2>&1 | tail -1; done
+# tools/exp_run.sh -- on the GPU box: time variant builds against the product build; every run under `timeout`
+run() { HRD_LIB=$1 timeout 60 python tools/prof_run.py $2 $3 4096 0.5 8 2>&1 | tail -1; }
+echo "product:"; for c in "rx am" "rx fm" "rx wbfm"; do run "" $c; done
+echo "RX_DEPTH=1:"; for c in "rx am" "rx fm"; do run build/exp/libhrd_b200_RX1.so $c; done
+echo "WB_DEPTH=1:"; run build/exp/libhrd_b200_WB1.so rx wbfm
