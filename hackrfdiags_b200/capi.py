@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("HRD_LIB") or os.path.join(_HERE, "libhrd_b200.so")
 
 RX, TX = 0, 1
 MODE_NONE, MODE_AM, MODE_FM, MODE_WBFM, MODE_LSB, MODE_USB = range(6)
-MODE_IQ8K, MODE_DSB, MODE_PM, MODE_AM_PROTO = 6, 7, 8, 9  # Tx only: the tool chain of signals/
+MODE_IQ8K, MODE_DSB, MODE_PM, MODE_AM_PROTO, MODE_FM_PROTO = 6, 7, 8, 9, 10  # Tx only: the tool chain of signals/
 (PARAM_AM_GAIN, PARAM_FM_GAIN, PARAM_WBFM_GAIN, PARAM_SSB_GAIN,
  PARAM_AM_INDEX, PARAM_FM_DEV, PARAM_WBFM_DEV, PARAM_SQUELCH_THRESHOLD, PARAM_RX_GAIN_DB) = range(9)
 UNIT_AM, UNIT_FM, UNIT_WBFM, UNIT_SSB, UNIT_FRONT_END, UNIT_ALL, UNIT_SIGNALS = range(7)

@@ -259,7 +259,8 @@ int kernel_kind_of_mode(int mode)
     case HRD_MODE_IQ8K:
     case HRD_MODE_DSB:
     case HRD_MODE_PM:
-    case HRD_MODE_AM_PROTO: return hrd::K_IQ;
+    case HRD_MODE_AM_PROTO:
+    case HRD_MODE_FM_PROTO: return hrd::K_IQ;
     default: return hrd::K_NONE;
     }
 }
@@ -282,6 +283,8 @@ struct hrd_batch {
     void *d_wbv = nullptr;                 // Rx WBFM: verification pairs, [n][n_tiles] float2
     void *d_fmph = nullptr;                // Tx FM: NCO phase per PCM sample, [n_fm][n8]
     size_t d_fmph_cap = 0;
+    void *d_sigph = nullptr;               // Tx signals/fm.cc head: theta per PCM sample, [n_iq][n8]
+    size_t d_sigph_cap = 0;
     size_t d_wbv_cap = 0;
     uint32_t *d_wbflag = nullptr;          // [0] = streams to re-run in this call; +2 words: 64-bit total
     int32_t *d_wbrerun = nullptr;          // their ids, [n]
@@ -573,6 +576,7 @@ int hrd_destroy(hrd_batch_t *b)
     cudaFree(b->d_pre);
     cudaFree(b->d_wbv);
     cudaFree(b->d_fmph);
+    cudaFree(b->d_sigph);
     cudaFree(b->d_wbflag);
     cudaFree(b->d_wbrerun);
     cudaFree(b->d_ids);
@@ -607,7 +611,7 @@ int hrd_set_mode(hrd_batch_t *b, int stream, int mode)
 {
     int rc = check_stream_arg(b, stream);
     if (rc) return rc;
-    if (mode < HRD_MODE_NONE || mode > (b->kind == HRD_TX ? HRD_MODE_AM_PROTO : HRD_MODE_USB))
+    if (mode < HRD_MODE_NONE || mode > (b->kind == HRD_TX ? HRD_MODE_FM_PROTO : HRD_MODE_USB))
         return fail(HRD_EINVAL, "bad mode %d", mode);
     const int lo = stream == HRD_ALL_STREAMS ? 0 : stream, hi = stream == HRD_ALL_STREAMS ? b->n : stream + 1;
     for (int s = lo; s < hi; s++) {
@@ -732,7 +736,7 @@ int hrd_reset(hrd_batch_t *b, int stream, int unit)
             if (!rc) rc = zero_state(b, stream, RANGE(TxState, ssb_h8, pad));
             break;
         case HRD_UNIT_WBFM: rc = zero_state(b, stream, RANGE(TxState, wb, fm_phase)); break; // phase kept
-        case HRD_UNIT_SIGNALS: rc = zero_state(b, stream, offsetof(TxState, sig), sizeof(hrd::TxRail8)); break;
+        case HRD_UNIT_SIGNALS: rc = zero_state(b, stream, offsetof(TxState, sig), sizeof(hrd::TxRail8) + sizeof(float)); break;
         case HRD_UNIT_ALL: rc = zero_state(b, stream, 0, sizeof(TxState)); break;
         default: return fail(HRD_EINVAL, "bad unit %d", unit);
         }
@@ -1244,6 +1248,18 @@ int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size
             int e = hrd::launch_tx_fm_phase(p, ks);
             if (e) return fail(HRD_ECUDA, "tx FM phase launch failed: %s", cudaGetErrorString((cudaError_t)e));
             b->launches++;
+        }
+        if (k == hrd::K_IQ) { // signals/fm.cc streams: their theta recurrence first (own scratch: K_FM may run beside)
+            bool any = false;
+            for (int i = 0; i < b->n; i++) any |= b->mode[(size_t)i] == HRD_MODE_FM_PROTO;
+            if (any) {
+                rc = ensure_cap(&b->d_sigph, &b->d_sigph_cap, sizeof(float) * (size_t)p.n_streams * n_per_stream);
+                if (rc) return rc;
+                p.fm_phase = (float *)b->d_sigph;
+                int e = hrd::launch_tx_sig_phase(p, ks);
+                if (e) return fail(HRD_ECUDA, "tx signals phase launch failed: %s", cudaGetErrorString((cudaError_t)e));
+                b->launches++;
+            }
         }
         int e = hrd::launch_tx(k, p, ks);
         if (e) return fail(HRD_ECUDA, "tx launch (kind %d) failed: %s", k, cudaGetErrorString((cudaError_t)e));

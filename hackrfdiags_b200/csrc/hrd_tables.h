@@ -102,6 +102,8 @@ struct TxState {
     uint32_t ssb_h8[30];   // PCM/2 history for the delay line / Hilbert FIR
     uint32_t pad[2];
     TxRail8 sig;           // signals/interpolateSignal.cc: its I and Q interpolator trees
+    float sig_theta;       // signals/fm.cc: theta
+    uint32_t pad2[3];
 };
 
 // ---------------------------------------------------------------- kernel parameters
@@ -181,7 +183,7 @@ struct TxParams {
 enum { K_NONE = 0, K_AM = 1, K_FM = 2, K_WBFM = 3, K_SSB = 4,
        K_IQ = 5 /* Tx only: the tool chain of signals/ (heads + interpolateSignal) */, K_COUNT = 6 };
 // HRD_MODE_* values of the signals/ heads (include/hrd.h), as the kernel sees them
-enum { SIG_MODE_IQ8K = 6, SIG_MODE_DSB = 7, SIG_MODE_PM = 8, SIG_MODE_AM_PROTO = 9 };
+enum { SIG_MODE_IQ8K = 6, SIG_MODE_DSB = 7, SIG_MODE_PM = 8, SIG_MODE_AM_PROTO = 9, SIG_MODE_FM_PROTO = 10 };
 
 // Items per CTA for the chain-warp kernels (at most `cap`): the smallest count that still needs no
 // more waves of CTAs than `cap` per CTA would, so that the last wave is as full as the others.
@@ -216,6 +218,7 @@ int launch_squelch_scatter(const int16_t *scratch, size_t scratch_stride, int16_
                            cudaStream_t s);
 int launch_tx(int kind, const TxParams &p, cudaStream_t s);
 int launch_tx_fm_phase(const TxParams &p, cudaStream_t s);   // FM streams, before their launch_tx
+int launch_tx_sig_phase(const TxParams &p, cudaStream_t s);  // signals/fm.cc streams of a K_IQ launch, before it
 int tx_resident_warps_per_sm(int kind);                      // occupancy of tx_kernel<kind> (cached)
 int tx_halo_samples(int kind);                               // PCM samples a tile > 0 runs ahead
 

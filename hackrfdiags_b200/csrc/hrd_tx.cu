@@ -288,6 +288,8 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxPara
             } else { // pm.cc:39-55: angle = x / 60000 * M_PI (double multiply), cosf/sinf, * 16000
                 float a = __fdiv_rn((float)x, 60000.f);
                 a = (float)((double)a * 3.14159265358979323846);
+                // fm.cc:41-62: theta comes from the serial pre-pass (tx_fm_phase_kernel<true>)
+                if (sub == SIG_MODE_FM_PROTO) a = (lane < nb) ? p.fm_phase[(size_t)slot * p.n8 + done + lane] : 0.f;
                 double sd, cd;
                 sincos((double)a, &sd, &cd); // evaluated in double and rounded (DESIGN.md "the one tolerance")
                 head = pack16(f32_to_i16(__fmul_rn((float)cd, 16000.f)), f32_to_i16(__fmul_rn((float)sd, 16000.f)));
@@ -751,6 +753,11 @@ struct SmemFp {
     uint32_t big[3][FP_ROWS];            // per row and chunk: some |step| >= 3 (see tx_wbfm_kernel's chain)
 };
 
+// PROTO: the same machine for the prototype FM head of signals/fm.cc:41-62 (streams of a K_IQ launch in mode
+// FM_PROTO; the others' rows stay idle): step = x/65536*3.5 in float, theta += step, ONE wrap at +-2*pi with the
+// reference's double expression (|step| < 1.75, so its while loops run at most once), and the value stored is
+// theta AFTER the update, which is what fm.cc takes the cosine of.
+template <bool PROTO>
 __global__ void __launch_bounds__((FP_WORKERS + 1) * 32) tx_fm_phase_kernel(const TxParams p)
 {
     __shared__ SmemFp sm;
@@ -764,9 +771,11 @@ __global__ void __launch_bounds__((FP_WORKERS + 1) * 32) tx_fm_phase_kernel(cons
     float phase = 0.f;
     int sid_chain = 0;
     const bool live = lane < rows_live; // chain warp: this lane has a stream
+    bool live_row = live; // PROTO: only the streams whose head is fm.cc
     if (chain_warp && live) {
         sid_chain = p.stream_ids[row0 + lane];
-        phase = p.state[sid_chain].fm_phase;
+        if (PROTO) live_row = p.mode_of[sid_chain] == SIG_MODE_FM_PROTO;
+        phase = PROTO ? p.state[sid_chain].sig_theta : p.state[sid_chain].fm_phase;
     }
 
     // workers: PCM of chunk c -> phase steps, rows warp, warp + FP_WORKERS, ...  All loads first (the rows
@@ -778,7 +787,8 @@ __global__ void __launch_bounds__((FP_WORKERS + 1) * 32) tx_fm_phase_kernel(cons
     for (int i = 0; i < FP_RPW; i++) {
         const int r = warp + i * FP_WORKERS;
         w_sid[i] = (!chain_warp && r < rows_live) ? p.stream_ids[row0 + r] : -1;
-        w_dev[i] = w_sid[i] >= 0 ? p.param[w_sid[i]] : 0.f;
+        if (PROTO && w_sid[i] >= 0 && p.mode_of[w_sid[i]] != SIG_MODE_FM_PROTO) w_sid[i] = -1;
+        w_dev[i] = (!PROTO && w_sid[i] >= 0) ? p.param[w_sid[i]] : 0.f;
     }
     auto produce = [&](uint32_t c) {
         int x[FP_RPW][FP_CH / 32];
@@ -798,9 +808,14 @@ __global__ void __launch_bounds__((FP_WORKERS + 1) * 32) tx_fm_phase_kernel(cons
             bool big = false;
 #pragma unroll
             for (int j = 0; j < FP_CH / 32; j++) {
-                const float f = __fdiv_rn(__fmul_rn(w_dev[i], (float)x[i][j]), 32768.f);
-                // PhaseAccumulator::setFrequency (:95-107): (float)((2*M_PI*f)/8000.0) in double
-                const float step = div_const_to_float<8000>(2.0 * 3.14159265358979323846 * (double)f);
+                float step;
+                if (PROTO) {
+                    step = __fmul_rn(__fdiv_rn((float)x[i][j], 65536.f), 3.5f); // fm.cc:43-45
+                } else {
+                    const float f = __fdiv_rn(__fmul_rn(w_dev[i], (float)x[i][j]), 32768.f);
+                    // PhaseAccumulator::setFrequency (:95-107): (float)((2*M_PI*f)/8000.0) in double
+                    step = div_const_to_float<8000>(2.0 * 3.14159265358979323846 * (double)f);
+                }
                 sm.t[c % 3][r][lane + 32 * j] = step;
                 big |= !(fabsf(step) < 3.0f);
             }
@@ -812,6 +827,18 @@ __global__ void __launch_bounds__((FP_WORKERS + 1) * 32) tx_fm_phase_kernel(cons
     auto walk = [&](uint32_t c) {
         const int nb = (int)min((uint32_t)FP_CH, p.n8 - c * FP_CH);
         float *row = sm.t[c % 3][lane];
+        if (PROTO) {
+            if (!live_row) return;
+            for (int n = 0; n < nb; n++) {
+                // theta = theta + thetaNew; while (theta > 2*M_PI) theta -= 2*M_PI; (and the mirror image).
+                // (double)a > 2*M_PI  <=>  a >= fl32(2*pi), the float just above 2*pi; |a| < 2*pi + 1.75: one wrap.
+                const float a = __fadd_rn(phase, row[n]);
+                const float w = (float)((double)a - copysign(2.0 * 3.14159265358979323846, (double)a));
+                phase = fabsf(a) >= HRD_2PI_HI ? w : a;
+                row[n] = phase;
+            }
+            return;
+        }
         const bool slow = __any_sync(HRD_FULL_MASK, live && (sm.big[c % 3][lane] != 0 || !(fabsf(phase) < HRD_PI_UP)));
         if (!live) return;
         if (!slow && nb == FP_CH) {
@@ -857,7 +884,7 @@ __global__ void __launch_bounds__((FP_WORKERS + 1) * 32) tx_fm_phase_kernel(cons
         __syncthreads();
     }
     if (!chain_warp) flush(n_chunks - 1);
-    if (chain_warp && live) p.state_out[sid_chain].fm_phase = phase;
+    if (chain_warp && live && live_row) (PROTO ? p.state_out[sid_chain].sig_theta : p.state_out[sid_chain].fm_phase) = phase;
 }
 
 // mode NONE: BasebandDataProcessor.cc:689-694 fills the block with 64
@@ -910,7 +937,15 @@ int launch_tx_fm_phase(const TxParams &p, cudaStream_t s)
 {
     if (p.n_streams <= 0 || p.n8 == 0) return 0;
     const int grid = (p.n_streams + FP_ROWS - 1) / FP_ROWS;
-    tx_fm_phase_kernel<<<grid, (FP_WORKERS + 1) * 32, 0, s>>>(p);
+    tx_fm_phase_kernel<false><<<grid, (FP_WORKERS + 1) * 32, 0, s>>>(p);
+    return (int)cudaGetLastError();
+}
+
+int launch_tx_sig_phase(const TxParams &p, cudaStream_t s)
+{
+    if (p.n_streams <= 0 || p.n8 == 0) return 0;
+    const int grid = (p.n_streams + FP_ROWS - 1) / FP_ROWS;
+    tx_fm_phase_kernel<true><<<grid, (FP_WORKERS + 1) * 32, 0, s>>>(p);
     return (int)cudaGetLastError();
 }
 

@@ -17,7 +17,7 @@
 //
 //   hrd_replay rx <am|fm|wbfm|lsb|usb> [-s squelch_dBFS] [-g demod_gain] <out_dir> <file.iq>...   -> <out_dir>/<name>.pcm
 //   hrd_replay fe <out_dir> <file.iq>...                                                           -> <out_dir>/<name>.iq256k
-//   hrd_replay tx <am|fm|wbfm|lsb|usb|dsb|pm> [-p index_or_deviation] <out_dir> <file.pcm>...      -> <out_dir>/<name>.iq
+//   hrd_replay tx <am|fm|wbfm|lsb|usb|dsb|pm|amproto|fmproto> [-p index_or_deviation] <out_dir> <file.pcm>...      -> <out_dir>/<name>.iq
 // There is no CPU fallback: without a B200 hrd_create fails and so does this program.
 #include <stdint.h>
 #include <stdio.h>
@@ -40,7 +40,8 @@ static int mode_of(const char *name, bool tx)
 {
     static const struct { const char *n; int m; bool tx_only; } table[] = {
         {"am", HRD_MODE_AM, false}, {"fm", HRD_MODE_FM, false}, {"wbfm", HRD_MODE_WBFM, false}, {"lsb", HRD_MODE_LSB, false},
-        {"usb", HRD_MODE_USB, false}, {"dsb", HRD_MODE_DSB, true}, {"pm", HRD_MODE_PM, true}};
+        {"usb", HRD_MODE_USB, false}, {"dsb", HRD_MODE_DSB, true}, {"pm", HRD_MODE_PM, true},
+        {"amproto", HRD_MODE_AM_PROTO, true}, {"fmproto", HRD_MODE_FM_PROTO, true}};
     for (const auto &e : table)
         if (!strcmp(name, e.n) && (tx || !e.tx_only)) return e.m;
     fprintf(stderr, "hrd_replay: unknown mode '%s'\n", name);

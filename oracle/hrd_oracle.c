@@ -776,6 +776,7 @@ struct hro_tx {
     fir16 ssb_delay, ssb_hilbert;
     /* signals/interpolateSignal.cc: the stand-alone I and Q interpolator trees */
     tx_rail sig[2];
+    float sig_theta; /* signals/fm.cc: theta */
 };
 
 hro_tx *hro_tx_new(void)
@@ -854,6 +855,7 @@ static void emit_iq(const int16_t *i8, const int16_t *q8, int n, int8_t *out)
  *      HRO_SIG_DSB: signals/dsb.cc:38-47   x/4 on both rails
  *      HRO_SIG_AM:  signals/am.cc:38-50    (x*0.8 + 65536)/4 on both rails (the *0.8 is a double multiply)
  *      HRO_SIG_PM:  signals/pm.cc:39-55    angle = x/60000*pi (double multiply), (cos, sin)*16000
+ *      HRO_SIG_FM:  signals/fm.cc:41-62    theta += x/65536*3.5, wrapped at +-2*pi, (cos, sin)*16000
  * Output: n*512 bytes of int8 I,Q at 2.048 MS/s. */
 size_t hro_tx_signals(hro_tx *tx, int head, const int16_t *in, size_t n, int8_t *iq)
 {
@@ -885,6 +887,19 @@ size_t hro_tx_signals(hro_tx *tx, int head, const int16_t *in, size_t n, int8_t 
             s = (float)((double)s * M_PI);
             /* C++ <math.h>: cos(float) is the float overload */
             volatile float c = cosf(s) * 16000, q = sinf(s) * 16000;
+            i16 = f32_to_i16(c);
+            q16 = f32_to_i16(q);
+            break;
+        }
+        case HRO_SIG_FM: { /* signals/fm.cc:41-62: kF = 3.5, theta wrapped at +-2*pi with double constants */
+            volatile float tn = (float)in[j];
+            tn = tn / 65536;
+            tn = tn * 3.5f;
+            volatile float theta = tx->sig_theta + tn;
+            while (theta > (2 * M_PI)) theta = (float)(theta - (2 * M_PI));
+            while (theta < (-(2 * M_PI))) theta = (float)(theta + (2 * M_PI));
+            tx->sig_theta = theta;
+            volatile float c = cosf(theta) * 16000, q = sinf(theta) * 16000;
             i16 = f32_to_i16(c);
             q16 = f32_to_i16(q);
             break;

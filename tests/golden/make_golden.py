@@ -125,7 +125,7 @@ def main():
     out["sig_pcm"] = pcm2
     out["sig_pairs"] = pairs
     out["sig_iq8k_iq"] = pipe(pairs, "interpolateSignal")
-    for head in ("dsb", "am", "pm"):
+    for head in ("dsb", "am", "pm", "fm"):
         out[f"sig_{head}_iq"] = pipe(pcm2, f"sig_{head}", "interpolateSignal")
 
     # ---- tables -------------------------------------------------------------------------

@@ -25,7 +25,7 @@ def golden():
 # ------------------------------------------------------------------------------------------
 # oracle vs golden (CPU)
 # ------------------------------------------------------------------------------------------
-SIG_HEADS = {"iq8k": 0, "dsb": 1, "am": 2, "pm": 3}
+SIG_HEADS = {"iq8k": 0, "dsb": 1, "am": 2, "pm": 3, "fm": 4}
 
 
 @pytest.mark.parametrize("head", list(SIG_HEADS))
@@ -179,7 +179,8 @@ def test_cuda_squelch(golden, name):
 @pytest.mark.parametrize("head", list(SIG_HEADS))
 def test_cuda_signals_chain(golden, head):
     from hackrfdiags_b200 import capi
-    mode = {"iq8k": capi.MODE_IQ8K, "dsb": capi.MODE_DSB, "am": capi.MODE_AM_PROTO, "pm": capi.MODE_PM}[head]
+    mode = {"iq8k": capi.MODE_IQ8K, "dsb": capi.MODE_DSB, "am": capi.MODE_AM_PROTO, "pm": capi.MODE_PM,
+            "fm": capi.MODE_FM_PROTO}[head]
     b = capi.Batch(1, capi.TX, 0)
     b.set_mode(mode)
     if head == "iq8k":
@@ -189,4 +190,4 @@ def test_cuda_signals_chain(golden, head):
         pcm = golden["sig_pcm"]
         got = np.concatenate([b.tx(pcm[None, :64].copy())[0], b.tx(pcm[None, 64:].copy())[0]])
     err = np.abs(got.astype(np.int32) - golden[f"sig_{head}_iq"].astype(np.int32)).max()
-    assert err <= (1 if head == "pm" else 0), f"{head}: max abs err {err}"
+    assert err <= (1 if head in ("pm", "fm") else 0), f"{head}: max abs err {err}"

@@ -8,7 +8,7 @@ from cpu_checkers import Oracle
 from hackrfdiags_b200 import capi, synth
 
 pytestmark = pytest.mark.gpu
-HEAD_OF_MODE = {capi.MODE_IQ8K: 0, capi.MODE_DSB: 1, capi.MODE_AM_PROTO: 2, capi.MODE_PM: 3}
+HEAD_OF_MODE = {capi.MODE_IQ8K: 0, capi.MODE_DSB: 1, capi.MODE_AM_PROTO: 2, capi.MODE_PM: 3, capi.MODE_FM_PROTO: 4}
 
 
 def test_mixed_batch_of_heads_and_modulators_streaming():
@@ -16,7 +16,8 @@ def test_mixed_batch_of_heads_and_modulators_streaming():
     lengths (tiles, halos and carried state), rows of 2n int16 because the batch holds I,Q-pair streams."""
     oracle = Oracle()
     modes = [capi.MODE_IQ8K, capi.MODE_DSB, capi.MODE_AM_PROTO, capi.MODE_PM, capi.MODE_PM, capi.MODE_IQ8K,
-             capi.MODE_DSB, capi.MODE_AM_PROTO, capi.MODE_LSB, capi.MODE_AM]
+             capi.MODE_DSB, capi.MODE_AM_PROTO, capi.MODE_LSB, capi.MODE_AM, capi.MODE_FM_PROTO, capi.MODE_FM,
+             capi.MODE_FM_PROTO]
     n_total, cuts = 800, [0, 320, 352, 800]
     kinds = ["sine", "noise", "square", None]
     pcm = [synth.tx_stream(n_total, stream=i, config=9, kind=kinds[i % 4]) for i in range(len(modes))]
@@ -45,7 +46,7 @@ def test_mixed_batch_of_heads_and_modulators_streaming():
         else:
             want = oracle.run_tx(m, pcm[i])
         err = np.abs(got[i].astype(np.int32) - want.astype(np.int32)).max()
-        assert err <= (1 if m == capi.MODE_PM else 0), f"stream {i} mode {m}: max abs err {err}"
+        assert err <= (1 if m in (capi.MODE_PM, capi.MODE_FM_PROTO, capi.MODE_FM) else 0), f"stream {i} mode {m}: max abs err {err}"
 
 
 def test_many_streams_tiled():

@@ -13,7 +13,7 @@ from hackrfdiags_b200 import synth
 REF = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_ref")
 needs_tools = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "interpolateSignal")),
                                  reason="oracle/_ref tools not built (no /root/reference)")
-HEADS = {"dsb": 1, "am": 2, "pm": 3}
+HEADS = {"dsb": 1, "am": 2, "pm": 3, "fm": 4}
 
 
 def _pipe(data: np.ndarray, *programs) -> np.ndarray:
