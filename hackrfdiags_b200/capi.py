@@ -30,6 +30,9 @@ OPT_RX_TILE_BATCHES, OPT_RX_WBFM_TILING, OPT_TX_TILE_SAMPLES, OPT_PROFILE, OPT_D
 EXPORTS = [
     "hrd_abi_version", "hrd_create", "hrd_destroy", "hrd_last_error", "hrd_set_mode", "hrd_get_mode",
     "hrd_set_param", "hrd_get_param", "hrd_reset", "hrd_set_option", "hrd_get_option", "hrd_rx_process", "hrd_rx_front_end", "hrd_rx_squelch_report", "hrd_tx_process",
+    "hrd_pcm_ring_create", "hrd_pcm_ring_destroy", "hrd_pcm_ring_start", "hrd_pcm_ring_write", "hrd_pcm_ring_read_all",
+    "hrd_pcm_ring_stats", "hrd_tx_from_ring", "hrd_iq_queue_create", "hrd_iq_queue_destroy", "hrd_iq_queue_push",
+    "hrd_iq_queue_pop_all", "hrd_iq_queue_stats", "hrd_rx_from_queue",
     "hrd_synchronize", "hrd_launch_count", "hrd_wbfm_fallback_count", "hrd_kernel_ms", "hrd_get_table", "hrd_get_taps", "hrd_state_bytes_per_stream",
 ]
 

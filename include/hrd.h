@@ -206,6 +206,42 @@ int hrd_rx_squelch_report(hrd_batch_t *b, uint32_t *magnitudes, uint8_t *allowed
 int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size_t pcm_stride,
                    int8_t *iq, size_t iq_stride, int mem, void *cuda_stream);
 
+/* ---- ingest / egress adapters (host side; hrd_adapt.cc) ---------------- */
+/*
+ * The reference puts a 16-slot block pool + queue between the libusb thread and IqDataProcessor (DataConsumer,
+ * src_diags/DataConsumer.cc:219-261, 319-351) and a 16-block PCM ring with drop / repeat rate matching between
+ * the stdin reader thread and the transmit callback (BasebandDataProcessor.cc:416-433, 482-605).  These are the
+ * same structures for MANY streams: producers push per stream, the consumer takes one block of EVERY stream per
+ * round -- the row matrix one hrd_rx_process / hrd_tx_process call reads.  One producer and one consumer thread
+ * may run concurrently, as in the reference.
+ */
+typedef struct hrd_pcm_ring hrd_pcm_ring_t;
+typedef struct hrd_iq_queue hrd_iq_queue_t;
+int hrd_pcm_ring_create(int n_streams, hrd_pcm_ring_t **out);
+int hrd_pcm_ring_destroy(hrd_pcm_ring_t *r);
+/* BasebandDataProcessor::start / stop: an idle stream sends zero blocks (BasebandDataProcessor.cc:588-601) */
+int hrd_pcm_ring_start(hrd_pcm_ring_t *r, int stream, int running);
+/* the reader thread's step: getNextUnfilledBuffer + fread of up to 512 samples (:416-433, :862-865) */
+int hrd_pcm_ring_write(hrd_pcm_ring_t *r, int stream, const int16_t *pcm, uint32_t n_samples);
+/* the transmit callback's getNextFilledBuffer (:482-605) for every stream: rows[s*row_stride .. +512); slots
+ * (optional) gets the ring slot each stream sent, -1 for the zero block */
+int hrd_pcm_ring_read_all(hrd_pcm_ring_t *r, int16_t *rows, size_t row_stride, int32_t *slots);
+/* buffersProduced, buffersConsumed, pcmBlocksDropped, pcmBlocksAdded */
+int hrd_pcm_ring_stats(hrd_pcm_ring_t *r, int stream, uint32_t out[4]);
+/* BasebandDataProcessor::getIqData for every stream of a Tx batch: one ring block each -> 262144 bytes each */
+int hrd_tx_from_ring(hrd_batch_t *b, hrd_pcm_ring_t *r, int8_t *iq, size_t iq_stride, int mem, void *cuda_stream);
+int hrd_iq_queue_create(int n_streams, hrd_iq_queue_t **out);
+int hrd_iq_queue_destroy(hrd_iq_queue_t *q);
+/* DataConsumer::acceptData (:219-261): at most 262144 bytes into the stream's next pool slot, queued */
+int hrd_iq_queue_push(hrd_iq_queue_t *q, int stream, uint32_t time_stamp, const void *data, uint32_t bytes);
+/* one round: returns 1 with one block of every stream in rows (bytes / time_stamps optional), 0 if a stream has none */
+int hrd_iq_queue_pop_all(hrd_iq_queue_t *q, int8_t *rows, size_t row_stride, uint32_t *bytes, uint32_t *time_stamps);
+/* blocks queued, shortBlockCount, lastTimeStamp */
+int hrd_iq_queue_stats(hrd_iq_queue_t *q, int stream, uint32_t out[3]);
+/* the consumer thread's step for every stream: one round through hrd_rx_process at the 2.048 MS/s entry
+ * (host pcm buffers); 1 = a round was processed, 0 = nothing to do */
+int hrd_rx_from_queue(hrd_batch_t *b, hrd_iq_queue_t *q, int16_t *pcm, size_t pcm_stride, uint32_t *pcm_counts);
+
 /* ---- introspection (tests, bench) ------------------------------------ */
 int hrd_synchronize(hrd_batch_t *b);
 /* with HRD_OPT_PROFILE set: device time of a recent process call's kernels; age 0 = the latest

@@ -72,6 +72,11 @@ struct RefTx {
 
 } // namespace
 
+/* the PCM ring of BasebandDataProcessor is private; the harness below drives it event by event (no threads) */
+#define private public
+#include "BasebandDataProcessor.h"
+#undef private
+
 extern "C" {
 
 void *ref_rx_new(void)
@@ -202,6 +207,47 @@ size_t ref_rx_run_2048k_squelch(void *h, const int8_t *iq, size_t nbytes, size_t
     rx->iqdp->registerSignalMagnitudeCallback(NULL, NULL);
     rx->iqdp->registerSignalStateCallback(NULL, NULL);
     return total;
+}
+
+/* ---- BasebandDataProcessor's PCM ring, event by event (BasebandDataProcessor.cc:416-433, 482-605) ---- */
+void *ref_bbp_new(void)
+{
+    BasebandDataProcessor *b = new BasebandDataProcessor();
+    /* the reference never initialises pcmBuffer; slots read before they are written hold heap garbage there.
+     * Zero them so that traces are reproducible (hrd_pcm_ring_create zeroes its rings). */
+    memset(b->pcmBuffer, 0, sizeof b->pcmBuffer);
+    return b;
+}
+void ref_bbp_free(void *h)
+{
+    BasebandDataProcessor *b = (BasebandDataProcessor *)h;
+    b->streamState = BasebandDataProcessor::Idle; /* no reader thread was started: stop() must not join one */
+    delete b;
+}
+void ref_bbp_run(void *h, int running)
+{
+    ((BasebandDataProcessor *)h)->streamState = running ? BasebandDataProcessor::Running : BasebandDataProcessor::Idle;
+}
+/* the reader thread's step: returns the slot written */
+int ref_bbp_write(void *h, const int16_t *pcm512)
+{
+    BasebandDataProcessor *b = (BasebandDataProcessor *)h;
+    int16_t *p = b->getNextUnfilledBuffer();
+    memcpy(p, pcm512, PCM_BLOCK_SIZE * sizeof(int16_t));
+    return (int)((p - &b->pcmBuffer[0][0]) / PCM_BLOCK_SIZE);
+}
+/* the transmit callback's step: returns the slot sent (-1 = the zero buffer) and copies the block */
+int ref_bbp_read(void *h, int16_t *out512)
+{
+    BasebandDataProcessor *b = (BasebandDataProcessor *)h;
+    int16_t *p = b->getNextFilledBuffer();
+    memcpy(out512, p, PCM_BLOCK_SIZE * sizeof(int16_t));
+    return p == b->zeroPcmBuffer ? -1 : (int)((p - &b->pcmBuffer[0][0]) / PCM_BLOCK_SIZE);
+}
+void ref_bbp_stats(void *h, uint32_t out[4])
+{
+    BasebandDataProcessor *b = (BasebandDataProcessor *)h;
+    out[0] = b->buffersProduced, out[1] = b->buffersConsumed, out[2] = b->pcmBlocksDropped, out[3] = b->pcmBlocksAdded;
 }
 
 /* stream a long buffer through in reference-sized blocks */
