@@ -56,7 +56,10 @@ constexpr int IT_SAMPLES = 64; // 256 kS/s samples per warp iteration
 // than depth 2 in all three kernels).  The distance comes from the L2 prefetch below instead.
 constexpr int RX_DEPTH = 1;
 constexpr int WB_DEPTH = 1;    // the same in rx_wbfm_kernel
-constexpr uint32_t RX_L2_AHEAD = 4; // ... and a 4 KiB chunk pulled into L2 this many iterations ahead (prefetch_chunk)
+#ifndef HRD_L2_AHEAD
+#define HRD_L2_AHEAD 4
+#endif
+constexpr uint32_t RX_L2_AHEAD = HRD_L2_AHEAD; // ... and a 4 KiB chunk pulled into L2 this many iterations ahead (prefetch_chunk)
 
 // batches a tile > 0 runs ahead of its first stored output.  Look-back of each cascade in PCM
 // periods (one batch = 32): AM 10, FM 23, SSB 40 (the 31-tap Hilbert FIR at 8 kS/s),
