@@ -73,13 +73,13 @@ template <> struct HaloOf<K_WBFM> { static constexpr int value = 2; };
 struct SmemNone {
     uint32_t dummy[4];
 };
-struct SmemAm { // AM and SSB streams (one launch runs both)
+struct alignas(16) SmemAm { // AM and SSB streams (one launch runs both)
     uint32_t r256[2 + BATCH256 / 2]; // packed int8 words, 2 samples each
     uint32_t d64[8 + BATCH256 / 4];  // I/Q int16 pairs
     uint32_t a16[14 + BATCH256 / 16];
     uint32_t d8[30 + 32];            // SSB only: I/Q pairs at 8 kS/s
 };
-struct SmemFm {
+struct alignas(16) SmemFm { // 16-byte multiples per warp: the tuner reads its 16 ring words as LDS.64 pairs
     uint32_t r256[14 + BATCH256 / 2];
     float th[4 + BATCH256 / 4];
     int16_t d64[8 + BATCH256 / 4];
@@ -447,6 +447,7 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
 
         if constexpr (KIND == K_FM) {
             // FmDemodulator.cc:395-442: tuner /4, 32 taps per rail, then the atan2 table
+#pragma unroll 4
             for (int j = lane; j < n64; j += 32) {
                 int yi, yq;
                 dec4_int8<32>(sm.r256, c_tab.fm_tuner, j, yi, yq);
@@ -460,10 +461,23 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
                 sm.d64[8 + j] = (int16_t)f32_to_i16(__fmul_rn(scale, d));
             }
             __syncwarp();
-            // FmDemodulator.cc:551-585: /4 (12 taps) then /2 (40 taps)
-            for (int k = lane; k < n16; k += 32) sm.a16[38 + k] = (int16_t)dec_real<12, 4>(sm.d64, c_tab.fm_post, k);
+            // FmDemodulator.cc:551-585: /4 (12 taps) then /2 (40 taps), two int16 samples and their two taps per
+            // mac_pair (output k of the first reads ring samples 4k .. 4k+11, of the second 2k .. 2k+39: whole words)
+            for (int k = lane; k < n16; k += 32) {
+                const uint32_t *r = reinterpret_cast<const uint32_t *>(sm.d64) + 2 * k;
+                int al = 1 << 14, ah = 0;
+#pragma unroll
+                for (int w = 0; w < 6; w++) mac_pair(r[w], c_tab.fm_post_sp[w], al, ah);
+                sm.a16[38 + k] = (int16_t)q15(al + (ah << 8));
+            }
             __syncwarp();
-            if (emit && lane < n8) pcm_out[lane] = (int16_t)dec_real<40, 2>(sm.a16, c_tab.audio40, lane);
+            if (lane < n8) {
+                const uint32_t *r = reinterpret_cast<const uint32_t *>(sm.a16) + lane;
+                int al = 1 << 14, ah = 0;
+#pragma unroll
+                for (int w = 0; w < 20; w++) mac_pair(r[w], c_tab.audio40_sp[w], al, ah);
+                if (emit) pcm_out[lane] = (int16_t)q15(al + (ah << 8));
+            }
             __syncwarp();
             ring_shift(sm.r256, 14, nb / 2, lane);
             ring_shift(sm.th, 4, n64, lane);
