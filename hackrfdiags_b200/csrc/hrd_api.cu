@@ -130,6 +130,8 @@ int build_tables(hrd::ConstTables &t)
     split_taps(t.wbfm_post1, 8, t.wb1_sp);
     split_taps(t.fm_post, 12, t.fm_post_sp);
     split_taps(t.audio40, 40, t.audio40_sp);
+    split_taps(t.am2, 12, t.am2_sp);
+    split_taps(t.am3, 16, t.am3_sp);
     for (int i = 0; i < 31; i++) t.hilbert[i] = quantise(k_hilbert31[i]);
     for (int i = 0; i < 16; i++) t.delay[i] = quantise(k_delay16[i]);
     for (int i = 0; i < 8; i++) t.tx_hb8[i] = quantise(k_tx_hb8[i]);

@@ -75,8 +75,9 @@ struct SmemNone {
 };
 struct alignas(16) SmemAm { // AM and SSB streams (one launch runs both)
     uint32_t r256[2 + BATCH256 / 2]; // packed int8 words, 2 samples each
-    uint32_t d64[8 + BATCH256 / 4];  // I/Q int16 pairs
-    uint32_t a16[14 + BATCH256 / 16];
+    // int16 samples per rail, so that a word holds two consecutive samples of ONE rail (mac_pair's operand)
+    int16_t d64i[8 + BATCH256 / 4], d64q[8 + BATCH256 / 4];
+    int16_t a16i[14 + BATCH256 / 16], a16q[14 + BATCH256 / 16];
     uint32_t d8[30 + 32];            // SSB only: I/Q pairs at 8 kS/s
 };
 struct alignas(16) SmemFm { // 16-byte multiples per warp: the tuner reads its 16 ring words as LDS.64 pairs
@@ -325,8 +326,16 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
     if constexpr (KIND == K_AM) {
         const RxDec32 &d = ssb ? st.ssb : st.am;
         ring_init(sm.r256, d.r256, 2, lane, first);
-        ring_init(sm.d64, d.d64, 8, lane, first);
-        ring_init(sm.a16, d.a16, 14, lane, first);
+        if (lane < 8) { // the state record keeps {I, Q} words per sample; the rings keep the rails apart
+            const uint32_t w = first ? d.d64[lane] : 0u;
+            sm.d64i[lane] = (int16_t)lo16(w);
+            sm.d64q[lane] = (int16_t)hi16(w);
+        }
+        if (lane < 14) {
+            const uint32_t w = first ? d.a16[lane] : 0u;
+            sm.a16i[lane] = (int16_t)lo16(w);
+            sm.a16q[lane] = (int16_t)hi16(w);
+        }
         if (ssb) {
             ring_init(sm.d8, st.ssb_d8, 30, lane, first);
             lsb = p.lsb[sid] != 0;
@@ -405,13 +414,37 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
             for (int j = lane; j < n64; j += 32) {
                 int yi, yq;
                 dec4_int8<8>(sm.r256, c_tab.am1, j, yi, yq);
-                sm.d64[8 + j] = pack16(yi, yq);
+                sm.d64i[8 + j] = (int16_t)yi;
+                sm.d64q[8 + j] = (int16_t)yq;
             }
             __syncwarp();
-            for (int k = lane; k < n16; k += 32) sm.a16[14 + k] = dec_pairs<12, 4>(sm.d64, c_tab.am2, k);
+            // /4 (12 taps): output k reads ring samples 4k .. 4k+11 = words 2k .. 2k+5 of each rail
+            for (int k = lane; k < n16; k += 32) {
+                const uint32_t *ri = reinterpret_cast<const uint32_t *>(sm.d64i) + 2 * k;
+                const uint32_t *rq = reinterpret_cast<const uint32_t *>(sm.d64q) + 2 * k;
+                int il = 1 << 14, ih = 0, ql = 1 << 14, qh = 0;
+#pragma unroll
+                for (int w = 0; w < 6; w++) {
+                    mac_pair(ri[w], c_tab.am2_sp[w], il, ih);
+                    mac_pair(rq[w], c_tab.am2_sp[w], ql, qh);
+                }
+                sm.a16i[14 + k] = (int16_t)q15(il + (ih << 8));
+                sm.a16q[14 + k] = (int16_t)q15(ql + (qh << 8));
+            }
             __syncwarp();
+            // /2 (16 taps): output k reads ring samples 2k .. 2k+15 = words k .. k+7
             uint32_t iq8 = 0;
-            if (lane < n8) iq8 = dec_pairs<16, 2>(sm.a16, c_tab.am3, lane);
+            if (lane < n8) {
+                const uint32_t *ri = reinterpret_cast<const uint32_t *>(sm.a16i) + lane;
+                const uint32_t *rq = reinterpret_cast<const uint32_t *>(sm.a16q) + lane;
+                int il = 1 << 14, ih = 0, ql = 1 << 14, qh = 0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    mac_pair(ri[w], c_tab.am3_sp[w], il, ih);
+                    mac_pair(rq[w], c_tab.am3_sp[w], ql, qh);
+                }
+                iq8 = pack16(q15(il + (ih << 8)), q15(ql + (qh << 8)));
+            }
             int x = 0; // what enters the DC-removal IIR (as float) in the reference
             if (!ssb) {
                 // AmDemodulator.cc:444-458: |I|,|Q| narrowed to int16, max + min/2
@@ -440,8 +473,10 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
             if (emit && lane < n8) p.pre_iir[(size_t)sid * p.pre_stride + pcm_at + lane] = __fsub_rn(xf, xp);
             __syncwarp();
             ring_shift(sm.r256, 2, nb / 2, lane);
-            ring_shift(sm.d64, 8, n64, lane);
-            ring_shift(sm.a16, 14, n16, lane);
+            ring_shift(sm.d64i, 8, n64, lane);
+            ring_shift(sm.d64q, 8, n64, lane);
+            ring_shift(sm.a16i, 14, n16, lane);
+            ring_shift(sm.a16q, 14, n16, lane);
             if (ssb) ring_shift(sm.d8, 30, n8, lane);
         }
 
@@ -510,8 +545,8 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxP
     if constexpr (KIND == K_AM) {
         RxDec32 &d = ssb ? so.ssb : so.am;
         ring_save_hist(sm.r256, d.r256, 2, lane);
-        ring_save_hist(sm.d64, d.d64, 8, lane);
-        ring_save_hist(sm.a16, d.a16, 14, lane);
+        if (lane < 8) d.d64[lane] = pack16(sm.d64i[lane], sm.d64q[lane]);
+        if (lane < 14) d.a16[lane] = pack16(sm.a16i[lane], sm.a16q[lane]);
         if (ssb) ring_save_hist(sm.d8, so.ssb_d8, 30, lane);
         if (lane == 0) d.x1 = x1; // y1 follows from rx_dc_iir_kernel
     }

@@ -35,7 +35,7 @@ struct ConstTables {
     int32_t wbfm_post1[8];  // WbFmDemodulator.cc:17-27  /4
     // The same taps for mac_pair (hrd_rx.cu): word w serves ring samples 2w (low half) and 2w+1, i.e.
     // taps q[N-1-2w] and q[N-2-2w], each split q = th*256 + tl and packed {tl0, tl1, th0, th1}
-    uint32_t wb1_sp[4], fm_post_sp[6], audio40_sp[20];
+    uint32_t wb1_sp[4], fm_post_sp[6], audio40_sp[20], am2_sp[6], am3_sp[8];
     int32_t hilbert[31];    // SsbDemodulator.cc:68-101, SsbModulator.cc:129-162
     int32_t delay[16];      // SsbDemodulator.cc:65: {0,...,0,-32768}
     // Tx half-band interpolators (AmModulator.cc:57-123)
