@@ -282,8 +282,11 @@ __device__ __forceinline__ void prefetch_chunk(const int8_t *src, uint32_t pf, u
 // ------------------------------------------------------------------------------------
 // the tile kernel
 // ------------------------------------------------------------------------------------
+#ifndef HRD_RX_MIN_CTAS
+#define HRD_RX_MIN_CTAS 8
+#endif
 template <int KIND, int ENTRY>
-__global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, 8) rx_kernel(const RxParams p)
+__global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, HRD_RX_MIN_CTAS) rx_kernel(const RxParams p)
 {
     typedef typename SmemOf<KIND>::type Smem;
     typedef typename RawOf<ENTRY>::type Raw;

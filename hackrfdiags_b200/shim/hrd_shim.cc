@@ -39,6 +39,7 @@
 #include "FmModulator.h"
 #include "WbFmModulator.h"
 #include "SsbModulator.h"
+#include "IqDataProcessor.h"
 
 // supplied by the host application, exactly as for the reference classes
 // (diagUi.cc:2881; the test programs define their own, am.cc:93-110)
@@ -68,6 +69,7 @@ struct HrdShimRx
   int resetUnit;
   float demodulatorGain;
   bool lsbDemodulationMode;
+  unsigned resetCount; // resetDemodulator() calls so far (an attached IqDataProcessor follows them)
   void (*pcmCallbackPtr)(int16_t *bufferPtr,uint32_t bufferLength);
 
   // acceptIqData() hands whole PCM samples (64 bytes of IQ at 256000 S/s) to
@@ -87,6 +89,7 @@ static HrdShimRx *rxCreate(int mode,int gainParameter,int resetUnit,
   p->gainParameter = gainParameter;
   p->resetUnit = resetUnit;
   p->lsbDemodulationMode = true;
+  p->resetCount = 0;
   p->pcmCallbackPtr = pcmCallbackPtr;
   if (hrd_create(shimDevice(),1,HRD_RX,&p->batchPtr) != HRD_OK) shimDie("hrd_create");
   if (hrd_set_mode(p->batchPtr,0,mode) != HRD_OK) shimDie("hrd_set_mode");
@@ -145,6 +148,7 @@ static void rxSetGain(HrdShimRx *p,float gain)
 static void rxReset(HrdShimRx *p)
 {
   p->pending.clear();
+  p->resetCount++;
   if (hrd_reset(p->batchPtr,0,p->resetUnit) != HRD_OK) shimDie("hrd_reset");
 }
 
@@ -342,5 +346,257 @@ void SsbModulator::displayInternalInformation(void)
   else
   {
     nprintf(stderr,"USB\n");
+  }
+}
+
+//**************************************************************************
+// IqDataProcessor (radioDiags/src_diags/IqDataProcessor.cc): the 2.048 MS/s entry.
+//**************************************************************************
+// One stream of an Rx batch at HRD_ENTRY_2048K does what acceptIqData does
+// (IqDataProcessor.cc:926-1038): three half-band decimators, the Fs/4 rotation,
+// Squelch::run on the 256 kS/s block, the gated demodulator.  The demodulator
+// OBJECTS the application hands in stay the owners of their parameters and PCM
+// callbacks: before every block the active one's gain and reset count are
+// mirrored into this object's batch, and its callback receives the PCM -- once
+// per block the squelch lets through, exactly when the reference would have
+// called <X>Demodulator::acceptIqData.
+// The UDP dump of the 256 kS/s stream (IqDataProcessor.cc:953-957) is network
+// I/O and stays out: the enable flag is kept and reported, nothing is sent.
+
+// the receive gain Squelch::run refers the level to (Radio.cc:15,413,1599)
+extern uint32_t radio_adjustableReceiveGainInDb;
+
+struct HrdShimIqdp
+{
+  hrd_batch_t *batchPtr;      // acceptIqData: the whole chain
+  hrd_batch_t *frontEndPtr;   // reduceSampleRate() called on its own
+  IqDataProcessor::demodulatorType demodulatorMode;
+  int32_t signalDetectThreshold;
+  HrdShimRx *demodulator[4];  // AM, FM, WBFM, SSB as handed in
+  float pushedGain[4];
+  unsigned seenReset[4];
+  uint32_t pushedReceiveGain;
+  unsigned long blockBytes;
+  bool iqDumpEnabled;
+  bool signalNotificationEnabled;
+  void *signalCallbackContextPtr;
+  void (*signalCallbackPtr)(bool signalPresent,void *contextPtr);
+  bool signalMagnitudeNotificationEnabled;
+  void *signalMagnitudeCallbackContextPtr;
+  void (*signalMagnitudeCallbackPtr)(uint32_t signalMagnitude,void *contextPtr);
+  std::vector<int16_t> pcmData;
+};
+
+IqDataProcessor::IqDataProcessor(char *hostIpAddress,int hostPort)
+{
+  (void)hostIpAddress;
+  (void)hostPort;
+  HrdShimIqdp *p = new HrdShimIqdp;
+  p->batchPtr = NULL;
+  p->frontEndPtr = NULL;
+  p->demodulatorMode = None;        // IqDataProcessor.cc:70
+  p->signalDetectThreshold = -200;  // IqDataProcessor.cc:120
+  for (int i = 0; i < 4; i++)
+  {
+    p->demodulator[i] = NULL;
+    p->pushedGain[i] = 0;
+    p->seenReset[i] = 0;
+  }
+  p->pushedReceiveGain = 16;
+  p->blockBytes = 0;
+  p->iqDumpEnabled = false;
+  p->signalNotificationEnabled = false;
+  p->signalCallbackPtr = NULL;
+  p->signalCallbackContextPtr = NULL;
+  p->signalMagnitudeNotificationEnabled = false;
+  p->signalMagnitudeCallbackPtr = NULL;
+  p->signalMagnitudeCallbackContextPtr = NULL;
+  if (hrd_create(shimDevice(),1,HRD_RX,&p->batchPtr) != HRD_OK) shimDie("hrd_create");
+  // always the squelched path: the magnitude and the decision of every block are part of the interface
+  if (hrd_set_option(p->batchPtr,HRD_OPT_RX_SQUELCH,1) != HRD_OK) shimDie("hrd_set_option");
+  memset(decimatedData,0,sizeof decimatedData);
+  implPtr = p;
+}
+
+IqDataProcessor::~IqDataProcessor(void)
+{
+  hrd_destroy(implPtr->batchPtr);
+  hrd_destroy(implPtr->frontEndPtr);
+  delete implPtr;
+}
+
+void IqDataProcessor::setAmDemodulator(AmDemodulator *demodulatorPtr) { implPtr->demodulator[0] = demodulatorPtr->implPtr; }
+void IqDataProcessor::setFmDemodulator(FmDemodulator *demodulatorPtr) { implPtr->demodulator[1] = demodulatorPtr->implPtr; }
+void IqDataProcessor::setWbFmDemodulator(WbFmDemodulator *demodulatorPtr) { implPtr->demodulator[2] = demodulatorPtr->implPtr; }
+void IqDataProcessor::setSsbDemodulator(SsbDemodulator *demodulatorPtr) { implPtr->demodulator[3] = demodulatorPtr->implPtr; }
+
+// IqDataProcessor.cc:346-372: LSB / USB also flip the SSB demodulator object's sideband
+void IqDataProcessor::setDemodulatorMode(demodulatorType mode)
+{
+  implPtr->demodulatorMode = mode;
+  if (implPtr->demodulator[3] != NULL)
+  {
+    if (mode == Lsb) implPtr->demodulator[3]->lsbDemodulationMode = true;
+    if (mode == Usb) implPtr->demodulator[3]->lsbDemodulationMode = false;
+  }
+  if (hrd_set_mode(implPtr->batchPtr,0,(int)mode) != HRD_OK) shimDie("hrd_set_mode");
+}
+
+// IqDataProcessor.cc:392-405
+void IqDataProcessor::setSignalDetectThreshold(int32_t threshold)
+{
+  implPtr->signalDetectThreshold = threshold;
+  if (hrd_set_param(implPtr->batchPtr,0,HRD_PARAM_SQUELCH_THRESHOLD,(float)threshold) != HRD_OK)
+    shimDie("hrd_set_param");
+}
+
+void IqDataProcessor::enableSignalNotification(void) { implPtr->signalNotificationEnabled = true; }
+void IqDataProcessor::disableSignalNotification(void) { implPtr->signalNotificationEnabled = false; }
+void IqDataProcessor::registerSignalStateCallback(void (*callbackPtr)(bool signalPresent,void *contextPtr),void *contextPtr)
+{
+  implPtr->signalCallbackContextPtr = contextPtr;
+  implPtr->signalCallbackPtr = callbackPtr;
+}
+void IqDataProcessor::enableSignalMagnitudeNotification(void) { implPtr->signalMagnitudeNotificationEnabled = true; }
+void IqDataProcessor::disableSignalMagnitudeNotification(void) { implPtr->signalMagnitudeNotificationEnabled = false; }
+void IqDataProcessor::registerSignalMagnitudeCallback(void (*callbackPtr)(uint32_t signalMagnitude,void *contextPtr),void *contextPtr)
+{
+  implPtr->signalMagnitudeCallbackContextPtr = contextPtr;
+  implPtr->signalMagnitudeCallbackPtr = callbackPtr;
+}
+void IqDataProcessor::enableIqDump(void) { implPtr->iqDumpEnabled = true; }
+void IqDataProcessor::disableIqDump(void) { implPtr->iqDumpEnabled = false; }
+bool IqDataProcessor::isIqDumpEnabled(void) { return (implPtr->iqDumpEnabled); }
+
+// IqDataProcessor.cc:926-1038
+void IqDataProcessor::acceptIqData(unsigned long timeStamp,int8_t *bufferPtr,unsigned long byteCount)
+{
+  (void)timeStamp;
+  HrdShimIqdp *p = implPtr;
+  static const int gainParameter[4] = {HRD_PARAM_AM_GAIN,HRD_PARAM_FM_GAIN,HRD_PARAM_WBFM_GAIN,HRD_PARAM_SSB_GAIN};
+  static const int resetUnit[4] = {HRD_UNIT_AM,HRD_UNIT_FM,HRD_UNIT_WBFM,HRD_UNIT_SSB};
+  static const int slotOfMode[6] = {-1,0,1,2,3,3};
+
+  byteCount -= byteCount % 512; // whole PCM samples (the reference's caller always passes 262144)
+  if (byteCount == 0) return;
+
+  // one call is one squelch decision
+  if (byteCount != p->blockBytes)
+  {
+    if (hrd_set_option(p->batchPtr,HRD_OPT_RX_SQUELCH_BLOCK,(int)byteCount) != HRD_OK) shimDie("hrd_set_option");
+    p->blockBytes = byteCount;
+  }
+  if (radio_adjustableReceiveGainInDb != p->pushedReceiveGain)
+  {
+    if (hrd_set_param(p->batchPtr,0,HRD_PARAM_RX_GAIN_DB,(float)radio_adjustableReceiveGainInDb) != HRD_OK)
+      shimDie("hrd_set_param");
+    p->pushedReceiveGain = radio_adjustableReceiveGainInDb;
+  }
+  // the demodulator objects own their parameters: follow them
+  for (int i = 0; i < 4; i++)
+  {
+    HrdShimRx *d = p->demodulator[i];
+    if (d == NULL) continue;
+    if (d->demodulatorGain != p->pushedGain[i])
+    {
+      if (hrd_set_param(p->batchPtr,0,gainParameter[i],d->demodulatorGain) != HRD_OK) shimDie("hrd_set_param");
+      p->pushedGain[i] = d->demodulatorGain;
+    }
+    if (d->resetCount != p->seenReset[i])
+    {
+      if (hrd_reset(p->batchPtr,0,resetUnit[i]) != HRD_OK) shimDie("hrd_reset");
+      p->seenReset[i] = d->resetCount;
+    }
+  }
+
+  const size_t sampleCount = byteCount / 512;
+  if (p->pcmData.size() < sampleCount + 1) p->pcmData.resize(sampleCount + 1);
+  uint32_t produced = 0;
+  if (hrd_rx_process(p->batchPtr,bufferPtr,byteCount,byteCount,HRD_ENTRY_2048K,p->pcmData.data(),
+                     p->pcmData.size(),&produced,HRD_MEM_HOST,NULL) != HRD_OK)
+    shimDie("hrd_rx_process");
+  uint32_t magnitude = 0, blocks = 0;
+  uint8_t allowed = 0;
+  if (hrd_rx_squelch_report(p->batchPtr,&magnitude,&allowed,1,&blocks) != HRD_OK) shimDie("hrd_rx_squelch_report");
+
+  if (p->signalNotificationEnabled && (p->signalCallbackPtr != NULL))
+    p->signalCallbackPtr(allowed != 0,p->signalCallbackContextPtr);
+  if (p->signalMagnitudeNotificationEnabled && (p->signalMagnitudeCallbackPtr != NULL))
+    p->signalMagnitudeCallbackPtr(magnitude,p->signalMagnitudeCallbackContextPtr);
+
+  if (allowed)
+  {
+    const int slot = slotOfMode[(int)p->demodulatorMode];
+    if ((slot >= 0) && (p->demodulator[slot] != NULL) && (p->demodulator[slot]->pcmCallbackPtr != NULL))
+      p->demodulator[slot]->pcmCallbackPtr(p->pcmData.data(),produced);
+  }
+}
+
+// reduceSampleRate on its own (IqDataProcessor.cc:429-500): the front end of a second one-stream batch,
+// with the rotation the library fuses into it taken back out, so that decimatedData holds what the
+// reference's holds at this point.  (acceptIqData does not come through here.)
+uint32_t IqDataProcessor::reduceSampleRate(int8_t *bufferPtr,uint32_t bufferLength)
+{
+  HrdShimIqdp *p = implPtr;
+  if (p->frontEndPtr == NULL)
+  {
+    if (hrd_create(shimDevice(),1,HRD_RX,&p->frontEndPtr) != HRD_OK) shimDie("hrd_create");
+  }
+  bufferLength -= bufferLength % 512;
+  if (bufferLength > 262144) bufferLength = 262144;
+  if (bufferLength == 0) return (0);
+  if (hrd_rx_front_end(p->frontEndPtr,bufferPtr,bufferLength,bufferLength,decimatedData,sizeof decimatedData,
+                       HRD_MEM_HOST,NULL) != HRD_OK)
+    shimDie("hrd_rx_front_end");
+  downconvertByFsOver4(decimatedData,bufferLength / 8);
+  return (bufferLength / 8);
+}
+
+// IqDataProcessor.cc:771-815: multiply by {1, j, -1, -j}; int8 negation wraps like the reference's
+void IqDataProcessor::upconvertByFsOver4(int8_t *bufferPtr,uint32_t byteCount)
+{
+  for (uint32_t i = 0; i + 7 < byteCount; i += 8)
+  {
+    int8_t x,y;
+    x = bufferPtr[i + 2]; y = bufferPtr[i + 3];
+    bufferPtr[i + 2] = (int8_t)-y; bufferPtr[i + 3] = x;
+    bufferPtr[i + 4] = (int8_t)-bufferPtr[i + 4]; bufferPtr[i + 5] = (int8_t)-bufferPtr[i + 5];
+    x = bufferPtr[i + 6]; y = bufferPtr[i + 7];
+    bufferPtr[i + 6] = y; bufferPtr[i + 7] = (int8_t)-x;
+  }
+}
+
+// IqDataProcessor.cc:715-759: multiply by {1, -j, -1, j}
+void IqDataProcessor::downconvertByFsOver4(int8_t *bufferPtr,uint32_t byteCount)
+{
+  for (uint32_t i = 0; i + 7 < byteCount; i += 8)
+  {
+    int8_t x,y;
+    x = bufferPtr[i + 2]; y = bufferPtr[i + 3];
+    bufferPtr[i + 2] = y; bufferPtr[i + 3] = (int8_t)-x;
+    bufferPtr[i + 4] = (int8_t)-bufferPtr[i + 4]; bufferPtr[i + 5] = (int8_t)-bufferPtr[i + 5];
+    x = bufferPtr[i + 6]; y = bufferPtr[i + 7];
+    bufferPtr[i + 6] = (int8_t)-y; bufferPtr[i + 7] = x;
+  }
+}
+
+// IqDataProcessor.cc:1058-1124
+void IqDataProcessor::displayInternalInformation(void)
+{
+  static const char *modeName[6] = {"None","AM","FM","WBFM","LSB","USB"};
+  nprintf(stderr,"\n--------------------------------------------\n");
+  nprintf(stderr,"IQ Data Processor Internal Information\n");
+  nprintf(stderr,"--------------------------------------------\n");
+  nprintf(stderr,"Demodulator Mode         : ");
+  if (((int)implPtr->demodulatorMode >= 0) && ((int)implPtr->demodulatorMode <= 5))
+    nprintf(stderr,"%s\n",modeName[(int)implPtr->demodulatorMode]);
+  nprintf(stderr,"Signal Detect Threhold   : %d dBFs\n",implPtr->signalDetectThreshold);
+  if (implPtr->iqDumpEnabled)
+  {
+    nprintf(stderr,"IQ Dump Enabled          : Yes\n");
+  }
+  else
+  {
+    nprintf(stderr,"IQ Dump Enabled          : No\n");
   }
 }

@@ -37,6 +37,8 @@ class AmDemodulator
   AmDemodulator(const AmDemodulator &);
   AmDemodulator &operator=(const AmDemodulator &);
 
+  friend class IqDataProcessor; // the shim's IqDataProcessor reads gain / sideband / resets from here
+
   HrdShimRx *implPtr;
 };
 

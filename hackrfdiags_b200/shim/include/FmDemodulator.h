@@ -37,6 +37,8 @@ class FmDemodulator
   FmDemodulator(const FmDemodulator &);
   FmDemodulator &operator=(const FmDemodulator &);
 
+  friend class IqDataProcessor; // the shim's IqDataProcessor reads gain / sideband / resets from here
+
   HrdShimRx *implPtr;
 };
 

@@ -39,6 +39,8 @@ class SsbDemodulator
   SsbDemodulator(const SsbDemodulator &);
   SsbDemodulator &operator=(const SsbDemodulator &);
 
+  friend class IqDataProcessor; // the shim's IqDataProcessor reads gain / sideband / resets from here
+
   HrdShimRx *implPtr;
 };
 

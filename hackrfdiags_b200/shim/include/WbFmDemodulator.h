@@ -37,6 +37,8 @@ class WbFmDemodulator
   WbFmDemodulator(const WbFmDemodulator &);
   WbFmDemodulator &operator=(const WbFmDemodulator &);
 
+  friend class IqDataProcessor; // the shim's IqDataProcessor reads gain / sideband / resets from here
+
   HrdShimRx *implPtr;
 };
 

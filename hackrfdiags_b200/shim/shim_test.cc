@@ -9,6 +9,9 @@
 // BasebandDataProcessor.cc:648-687 for the modulators), so byte-identical output
 // files are the drop-in proof.  tests/test_gpu_shim.py runs both.
 //
+//   shim_test iqdp <none|am|fm|wbfm|lsb|usb> <iq2048k.s8> <pcm.s16> [squelch threshold dBFS]
+//       Radio.cc's use of IqDataProcessor: the four demodulators handed in, 262144-byte blocks through
+//       acceptIqData (DataConsumer.cc:319-351), signal state / magnitude callbacks printed per block
 //   shim_test rx <am|fm|wbfm|lsb|usb> <iq256k.s8> <pcm.s16> [gain]
 //   shim_test tx <am|fm|wbfm|lsb|usb> <pcm.s16> <iq.s8> [index-or-deviation]
 //**************************************************************************
@@ -28,6 +31,10 @@
 #include "FmModulator.h"
 #include "WbFmModulator.h"
 #include "SsbModulator.h"
+#include "IqDataProcessor.h"
+
+// Radio.cc:15,413: the receive gain the squelch refers the signal level to
+uint32_t radio_adjustableReceiveGainInDb = 16;
 
 // the classes print through this (diagUi.cc:2881; am.cc:93-110)
 void nprintf(FILE *s,const char *formatPtr, ...)
@@ -88,6 +95,62 @@ static void runDemodulator(Demodulator &d,std::vector<char> &iq)
   fprintf(stderr,"calls %u callbacks %u\n",calls,callbackCount);
 }
 
+static void signalStateCallback(bool signalPresent,void *contextPtr)
+{
+  (void)contextPtr;
+  fprintf(stderr,"signal %d\n",signalPresent ? 1 : 0);
+}
+
+static void signalMagnitudeCallback(uint32_t signalMagnitude,void *contextPtr)
+{
+  (void)contextPtr;
+  fprintf(stderr,"magnitude %u\n",(unsigned)signalMagnitude);
+}
+
+// What Radio.cc does with an IqDataProcessor (Radio.cc:150-200, 2396-2633) and what dataConsumerThread
+// feeds it (DataConsumer.cc:319-351)
+static void runIqDataProcessor(const char *mode,std::vector<char> &iq,bool haveThreshold,int threshold)
+{
+  char host[] = "127.0.0.1";
+  IqDataProcessor processor(host,8001);
+  AmDemodulator am(pcmCallback);
+  FmDemodulator fm(pcmCallback);
+  WbFmDemodulator wbFm(pcmCallback);
+  SsbDemodulator ssb(pcmCallback);
+  processor.setAmDemodulator(&am);
+  processor.setFmDemodulator(&fm);
+  processor.setWbFmDemodulator(&wbFm);
+  processor.setSsbDemodulator(&ssb);
+  IqDataProcessor::demodulatorType type = IqDataProcessor::None;
+  if (strcmp(mode,"am") == 0) type = IqDataProcessor::Am;
+  if (strcmp(mode,"fm") == 0) type = IqDataProcessor::Fm;
+  if (strcmp(mode,"wbfm") == 0) type = IqDataProcessor::WbFm;
+  if (strcmp(mode,"lsb") == 0) type = IqDataProcessor::Lsb;
+  if (strcmp(mode,"usb") == 0) type = IqDataProcessor::Usb;
+  processor.setDemodulatorMode(type);
+  if (haveThreshold) processor.setSignalDetectThreshold(threshold);
+  processor.registerSignalStateCallback(signalStateCallback,NULL);
+  processor.registerSignalMagnitudeCallback(signalMagnitudeCallback,NULL);
+  processor.enableSignalNotification();
+  processor.enableSignalMagnitudeNotification();
+  const size_t block = 262144;
+  size_t offset = 0;
+  unsigned calls = 0;
+  while (offset < iq.size())
+  {
+    size_t n = iq.size() - offset;
+    if (n > block) n = block;
+    processor.acceptIqData(calls,(int8_t *)&iq[offset],n);
+    offset += n;
+    calls++;
+    if (calls == 2) { am.setDemodulatorGain(150.0f); fm.resetDemodulator(); ssb.setDemodulatorGain(450.0f); }
+    if (calls == 4) radio_adjustableReceiveGainInDb = 24;
+  }
+  processor.displayInternalInformation();
+  ssb.displayInternalInformation();
+  fprintf(stderr,"calls %u callbacks %u\n",calls,callbackCount);
+}
+
 template <class Modulator>
 static std::vector<int8_t> runModulator(Modulator &m,std::vector<char> &pcmBytes)
 {
@@ -116,7 +179,7 @@ int main(int argc,char **argv)
 {
   if (argc < 5)
   {
-    fprintf(stderr,"usage: %s rx|tx am|fm|wbfm|lsb|usb <in> <out> [parameter]\n",argv[0]);
+    fprintf(stderr,"usage: %s rx|tx|iqdp am|fm|wbfm|lsb|usb <in> <out> [parameter]\n",argv[0]);
     return (2);
   }
   const char *dir = argv[1], *mode = argv[2];
@@ -124,7 +187,12 @@ int main(int argc,char **argv)
   const bool haveParameter = argc > 5;
   const float parameter = haveParameter ? (float)atof(argv[5]) : 0;
 
-  if (strcmp(dir,"rx") == 0)
+  if (strcmp(dir,"iqdp") == 0)
+  {
+    runIqDataProcessor(mode,in,haveParameter,(int)parameter);
+    writeFile(argv[4],pcmSink.data(),pcmSink.size() * sizeof(int16_t));
+  }
+  else if (strcmp(dir,"rx") == 0)
   {
     if (strcmp(mode,"am") == 0)
     {
