@@ -150,11 +150,6 @@ __device__ __forceinline__ float phase_advance_lockstep(float acc, float step, u
     return out;
 }
 
-// PhaseAccumulator::setFrequency (:95-107): (float)((2*M_PI*f)/fs) in double
-__device__ __forceinline__ float phase_step(float f, double fs)
-{
-    return (float)((2.0 * 3.14159265358979323846 * (double)f) / fs);
-}
 
 // Stages 5..8 of one rail for one 128 kS/s input sample x (with its three predecessors):
 // 16 outputs as accumulators whose byte 2 is the (int8_t) value (doubled taps, see hrd_rx.cu).
