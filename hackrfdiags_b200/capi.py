@@ -29,7 +29,7 @@ OPT_RX_TILE_BATCHES, OPT_RX_WBFM_TILING, OPT_TX_TILE_SAMPLES, OPT_PROFILE, OPT_D
 # every symbol include/hrd.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "hrd_abi_version", "hrd_create", "hrd_destroy", "hrd_last_error", "hrd_set_mode", "hrd_get_mode",
-    "hrd_set_param", "hrd_get_param", "hrd_reset", "hrd_set_option", "hrd_get_option", "hrd_rx_process", "hrd_rx_front_end", "hrd_rx_squelch_report", "hrd_tx_process",
+    "hrd_set_param", "hrd_get_param", "hrd_reset", "hrd_set_option", "hrd_get_option", "hrd_rx_process", "hrd_rx_front_end", "hrd_rx_squelch_report", "hrd_rx_fs4_rotate", "hrd_tx_process",
     "hrd_pcm_ring_create", "hrd_pcm_ring_destroy", "hrd_pcm_ring_start", "hrd_pcm_ring_write", "hrd_pcm_ring_read_all",
     "hrd_pcm_ring_stats", "hrd_tx_from_ring", "hrd_iq_queue_create", "hrd_iq_queue_destroy", "hrd_iq_queue_push",
     "hrd_iq_queue_pop_all", "hrd_iq_queue_stats", "hrd_rx_from_queue",
@@ -68,6 +68,7 @@ def load():
     lib.hrd_rx_front_end.argtypes = [vp, vp, sz, sz, vp, sz, i, vp]
     lib.hrd_tx_process.argtypes = [vp, vp, sz, sz, vp, sz, i, vp]
     lib.hrd_rx_squelch_report.argtypes = [vp, vp, vp, sz, C.POINTER(C.c_uint32)]
+    lib.hrd_rx_fs4_rotate.argtypes = [vp, vp, sz, i, i, vp]
     lib.hrd_synchronize.argtypes = [vp]
     lib.hrd_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.hrd_kernel_ms.argtypes = [vp, i, i, C.POINTER(C.c_float)]

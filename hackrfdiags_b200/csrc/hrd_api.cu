@@ -1151,6 +1151,32 @@ int hrd_rx_front_end(hrd_batch_t *b, const int8_t *iq, size_t bytes_per_stream, 
                      mem, cuda_stream, true);
 }
 
+int hrd_rx_fs4_rotate(hrd_batch_t *b, int8_t *iq, size_t bytes, int up, int mem, void *cuda_stream)
+{
+    if (!b || b->kind != HRD_RX) return fail(HRD_EINVAL, "not an Rx batch");
+    if (!iq || bytes % 8) return fail(HRD_EINVAL, "iq is null or bytes is not a multiple of 8 (four I,Q samples)");
+    if (mem != HRD_MEM_HOST && mem != HRD_MEM_DEVICE) return fail(HRD_EINVAL, "bad mem %d", mem);
+    if (!bytes) return HRD_OK;
+    DeviceGuard guard(b->device);
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : (mem == HRD_MEM_HOST ? b->own : (cudaStream_t) nullptr);
+    int8_t *d = iq;
+    if (mem == HRD_MEM_HOST) {
+        int rc = ensure_cap(&b->d_in, &b->d_in_cap, bytes);
+        if (rc) return rc;
+        d = (int8_t *)b->d_in;
+        HRD_CUDA(cudaMemcpyAsync(d, iq, bytes, cudaMemcpyHostToDevice, s));
+    } else if ((uintptr_t)iq % 4) {
+        return fail(HRD_EINVAL, "device iq pointer must be 4-byte aligned");
+    }
+    if (hrd::launch_fs4_rotate(d, bytes / 8, up != 0, s)) return fail(HRD_ECUDA, "rotate launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    b->launches++;
+    if (mem == HRD_MEM_HOST) {
+        HRD_CUDA(cudaMemcpyAsync(iq, d, bytes, cudaMemcpyDeviceToHost, s));
+        HRD_CUDA(cudaStreamSynchronize(s));
+    }
+    return HRD_OK;
+}
+
 int hrd_rx_squelch_report(hrd_batch_t *b, uint32_t *magnitudes, uint8_t *allowed, size_t blocks_cap, uint32_t *n_blocks)
 {
     if (!b || b->kind != HRD_RX) return fail(HRD_EINVAL, "not an Rx batch");

@@ -216,6 +216,7 @@ int launch_squelch_track(const uint32_t *magnitude, int n_streams, int n_blocks,
 int launch_squelch_scatter(const int16_t *scratch, size_t scratch_stride, int16_t *pcm, size_t pcm_stride, const uint32_t *out_at,
                            const uint8_t *allowed, const uint8_t *kind_of, int n_streams, int n_blocks, int blk, uint32_t n,
                            cudaStream_t s);
+int launch_fs4_rotate(int8_t *iq, size_t n_groups, int up, cudaStream_t s);
 int launch_tx(int kind, const TxParams &p, cudaStream_t s);
 int launch_tx_fm_phase(const TxParams &p, cudaStream_t s);   // FM streams, before their launch_tx
 int launch_tx_sig_phase(const TxParams &p, cudaStream_t s);  // signals/fm.cc streams of a K_IQ launch, before it

@@ -552,33 +552,19 @@ uint32_t IqDataProcessor::reduceSampleRate(int8_t *bufferPtr,uint32_t bufferLeng
   return (bufferLength / 8);
 }
 
-// IqDataProcessor.cc:771-815: multiply by {1, j, -1, -j}; int8 negation wraps like the reference's
-void IqDataProcessor::upconvertByFsOver4(int8_t *bufferPtr,uint32_t byteCount)
+// IqDataProcessor.cc:771-815 and 715-759: the Fs/4 rotations on their own, in place (hrd_rx_fs4_rotate)
+static void shimRotate(HrdShimIqdp *p,int8_t *bufferPtr,uint32_t byteCount,int up)
 {
-  for (uint32_t i = 0; i + 7 < byteCount; i += 8)
+  if (p->frontEndPtr == NULL)
   {
-    int8_t x,y;
-    x = bufferPtr[i + 2]; y = bufferPtr[i + 3];
-    bufferPtr[i + 2] = (int8_t)-y; bufferPtr[i + 3] = x;
-    bufferPtr[i + 4] = (int8_t)-bufferPtr[i + 4]; bufferPtr[i + 5] = (int8_t)-bufferPtr[i + 5];
-    x = bufferPtr[i + 6]; y = bufferPtr[i + 7];
-    bufferPtr[i + 6] = y; bufferPtr[i + 7] = (int8_t)-x;
+    if (hrd_create(shimDevice(),1,HRD_RX,&p->frontEndPtr) != HRD_OK) shimDie("hrd_create");
   }
+  byteCount -= byteCount % 8;
+  if (hrd_rx_fs4_rotate(p->frontEndPtr,bufferPtr,byteCount,up,HRD_MEM_HOST,NULL) != HRD_OK) shimDie("hrd_rx_fs4_rotate");
 }
 
-// IqDataProcessor.cc:715-759: multiply by {1, -j, -1, j}
-void IqDataProcessor::downconvertByFsOver4(int8_t *bufferPtr,uint32_t byteCount)
-{
-  for (uint32_t i = 0; i + 7 < byteCount; i += 8)
-  {
-    int8_t x,y;
-    x = bufferPtr[i + 2]; y = bufferPtr[i + 3];
-    bufferPtr[i + 2] = y; bufferPtr[i + 3] = (int8_t)-x;
-    bufferPtr[i + 4] = (int8_t)-bufferPtr[i + 4]; bufferPtr[i + 5] = (int8_t)-bufferPtr[i + 5];
-    x = bufferPtr[i + 6]; y = bufferPtr[i + 7];
-    bufferPtr[i + 6] = (int8_t)-y; bufferPtr[i + 7] = x;
-  }
-}
+void IqDataProcessor::upconvertByFsOver4(int8_t *bufferPtr,uint32_t byteCount) { shimRotate(implPtr,bufferPtr,byteCount,1); }
+void IqDataProcessor::downconvertByFsOver4(int8_t *bufferPtr,uint32_t byteCount) { shimRotate(implPtr,bufferPtr,byteCount,0); }
 
 // IqDataProcessor.cc:1058-1124
 void IqDataProcessor::displayInternalInformation(void)

@@ -187,6 +187,10 @@ int hrd_rx_process(hrd_batch_t *b, const int8_t *iq, size_t bytes_per_stream, si
 int hrd_rx_front_end(hrd_batch_t *b, const int8_t *iq, size_t bytes_per_stream, size_t iq_stride,
                      int8_t *out256k, size_t out_stride, int mem, void *cuda_stream);
 
+/* IqDataProcessor::upconvertByFsOver4 (up != 0, IqDataProcessor.cc:771-815) or downconvertByFsOver4 (up == 0,
+ * :715-759) on their own, in place on bytes (a multiple of 8) of int8 I,Q: the rotation hrd_rx_process fuses into
+ * its front end, for callers that use the two public methods separately. */
+int hrd_rx_fs4_rotate(hrd_batch_t *b, int8_t *iq, size_t bytes, int up, int mem, void *cuda_stream);
 /* What the reference reports through registerSignalMagnitudeCallback / registerSignalStateCallback
  * (IqDataProcessor.cc:961-988), for every stream and block of the latest squelched hrd_rx_process call:
  * magnitudes[s * blocks_cap + b] = Squelch::getSignalMagnitude(), allowed[...] = Squelch::run()'s result.

@@ -94,3 +94,29 @@ def test_squelch_edge_inputs_device_memory():
         want_pcm, want_mag, want_open = oracle.run_rx_squelch(capi.MODE_WBFM, iq[i], thr[i])
         assert np.array_equal(mags[i], want_mag) and np.array_equal(allowed[i], want_open), edges[i]
         assert np.array_equal(pcm[i, :want_pcm.size], want_pcm), edges[i]
+
+
+def test_fs4_rotation_on_its_own():
+    """hrd_rx_fs4_rotate = IqDataProcessor::upconvertByFsOver4 / downconvertByFsOver4 (IqDataProcessor.cc:771-815,
+    715-759), int8 negation wrapping (-(-128) = -128) included."""
+    import ctypes as C
+    rng = np.random.default_rng(8)
+    iq = rng.integers(-128, 128, size=8 * 1000, dtype=np.int64).astype(np.int8)
+    iq[:16] = -128
+    z = iq.reshape(-1, 4, 2).astype(np.int16)  # groups of four (I, Q) samples
+
+    def neg(v):
+        return (-v).astype(np.int8)  # wraps -(-128) to -128 like the int8_t assignment in the reference
+
+    up = z.copy().astype(np.int8)
+    up[:, 1, 0], up[:, 1, 1] = neg(z[:, 1, 1]), z[:, 1, 0].astype(np.int8)
+    up[:, 2, 0], up[:, 2, 1] = neg(z[:, 2, 0]), neg(z[:, 2, 1])
+    up[:, 3, 0], up[:, 3, 1] = z[:, 3, 1].astype(np.int8), neg(z[:, 3, 0])
+    b = capi.Batch(1, capi.RX, 0)
+    buf = iq.copy()
+    assert b.lib.hrd_rx_fs4_rotate(b.h, buf.ctypes.data, buf.size, 1, capi.MEM_HOST, None) == 0
+    assert np.array_equal(buf, up.reshape(-1))
+    # down undoes up wherever no -128 is involved; and the front end is reduce + up
+    ok = (np.abs(z) < 128).all(axis=(1, 2))
+    assert b.lib.hrd_rx_fs4_rotate(b.h, buf.ctypes.data, buf.size, 0, capi.MEM_HOST, None) == 0
+    assert np.array_equal(buf.reshape(-1, 8)[ok], iq.reshape(-1, 8)[ok])
