@@ -400,7 +400,7 @@ def run_next_rows(torch, capi, device, args, peak):
                               "hbm_frac": round(sps * BYTES_PER_IN_SAMPLE_RX / 1e9 / peak, 4),
                               "blocks_per_call": int(blocks), "open_fraction": round(float(allowed.mean()), 3),
                               "note": "gated path: front end + magnitudes for every block, one host read of the decisions, "
-                                      "demodulators block by block for the open ones"}
+                                      "demodulators over runs of like blocks for the open ones"}
     del b, iq, pcm
     torch.cuda.empty_cache()
     n_pcm = n_samples // 256

@@ -891,7 +891,6 @@ static int rx_squelched(hrd_batch_t *b, hrd::RxParams p, size_t n256, int16_t *d
 {
     // one reference call: 262144 bytes at 2.048 MS/s (hackRf/hackrf.c:101) = 16384 samples at 256 kS/s
     const size_t blk256 = b->opt[HRD_OPT_RX_SQUELCH_BLOCK] > 0 ? (size_t)b->opt[HRD_OPT_RX_SQUELCH_BLOCK] / 16 : 16384;
-    const size_t blk_pcm = blk256 / 32;
     const int n_blocks = (int)((n256 + blk256 - 1) / blk256);
     const size_t n = (size_t)b->n, cells = n * (size_t)n_blocks;
     const size_t row256 = (n256 * 2 + 31) & ~(size_t)31;
@@ -899,7 +898,6 @@ static int rx_squelched(hrd_batch_t *b, hrd::RxParams p, size_t n256, int16_t *d
     if (!rc) rc = ensure_cap(&b->d_sq_mag, &b->d_sq_mag_cap, cells * sizeof(uint32_t));
     if (!rc) rc = ensure_cap(&b->d_sq_open, &b->d_sq_open_cap, cells);
     if (!rc) rc = ensure_cap(&b->d_sq_at, &b->d_sq_at_cap, cells * sizeof(uint32_t));
-    if (!rc) rc = ensure_cap(&b->d_sq_pcm, &b->d_sq_pcm_cap, n * blk_pcm * sizeof(int16_t));
     if (!rc) rc = ensure_cap(&b->d_sq_ids, &b->d_sq_ids_cap, cells * sizeof(int32_t));
     if (rc) return rc;
 
@@ -932,7 +930,6 @@ static int rx_squelched(hrd_batch_t *b, hrd::RxParams p, size_t n256, int16_t *d
     // 3. where every open block's PCM goes, and who runs in which block
     std::vector<uint32_t> at(cells);
     std::vector<int32_t> ids(cells);
-    std::vector<int> cnt((size_t)n_blocks * 4, 0), off((size_t)n_blocks * 4, 0);
     for (size_t st = 0; st < n; st++) {
         uint32_t o = 0;
         const bool demod = b->h_kind[st] != hrd::K_NONE;
@@ -944,50 +941,73 @@ static int rx_squelched(hrd_batch_t *b, hrd::RxParams p, size_t n256, int16_t *d
         if (pcm_counts) pcm_counts[st] = o;
     }
     static const int list_of_kind[5] = {hrd::K_NONE, hrd::K_AM, hrd::K_FM, hrd::K_WBFM, hrd::K_AM}; // SSB rides with AM
+    // Consecutive blocks that the gate treats alike (the same streams open) are demodulated as ONE call: the
+    // demodulators do not care where the reference cut its calls (block-size invariance, tests/), and a run of
+    // r blocks costs one set of launches instead of r.
+    std::vector<int> run_begin; // block index where each run starts, plus the end sentinel
+    for (int k = 0; k < n_blocks; k++) {
+        bool same = k > 0;
+        for (size_t st = 0; same && st < n; st++)
+            same = b->sq_open[st * n_blocks + k] == b->sq_open[st * n_blocks + k - 1];
+        if (!same) run_begin.push_back(k);
+    }
+    run_begin.push_back(n_blocks);
+    const int n_runs = (int)run_begin.size() - 1;
+    std::vector<int> cnt((size_t)n_runs * 4, 0), off((size_t)n_runs * 4, 0);
     size_t fill = 0;
-    for (int k = 0; k < n_blocks; k++)
+    for (int r = 0; r < n_runs; r++)
         for (int list = 1; list < 4; list++) {
-            off[(size_t)k * 4 + list] = (int)fill;
+            const int k = run_begin[(size_t)r];
+            off[(size_t)r * 4 + list] = (int)fill;
             for (size_t st = 0; st < n; st++)
                 if (list_of_kind[b->h_kind[st]] == list && b->sq_open[st * n_blocks + k]) ids[fill++] = (int32_t)st;
-            cnt[(size_t)k * 4 + list] = (int)fill - off[(size_t)k * 4 + list];
+            cnt[(size_t)r * 4 + list] = (int)fill - off[(size_t)r * 4 + list];
         }
     HRD_CUDA(cudaMemcpyAsync(b->d_sq_at, at.data(), cells * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     if (fill) HRD_CUDA(cudaMemcpyAsync(b->d_sq_ids, ids.data(), fill * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     HRD_CUDA(cudaStreamSynchronize(s)); // at / ids are stack-lived host vectors
-    // 4. the demodulators, one reference call (block) at a time
-    const size_t pre_need = (blk_pcm + 7) & ~(size_t)7;
+    // 4. the demodulators, one run of like blocks at a time
+    size_t longest = 0;
+    for (int r = 0; r < n_runs; r++)
+        longest = std::max(longest, std::min(n256, (size_t)run_begin[(size_t)r + 1] * blk256) - (size_t)run_begin[(size_t)r] * blk256);
+    const size_t run_pcm = longest / 32;
+    rc = ensure_cap(&b->d_sq_pcm, &b->d_sq_pcm_cap, n * run_pcm * sizeof(int16_t));
+    if (rc) return rc;
+    const size_t pre_need = (run_pcm + 7) & ~(size_t)7;
+    if (pre_need * n >= ((size_t)1 << 32)) return fail(HRD_EINVAL, "call too long for %d squelched AM/SSB streams", b->n);
     if (b->pre_stride < pre_need) {
         rc = ensure_cap((void **)&b->d_pre, &b->d_pre_cap, pre_need * sizeof(float) * n);
         if (rc) return rc;
         b->pre_stride = pre_need;
     }
-    for (int k = 0; k < n_blocks; k++) {
-        const size_t len = std::min(blk256, n256 - (size_t)k * blk256);
-        if (!(cnt[(size_t)k * 4 + 1] + cnt[(size_t)k * 4 + 2] + cnt[(size_t)k * 4 + 3])) continue; // gate closed everywhere
+    for (int r = 0; r < n_runs; r++) {
+        const int k = run_begin[(size_t)r];
+        const size_t begin = (size_t)k * blk256;
+        const size_t len = std::min(n256, (size_t)run_begin[(size_t)r + 1] * blk256) - begin;
+        if (!(cnt[(size_t)r * 4 + 1] + cnt[(size_t)r * 4 + 2] + cnt[(size_t)r * 4 + 3])) continue; // gate closed everywhere
         hrd::RxParams q = p;
-        q.iq = (const int8_t *)b->d_sq256 + (size_t)k * blk256 * 2;
+        q.iq = (const int8_t *)b->d_sq256 + begin * 2;
         q.iq_stride = row256;
         q.n256 = (uint32_t)len;
         q.pcm = (int16_t *)b->d_sq_pcm;
-        q.pcm_stride = blk_pcm;
+        q.pcm_stride = run_pcm;
         q.state_in = (const hrd::RxState *)b->d_state[b->cur];
         q.state_out = (hrd::RxState *)b->d_state[b->cur ^ 1];
         q.pre_iir = b->d_pre;
         q.pre_stride = b->pre_stride;
         q.kind_of = b->d_kind;
         q.gain_ssb = b->d_param[HRD_PARAM_SSB_GAIN];
-        // streams that do not run in this block keep their record
+        // streams that do not run in this run keep their record
         HRD_CUDA(cudaMemcpyAsync(b->d_state[b->cur ^ 1], b->d_state[b->cur], sizeof(hrd::RxState) * n, cudaMemcpyDeviceToDevice, s));
         const int32_t *ids_of[4];
         int cnt_of[4];
         for (int list = 0; list < 4; list++) {
-            ids_of[list] = (const int32_t *)b->d_sq_ids + off[(size_t)k * 4 + list];
-            cnt_of[list] = list ? cnt[(size_t)k * 4 + list] : 0;
+            ids_of[list] = (const int32_t *)b->d_sq_ids + off[(size_t)r * 4 + list];
+            cnt_of[list] = list ? cnt[(size_t)r * 4 + list] : 0;
         }
         rc = run_demods(b, q, HRD_ENTRY_256K, (uint32_t)((len + 1023) / 1024), ids_of, cnt_of, s, nullptr);
         if (rc) return rc;
-        if (hrd::launch_squelch_scatter((const int16_t *)b->d_sq_pcm, blk_pcm, d_pcm, d_pcm_stride, (const uint32_t *)b->d_sq_at,
+        if (hrd::launch_squelch_scatter((const int16_t *)b->d_sq_pcm, run_pcm, d_pcm, d_pcm_stride, (const uint32_t *)b->d_sq_at,
                                         (const uint8_t *)b->d_sq_open, b->d_kind, b->n, n_blocks, k, (uint32_t)(len / 32), s))
             return fail(HRD_ECUDA, "squelch scatter launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         b->launches++;
