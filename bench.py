@@ -252,12 +252,23 @@ def run_ours(args):
     torch.cuda.set_device(device)
     dist = None
     if world > 1:
-        # NCCL_DEBUG=VERSION makes NCCL print its version on STDOUT, in front of the one JSON line the
-        # contract asks for; keep warnings, drop the banner (INFO and above are left as the caller set them)
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        # NCCL prints a version banner on STDOUT when its debug level is VERSION (environment or nccl.conf), in
+        # front of the one JSON line the contract asks for.  Ask for warnings only unless the caller chose a
+        # level, and send whatever the library still writes to fd 1 while the communicator comes up to stderr.
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=device)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()  # the communicator (and its banner) is created here at the latest
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     peak, peak_src = measured_peak_gbs()
 
     n_samples = int(args.seconds * FS) // 8192 * 8192
