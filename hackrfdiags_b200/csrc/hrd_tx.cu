@@ -526,6 +526,12 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
     auto produce = [&](uint32_t t) {
         const uint32_t done = t * TW_STEP8;
         const int nb = (int)min((uint32_t)TW_STEP8, p.n8 - done);
+#if HRD_EXP & 256
+        const bool front = (t & 3) == 0; // timing experiment: stages 1..4 on every fourth step only
+#else
+        const bool front = true;
+#endif
+        if (front) {
         if (lane < nb) it.s0[19 + lane] = (int)src[done + lane];
         __syncwarp();
         if (lane < nb) { // stage 1: 40 taps, L = 2 (the only stage whose output may wrap: keep q15)
@@ -549,6 +555,7 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
         __syncwarp();
         for (int n = lane; n < 8 * nb; n += 32) interp8_real(it.s3, n, it.s4[3 + 2 * n], it.s4[3 + 2 * n + 1]);
         __syncwarp();
+        }
         float *out = sm.ph[t & 1][row];
         bool big = false;
         for (int n = lane; n < 16 * nb; n += 32) {
@@ -568,10 +575,12 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
         big = __any_sync(HRD_FULL_MASK, big);
         if (lane == 0) sm.big[t & 1][row] = big;
         __syncwarp();
-        ring_shift(it.s0, 19, nb, lane);
-        ring_shift(it.s1, 3, 2 * nb, lane);
-        ring_shift(it.s2, 1, 4 * nb, lane);
-        ring_shift(it.s3, 3, 8 * nb, lane);
+        if (front) {
+            ring_shift(it.s0, 19, nb, lane);
+            ring_shift(it.s1, 3, 2 * nb, lane);
+            ring_shift(it.s2, 1, 4 * nb, lane);
+            ring_shift(it.s3, 3, 8 * nb, lane);
+        }
         ring_shift(it.s4, 3, 16 * nb, lane);
     };
 
