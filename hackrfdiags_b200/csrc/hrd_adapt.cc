@@ -56,10 +56,13 @@ struct IqStream {
 struct hrd_pcm_ring {
     int n = 0;
     PcmStream *s = nullptr;
+    std::vector<int16_t> rows;   // hrd_tx_from_ring: one gathered block per stream
 };
 struct hrd_iq_queue {
     int n = 0;
     IqStream *s = nullptr;
+    std::vector<int8_t> rows;    // hrd_rx_from_queue: one gathered block per stream
+    std::vector<uint32_t> bytes;
 };
 
 extern "C" {
@@ -174,11 +177,11 @@ int hrd_pcm_ring_stats(hrd_pcm_ring_t *r, int stream, uint32_t out[4])
 int hrd_tx_from_ring(hrd_batch_t *b, hrd_pcm_ring_t *r, int8_t *iq, size_t iq_stride, int mem, void *cuda_stream)
 {
     if (!b || !r) return HRD_EINVAL;
-    std::vector<int16_t> rows((size_t)r->n * BLOCK);
-    int rc = hrd_pcm_ring_read_all(r, rows.data(), BLOCK, nullptr);
-    if (rc) return rc;
     if (mem != HRD_MEM_HOST) return HRD_EINVAL; // the gathered rows live in host memory
-    return hrd_tx_process(b, rows.data(), BLOCK, BLOCK, iq, iq_stride, HRD_MEM_HOST, cuda_stream);
+    r->rows.resize((size_t)r->n * BLOCK);
+    int rc = hrd_pcm_ring_read_all(r, r->rows.data(), BLOCK, nullptr);
+    if (rc) return rc;
+    return hrd_tx_process(b, r->rows.data(), BLOCK, BLOCK, iq, iq_stride, HRD_MEM_HOST, cuda_stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -261,13 +264,13 @@ int hrd_iq_queue_stats(hrd_iq_queue_t *q, int stream, uint32_t out[3])
 int hrd_rx_from_queue(hrd_batch_t *b, hrd_iq_queue_t *q, int16_t *pcm, size_t pcm_stride, uint32_t *pcm_counts)
 {
     if (!b || !q) return HRD_EINVAL;
-    std::vector<int8_t> rows((size_t)q->n * IQ_BLOCK);
-    std::vector<uint32_t> bytes((size_t)q->n);
-    const int got = hrd_iq_queue_pop_all(q, rows.data(), IQ_BLOCK, bytes.data(), nullptr);
+    q->rows.resize((size_t)q->n * IQ_BLOCK); // allocated once, reused every round
+    q->bytes.resize((size_t)q->n);
+    const int got = hrd_iq_queue_pop_all(q, q->rows.data(), IQ_BLOCK, q->bytes.data(), nullptr);
     if (got <= 0) return got;
     for (int i = 1; i < q->n; i++)
-        if (bytes[(size_t)i] != bytes[0]) return HRD_EINVAL;
-    const int rc = hrd_rx_process(b, rows.data(), bytes[0] / 512 * 512, IQ_BLOCK, HRD_ENTRY_2048K, pcm, pcm_stride, pcm_counts,
+        if (q->bytes[(size_t)i] != q->bytes[0]) return HRD_EINVAL;
+    const int rc = hrd_rx_process(b, q->rows.data(), q->bytes[0] / 512 * 512, IQ_BLOCK, HRD_ENTRY_2048K, pcm, pcm_stride, pcm_counts,
                                   HRD_MEM_HOST, nullptr);
     return rc ? rc : 1;
 }
