@@ -140,3 +140,47 @@ def test_config4_tx_4096_streams(env, oracle, mode):
     b2.tx_device(pcm.data_ptr() + 2 * cut, n_pcm - cut, pcm.stride(0), iq2.data_ptr() + cut * 512, iq2.stride(0), 0)
     torch.cuda.synchronize()
     assert torch.equal(iq, iq2)
+
+
+def test_squelched_batch_1024_streams(env, oracle):
+    """SURVEY 8f row 1 at batch size: 1024 mixed-mode streams x 8 transfer blocks, levels that cross a -40 dBFS
+    threshold, per-stream thresholds and receive gains.  A sample of streams against the oracle (PCM, magnitudes,
+    decisions); streams fed identical inputs and parameters agree wherever they sit; the counts add up."""
+    torch, bench, capi, dev = env
+    from hackrfdiags_b200 import synth
+    n_streams, n_blocks = 1024, 8
+    modes = [(capi.MODE_AM, capi.MODE_FM, capi.MODE_WBFM, capi.MODE_LSB, capi.MODE_USB, capi.MODE_NONE)[s % 6] for s in range(n_streams)]
+    thr = [(-40, -30, -200, -45)[(s // 6) % 4] for s in range(n_streams)]
+    gain = [(16, 0, 24)[(s // 24) % 3] for s in range(n_streams)]
+    distinct = [synth.rx_bursty_stream(capi.MODE_FM, n_blocks, stream=k) for k in range(8)]
+    host = np.stack([distinct[(s // 72) % 8] for s in range(n_streams)])  # 72 = lcm of the parameter periods
+    iq = torch.from_numpy(host).to(dev)
+    pcm = torch.zeros((n_streams, n_blocks * 512), dtype=torch.int16, device=dev)
+    b = capi.Batch(n_streams, capi.RX, 0)
+    for s in range(n_streams):
+        b.set_mode(modes[s], s)
+        b.set_param(capi.PARAM_SQUELCH_THRESHOLD, thr[s], s)
+        b.set_param(capi.PARAM_RX_GAIN_DB, gain[s], s)
+    counts = np.zeros(n_streams, dtype=np.uint32)
+    rc = b.lib.hrd_rx_process(b.h, iq.data_ptr(), iq.shape[1], iq.stride(0), capi.ENTRY_2048K, pcm.data_ptr(), pcm.stride(0),
+                              counts.ctypes.data, capi.MEM_DEVICE, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    got = pcm.cpu().numpy()
+    mags, allowed = b.squelch_report()
+    assert mags.shape == (n_streams, n_blocks)
+    for s in range(n_streams):
+        want_count = 0 if modes[s] == capi.MODE_NONE else 512 * int(allowed[s].sum())
+        assert counts[s] == want_count, s
+    # streams with the same input and parameters: 72 apart, same block of eight distinct inputs every 576
+    for s in (0, 5, 17, 100):
+        t = s + 576
+        assert np.array_equal(allowed[s], allowed[t]) and np.array_equal(got[s], got[t]), (s, t)
+    gated = 0
+    for s in (0, 1, 2, 3, 4, 7, 30, 77, 500, 1023):
+        want_pcm, want_mag, want_open = oracle.run_rx_squelch(modes[s], host[s], thr[s], gain[s])
+        assert np.array_equal(mags[s], want_mag) and np.array_equal(allowed[s], want_open), s
+        if modes[s] != capi.MODE_NONE:
+            assert np.array_equal(got[s, :counts[s]], want_pcm), f"stream {s} mode {modes[s]}"
+        gated += int((want_open == 0).sum())
+    assert gated > 0
