@@ -49,7 +49,7 @@ void upload_tables(const ConstTables &t) { cudaMemcpyToSymbol(c_tab, &t, sizeof 
 namespace {
 
 constexpr int BATCH256 = 1024; // 256 kS/s samples per batch
-constexpr int IT_SAMPLES = 64; // 256 kS/s samples per warp iteration
+constexpr int IT_SAMPLES = 128; // 256 kS/s samples per warp iteration: FOUR per lane (32 input samples, 64 bytes)
 // Register prefetch depth, in warp iterations.  ONE, on purpose: ptxas puts every global load of the loop on one
 // counting scoreboard (tools/sass_ctl.py), so with two buffers the consumer of the older load also waits for
 // the younger one and the second buffer buys nothing but register pressure (measured: depth 1 is 1-4 % faster
@@ -146,11 +146,50 @@ __device__ __forceinline__ void halfband_split(const uint32_t (&ini)[N], const u
     }
 }
 
-// 16 input samples (8 raw words {I,Q,I,Q}) -> one ring word {I0,I1,Q0,Q1} at 256 kS/s,
+// 32 input samples (16 raw words {I,Q,I,Q}) -> two ring words {I0,I1,Q0,Q1}, {I2,I3,Q2,Q3} at 256 kS/s,
 // rotated by +Fs/4 (IqDataProcessor.cc:771-815) and narrowed like (int8_t) does.
 // t[] is the raw input already transposed to {I_e, I_o, Q_e, Q_o} (the caller does that first
 // so that the raw registers are free to receive the next prefetch in place).
-__device__ __forceinline__ uint32_t front_end_iter(const uint32_t (&t)[8], FeCarry &c, const FeTaps &k, int lane)
+// A lane takes FOUR output samples, not two: one neighbour shuffle per stage serves twice the samples, and
+// the lane's samples always sit at rotation phases 0,1,2,3, so the rotation needs no per-lane selects.
+__device__ __forceinline__ uint2 front_end_iter(const uint32_t (&t)[16], FeCarry &c, const FeTaps &k, int lane)
+{
+    int pi16[16], pq16[16];
+    halfband_stage<16>(t, from_left(t[15], c.t, lane), k.a0, k.b0, pi16, pq16);
+    // Stages 2 and 3 keep the I pairs and the Q pairs in separate words (pack_b2 puts a pair into bytes 0,1,
+    // which is all dp2a.lo reads): merging them into {I,I,Q,Q} words first would cost a third PRMT per word.
+    // Only the word that crosses to the next lane is merged, so the carried state keeps its layout.
+    uint32_t vi[8], vq[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        vi[j] = pack_b2(pi16[2 * j], pi16[2 * j + 1]);
+        vq[j] = pack_b2(pq16[2 * j], pq16[2 * j + 1]);
+    }
+    int pi8[8], pq8[8];
+    halfband_split<8>(vi, vq, from_left(merge16(vi[7], vq[7]), c.v, lane), k.a1, k.b1, pi8, pq8);
+    uint32_t ui[4], uq[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        ui[j] = pack_b2(pi8[2 * j], pi8[2 * j + 1]);
+        uq[j] = pack_b2(pq8[2 * j], pq8[2 * j + 1]);
+    }
+    int pi4[4], pq4[4];
+    halfband_split<4>(ui, uq, from_left(merge16(ui[3], uq[3]), c.u, lane), k.a2, k.b2, pi4, pq4);
+    // rotation, samples 0..3 of the lane = phases 0..3 of the call (a call starts at a multiple of four
+    // samples):  0:(x,y) 1:(-y,x) 2:(-x,-y) 3:(y,-x).  Negating "acc>>16" is (65535-acc)>>16.
+    const int i0 = pi4[0], q0 = pq4[0];
+    const int i1 = 65535 - pq4[1], q1 = pi4[1];
+    const int i2 = 65535 - pi4[2], q2 = 65535 - pq4[2];
+    const int i3 = pq4[3], q3 = 65535 - pi4[3];
+    return make_uint2(merge16(pack_b2(i0, i1), pack_b2(q0, q1)), merge16(pack_b2(i2, i3), pack_b2(q2, q3)));
+}
+
+// The narrow form, kept for rx_wbfm_kernel (whose item warps have no registers to spare: the wide form spills there
+// and was 14 % slower): 16 input samples (8 raw words {I,Q,I,Q}) -> one ring word {I0,I1,Q0,Q1} at 256 kS/s,
+// rotated by +Fs/4 (IqDataProcessor.cc:771-815) and narrowed like (int8_t) does.
+// t[] is the raw input already transposed to {I_e, I_o, Q_e, Q_o} (the caller does that first
+// so that the raw registers are free to receive the next prefetch in place).
+__device__ __forceinline__ uint32_t front_end_iter_narrow(const uint32_t (&t)[8], FeCarry &c, const FeTaps &k, int lane)
 {
     int pi8[8], pq8[8];
     halfband_stage<8>(t, from_left(t[7], c.t, lane), k.a0, k.b0, pi8, pq8);
@@ -251,9 +290,12 @@ __device__ __forceinline__ void ring_init(T *ring, const T *state, int hist, int
     for (int i = lane; i < hist; i += 32) ring[i] = from_state ? state[i] : T();
 }
 
-// input of one warp iteration: 32 bytes per lane at the 2.048 MS/s entry, 4 at the 256 kS/s one
-template <int ENTRY> struct RawOf { typedef u32x8 type; };
-template <> struct RawOf<1> { typedef uint32_t type; };
+// input of one warp iteration: 64 bytes per lane at the 2.048 MS/s entry, 8 at the 256 kS/s one
+struct u32x16 {
+    u32x8 a, b;
+};
+template <int ENTRY> struct RawOf { typedef u32x16 type; };
+template <> struct RawOf<1> { typedef uint2 type; };
 
 // Unconditional load at a clamped offset: lanes past the end of the tile re-read its last
 // chunk instead of being predicated off (a predicated LDG.256 costs 16 register moves to keep
@@ -261,6 +303,40 @@ template <> struct RawOf<1> { typedef uint32_t type; };
 // data only flows from lower to higher lanes, and a partly filled iteration is the tile's last.
 template <int ENTRY>
 __device__ __forceinline__ typename RawOf<ENTRY>::type load_raw(const int8_t *src, uint32_t off, uint32_t off_last)
+{
+    const uint32_t o = min(off, off_last);
+    if constexpr (ENTRY == 0) {
+        u32x16 r;
+        r.a = ldg_stream_256(src + o);
+        r.b = ldg_stream_256(src + o + 32);
+        return r;
+    } else { // rows are only 4-byte aligned at this entry
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(src + o);
+        return make_uint2(__ldg(q), __ldg(q + 1));
+    }
+}
+
+// An L2 prefetch needs no register and no scoreboard: once every two iterations the warp pulls the 4 KiB it
+// will read RX_L2_AHEAD KiB from now out of DRAM (lane l takes the 128-byte line l), and the LDG that
+// follows later hits in L2 (a few hundred cycles instead of a DRAM round trip under load).
+// pf is the lane's own next load offset (warp base + 64 * lane).
+__device__ __forceinline__ void prefetch_chunk(const int8_t *src, uint32_t pf, uint32_t pf_last, int lane)
+{
+    prefetch_l2(src + min(pf + 64u * (uint32_t)lane + RX_L2_AHEAD * 1024u, pf_last));
+}
+
+// ---- the same for the narrow form (two samples per lane, IT_NARROW samples per warp iteration) ----
+constexpr int IT_NARROW = 64;
+// input of one warp iteration: 32 bytes per lane at the 2.048 MS/s entry, 4 at the 256 kS/s one
+template <int ENTRY> struct RawNarrowOf { typedef u32x8 type; };
+template <> struct RawNarrowOf<1> { typedef uint32_t type; };
+
+// Unconditional load at a clamped offset: lanes past the end of the tile re-read its last
+// chunk instead of being predicated off (a predicated LDG.256 costs 16 register moves to keep
+// the old value alive).  What they compute is never stored and never reaches a live lane:
+// data only flows from lower to higher lanes, and a partly filled iteration is the tile's last.
+template <int ENTRY>
+__device__ __forceinline__ typename RawNarrowOf<ENTRY>::type load_raw_narrow(const int8_t *src, uint32_t off, uint32_t off_last)
 {
     const uint32_t o = min(off, off_last);
     if constexpr (ENTRY == 0) {
@@ -274,9 +350,9 @@ __device__ __forceinline__ typename RawOf<ENTRY>::type load_raw(const int8_t *sr
 // will read RX_L2_AHEAD iterations from now out of DRAM (lane l takes the 128-byte line l), and the LDG that
 // follows later hits in L2 (a few hundred cycles instead of a DRAM round trip under load).
 // pf is the lane's own next load offset (warp base + 32 * lane).
-__device__ __forceinline__ void prefetch_chunk(const int8_t *src, uint32_t pf, uint32_t pf_last, int lane)
+__device__ __forceinline__ void prefetch_chunk_narrow(const int8_t *src, uint32_t pf, uint32_t pf_last, int lane)
 {
-    prefetch_l2(src + min(pf + 96u * (uint32_t)lane + RX_L2_AHEAD * IT_SAMPLES * 16, pf_last));
+    prefetch_l2(src + min(pf + 96u * (uint32_t)lane + RX_L2_AHEAD * IT_NARROW * 16, pf_last));
 }
 
 // ------------------------------------------------------------------------------------
@@ -357,8 +433,8 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, HRD_RX_MIN_CTAS) rx_ke
 
     // ---- software prefetch: RX_DEPTH iterations of input in flight ------------------------
     constexpr uint32_t BPS = ENTRY == 0 ? 16 : 2;           // input bytes per 256 kS/s sample
-    uint32_t pf = (done256 + 2 * lane) * BPS;               // this lane's next prefetch offset
-    const uint32_t pf_last = (end256 - 2) * BPS;            // its clamp: the tile's last lane chunk
+    uint32_t pf = (done256 + 4 * lane) * BPS;               // this lane's next prefetch offset
+    const uint32_t pf_last = (end256 - 4) * BPS;            // its clamp: the tile's last lane chunk
     Raw buf[RX_DEPTH];
 #pragma unroll
     for (int d = 0; d < RX_DEPTH; d++) {
@@ -372,35 +448,40 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, HRD_RX_MIN_CTAS) rx_ke
         const uint32_t nb = min((uint32_t)BATCH256, end256 - done256); // multiple of 32
         const uint32_t n_it = (nb + IT_SAMPLES - 1) / IT_SAMPLES;
         const bool emit = done256 >= emit_from;
-        last_active = min(32u, (nb - (n_it - 1) * IT_SAMPLES) / 2);
+        last_active = min(32u, (nb - (n_it - 1) * IT_SAMPLES) / 4);
 
         // ---- A. front end (or plain load at the 256 kS/s entry) ----------------------
         // one iteration: consume b (loaded RX_DEPTH iterations ago), refill it in place
         auto step = [&](Raw &b, const uint32_t it) {
-            uint32_t word;
+            uint2 words;
             if constexpr (ENTRY == 0) {
-                uint32_t t[8];
+                uint32_t t[16];
 #pragma unroll
-                for (int r = 0; r < 8; r++) t[r] = __byte_perm(b.v[r], 0, 0x3120);
+                for (int r = 0; r < 8; r++) {
+                    t[r] = __byte_perm(b.a.v[r], 0, 0x3120);
+                    t[8 + r] = __byte_perm(b.b.v[r], 0, 0x3120);
+                }
                 b = load_raw<ENTRY>(src, pf, pf_last); // in place: b is dead now
-                if ((it & 3) == 0) prefetch_chunk(src, pf, pf_last, lane);
-                word = front_end_iter(t, fc, fk, lane);
+                if ((it & 1) == 0) prefetch_chunk(src, pf, pf_last, lane);
+                words = front_end_iter(t, fc, fk, lane);
             } else {
-                word = __byte_perm(b, 0, 0x3120);
+                words = make_uint2(__byte_perm(b.x, 0, 0x3120), __byte_perm(b.y, 0, 0x3120));
                 b = load_raw<ENTRY>(src, pf, pf_last);
             }
             pf += IT_SAMPLES * BPS;
-            const uint32_t widx = it * 32 + lane; // word index inside the batch
+            const uint32_t widx = it * (IT_SAMPLES / 2) + 2 * lane; // word index inside the batch (even)
             // lanes past the end of the tile write ring slots nothing reads
             if constexpr (KIND == K_NONE) {
-                const uint32_t s0 = done256 + it * IT_SAMPLES + 2 * lane;
-                if (p.out256 && s0 < end256 && emit)
-                    *reinterpret_cast<uint32_t *>(p.out256 + (size_t)sid * p.out_stride + (size_t)s0 * 2) =
-                        __byte_perm(word, 0, 0x3120);
+                const uint32_t s0 = done256 + it * IT_SAMPLES + 4 * lane;
+                if (p.out256 && s0 < end256 && emit) {
+                    uint32_t *o = reinterpret_cast<uint32_t *>(p.out256 + (size_t)sid * p.out_stride + (size_t)s0 * 2);
+                    o[0] = __byte_perm(words.x, 0, 0x3120);
+                    o[1] = __byte_perm(words.y, 0, 0x3120);
+                }
             } else if constexpr (KIND == K_AM) {
-                sm.r256[2 + widx] = word;
+                *reinterpret_cast<uint2 *>(&sm.r256[2 + widx]) = words;
             } else {
-                sm.r256[14 + widx] = word;
+                *reinterpret_cast<uint2 *>(&sm.r256[14 + widx]) = words;
             }
         };
 #pragma unroll 2
@@ -629,7 +710,7 @@ struct SmemWb {
 template <int ENTRY, bool TILED>
 __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
 {
-    typedef typename RawOf<ENTRY>::type Raw;
+    typedef typename RawNarrowOf<ENTRY>::type Raw;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // the exact re-run after a failed verification: only the streams the verifier listed
     const int n_streams = p.run_if ? (int)*p.run_if : p.n_streams;
@@ -709,8 +790,8 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
         pf_last = (end - 2) * BPS;
 #pragma unroll
         for (int d = 0; d < WB_DEPTH; d++) {
-            buf[d] = load_raw<ENTRY>(src, pf, pf_last);
-            pf += IT_SAMPLES * BPS;
+            buf[d] = load_raw_narrow<ENTRY>(src, pf, pf_last);
+            pf += IT_NARROW * BPS;
         }
     }
     __syncwarp();
@@ -722,13 +803,13 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
             uint32_t t[8];
 #pragma unroll
             for (int r = 0; r < 8; r++) t[r] = __byte_perm(b.v[r], 0, 0x3120);
-            b = load_raw<ENTRY>(src, pf, pf_last);
-            word = front_end_iter(t, fc, fk, lane);
+            b = load_raw_narrow<ENTRY>(src, pf, pf_last);
+            word = front_end_iter_narrow(t, fc, fk, lane);
         } else {
             word = __byte_perm(b, 0, 0x3120);
-            b = load_raw<ENTRY>(src, pf, pf_last);
+            b = load_raw_narrow<ENTRY>(src, pf, pf_last);
         }
-        pf += IT_SAMPLES * BPS;
+        pf += IT_NARROW * BPS;
 #if HRD_EXP & 4
         *reinterpret_cast<float2 *>(dst + 2 * lane) = make_float2(__int_as_float(word), 0.f);
         return;
@@ -769,15 +850,15 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
         const uint32_t done = start + t * WB_STEP;
         if (done >= end) return;
         const uint32_t nb = min((uint32_t)WB_STEP, end - done);
-        const uint32_t n_it = (nb + IT_SAMPLES - 1) / IT_SAMPLES;
-        last_active = min(32u, (nb - (n_it - 1) * IT_SAMPLES) / 2);
-        if constexpr (ENTRY == 0) prefetch_chunk(src, pf, pf_last, lane); // a step is four iterations = 4 KiB
+        const uint32_t n_it = (nb + IT_NARROW - 1) / IT_NARROW;
+        last_active = min(32u, (nb - (n_it - 1) * IT_NARROW) / 2);
+        if constexpr (ENTRY == 0) prefetch_chunk_narrow(src, pf, pf_last, lane); // a step is four iterations = 4 KiB
         float *dst = sm.f[t & 1][row];
-        if (n_it == WB_STEP / IT_SAMPLES) { // a full step, unrolled: the in-place refill of buf needs no register moves
+        if (n_it == WB_STEP / IT_NARROW) { // a full step, unrolled: the in-place refill of buf needs no register moves
 #pragma unroll
-            for (uint32_t i = 0; i < WB_STEP / IT_SAMPLES; i++) iter(buf[0], dst + i * IT_SAMPLES);
+            for (uint32_t i = 0; i < WB_STEP / IT_NARROW; i++) iter(buf[0], dst + i * IT_NARROW);
         } else {
-            for (uint32_t i = 0; i < n_it; i++) iter(buf[0], dst + i * IT_SAMPLES);
+            for (uint32_t i = 0; i < n_it; i++) iter(buf[0], dst + i * IT_NARROW);
         }
         __syncwarp();
     };
