@@ -155,35 +155,45 @@ __device__ __forceinline__ float phase_advance_lockstep(float acc, float step, u
 // 16 outputs as accumulators whose byte 2 is the (int8_t) value (doubled taps, see hrd_rx.cu).
 // Stage 5 is the 8-tap half-band {a,0,b,16384,b,0,a,0} (AmModulator.cc:57-67; structure asserted
 // on the host): its even branch is a*(x0+x3) + b*(x1+x2), its odd branch is 16384*x[n-1].
-__device__ __forceinline__ void tail4(int x0, int x1, int x2, int x3, int (&out)[16])
+// m5 / m6 / m7 are the values "one output before" this sample's first output at stages 5 / 6 / 7 (the odd-phase
+// outputs of the sample before); they come in from the caller and go out updated for the next sample, so a lane
+// that takes consecutive samples computes them once.
+__device__ __forceinline__ void tail4(int x0, int x1, int x2, int x3, int &m5, int &m6, int &m7, int (&out)[16])
 {
     const int ha = c_tabtx.tx_hb8[0], hb = c_tabtx.tx_hb8[2];
-    int y5[2], y5m1;
+    int y5[2];
     y5[0] = ((1 << 14) + ha * (x0 + x3) + hb * (x1 + x2)) >> 15; // |.| <= 21986: fits int16
     y5[1] = (x1 + 1) >> 1;
-    y5m1 = (x2 + 1) >> 1;    // odd output of the previous input sample
     const int c6 = c_tabtx.tx_c3, c7 = c_tabtx.tx_c7, c8d = 2 * c_tabtx.tx_c8;
     const int k15 = c_tabtx.k_32768;
-    int y6[4], y6m1;
-    y6m1 = (y5m1 + 1) >> 1;
-    y6[0] = hb4_even(c6, y5[0], y5m1);
+    int y6[4];
+    y6[0] = hb4_even(c6, y5[0], m5);
     y6[1] = hb4_odd(y5[0]);
     y6[2] = hb4_even(c6, y5[1], y5[0]);
     y6[3] = hb4_odd(y5[1]);
-    int y7[8], y7m1;
-    y7m1 = hb4_odd(y6m1);
+    int y7[8];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        y7[2 * k] = hb4_even(c7, y6[k], k ? y6[k - 1] : y6m1);
+        y7[2 * k] = hb4_even(c7, y6[k], k ? y6[k - 1] : m6);
         y7[2 * k + 1] = hb4_odd(y6[k]);
     }
     // stage 8 with doubled taps: (int8_t)(acc>>15) == byte 2 of 2*acc
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        int left = k ? y7[k - 1] : y7m1;
+        int left = k ? y7[k - 1] : m7;
         out[2 * k] = (1 << 15) + c8d * (y7[k] + left);
         out[2 * k + 1] = y7[k] * k15 + k15;
     }
+    m5 = y5[1];
+    m6 = y6[3];
+    m7 = y7[7];
+}
+// the three carried values at the start of a run: the odd-phase chain of the sample before (x2 of the first call)
+__device__ __forceinline__ void tail4_start(int x2, int &m5, int &m6, int &m7)
+{
+    m5 = (x2 + 1) >> 1;
+    m6 = hb4_odd(m5);
+    m7 = hb4_odd(m6);
 }
 
 __device__ __forceinline__ uint32_t pack_b2(int a, int b) { return __byte_perm((uint32_t)a, (uint32_t)b, 0x0062); }
@@ -346,22 +356,31 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxPara
 
         // ---- 3. hot loop: stages 5..8, 32 bytes per lane per iteration ------------------------
         int8_t *out = dst + (size_t)done * 512;
-        for (int n = lane; n < 16 * nb; n += 32) {
-            uint32_t w0 = sm.s4[3 + n], w1 = sm.s4[2 + n], w2 = sm.s4[1 + n], w3 = sm.s4[n];
-            int oi[16];
-            tail4(lo16(w0), lo16(w1), lo16(w2), lo16(w3), oi);
-            u32x8 o;
-            if constexpr (KIND == K_AM) { // both rails carry the same samples (AmModulator.cc:601-602)
+        // a lane takes TWO consecutive 128 kS/s samples (64 output bytes): five ring words instead of eight, and the
+        // second sample's left-neighbour chain is the first one's own tail
+        for (int n = 2 * lane; n < 16 * nb; n += 64) {
+            const uint32_t wa = sm.s4[4 + n], w0 = sm.s4[3 + n], w1 = sm.s4[2 + n], w2 = sm.s4[1 + n], w3 = sm.s4[n];
+            int mi5, mi6, mi7, mq5, mq6, mq7;
+            tail4_start(lo16(w2), mi5, mi6, mi7);
+            if constexpr (KIND != K_AM) tail4_start(hi16(w2), mq5, mq6, mq7);
 #pragma unroll
-                for (int k = 0; k < 8; k++) o.v[k] = __byte_perm((uint32_t)oi[2 * k], (uint32_t)oi[2 * k + 1], 0x6622);
-            } else {
-                int oq[16];
-                tail4(hi16(w0), hi16(w1), hi16(w2), hi16(w3), oq);
+            for (int h = 0; h < 2; h++) {
+                const uint32_t a0 = h ? wa : w0, a1 = h ? w0 : w1, a2 = h ? w1 : w2, a3 = h ? w2 : w3;
+                int oi[16];
+                tail4(lo16(a0), lo16(a1), lo16(a2), lo16(a3), mi5, mi6, mi7, oi);
+                u32x8 o;
+                if constexpr (KIND == K_AM) { // both rails carry the same samples (AmModulator.cc:601-602)
 #pragma unroll
-                for (int k = 0; k < 8; k++) // bytes {I[2k], Q[2k], I[2k+1], Q[2k+1]}
-                    o.v[k] = merge16(pack_b2(oi[2 * k], oq[2 * k]), pack_b2(oi[2 * k + 1], oq[2 * k + 1]));
+                    for (int k = 0; k < 8; k++) o.v[k] = __byte_perm((uint32_t)oi[2 * k], (uint32_t)oi[2 * k + 1], 0x6622);
+                } else {
+                    int oq[16];
+                    tail4(hi16(a0), hi16(a1), hi16(a2), hi16(a3), mq5, mq6, mq7, oq);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) // bytes {I[2k], Q[2k], I[2k+1], Q[2k+1]}
+                        o.v[k] = merge16(pack_b2(oi[2 * k], oq[2 * k]), pack_b2(oi[2 * k + 1], oq[2 * k + 1]));
+                }
+                if (emit) stg_stream_256(out + (size_t)(n + h) * 32, o);
             }
-            if (emit) stg_stream_256(out + (size_t)n * 32, o);
         }
         __syncwarp();
         ring_shift(sm.s0, 19, nb, lane);
