@@ -360,6 +360,10 @@ int ensure_cap(void **ptr, size_t *cap, size_t need)
     *cap = 0;
     HRD_CUDA(cudaMalloc(ptr, need));
     *cap = need;
+    // Scratch rows are padded (8 floats, 16-byte copies): kernels copy the padding along and never use it.  Zero it
+    // once, on growth only, so that nothing ever reads uninitialised memory (compute-sanitizer initcheck stays clean).
+    HRD_CUDA(cudaMemset(*ptr, 0, need));
+    HRD_CUDA(cudaDeviceSynchronize());
     return HRD_OK;
 }
 

@@ -44,12 +44,19 @@ __device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xffff
 __device__ __forceinline__ int hi16(uint32_t w) { return ((int)w) >> 16; }
 __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
 
-struct SmemTx {
+// Samples per lane per iteration of the hot loop (stages 5..8): consecutive ones, so that they share ring words and
+// the left-neighbour chain of the half-band stages is carried from one to the next.  Measured (4096 streams x 0.5 s):
+// FM 1.931 ms (two, scalar LDS) / 1.924 (two, vector LDS) / 1.868 (four, LDS.128); SSB 1.895 / 1.917 / 1.845;
+// AM 1.308 / 1.296 / 1.326 (four costs it registers: 40 -> 48).  So: four for the two-rail modulators, two with
+// scalar loads for AM and for the signals/ kind (72 registers with four; not timed, left as it was).
+template <int KIND> struct TxSplOf { static constexpr int value = (KIND == K_FM || KIND == K_SSB) ? 4 : 2; };
+
+struct alignas(16) SmemTx {
+    alignas(16) uint32_t s4[4 + 16 * NB8];  // stage 5 input  @128k (the hot loop reads it with vector loads; one pad word)
     uint32_t s0[19 + NB8];      // stage 1 input  @8k   I/Q pairs (WBFM: PCM in the low half)
     uint32_t s1[3 + 2 * NB8];   // stage 2 input  @16k
     uint32_t s2[1 + 4 * NB8];   // stage 3 input  @32k
     uint32_t s3[3 + 8 * NB8];   // stage 4 input  @64k
-    uint32_t s4[3 + 16 * NB8];  // stage 5 input  @128k
     uint32_t h8[30 + NB8];      // SSB: PCM/2 history for delay line / Hilbert
 };
 
@@ -356,25 +363,32 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxPara
 
         // ---- 3. hot loop: stages 5..8, 32 bytes per lane per iteration ------------------------
         int8_t *out = dst + (size_t)done * 512;
-        // a lane takes TWO consecutive 128 kS/s samples (64 output bytes): five ring words instead of eight, and the
-        // second sample's left-neighbour chain is the first one's own tail
-        for (int n = 2 * lane; n < 16 * nb; n += 64) {
-            const uint32_t wa = sm.s4[4 + n], w0 = sm.s4[3 + n], w1 = sm.s4[2 + n], w2 = sm.s4[1 + n], w3 = sm.s4[n];
-            int mi5, mi6, mi7, mq5, mq6, mq7;
-            tail4_start(lo16(w2), mi5, mi6, mi7);
-            if constexpr (KIND != K_AM) tail4_start(hi16(w2), mq5, mq6, mq7);
+        // a lane takes TX_SPL consecutive 128 kS/s samples (32 output bytes each): TX_SPL + 3 ring words
+        // instead of 4 per sample, and each sample's left-neighbour chain is the tail of the one before
+        constexpr int TX_SPL = TxSplOf<KIND>::value;
+        for (int n = TX_SPL * lane; n < 16 * nb; n += 32 * TX_SPL) {
+            uint32_t w[TX_SPL + 3]; // w[j] = s4[n + j]: sample n + h reads w[h + 3] (newest) .. w[h]
+            if constexpr (TX_SPL == 4) { // s4 is 16-byte aligned and n a multiple of four: two LDS.128
+                const uint4 a = *reinterpret_cast<const uint4 *>(sm.s4 + n), b = *reinterpret_cast<const uint4 *>(sm.s4 + n + 4);
+                w[0] = a.x, w[1] = a.y, w[2] = a.z, w[3] = a.w, w[4] = b.x, w[5] = b.y, w[6] = b.z;
+            } else {
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const uint32_t a0 = h ? wa : w0, a1 = h ? w0 : w1, a2 = h ? w1 : w2, a3 = h ? w2 : w3;
+                for (int j = 0; j < 5; j++) w[j] = sm.s4[n + j];
+            }
+            int mi5, mi6, mi7, mq5, mq6, mq7;
+            tail4_start(lo16(w[1]), mi5, mi6, mi7);
+            if constexpr (KIND != K_AM) tail4_start(hi16(w[1]), mq5, mq6, mq7);
+#pragma unroll
+            for (int h = 0; h < TX_SPL; h++) {
                 int oi[16];
-                tail4(lo16(a0), lo16(a1), lo16(a2), lo16(a3), mi5, mi6, mi7, oi);
+                tail4(lo16(w[h + 3]), lo16(w[h + 2]), lo16(w[h + 1]), lo16(w[h]), mi5, mi6, mi7, oi);
                 u32x8 o;
                 if constexpr (KIND == K_AM) { // both rails carry the same samples (AmModulator.cc:601-602)
 #pragma unroll
                     for (int k = 0; k < 8; k++) o.v[k] = __byte_perm((uint32_t)oi[2 * k], (uint32_t)oi[2 * k + 1], 0x6622);
                 } else {
                     int oq[16];
-                    tail4(hi16(a0), hi16(a1), hi16(a2), hi16(a3), mq5, mq6, mq7, oq);
+                    tail4(hi16(w[h + 3]), hi16(w[h + 2]), hi16(w[h + 1]), hi16(w[h]), mq5, mq6, mq7, oq);
 #pragma unroll
                     for (int k = 0; k < 8; k++) // bytes {I[2k], Q[2k], I[2k+1], Q[2k+1]}
                         o.v[k] = merge16(pack_b2(oi[2 * k], oq[2 * k]), pack_b2(oi[2 * k + 1], oq[2 * k + 1]));
