@@ -508,7 +508,10 @@ def run_reference(args):
            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": round(t_tot / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "int16 Q15 / f32 (reference CPU arithmetic)", "data": "synthetic",
-           "config": {"workload": "BASELINE configs[1] mode mix, bounded sample (see cpu_baseline.sample)"},
+           # the product arm's workload, named the same way; each step times a bounded sample of it
+           "config": {"workload": "BASELINE configs[1]: 1024 streams/GPU = 512 AM + 256 LSB + 256 USB, "
+                                  f"{n_samples / FS:.3f} s of int8 IQ @2.048 MS/s each, IqDataProcessor entry",
+                      "streams_per_gpu": args.streams, "bounded_sample": "see cpu_baseline.sample"},
            "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "reference",
                             "sample": sample},
            "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
