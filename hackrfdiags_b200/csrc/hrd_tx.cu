@@ -48,8 +48,13 @@ __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)l
 // the left-neighbour chain of the half-band stages is carried from one to the next.  Measured (4096 streams x 0.5 s):
 // FM 1.931 ms (two, scalar LDS) / 1.924 (two, vector LDS) / 1.868 (four, LDS.128); SSB 1.895 / 1.917 / 1.845;
 // AM 1.308 / 1.296 / 1.326 (four costs it registers: 40 -> 48).  So: four for the two-rail modulators, two with
-// scalar loads for AM and for the signals/ kind (72 registers with four; not timed, left as it was).
-template <int KIND> struct TxSplOf { static constexpr int value = (KIND == K_FM || KIND == K_SSB) ? 4 : 2; };
+// scalar loads for AM and for the signals/ kind (72 registers with four; not timed yet: -DHRD_TX_SPL_IQ=4 builds it).
+#ifndef HRD_TX_SPL_IQ
+#define HRD_TX_SPL_IQ 2
+#endif
+template <int KIND> struct TxSplOf {
+    static constexpr int value = (KIND == K_FM || KIND == K_SSB) ? 4 : (KIND == K_IQ ? HRD_TX_SPL_IQ : 2);
+};
 
 struct alignas(16) SmemTx {
     alignas(16) uint32_t s4[4 + 16 * NB8];  // stage 5 input  @128k (the hot loop reads it with vector loads; one pad word)
