@@ -1,0 +1,41 @@
+"""The parameter sweeps of tests/test_gpu_params.py, oracle against the compiled unmodified reference (CPU only): the
+oracle the GPU test trusts is pinned on exactly these settings."""
+import numpy as np
+import pytest
+
+from hackrfdiags_b200 import capi, synth
+from param_sweeps import DEFAULT_GAIN, NAMES, RX_MODES, rx_gain_sweep, tx_setter_sweeps
+
+
+@pytest.mark.parametrize("entry", ["2048k", "256k"])
+@pytest.mark.parametrize("mode", RX_MODES)
+def test_rx_gain_sweep_oracle_vs_reference(oracle, ref, mode, entry):
+    gains = rx_gain_sweep(DEFAULT_GAIN[mode])
+    n = 131072 + 8192 if entry == "2048k" else 16384 + 1024
+    iq = synth.rx_batch(mode, len(gains), n, config=3, entry=entry)
+    for s, g in enumerate(gains):
+        a = oracle.run_rx(mode, iq[s], entry=entry, gain=g)
+        b = ref.run_rx(mode, iq[s], entry=entry, gain=g)
+        assert np.array_equal(a, b), f"{NAMES[mode]} {entry} stream {s} gain {g}"
+
+
+@pytest.mark.parametrize("mode", [capi.MODE_AM, capi.MODE_FM, capi.MODE_WBFM])
+def test_tx_setter_sweeps_oracle_vs_reference(oracle, ref, mode):
+    sweeps = tx_setter_sweeps(mode)
+    pcm = synth.tx_batch(len(sweeps), 32 * 6 + 5, config=3)
+    outs = []
+    for lib in (oracle, ref):
+        rows = []
+        for s, calls in enumerate(sweeps):
+            h = lib.tx_new()
+            setter = {capi.MODE_AM: lib.tx_set_am_index, capi.MODE_FM: lib.tx_set_fm_deviation,
+                      capi.MODE_WBFM: lib.tx_set_wbfm_deviation}[mode]
+            for v in calls:
+                setter(h, v)
+            rows.append(lib.tx_accept(h, mode, pcm[s]))
+            lib.tx_free(h)
+        outs.append(rows)
+    for s, calls in enumerate(sweeps):
+        assert np.array_equal(outs[0][s], outs[1][s]), f"{NAMES[mode]} stream {s} setters {calls}"
+    # the sweeps are not vacuous: different settings give different outputs
+    assert any(not np.array_equal(outs[0][0], outs[0][s]) for s in range(1, len(sweeps)))
