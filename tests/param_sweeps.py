@@ -1,4 +1,4 @@
-"""Parameter sweeps shared by tests/test_gpu_params.py (CUDA path vs oracle) and tests/test_params_cpu.py (oracle vs the
+"""Parameter sweeps shared by tests/test_gpu_z_params.py (CUDA path vs oracle) and tests/test_params_cpu.py (oracle vs the
 compiled reference): SURVEY 8d's non-default settings plus the setters' guards."""
 import math
 

@@ -1,6 +1,7 @@
 """GPU parity with NON-DEFAULT parameters, a different setting on every stream of one batch, through the C ABI
 (gains x0.1 / x10, modulation index 0.3 / 1.0, deviation 1000 / 112000; plus the setters' guards).
-The same sweeps run oracle-vs-reference on the CPU in tests/test_params_cpu.py."""
+The same sweeps run oracle-vs-reference on the CPU in tests/test_params_cpu.py.
+(File name: collected last, after the parity tests it extends.)"""
 import numpy as np
 import pytest
 

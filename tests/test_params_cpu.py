@@ -1,4 +1,4 @@
-"""The parameter sweeps of tests/test_gpu_params.py, oracle against the compiled unmodified reference (CPU only): the
+"""The parameter sweeps of tests/test_gpu_z_params.py, oracle against the compiled unmodified reference (CPU only): the
 oracle the GPU test trusts is pinned on exactly these settings."""
 import numpy as np
 import pytest
