@@ -2,6 +2,7 @@
 // parameters with the reference's setter semantics, table construction, host<->device
 // staging and kernel dispatch.  No DSP happens on the host; without a CUDA device every
 // entry point fails (there is deliberately no CPU fallback).
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -10,6 +11,7 @@
 #include <new>
 #include <vector>
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "../../include/hrd.h"
@@ -244,8 +246,27 @@ int ensure_tables(int device)
     thr[8193] = INFINITY;
     HRD_CUDA(cudaMalloc(&d.nco_thr, thr.size() * sizeof(float)));
     HRD_CUDA(cudaMemcpy(d.nco_thr, thr.data(), thr.size() * sizeof(float), cudaMemcpyHostToDevice));
-    HRD_CUDA(cudaMalloc(&d.nco_iq900, 16384 * sizeof(uint32_t)));
-    HRD_CUDA(cudaMemcpy(d.nco_iq900, iq900.data(), 16384 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    // folded about phase 0 (Nco::runFast truncates toward zero, so the index is 8192 +- k with k from |phase|,
+    // clamped to 16383): [k] serves phase >= 0, [8193 + k] phase < 0
+    std::vector<uint32_t> fold(2 * 8193);
+    for (int k = 0; k <= 8192; k++) {
+        fold[(size_t)k] = iq900[(size_t)std::min(8192 + k, 16383)];
+        fold[(size_t)(8193 + k)] = iq900[(size_t)(8192 - k)];
+    }
+#if HRD_TW_H2
+    // stages 6-8 run on fp16 pairs (hrd_tx.cu tail3_h2): the table holds the same integers as binary16 numbers
+    for (uint32_t &w : fold) {
+        const int vi = (int16_t)(w & 0xffffu), vq = (int16_t)(w >> 16);
+        if (abs(vi) > 900 || abs(vq) > 900) return fail(HRD_EINVAL, "NCO table entry beyond 900");
+        const __half hi = __float2half((float)vi), hq = __float2half((float)vq);
+        uint16_t bi, bq;
+        memcpy(&bi, &hi, 2);
+        memcpy(&bq, &hq, 2);
+        w = (uint32_t)bi | (uint32_t)bq << 16;
+    }
+#endif
+    HRD_CUDA(cudaMalloc(&d.nco_iq900, fold.size() * sizeof(uint32_t)));
+    HRD_CUDA(cudaMemcpy(d.nco_iq900, fold.data(), fold.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     d.ready = true;
     return HRD_OK;
 }

@@ -207,6 +207,30 @@ __device__ __forceinline__ float wrap_pi_select(float d)
     return (s >= HRD_PI_UP) ? w : d;
 }
 
+// One step of PhaseAccumulator::run (Nco/PhaseAccumulator.cc:157-181) on the serial NCO chains of hrd_tx.cu, for
+// |phase| < pi and |step| < 3 (so |phase + step| < 6.2 and at most one wrap, in the direction of the step):
+// acc += step; then (float)((double)acc -+ 2*M_PI) when |acc| passed pi.
+// The chain is the critical path of those kernels and its cost is LATENCY, so the form below has no predicate and no
+// select in the dependency chain (measured on B200: a compare feeding a predicated FMA or an FSEL costs ~25 cycles
+// per sample, as much as five dependent adds): four dependent FMA-pipe operations,
+//   a = acc + step
+//   k = sat((|a| - P_DN) * 2^30)            exactly 0.0 or 1.0: P_DN is the float just below pi, floats are >= 2^-22 apart
+//   t = fma(k, -+2PI_HI, a)                 k = 1: exact (Sterbenz);      k = 0: a
+//   r = fma(k, -+2PI_LO, t)                 k = 1: one rounding, the fp32 wrap proved equal to the double expression
+//                                           for |t| >= 2^-10 (here |t| > 0.14; tools/verify_fp_tricks.c checks 1 and 1c)
+// with the signs of the two constants taken from the step (off the chain).  (fma(0, c, -0.0) is +0.0: only the sign
+// of a zero phase can differ from the reference, and nothing downstream reads it.)
+#define HRD_PI_DN 3.14159250259399414062f /* 0x40490fda */
+__device__ __forceinline__ float phase_step_fast(float phase, float step)
+{
+    const float a = __fadd_rn(phase, step);
+    const int sgn = __float_as_int(step) & (int)0x80000000;
+    const float hs = __int_as_float(__float_as_int(-HRD_2PI_HI) ^ sgn); // -2PI_HI for a step >= 0 (only +pi can be passed)
+    const float ls = __int_as_float(__float_as_int(-HRD_2PI_LO) ^ sgn);
+    const float k = __saturatef(__fmaf_rn(fabsf(a), 0x1p30f, -HRD_PI_DN * 0x1p30f));
+    return __fmaf_rn(k, ls, __fmaf_rn(k, hs, a));
+}
+
 // ------------------------------------------------------------------------------------
 // per-warp shared-memory rings: [hist old samples][new samples of this batch]
 // ------------------------------------------------------------------------------------

@@ -7,6 +7,13 @@
 // 1.0 to -32768 for the SSB delay line.
 #pragma once
 
+// tx_wbfm_kernel, stages 6-8: 1 = both rails per instruction as fp16 pairs (hrd_tx.cu tail3_h2, proved equal to the
+// integer form by tools/verify_tx_tail_h2.c), 0 = the integer form per rail (tail3).  The NCO table the host builds
+// holds halves in the first case and int16 in the second.
+#ifndef HRD_TW_H2
+#define HRD_TW_H2 1
+#endif
+
 #include <cstddef>
 #include <cstdint>
 
@@ -95,7 +102,9 @@ struct TxRail8 {           // histories of the eight interpolators of one I/Q pa
 
 struct TxState {
     TxRail8 am, fm, ssb;
-    // WbFmModulator: stages 1-5 on the real PCM (low halves used), 6-8 on I/Q
+    // WbFmModulator: stages 1-5 on the real PCM (low halves used), 6-8 on I/Q.  tx_wbfm_kernel keeps s0 (PCM),
+    // s1 (16 kS/s), s3 = the last THREE 32 kS/s samples (stages 3-5 are recomputed from them, so s2 and s4 stay
+    // unused) and s5[0] = the last (cos, sin) * 900 pair.
     TxRail8 wb;
     float fm_phase;        // PhaseAccumulator::phaseAccumulator of the FM NCO (8 kS/s)
     float wb_phase;        // ... of the WBFM NCO (256 kS/s)
@@ -173,7 +182,9 @@ struct TxParams {
     const uint8_t *lsb;
     const float *nco_sin, *nco_cos;
     // WBFM: {(int16_t)(cos*900), (int16_t)(sin*900)} per NCO table entry, packed I = low half
-    // (WbFmModulator.cc:606-626 applied to Nco.cc's tables once, at table build)
+    // (WbFmModulator.cc:606-626 applied to Nco.cc's tables once, at table build), FOLDED about phase 0:
+    // [k] = entry min(8192 + k, 16383), [8193 + k] = entry 8192 - k, k = 0..8192 (hrd_tx.cu nco_fold_offset).
+    // With HRD_TW_H2 the two values are binary16 numbers (exact: |v| <= 900) instead of int16.
     const uint32_t *nco_iq900;
     const float *nco_thr;      // [8194] Nco::runFast index thresholds (hrd_tx.cu nco_index)
     int32_t items_per_cta;     // tx_wbfm_kernel: streams per CTA, <= 31 (see RxParams)

@@ -24,6 +24,8 @@
 // All interpolation is the reference's Q15 arithmetic stage by stage (each stage rounds to
 // int16, so stages cannot be merged): y[nL+i] = (16384 + sum_k q[i+kL]*x[n-k]) >> 15
 // (Interpolator_int16.cc:398-418).
+#include <cuda_fp16.h>
+
 #include "hrd_device.cuh"
 
 #ifndef HRD_EXP
@@ -235,6 +237,67 @@ __device__ __forceinline__ void tail3(int x0, int xm1, int (&out)[8])
     }
 }
 
+// ---- stages 6..8 on BOTH rails at once (WBFM) ---------------------------------------------------------------
+// The NCO samples are 11-bit ((int16_t)(cos*900)), every stage halves the range, and an integer below 2048 is an
+// exact binary16 number: the two rails of one sample ride in one register as an fp16 pair and every operation
+// below serves both.  Forms of an integer v:  U = v;  B+ = 1536 + v (bits 0x6600 + v: v sits in the mantissa, the
+// low byte IS (int8_t)v);  B- = v - 1536.  Rounding a sum to the integer grid of [1024, 2048) is what turns an FMA
+// into the reference's ">> 15" (the products never tie), and a B+ plus a B- is their exact integer sum:
+//   even6 = fma(x + xm, 1053/4096, 1536)            8424/32768 = 1053/4096 is a binary16 number
+//   odd(v) = fma(v + 1/2, 1/2, -1536)               = rint(v/2 + 1/4) = (v + 1) >> 1;  odd(odd(v)) = fma(v + 3/2, 1/4, ..)
+//   even7: 8249/32768 needs 14 bits -> per rail in fp32, fma(s, 8249/32768, 1.5*2^23 + 0x6600): exact product, one
+//          rounding, and the low 16 bits of the result are the B+ bits
+//   even8 = fma(s, 1/4 + 2^-12, 1536)               c8 = 8206 only breaks the ties of s/4
+//   stage-8 odd outputs: integer shifts on the B-form bits, (bits + 1) >> 1 resp. (0xe801 - bits) >> 1 per half
+// tools/verify_tx_tail_h2.c proves the whole block equal to tail3 for every (x, xm) in [-900, 900]^2.
+struct TailCarry {
+    __half2 xm;  // U:  the sample before
+    __half2 bm;  // B-: its stage-6 odd output
+    __half2 p3m; // B-: ... and the stage-7 odd output of that
+};
+__device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<uint32_t *>(&v); }
+__device__ __forceinline__ __half2 h2_from(uint32_t w) { return *reinterpret_cast<__half2 *>(&w); }
+__device__ __forceinline__ __half2 h2_const(float v) { return __float2half2_rn(v); }
+
+__device__ __forceinline__ void tail_carry_from(__half2 xm, TailCarry &c)
+{
+    c.xm = xm;
+    c.bm = __hfma2(__hadd2(xm, h2_const(0.5f)), h2_const(0.5f), h2_const(-1536.f));
+    c.p3m = __hfma2(__hadd2(xm, h2_const(1.5f)), h2_const(0.25f), h2_const(-1536.f));
+}
+__device__ __forceinline__ __half2 tail_even7(__half2 s)
+{
+    const float c7 = 8249.0f / 32768.0f, m32 = 12582912.0f + 26112.0f;
+    const uint32_t ri = __float_as_uint(__fmaf_rn(__low2float(s), c7, m32));
+    const uint32_t rq = __float_as_uint(__fmaf_rn(__high2float(s), c7, m32));
+    return h2_from(__byte_perm(ri, rq, 0x5410));
+}
+// one 256 kS/s sample (both rails) -> eight output samples {I, Q, I, Q} x 4 words
+__device__ __forceinline__ void tail3_h2(__half2 x, TailCarry &c, uint32_t *o)
+{
+    const __half2 mg = h2_const(1536.f), nmg = h2_const(-1536.f), hf = h2_const(0.5f), qt = h2_const(0.25f);
+    const __half2 c6 = h2_const(1053.0f / 4096.0f), c8 = h2_const(0.25f + 1.0f / 4096.0f);
+    const __half2 a = __hfma2(__hadd2(x, c.xm), c6, mg);                             // B+  stage 6 even
+    const __half2 b = __hfma2(__hadd2(x, hf), hf, nmg);                              // B-  stage 6 odd
+    const __half2 p0 = tail_even7(__hadd2(a, c.bm));                                 // B+  stage 7
+    const __half2 p2 = tail_even7(__hadd2(b, a));                                    // B+
+    const __half2 p1 = __hfma2(__hadd2(__hadd2(a, nmg), hf), hf, nmg);               // B-
+    const __half2 p3 = __hfma2(__hadd2(x, h2_const(1.5f)), qt, nmg);                 // B-
+    const uint32_t e0 = h2_bits(__hfma2(__hadd2(p0, c.p3m), c8, mg));                // stage 8 even outputs, B+
+    const uint32_t e1 = h2_bits(__hfma2(__hadd2(p1, p0), c8, mg));
+    const uint32_t e2 = h2_bits(__hfma2(__hadd2(p2, p1), c8, mg));
+    const uint32_t e3 = h2_bits(__hfma2(__hadd2(p3, p2), c8, mg));
+    const uint32_t o0 = (h2_bits(p0) + 0x00010001u) >> 1, o2 = (h2_bits(p2) + 0x00010001u) >> 1; // odd outputs
+    const uint32_t o1 = (0xe801e801u - h2_bits(p1)) >> 1, o3 = (0xe801e801u - h2_bits(p3)) >> 1;
+    o[0] = __byte_perm(e0, o0, 0x6420); // bytes {I even, Q even, I odd, Q odd}
+    o[1] = __byte_perm(e1, o1, 0x6420);
+    o[2] = __byte_perm(e2, o2, 0x6420);
+    o[3] = __byte_perm(e3, o3, 0x6420);
+    c.xm = x;
+    c.bm = b;
+    c.p3m = p3;
+}
+
 // ------------------------------------------------------------------------------------
 // AM / FM / SSB kernel
 // ------------------------------------------------------------------------------------
@@ -442,21 +505,35 @@ constexpr int TW_ITEMS = 31;
 constexpr int TW_STEP8 = 8;               // PCM samples per pipeline step
 constexpr int TW_STEP = TW_STEP8 * 32;    // 256 kS/s samples per step
 constexpr int TW_PITCH = TW_STEP + 4;     // floats per row: conflict-free LDS.128 by row
+constexpr int TW_SUPER8 = 32;             // PCM samples per super-step: stages 1 and 2 run once per four steps, on all lanes
+constexpr int TW_LUT_HALF = 2048;         // the phase-step table covers stage-5 outputs in [-2048, 2047]
+constexpr uint32_t TW_FOLD = 8193;        // entries per half of the folded NCO table
 
+// Per item: what stages 1 and 2 need, and the 32 kS/s samples of the current super-step.  Stages 3, 4 and 5
+// keep NO ring: a lane owns one 32 kS/s sample per step (eight 256 kS/s samples) and recomputes the few
+// 64 and 128 kS/s values before its own from the three 32 kS/s samples before it -- no shuffles, no ring
+// shifts, no __syncwarp between the stages, all lanes busy.
 struct SmemTwItem {                       // real samples, sign-extended
-    int32_t s0[19 + TW_STEP8];            // stage 1 input @8k
-    int32_t s1[3 + 2 * TW_STEP8];         // stage 2 input @16k
-    int32_t s2[1 + 4 * TW_STEP8];         // stage 3 input @32k
-    int32_t s3[3 + 8 * TW_STEP8];         // stage 4 input @64k
-    int32_t s4[3 + 16 * TW_STEP8];        // stage 5 input @128k
+    alignas(16) int32_t x32[4 + 4 * TW_SUPER8]; // stage 3 input @32k: [1..3] history, [4 + n] sample n of the super-step
+    int32_t s0[19 + TW_SUPER8];           // stage 1 input @8k
+    int32_t s1[3 + 2 * TW_SUPER8 + 2];    // stage 2 input @16k (+2: the struct stays a multiple of 16 bytes)
 };
 struct SmemTw {
     float ph[2][32][TW_PITCH];
     SmemTwItem item[TW_ITEMS];
     uint32_t big[2][32];                  // per row and step: some |phase step| >= 3 (the chain's slow path)
-    alignas(16) uint32_t iq900[16384];    // {(int16_t)(cos*900), (int16_t)(sin*900)} per NCO entry
-    float thr[8194 + 2];                  // nco_index thresholds
+    // phase step by stage-5 output value, for a CTA whose streams share one deviation.  It sits in the MIDDLE of
+    // the block on purpose: a value outside the table is detected after its (discarded) load, which then still
+    // falls inside the CTA's shared memory (|stage-5 output| <= 5091, see produce).
+    float step_lut[2 * TW_LUT_HALF];
+    alignas(16) uint32_t iqfold[2 * TW_FOLD + 2]; // {(int16_t)(cos*900), (int16_t)(sin*900)}: [k] phase >= 0, [8193 + k] phase < 0
+    float thr[8194 + 2];                  // nco_fold_offset thresholds
+    uint32_t lut_dev;                     // the shared deviation (bits)
+    int32_t lut_on;                       // every live stream of the CTA has that deviation
+    int32_t e_lim;                        // |stage-5 output| below which the table applies and |step| < 3
 };
+static_assert(sizeof(SmemTwItem) % 16 == 0, "items are 16-byte aligned");
+static_assert(sizeof(SmemTw) <= 227 * 1024, "tx_wbfm_kernel shared memory");
 
 __device__ __forceinline__ void load_real_hist(int32_t *ring, const uint32_t *state, int hist, int lane)
 {
@@ -467,11 +544,16 @@ __device__ __forceinline__ void save_real_hist(const int32_t *ring, uint32_t *st
     for (int i = lane; i < hist; i += 32) state[i] = (uint32_t)ring[i] & 0xffffu;
 }
 
-// 8-tap half-band {a,0,b,16384,b,0,a,0} on a real ring (hist 3): input n -> outputs 2n, 2n+1
+// 8-tap half-band {a,0,b,16384,b,0,a,0} (stages 2, 4, 5; Interpolator_int16.cc:398-418 with these taps): input n
+// gives the even output a*(x[n]+x[n-3]) + b*(x[n-1]+x[n-2]) and the odd output 16384*x[n-1], i.e. (x[n-1]+1)>>1
+__device__ __forceinline__ int hb8_even(int ha, int hb, int x0, int x1, int x2, int x3)
+{
+    return ((1 << 14) + ha * (x0 + x3) + hb * (x1 + x2)) >> 15;
+}
+// the same on a real ring (hist 3): input n -> outputs 2n, 2n+1
 __device__ __forceinline__ void interp8_real(const int32_t *in, int n, int &even, int &odd)
 {
-    const int ha = c_tabtx.tx_hb8[0], hb = c_tabtx.tx_hb8[2];
-    even = ((1 << 14) + ha * (in[3 + n] + in[n]) + hb * (in[2 + n] + in[1 + n])) >> 15;
+    even = hb8_even(c_tabtx.tx_hb8[0], c_tabtx.tx_hb8[2], in[3 + n], in[2 + n], in[1 + n], in[n]);
     odd = (in[2 + n] + 1) >> 1;
 }
 
@@ -497,25 +579,34 @@ __device__ __forceinline__ float div_const_to_float(double a)
     if (risky && a != 0.0) return D == 256000 ? div_256000_exact(a) : div_8000_exact(a);
     return (float)r;
 }
-__device__ __forceinline__ float div_256000_to_float(double a) { return div_const_to_float<256000>(a); }
 
-// Nco::runFast's table index (Nco.cc:231-248): (int16_t)((double)(phase*16384.0f)/(2*M_PI)) + 8192,
-// clamped to [0,16383].  The double division is replaced by a search in a table of thresholds built
-// on the host WITH that very expression: T[k] = the smallest float p >= 0 whose reference index is
-// >= k (hrd_api.cu; T[0] = 0, T[8193] = +inf).  An fp32 estimate lands within +-1 of the answer and
-// two comparisons settle it.  Truncation toward zero makes negative phases mirror images.
-// tools/verify_fp_tricks.c checks the search against the expression for every float in [0, pi].
-__device__ __forceinline__ int nco_index(float phase, const float *T)
+// WbFmModulator.cc:596-604 + PhaseAccumulator.cc:103 for one 256 kS/s sample e of the interpolated PCM:
+//   ncoFrequency = frequencyDeviation * (float)e / 1024   (dividing by 2^10 is exact scaling)
+//   phaseStepSize = (float)((2*M_PI*ncoFrequency)/256000.0)
+__device__ __forceinline__ float wb_phase_step(float dev, int e)
+{
+    const float f = __fmul_rn(__fmul_rn(dev, (float)e), 0.0009765625f);
+    return div_const_to_float<256000>(2.0 * 3.14159265358979323846 * (double)f);
+}
+
+// Nco::runFast's table index (Nco.cc:231-248): (int16_t)((double)(phase*16384.0f)/(2*M_PI)) + 8192, clamped to
+// [0,16383].  The double division is replaced by ONE comparison against a table of thresholds built on the host
+// WITH that very expression: T[k] = the smallest float p >= 0 whose reference index offset is >= k (hrd_api.cu;
+// T[0] = 0, T[8193] = +inf).  An FMA with a slightly low constant and the addend 2^23 - 0.5 leaves k or k + 1 in
+// the mantissa (never less, never more: tools/verify_fp_tricks.c checks every float in [0, pi]), so
+// k = k1 - (|phase| < T[k1]).  Truncation toward zero makes negative phases mirror images: the table of
+// (cos, sin) * 900 pairs is stored folded, [k] for phase >= 0 and [8193 + k] for phase < 0 (hrd_api.cu), and the
+// result here is the BYTE offset into it.
+#define HRD_NCO_C_LO 2607.5920f
+__device__ __forceinline__ uint32_t nco_fold_offset(float phase, const float *T)
 {
     const float ap = fabsf(phase);
-    // round(ap * 16384/(2 pi)) by the 2^23 trick (no F2I: the XU pipe is 8x slower than FFMA)
-    int k = __float_as_int(__fmaf_rn(ap, 2607.59448f, 8388608.0f)) - 0x4b000000;
-    k = min(max(k, 0), 8192);
-    const float lo = T[k], hi = T[k + 1];
-    k += (ap >= hi) ? 1 : 0;
-    k -= (ap < lo) ? 1 : 0;
-    const int idx = 8192 + ((__float_as_int(phase) < 0) ? -k : k);
-    return min(idx, 16383);
+    uint32_t k4 = (uint32_t)__float_as_int(__fmaf_rn(ap, HRD_NCO_C_LO, 8388607.5f)) * 4u - 0x4affffffu * 4u;
+    k4 = min(k4, 8193u * 4u); // (NaN or a phase outside [-pi, pi] must not leave the table)
+    const float t = *reinterpret_cast<const float *>(reinterpret_cast<const char *>(T) + k4);
+    if (ap < t) k4 -= 4u;
+    if (phase < 0.0f) k4 += TW_FOLD * 4u;
+    return k4;
 }
 
 __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
@@ -524,108 +615,166 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
     SmemTw &sm = *reinterpret_cast<SmemTw *>(smem_raw);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    // the chain warp is the LAST warp of the CTA: the warp scheduler favours the highest warp id among
-    // eligible warps, and the chain (two dependent instructions per sample) is the CTA's critical path
-    const bool chain_warp = warp == p.items_per_cta;
-    const int row = chain_warp ? lane : warp;
+    // WARP ROLES.  The chain (four dependent operations per sample) is the CTA's critical path, and what slows it
+    // under load is not latency but losing the issue slot to the item warps of its scheduler (ncu: the chain warp
+    // sat in "not selected" a third of the time when it shared a scheduler with seven item warps).  A warp's
+    // scheduler is warp id % 4, so the CTA always has 32 warp slots: the chain is warp 31 (scheduler 3, and the
+    // arbiter favours the highest warp id), items fill schedulers 0, 1, 2 first (24 slots) and only the items
+    // beyond 24 join scheduler 3; unused slots help load the tables and leave.
+    const bool chain_warp = warp == 31;
+    const int item_of_warp = (warp & 3) != 3 ? (warp >> 2) * 3 + (warp & 3) : 24 + (warp >> 2);
+    const int row = chain_warp ? lane : item_of_warp;
     const int slot = blockIdx.x * p.items_per_cta + row;
+    const bool member = chain_warp || item_of_warp < p.items_per_cta; // takes part in the pipeline's barriers
     const bool live = row < p.items_per_cta && slot < p.n_streams;
     const int sid = live ? p.stream_ids[slot] : 0;
     TxState &st = p.state_out[sid]; // == state[sid]: the host copied the records over before the launch
     TxRail8 &rs = st.wb;
-    SmemTwItem &it = sm.item[chain_warp ? 0 : warp];
+    SmemTwItem &it = sm.item[chain_warp || !member ? 0 : item_of_warp];
     const int16_t *src = p.pcm + (size_t)sid * p.pcm_stride;
     int8_t *dst = p.iq + (size_t)sid * p.iq_stride;
     const uint32_t n_steps = (p.n8 + TW_STEP8 - 1) / TW_STEP8;
 
-    for (int i = threadIdx.x; i < 16384 / 4; i += blockDim.x)
-        reinterpret_cast<uint4 *>(sm.iq900)[i] = __ldg(reinterpret_cast<const uint4 *>(p.nco_iq900) + i);
+    for (int i = threadIdx.x; i < (int)(2 * TW_FOLD); i += blockDim.x) sm.iqfold[i] = __ldg(p.nco_iq900 + i);
     for (int i = threadIdx.x; i < 8194; i += blockDim.x) sm.thr[i] = __ldg(p.nco_thr + i);
-    __syncthreads();
 
     float phase = 0.f, dev = 0.f;
     uint32_t iq_keep = 0; // the (cos,sin)*900 pair of the previous 256 kS/s sample (stage 6 history)
     if (live) {
+        dev = p.param[sid];
         if (chain_warp) {
             phase = st.wb_phase;
         } else {
             load_real_hist(it.s0, rs.s0, 19, lane);
             load_real_hist(it.s1, rs.s1, 3, lane);
-            load_real_hist(it.s2, rs.s2, 1, lane);
-            load_real_hist(it.s3, rs.s3, 3, lane);
-            load_real_hist(it.s4, rs.s4, 3, lane);
+            if (lane < 3) it.x32[1 + lane] = lo16(rs.s3[lane]); // the last three 32 kS/s samples
             iq_keep = rs.s5[0];
-            dev = p.param[sid];
         }
     }
-    __syncwarp();
+    if (chain_warp) { // do all streams of this CTA share one deviation?  (lane 0 always has a stream)
+        const uint32_t d0 = __shfl_sync(HRD_FULL_MASK, __float_as_uint(dev), 0);
+        const bool same = __all_sync(HRD_FULL_MASK, !live || __float_as_uint(dev) == d0);
+        if (lane == 0) {
+            sm.lut_dev = d0;
+            sm.lut_on = same;
+            sm.e_lim = TW_LUT_HALF;
+        }
+    }
+    __syncthreads();
+    // The phase step is a pure function of (deviation, stage-5 output), and the interpolated PCM stays small: the
+    // reference's own double expression is evaluated ONCE per value here (IEEE division) instead of once per sample.
+    const bool lut_on = sm.lut_on != 0;
+    if (lut_on) {
+        const float d = __uint_as_float(sm.lut_dev);
+        for (int i = threadIdx.x; i < 2 * TW_LUT_HALF; i += blockDim.x) {
+            const int e = i - TW_LUT_HALF;
+            const float f = __fmul_rn(__fmul_rn(d, (float)e), 0.0009765625f);
+            const float stp = (float)((2.0 * 3.14159265358979323846 * (double)f) / 256000.0);
+            sm.step_lut[i] = stp;
+            if (!(fabsf(stp) < 3.0f)) atomicMin(&sm.e_lim, abs(e)); // the chain's fast path needs |step| < 3
+        }
+    }
+    __syncthreads();
+    if (!member) return; // (a spare warp slot: exited warps do not count at later barriers)
+    // the table applies to |e| < e_lim: index (e + e_lim - 1) against the bound 2 e_lim - 1, one unsigned compare
+    const int e_lim4 = (sm.e_lim - 1) * 4;
+    const uint32_t e_bound4 = (uint32_t)max(2 * sm.e_lim - 1, 0) * 4u;
+    const char *lut_base = reinterpret_cast<const char *>(sm.step_lut) + (TW_LUT_HALF * 4 - e_lim4);
 
     // WbFmModulator.cc:389-441 + 596-604 on step t: PCM -> stages 1..5 -> phase steps
     auto produce = [&](uint32_t t) {
-        const uint32_t done = t * TW_STEP8;
-        const int nb = (int)min((uint32_t)TW_STEP8, p.n8 - done);
-#if HRD_EXP & 256
-        const bool front = (t & 3) == 0; // timing experiment: stages 1..4 on every fourth step only
-#else
-        const bool front = true;
-#endif
-        if (front) {
-        if (lane < nb) it.s0[19 + lane] = (int)src[done + lane];
-        __syncwarp();
-        if (lane < nb) { // stage 1: 40 taps, L = 2 (the only stage whose output may wrap: keep q15)
-            unsigned e = 1u << 14, o = 1u << 14;
-#pragma unroll
-            for (int k = 0; k < 20; k++) {
-                const int x = it.s0[19 + lane - k];
-                e += (unsigned)(c_tabtx.audio40[2 * k] * x);
-                o += (unsigned)(c_tabtx.audio40[2 * k + 1] * x);
+        const uint32_t j = t & 3;
+        if (j == 0) { // stages 1 and 2 for the next (up to) 32 PCM samples, one PCM sample per lane
+            const uint32_t done = t * TW_STEP8;
+            const int nb8 = (int)min((uint32_t)TW_SUPER8, p.n8 - done);
+            if (t) { // histories to the front (every super-step but the last is a full one)
+                ring_shift(it.s0, 19, TW_SUPER8, lane);
+                ring_shift(it.s1, 3, 2 * TW_SUPER8, lane);
+                int v = 0;
+                if (lane < 3) v = it.x32[1 + 4 * TW_SUPER8 + lane];
+                __syncwarp();
+                if (lane < 3) it.x32[1 + lane] = v;
             }
-            it.s1[3 + 2 * lane] = q15((int)e);
-            it.s1[3 + 2 * lane + 1] = q15((int)o);
+            if (lane < nb8) it.s0[19 + lane] = (int)src[done + lane];
+            __syncwarp();
+            if (lane < nb8) { // stage 1: 40 taps, L = 2 (the only stage whose output may wrap: keep q15)
+                unsigned e = 1u << 14, o = 1u << 14;
+#pragma unroll
+                for (int k = 0; k < 20; k++) {
+                    const int x = it.s0[19 + lane - k];
+                    e += (unsigned)(c_tabtx.audio40[2 * k] * x);
+                    o += (unsigned)(c_tabtx.audio40[2 * k + 1] * x);
+                }
+                it.s1[3 + 2 * lane] = q15((int)e);
+                it.s1[3 + 2 * lane + 1] = q15((int)o);
+            }
+            __syncwarp();
+            if (lane < nb8) { // stage 2: two inputs, four outputs
+                int4 y;
+                interp8_real(it.s1, 2 * lane, y.x, y.y);
+                interp8_real(it.s1, 2 * lane + 1, y.z, y.w);
+                *reinterpret_cast<int4 *>(it.x32 + 4 + 4 * lane) = y;
+            }
+            __syncwarp();
         }
-        __syncwarp();
-        if (lane < 2 * nb) interp8_real(it.s1, lane, it.s2[1 + 2 * lane], it.s2[1 + 2 * lane + 1]);
-        __syncwarp();
-        if (lane < 4 * nb) {
-            it.s3[3 + 2 * lane] = hb4_even(c_tabtx.tx_c3, it.s2[1 + lane], it.s2[lane]);
-            it.s3[3 + 2 * lane + 1] = (it.s2[1 + lane] + 1) >> 1;
+        // stages 3, 4, 5 and the phase steps: lane <-> 32 kS/s sample m = 32 j + lane of the super-step
+        const int nb = (int)min((uint32_t)TW_STEP8, p.n8 - t * TW_STEP8);
+        const bool valid = lane < 4 * nb;
+        const int32_t *xr = it.x32 + 4 + 32 * j + lane;
+        int xa = xr[0], xb = xr[-1], xc = xr[-2], xd = xr[-3];
+        if (!valid) xa = xb = xc = xd = 0; // (stale ring words must not reach the table index)
+        const int c3 = c_tabtx.tx_c3, ha = c_tabtx.tx_hb8[0], hb = c_tabtx.tx_hb8[2];
+        // stage 3 @64k: u[i] = y3[2m - 4 + i]
+        const int u0 = hb4_even(c3, xc, xd), u1 = hb4_odd(xc), u2 = hb4_even(c3, xb, xc), u3 = hb4_odd(xb);
+        const int u4 = hb4_even(c3, xa, xb), u5 = hb4_odd(xa);
+        // stage 4 @128k: v[i] = y4[4m - 3 + i]
+        int v[7];
+        v[0] = hb4_odd(u1);
+        v[1] = hb8_even(ha, hb, u3, u2, u1, u0);
+        v[2] = hb4_odd(u2);
+        v[3] = hb8_even(ha, hb, u4, u3, u2, u1);
+        v[4] = hb4_odd(u3);
+        v[5] = hb8_even(ha, hb, u5, u4, u3, u2);
+        v[6] = hb4_odd(u4);
+        // stage 5 @256k: e[i] = y5[8m + i].  |e| <= 5091: stage 1 wraps into int16, the 8-tap stages scale a
+        // bound by 2(|a|+|b|)/32768 <= 0.671 and stage 3 by 2c/32768 <= 0.515.
+        int e[8];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            e[2 * q] = hb8_even(ha, hb, v[3 + q], v[2 + q], v[1 + q], v[q]);
+            e[2 * q + 1] = hb4_odd(v[2 + q]);
         }
-        __syncwarp();
-        for (int n = lane; n < 8 * nb; n += 32) interp8_real(it.s3, n, it.s4[3 + 2 * n], it.s4[3 + 2 * n + 1]);
-        __syncwarp();
-        }
-        float *out = sm.ph[t & 1][row];
+        float stp[8];
         bool big = false;
-        for (int n = lane; n < 16 * nb; n += 32) {
-            int e, o;
-            interp8_real(it.s4, n, e, o);
-            // ncoFrequency = frequencyDeviation * (float)pcm / 1024   (dividing by 2^10 is exact scaling)
-            const float fe = __fmul_rn(__fmul_rn(dev, (float)e), 0.0009765625f);
-            const float fo = __fmul_rn(__fmul_rn(dev, (float)o), 0.0009765625f);
-            // phaseStepSize = (2*M_PI*frequency)/sampleRate   (PhaseAccumulator.cc:103)
-            const double two_pi = 2.0 * 3.14159265358979323846;
-            float2 stp;
-            stp.x = div_256000_to_float(two_pi * (double)fe);
-            stp.y = div_256000_to_float(two_pi * (double)fo);
-            *reinterpret_cast<float2 *>(out + 2 * n) = stp;
-            big |= !(fabsf(stp.x) < 3.0f) | !(fabsf(stp.y) < 3.0f);
+        bool slow = !lut_on;
+        if (lut_on) {
+            bool out = false;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t ix = (uint32_t)(e[i] * 4 + e_lim4);
+                out |= ix >= e_bound4;
+                stp[i] = *reinterpret_cast<const float *>(lut_base + ix);
+            }
+            slow = out;
         }
-        big = __any_sync(HRD_FULL_MASK, big);
+        if (slow) { // mixed deviations in this CTA, or a sample beyond the table / a step of 3 rad or more
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                stp[i] = wb_phase_step(dev, e[i]);
+                big |= !(fabsf(stp[i]) < 3.0f);
+            }
+        }
+        float *out = sm.ph[t & 1][row] + 8 * lane;
+        *reinterpret_cast<float4 *>(out) = make_float4(stp[0], stp[1], stp[2], stp[3]);
+        *reinterpret_cast<float4 *>(out + 4) = make_float4(stp[4], stp[5], stp[6], stp[7]);
+        big = __any_sync(HRD_FULL_MASK, big && valid);
         if (lane == 0) sm.big[t & 1][row] = big;
-        __syncwarp();
-        if (front) {
-            ring_shift(it.s0, 19, nb, lane);
-            ring_shift(it.s1, 3, 2 * nb, lane);
-            ring_shift(it.s2, 1, 4 * nb, lane);
-            ring_shift(it.s3, 3, 8 * nb, lane);
-        }
-        ring_shift(it.s4, 3, 16 * nb, lane);
     };
 
     // PhaseAccumulator::run for every sample of step t: row[n] <- phase before step n.
     // The item warps flag rows with a step of 3 rad or more (a deviation setting beyond the reference's
-    // limits, or NaN).  Without one, |phase + step| < pi + 3 < 2*pi - 2^-10, so a single fp32 wrap is the
-    // exact one (hrd_device.cuh wrap_pi_select) and the chain is six operations per sample with no
+    // limits, or NaN).  Without one, |phase + step| < pi + 3 < 6.2, so the single-FMA wrap is the exact one
+    // (hrd_device.cuh phase_step_fast) and the chain is three dependent operations per sample with no
     // bookkeeping; with one, the lock-step version with its exact per-chunk redo runs instead.
     auto chain = [&](uint32_t t) {
         const uint32_t nb = min((uint32_t)TW_STEP8, p.n8 - t * TW_STEP8) * 32;
@@ -634,18 +783,22 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
         const bool slow = __any_sync(HRD_FULL_MASK, live && (sm.big[t & 1][lane] != 0 || !(fabsf(phase) < HRD_PI_UP)));
         if (!live) return;
         if (!slow) {
-            for (uint32_t c = 0; c < nb; c += 32) {
-                float4 v[8];
+            // the row is read four groups (16 samples, ~300 cycles of chain) ahead of its use: under load a
+            // shared-memory load takes far longer than the 29 cycles it takes alone
+            float4 q[4];
 #pragma unroll
-                for (int g = 0; g < 8; g++) v[g] = *reinterpret_cast<float4 *>(r + c + 4 * g);
+            for (int g = 0; g < 4; g++) q[g] = *reinterpret_cast<float4 *>(r + 4 * g);
+            for (uint32_t c = 0; c < nb; c += 16) {
 #pragma unroll
-                for (int g = 0; g < 8; g++) {
+                for (int g = 0; g < 4; g++) {
+                    float4 v = q[g];
+                    if (c + 16 < nb) q[g] = *reinterpret_cast<float4 *>(r + c + 16 + 4 * g);
                     float s;
-                    s = v[g].x; v[g].x = phase; phase = wrap_pi_select(__fadd_rn(phase, s));
-                    s = v[g].y; v[g].y = phase; phase = wrap_pi_select(__fadd_rn(phase, s));
-                    s = v[g].z; v[g].z = phase; phase = wrap_pi_select(__fadd_rn(phase, s));
-                    s = v[g].w; v[g].w = phase; phase = wrap_pi_select(__fadd_rn(phase, s));
-                    *reinterpret_cast<float4 *>(r + c + 4 * g) = v[g];
+                    s = v.x; v.x = phase; phase = phase_step_fast(phase, s);
+                    s = v.y; v.y = phase; phase = phase_step_fast(phase, s);
+                    s = v.z; v.z = phase; phase = phase_step_fast(phase, s);
+                    s = v.w; v.w = phase; phase = phase_step_fast(phase, s);
+                    *reinterpret_cast<float4 *>(r + c + 4 * g) = v;
                 }
             }
             return;
@@ -680,64 +833,72 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
 
     // Nco::runFast + x900 (WbFmModulator.cc:606-626), stages 6..8 (:471-531): two 256 kS/s samples
     // per lane -> 16 output samples = 32 bytes
+    // two samples of a lane: table words w0, w1 and the word before them -> 16 output samples = 32 bytes
+    auto emit_pair = [&](uint32_t wm, uint32_t w0, uint32_t w1, int8_t *at) {
+        u32x8 o;
+#if HRD_TW_H2
+        TailCarry c;
+        tail_carry_from(h2_from(wm), c);
+        tail3_h2(h2_from(w0), c, o.v);
+        tail3_h2(h2_from(w1), c, o.v + 4);
+#else
+        int oi[8], oq[8];
+        tail3(lo16(w0), lo16(wm), oi);
+        tail3(hi16(w0), hi16(wm), oq);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            o.v[k] = merge16(pack_b2(oi[2 * k], oq[2 * k]), pack_b2(oi[2 * k + 1], oq[2 * k + 1]));
+        tail3(lo16(w1), lo16(w0), oi);
+        tail3(hi16(w1), hi16(w0), oq);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            o.v[4 + k] = merge16(pack_b2(oi[2 * k], oq[2 * k]), pack_b2(oi[2 * k + 1], oq[2 * k + 1]));
+#endif
+        stg_stream_256(at, o);
+    };
+    // Nco::runFast + x900 (WbFmModulator.cc:606-626), stages 6..8 (:471-531): two 256 kS/s samples
+    // per lane -> 16 output samples = 32 bytes
     auto consume = [&](uint32_t t) {
         const uint32_t done = t * TW_STEP8;
         const int nb = (int)min((uint32_t)TW_STEP8, p.n8 - done) * 32;
         const float *ph = sm.ph[t & 1][row];
+        const char *fold = reinterpret_cast<const char *>(sm.iqfold);
         int8_t *out = dst + (size_t)done * 512;
+        if (nb == TW_STEP) { // a full step: four rounds, every lane busy, nothing to clip
+#pragma unroll 1
+            for (int base = 0; base < TW_STEP; base += 64) {
+                const int n = base + 2 * lane;
+                const float2 pp = *reinterpret_cast<const float2 *>(ph + n);
+                const uint32_t w0 = *reinterpret_cast<const uint32_t *>(fold + nco_fold_offset(pp.x, sm.thr));
+                const uint32_t w1 = *reinterpret_cast<const uint32_t *>(fold + nco_fold_offset(pp.y, sm.thr));
+                // the sample before w0: previous lane's w1 (lane 0: kept from the previous round)
+                const uint32_t wm = __shfl_sync(HRD_FULL_MASK, (lane == 31) ? iq_keep : w1, (lane + 31) & 31);
+                iq_keep = __shfl_sync(HRD_FULL_MASK, w1, 31);
+                emit_pair(wm, w0, w1, out + (size_t)n * 16);
+            }
+            return;
+        }
         for (int base = 0; base < nb; base += 64) { // warp-uniform trip count: shuffles inside
             const int n = base + 2 * lane;
             const bool valid = n < nb;               // a short last step leaves the upper lanes idle
             const int last_lane = min(32, (nb - base) / 2) - 1;
             const float2 pp = *reinterpret_cast<const float2 *>(ph + (valid ? n : 0));
-            const uint32_t w0 = sm.iq900[nco_index(pp.x, sm.thr)];
-            const uint32_t w1 = sm.iq900[nco_index(pp.y, sm.thr)];
-            // the sample before w0: previous lane's w1 (lane 0: kept from the previous round)
+            const uint32_t w0 = *reinterpret_cast<const uint32_t *>(fold + nco_fold_offset(pp.x, sm.thr));
+            const uint32_t w1 = *reinterpret_cast<const uint32_t *>(fold + nco_fold_offset(pp.y, sm.thr));
             const uint32_t sel = (lane == 31) ? iq_keep : w1;
             const uint32_t wm = __shfl_sync(HRD_FULL_MASK, sel, (lane + 31) & 31);
             iq_keep = __shfl_sync(HRD_FULL_MASK, w1, last_lane);
-            if (!valid) continue;
-            int oi[8], oq[8];
-            u32x8 o;
-            tail3(lo16(w0), lo16(wm), oi);
-            tail3(hi16(w0), hi16(wm), oq);
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                o.v[k] = merge16(pack_b2(oi[2 * k], oq[2 * k]), pack_b2(oi[2 * k + 1], oq[2 * k + 1]));
-            tail3(lo16(w1), lo16(w0), oi);
-            tail3(hi16(w1), hi16(w0), oq);
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                o.v[4 + k] = merge16(pack_b2(oi[2 * k], oq[2 * k]), pack_b2(oi[2 * k + 1], oq[2 * k + 1]));
-            stg_stream_256(out + (size_t)n * 16, o);
+            if (valid) emit_pair(wm, w0, w1, out + (size_t)n * 16);
         }
     };
 
     // hand-over by named barriers, as in rx_wbfm_kernel (hrd_rx.cu): item warps arrive on "produced"
     // and wait on "chained"; the chain warp does the opposite
-    const int bar_threads = (int)blockDim.x;
-#if HRD_EXP & 128
-    if (!chain_warp && live) produce(0);
-    __syncthreads();
-    for (uint32_t t = 0; t < n_steps; t++) {
-        if (chain_warp) {
-#if !(HRD_EXP & 16)
-            chain(t);
-#endif
-        } else if (live) {
-            if (t >= 1) consume(t - 1);
-            if (t + 1 < n_steps) produce(t + 1);
-        }
-        __syncthreads();
-    }
-    if (!chain_warp && live) consume(n_steps - 1);
-#else
+    const int bar_threads = (p.items_per_cta + 1) * 32;
     if (chain_warp) {
         for (uint32_t t = 0; t < n_steps; t++) {
             named_bar_sync(HRD_BAR_PRODUCED, t, bar_threads);
-#if !(HRD_EXP & 16)
             chain(t);
-#endif
             named_bar_arrive(HRD_BAR_CHAINED, t, bar_threads);
         }
     } else {
@@ -749,22 +910,19 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
                 named_bar_arrive(HRD_BAR_PRODUCED, t + 1, bar_threads);
             }
             named_bar_sync(HRD_BAR_CHAINED, t, bar_threads);
-#if !(HRD_EXP & 32)
             if (live) consume(t);
-#endif
         }
     }
-#endif
     __syncthreads();
     if (live) {
         if (chain_warp) {
             st.wb_phase = phase;
         } else {
-            save_real_hist(it.s0, rs.s0, 19, lane);
-            save_real_hist(it.s1, rs.s1, 3, lane);
-            save_real_hist(it.s2, rs.s2, 1, lane);
-            save_real_hist(it.s3, rs.s3, 3, lane);
-            save_real_hist(it.s4, rs.s4, 3, lane);
+            // the histories sit behind the samples of the last super-step
+            const int nb8 = (int)(p.n8 - ((n_steps - 1) / 4) * TW_SUPER8);
+            save_real_hist(it.s0 + nb8, rs.s0, 19, lane);
+            save_real_hist(it.s1 + 2 * nb8, rs.s1, 3, lane);
+            save_real_hist(it.x32 + 1 + 4 * nb8, rs.s3, 3, lane);
             if (lane == 0) rs.s5[0] = iq_keep;
         }
     }
@@ -884,12 +1042,12 @@ __global__ void __launch_bounds__((FP_WORKERS + 1) * 32) tx_fm_phase_kernel(cons
         const bool slow = __any_sync(HRD_FULL_MASK, live && (sm.big[c % 3][lane] != 0 || !(fabsf(phase) < HRD_PI_UP)));
         if (!live) return;
         if (!slow && nb == FP_CH) {
-            // |phase + step| < pi + 3 < 2*pi - 2^-10: one fp32 wrap is the exact one (wrap_pi_select)
+            // |phase + step| < pi + 3 < 6.2: the single-FMA wrap is the exact one (phase_step_fast)
 #pragma unroll 16
             for (int n = 0; n < FP_CH; n++) {
                 const float s = row[n];
                 row[n] = phase;
-                phase = wrap_pi_select(__fadd_rn(phase, s));
+                phase = phase_step_fast(phase, s);
             }
         } else {
             for (int n = 0; n < nb; n++) {
@@ -1008,7 +1166,7 @@ int launch_tx(int kind, const TxParams &p, cudaStream_t s)
             cudaFuncSetAttribute(tx_wbfm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTw));
             attr_set = true;
         }
-        tx_wbfm_kernel<<<grid, (q.items_per_cta + 1) * 32, sizeof(SmemTw), s>>>(q);
+        tx_wbfm_kernel<<<grid, 1024, sizeof(SmemTw), s>>>(q); // always 32 warp slots (see WARP ROLES)
         return (int)cudaGetLastError();
     }
     case K_NONE: {
