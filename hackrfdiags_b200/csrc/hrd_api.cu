@@ -138,6 +138,12 @@ int build_tables(hrd::ConstTables &t)
     for (int i = 0; i < 16; i++) t.delay[i] = quantise(k_delay16[i]);
     for (int i = 0; i < 8; i++) t.tx_hb8[i] = quantise(k_tx_hb8[i]);
     t.k_32768 = 32768;
+    {
+        const float hi = -6.28318548202514648438f, lo = 1.74845553146951715e-07f; // -fl32(2*pi), -(2*pi - fl32(2*pi))
+        t.k_sign = 0x80000000u;
+        memcpy(&t.k_m2pi_hi, &hi, 4);
+        memcpy(&t.k_m2pi_lo, &lo, 4);
+    }
     t.tx_c3 = quantise(k_fe3[0]);
     t.tx_m3 = quantise(k_fe3[1]);
     t.tx_c7 = quantise(k_fe2[0]);

@@ -221,12 +221,22 @@ __device__ __forceinline__ float wrap_pi_select(float d)
 // with the signs of the two constants taken from the step (off the chain).  (fma(0, c, -0.0) is +0.0: only the sign
 // of a zero phase can differ from the reference, and nothing downstream reads it.)
 #define HRD_PI_DN 3.14159250259399414062f /* 0x40490fda */
-__device__ __forceinline__ float phase_step_fast(float phase, float step)
+// the chain's three constants as values ptxas cannot see (ConstTables k_sign / k_m2pi_hi / k_m2pi_lo): kept in
+// registers, "(step & sign) ^ constant" is ONE LOP3 per constant instead of an AND and two XORs with immediates
+struct ChainConsts {
+    uint32_t sign, m2pi_hi, m2pi_lo;
+};
+__device__ __forceinline__ uint32_t lop3_and_xor(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); // (a & b) ^ c
+    return d;
+}
+__device__ __forceinline__ float phase_step_fast(float phase, float step, const ChainConsts &cc)
 {
     const float a = __fadd_rn(phase, step);
-    const int sgn = __float_as_int(step) & (int)0x80000000;
-    const float hs = __int_as_float(__float_as_int(-HRD_2PI_HI) ^ sgn); // -2PI_HI for a step >= 0 (only +pi can be passed)
-    const float ls = __int_as_float(__float_as_int(-HRD_2PI_LO) ^ sgn);
+    const float hs = __uint_as_float(lop3_and_xor(__float_as_uint(step), cc.sign, cc.m2pi_hi)); // -2PI_HI for a step >= 0
+    const float ls = __uint_as_float(lop3_and_xor(__float_as_uint(step), cc.sign, cc.m2pi_lo));
     const float k = __saturatef(__fmaf_rn(fabsf(a), 0x1p30f, -HRD_PI_DN * 0x1p30f));
     return __fmaf_rn(k, ls, __fmaf_rn(k, hs, a));
 }

@@ -39,6 +39,12 @@
 #ifndef HRD_EXP
 #define HRD_EXP 0 // timing experiments only (tools/exp_build.sh): bits switch parts of a kernel off
 #endif
+#ifndef HRD_RX_WB_ROLES
+#define HRD_RX_WB_ROLES 0 // rx_wbfm_kernel: 1 = chain on warp 31 / scheduler 3 with the fewest items (as tx_wbfm_kernel), 0 = behind the items
+#endif
+#ifndef HRD_RX_WB_DEP
+#define HRD_RX_WB_DEP 0 // rx_wbfm_kernel: transpose_after's scheduling dependency on (1) or off (0)
+#endif
 
 namespace hrd {
 
@@ -55,7 +61,10 @@ constexpr int IT_SAMPLES = 128; // 256 kS/s samples per warp iteration: FOUR per
 // the younger one and the second buffer buys nothing but register pressure (measured: depth 1 is 1-4 % faster
 // than depth 2 in all three kernels).  The distance comes from the L2 prefetch below instead.
 constexpr int RX_DEPTH = 1;
-constexpr int WB_DEPTH = 1;    // the same in rx_wbfm_kernel
+#ifndef HRD_WB_DEPTH
+#define HRD_WB_DEPTH 1
+#endif
+constexpr int WB_DEPTH = HRD_WB_DEPTH;    // the same in rx_wbfm_kernel
 #ifndef HRD_L2_AHEAD
 #define HRD_L2_AHEAD 4
 #endif
@@ -101,6 +110,19 @@ struct FeCarry {
 struct FeTaps {
     uint32_t a0, b0, a1, b1, a2, b2;
 };
+
+// The transposition {I,Q,I,Q} -> {I,I,Q,Q} of a raw input word, with a SCHEDULING dependency: selector 0x3120 takes
+// all four bytes from `raw`, so the second operand changes nothing -- but it makes the instruction wait for `after`,
+// a value the previous iteration produces at its END.  Without it ptxas hoists the next iteration's transpositions
+// to right behind the load that feeds them (the iterations are unrolled), and since every global load of the loop
+// counts on ONE scoreboard the warp then waits a full memory latency per iteration: the one-iteration register
+// prefetch was not a prefetch at all (ncu: long_scoreboard on these PRMTs was the top stall of every Rx kernel).
+__device__ __forceinline__ uint32_t transpose_after(uint32_t raw, uint32_t after)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, 0x3120;" : "=r"(d) : "r"(raw), "r"(after));
+    return d;
+}
 
 // byte 2 of a and byte 2 of b into bytes 0,1 (the >>16 of the doubled-tap accumulators)
 __device__ __forceinline__ uint32_t pack_b2(int a, int b) { return __byte_perm((uint32_t)a, (uint32_t)b, 0x0062); }
@@ -320,6 +342,8 @@ __device__ __forceinline__ typename RawOf<ENTRY>::type load_raw(const int8_t *sr
 // will read RX_L2_AHEAD KiB from now out of DRAM (lane l takes the 128-byte line l), and the LDG that
 // follows later hits in L2 (a few hundred cycles instead of a DRAM round trip under load).
 // pf is the lane's own next load offset (warp base + 64 * lane).
+// (ncu shows only ~55 % of the LDG sectors hitting in L2.  One prefetch per 64 bytes instead of per 128-byte line --
+// in case the L2 fetched 64 bytes per miss -- was measured and lost: AM 1.412 -> 1.465 ms, FM 1.588 -> 1.654 ms.)
 __device__ __forceinline__ void prefetch_chunk(const int8_t *src, uint32_t pf, uint32_t pf_last, int lane)
 {
     prefetch_l2(src + min(pf + 64u * (uint32_t)lane + RX_L2_AHEAD * 1024u, pf_last));
@@ -346,10 +370,8 @@ __device__ __forceinline__ typename RawNarrowOf<ENTRY>::type load_raw_narrow(con
         return __ldg(reinterpret_cast<const uint32_t *>(src + o));
 }
 
-// An L2 prefetch needs no register and no scoreboard: once every four iterations the warp pulls the 4 KiB it
-// will read RX_L2_AHEAD iterations from now out of DRAM (lane l takes the 128-byte line l), and the LDG that
-// follows later hits in L2 (a few hundred cycles instead of a DRAM round trip under load).
-// pf is the lane's own next load offset (warp base + 32 * lane).
+// The same for the narrow form, once per step of four iterations (4 KiB): lane l takes the 128-byte line l of the
+// step that starts RX_L2_AHEAD iterations from now.  pf is the lane's own next load offset (warp base + 32 * lane).
 __device__ __forceinline__ void prefetch_chunk_narrow(const int8_t *src, uint32_t pf, uint32_t pf_last, int lane)
 {
     prefetch_l2(src + min(pf + 96u * (uint32_t)lane + RX_L2_AHEAD * IT_NARROW * 16, pf_last));
@@ -443,6 +465,7 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, HRD_RX_MIN_CTAS) rx_ke
     }
 
     uint32_t last_active = 32;
+    uint32_t sched_dep = 0; // see transpose_after
 
     while (done256 < end256) {
         const uint32_t nb = min((uint32_t)BATCH256, end256 - done256); // multiple of 32
@@ -458,12 +481,13 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, HRD_RX_MIN_CTAS) rx_ke
                 uint32_t t[16];
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
-                    t[r] = __byte_perm(b.a.v[r], 0, 0x3120);
-                    t[8 + r] = __byte_perm(b.b.v[r], 0, 0x3120);
+                    t[r] = transpose_after(b.a.v[r], sched_dep);
+                    t[8 + r] = transpose_after(b.b.v[r], sched_dep);
                 }
                 b = load_raw<ENTRY>(src, pf, pf_last); // in place: b is dead now
                 if ((it & 1) == 0) prefetch_chunk(src, pf, pf_last, lane);
                 words = front_end_iter(t, fc, fk, lane);
+                sched_dep = words.y;
             } else {
                 words = make_uint2(__byte_perm(b.x, 0, 0x3120), __byte_perm(b.y, 0, 0x3120));
                 b = load_raw<ENTRY>(src, pf, pf_last);
@@ -679,7 +703,10 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, HRD_RX_MIN_CTAS) rx_ke
 // end, so it is hidden as long as the item warps have at least that much to do (they do: the
 // step is HBM- or issue-bound on them).  Results are bit-identical to the serial evaluation:
 // same operations, same order, per stream.
-constexpr int WB_ITEMS = 31;
+#ifndef HRD_WB_THREADS
+#define HRD_WB_THREADS 1024 // threads per CTA the kernel is compiled for: 1024 -> 64 registers, 800 -> 80
+#endif
+constexpr int WB_ITEMS = HRD_WB_THREADS / 32 - 1;
 constexpr int WB_STEP = 256;            // 256 kS/s samples per pipeline step (4 warp iterations)
 constexpr int WB_PITCH = WB_STEP + 4;   // floats per row
 
@@ -708,7 +735,7 @@ struct SmemWb {
 
 // TILED: the call is cut into time tiles (n_tiles > 1); only that instance carries the verification stores
 template <int ENTRY, bool TILED>
-__global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
+__global__ void __launch_bounds__(HRD_WB_THREADS, 1) rx_wbfm_kernel(const RxParams p)
 {
     typedef typename RawNarrowOf<ENTRY>::type Raw;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -719,15 +746,24 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
     SmemWb &sm = *reinterpret_cast<SmemWb *>(smem_raw);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    // the chain warp is the LAST warp of the CTA: the warp scheduler favours the highest warp id among
-    // eligible warps, and the chain (two dependent instructions per sample) is the CTA's critical path
+    // WARP ROLES.  A warp's scheduler is warp id % 4.  tx_wbfm_kernel puts its chain on the scheduler with the fewest
+    // items (its chain is two items' worth of instructions); here the chain is light (two operations per sample,
+    // less than one item's worth), so the even split -- items on warps 0.., the chain right behind them, seven
+    // or eight warps per scheduler -- balances better: measured 2.445 ms against 2.567 ms (4096 streams x 0.5 s).
+#if HRD_RX_WB_ROLES
+    const bool chain_warp = warp == 31;
+    const int item_of_warp = (warp & 3) != 3 ? (warp >> 2) * 3 + (warp & 3) : 24 + (warp >> 2);
+#else // items on warps 0.., the chain right behind them
     const bool chain_warp = warp == p.items_per_cta;
+    const int item_of_warp = warp;
+#endif
+    const bool member = chain_warp || item_of_warp < p.items_per_cta; // takes part in the pipeline's barriers
     const int n_items = n_streams * p.n_tiles;
 
     // ---- this thread's item: the warp's (item warps) or the lane's (chain warp) ---------
     const uint32_t tile_len = p.tile_batches * BATCH256;
     const uint32_t halo = (uint32_t)HaloOf<K_WBFM>::value * BATCH256;
-    const int row = chain_warp ? lane : warp;
+    const int row = chain_warp ? lane : item_of_warp;
     const int item = blockIdx.x * p.items_per_cta + row;
     const bool live = row < p.items_per_cta && item < n_items;
     int tile = 0, sid = 0, slot = 0;
@@ -751,7 +787,7 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
     if (chain_warp && live && first) y1 = st.wb_y1;
 
     // ---- item warp state -----------------------------------------------------------------
-    SmemWbItem &it = sm.item[chain_warp ? 0 : warp];
+    SmemWbItem &it = sm.item[chain_warp || !member ? 0 : item_of_warp];
     const int8_t *src = p.iq + (size_t)sid * p.iq_stride;
     asm volatile("" : "+l"(src));
     FeCarry fc;
@@ -763,6 +799,7 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
     float scale = 0.f, th_keep = 0.f, v_keep = 0.f, m_keep = 0.f;
     uint32_t keep2 = 0u, keep3 = 0u; // the last four narrowed samples @256k (history of the /4 decimator)
     int last_nl = 32;                // lanes that were live in the most recent consume
+    uint32_t sched_dep = 0;          // see transpose_after
     bool narrow_fast = false;
     constexpr uint32_t BPS = ENTRY == 0 ? 16 : 2;
     uint32_t pf = 0, pf_last = 0, last_active = 32;
@@ -802,9 +839,12 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
         if constexpr (ENTRY == 0) {
             uint32_t t[8];
 #pragma unroll
-            for (int r = 0; r < 8; r++) t[r] = __byte_perm(b.v[r], 0, 0x3120);
+            for (int r = 0; r < 8; r++) t[r] = transpose_after(b.v[r], sched_dep);
             b = load_raw_narrow<ENTRY>(src, pf, pf_last);
             word = front_end_iter_narrow(t, fc, fk, lane);
+#if HRD_RX_WB_DEP
+            sched_dep = word;
+#endif
         } else {
             word = __byte_perm(b, 0, 0x3120);
             b = load_raw_narrow<ENTRY>(src, pf, pf_last);
@@ -856,9 +896,9 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
         float *dst = sm.f[t & 1][row];
         if (n_it == WB_STEP / IT_NARROW) { // a full step, unrolled: the in-place refill of buf needs no register moves
 #pragma unroll
-            for (uint32_t i = 0; i < WB_STEP / IT_NARROW; i++) iter(buf[0], dst + i * IT_NARROW);
+            for (uint32_t i = 0; i < WB_STEP / IT_NARROW; i++) iter(buf[i % WB_DEPTH], dst + i * IT_NARROW);
         } else {
-            for (uint32_t i = 0; i < n_it; i++) iter(buf[0], dst + i * IT_NARROW);
+            for (uint32_t i = 0; i < n_it; i++) iter(buf[i % WB_DEPTH], dst + i * IT_NARROW);
         }
         __syncwarp();
     };
@@ -947,6 +987,10 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
         if (done >= end) return;
         const uint32_t nb = min((uint32_t)WB_STEP, end - done); // multiple of 32
         float *r = sm.f[t & 1][lane];
+        // (All eight loads of a 32-sample round first.  Reading the row a few groups AHEAD of its use instead was
+        // measured and lost: ptxas puts every shared-memory load of the loop on one counting scoreboard, so the
+        // consumer of an old load also waits for the one just issued -- a full load latency per group of four
+        // samples instead of one per round.)
         for (uint32_t c = 0; c < nb; c += 32) {
             float4 v[8];
 #pragma unroll
@@ -973,12 +1017,13 @@ __global__ void __launch_bounds__(1024, 1) rx_wbfm_kernel(const RxParams p)
     for (int i = threadIdx.x; i < (int)(sizeof(sm.lut) / 4); i += blockDim.x) // table rows q = 0..127 are rows 128..255; row 128 = -row 0
         sm.lut[i] = i < 128 * 256 ? __ldg(p.atan2_lut + 128 * 256 + i) : -__ldg(p.atan2_lut + (i - 128 * 256));
     __syncthreads(); // the tables are complete before any warp looks an angle up
+    if (!member) return; // (a spare warp slot: exited warps do not count at later barriers)
     // Hand-over between the item warps and the chain warp: two pairs of named barriers (by step parity)
     // instead of one __syncthreads per step.  Item warps ARRIVE on "produced" and go on; only the chain
     // warp waits there.  The chain warp arrives on "chained" after its step; item warps wait there before
     // they narrow that step.  No item warp ever waits for another item warp's consume, so a slow warp
     // costs the CTA nothing as long as it keeps within a step of the others.
-    const int bar_threads = (int)blockDim.x;
+    const int bar_threads = (p.items_per_cta + 1) * 32;
     if (chain_warp) {
         for (uint32_t t = 0; t < n_steps; t++) {
             named_bar_sync(HRD_BAR_PRODUCED, t, bar_threads);
@@ -1258,12 +1303,10 @@ int rx_resident_warps_per_sm(int kind, int entry)
 template <int ENTRY, bool TILED>
 int launch_wbfm_as(const RxParams &q, int grid, cudaStream_t s)
 {
-    static bool attr_set = false; // per template instance
-    if (!attr_set) {
-        cudaFuncSetAttribute(rx_wbfm_kernel<ENTRY, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemWb));
-        attr_set = true;
-    }
-    rx_wbfm_kernel<ENTRY, TILED><<<grid, (q.items_per_cta + 1) * 32, sizeof(SmemWb), s>>>(q);
+    static PerDeviceOnce optin; // per template instance
+    const cudaError_t e = optin.run([] { return cudaFuncSetAttribute(rx_wbfm_kernel<ENTRY, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemWb)); });
+    if (e != cudaSuccess) return (int)e;
+    rx_wbfm_kernel<ENTRY, TILED><<<grid, HRD_RX_WB_ROLES ? 1024 : (q.items_per_cta + 1) * 32, sizeof(SmemWb), s>>>(q);
     return (int)cudaGetLastError();
 }
 
@@ -1308,11 +1351,9 @@ int launch_rx_dc_iir(const RxParams &p, cudaStream_t s)
 {
     if (p.n_streams <= 0 || p.n256 == 0) return 0;
     const int grid = (p.n_streams + 31) / 32;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(rx_dc_iir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemIir));
-        attr_set = true;
-    }
+    static PerDeviceOnce optin;
+    const cudaError_t e = optin.run([] { return cudaFuncSetAttribute(rx_dc_iir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemIir)); });
+    if (e != cudaSuccess) return (int)e;
     rx_dc_iir_kernel<<<grid, 64 + IIR_POST_THREADS, sizeof(SmemIir), s>>>(p);
     return (int)cudaGetLastError();
 }

@@ -16,6 +16,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <mutex>
 
 #include <cuda_runtime.h>
 
@@ -50,6 +51,9 @@ struct ConstTables {
     int32_t tx_c3, tx_c7, tx_c8; // outer tap of stages 3&6 / 7 / 8 (8424 / 8249 / 8206)
     int32_t tx_m3, tx_m7, tx_m8; // their centre taps (16384 each after quantisation)
     int32_t k_32768;             // 32768 as a value ptxas cannot see (hrd_tx.cu PIPE BALANCE)
+    // the NCO chains (hrd_device.cuh phase_step_fast): sign mask, -2PI_HI and -2PI_LO as REGISTER operands, so that
+    // "(step & mask) ^ constant" is one LOP3 (with immediates ptxas needs two)
+    uint32_t k_sign, k_m2pi_hi, k_m2pi_lo;
 };
 
 // ---------------------------------------------------------------- Rx per-stream state
@@ -207,6 +211,24 @@ static inline int balanced_items_per_cta(long long items, int sms, int cap)
     if (ipc > cap) ipc = cap;
     return (int)ipc;
 }
+
+// cudaFuncSetAttribute (the opt-in to more than 48 KB of dynamic shared memory) is per DEVICE: one of these per
+// launch site remembers which devices have had it, so a process that opens batches on several GPUs gets it on each.
+struct PerDeviceOnce {
+    std::mutex m;
+    uint64_t done = 0; // bit d: device d is set up (hrd_create admits devices 0..63)
+    template <class Fn> cudaError_t run(Fn fn)
+    {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        std::lock_guard<std::mutex> lock(m);
+        if (dev >= 0 && dev < 64 && (done >> dev & 1)) return cudaSuccess;
+        e = fn();
+        if (e == cudaSuccess && dev >= 0 && dev < 64) done |= 1ull << dev;
+        return e;
+    }
+};
 
 void upload_tables(const ConstTables &t);            // hrd_rx.cu (owns the __constant__ copy)
 void upload_tables_tx(const ConstTables &t);         // hrd_tx.cu

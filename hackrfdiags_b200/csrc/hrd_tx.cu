@@ -640,8 +640,10 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
 
     float phase = 0.f, dev = 0.f;
     uint32_t iq_keep = 0; // the (cos,sin)*900 pair of the previous 256 kS/s sample (stage 6 history)
+    int pcm_next = 0;     // this lane's PCM sample of the NEXT super-step, loaded one super-step ahead
     if (live) {
         dev = p.param[sid];
+        if (!chain_warp && (uint32_t)lane < p.n8) pcm_next = (int)src[lane];
         if (chain_warp) {
             phase = st.wb_phase;
         } else {
@@ -695,7 +697,8 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
                 __syncwarp();
                 if (lane < 3) it.x32[1 + lane] = v;
             }
-            if (lane < nb8) it.s0[19 + lane] = (int)src[done + lane];
+            if (lane < nb8) it.s0[19 + lane] = pcm_next;
+            if (done + TW_SUPER8 + lane < p.n8) pcm_next = (int)src[done + TW_SUPER8 + lane];
             __syncwarp();
             if (lane < nb8) { // stage 1: 40 taps, L = 2 (the only stage whose output may wrap: keep q15)
                 unsigned e = 1u << 14, o = 1u << 14;
@@ -776,6 +779,7 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
     // limits, or NaN).  Without one, |phase + step| < pi + 3 < 6.2, so the single-FMA wrap is the exact one
     // (hrd_device.cuh phase_step_fast) and the chain is three dependent operations per sample with no
     // bookkeeping; with one, the lock-step version with its exact per-chunk redo runs instead.
+    const ChainConsts cc = {c_tabtx.k_sign, c_tabtx.k_m2pi_hi, c_tabtx.k_m2pi_lo};
     auto chain = [&](uint32_t t) {
         const uint32_t nb = min((uint32_t)TW_STEP8, p.n8 - t * TW_STEP8) * 32;
         float *r = sm.ph[t & 1][lane];
@@ -783,8 +787,9 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
         const bool slow = __any_sync(HRD_FULL_MASK, live && (sm.big[t & 1][lane] != 0 || !(fabsf(phase) < HRD_PI_UP)));
         if (!live) return;
         if (!slow) {
-            // the row is read four groups (16 samples, ~300 cycles of chain) ahead of its use: under load a
-            // shared-memory load takes far longer than the 29 cycles it takes alone
+            // the row is read four groups (16 samples) ahead of its use.  (Measured: 2.07 ms against 2.22 ms with all
+            // eight loads of a 32-sample round issued first; in rx_wbfm_kernel, whose chain is two operations per
+            // sample instead of four, the same change lost.)
             float4 q[4];
 #pragma unroll
             for (int g = 0; g < 4; g++) q[g] = *reinterpret_cast<float4 *>(r + 4 * g);
@@ -794,10 +799,10 @@ __global__ void __launch_bounds__(1024, 1) tx_wbfm_kernel(const TxParams p)
                     float4 v = q[g];
                     if (c + 16 < nb) q[g] = *reinterpret_cast<float4 *>(r + c + 16 + 4 * g);
                     float s;
-                    s = v.x; v.x = phase; phase = phase_step_fast(phase, s);
-                    s = v.y; v.y = phase; phase = phase_step_fast(phase, s);
-                    s = v.z; v.z = phase; phase = phase_step_fast(phase, s);
-                    s = v.w; v.w = phase; phase = phase_step_fast(phase, s);
+                    s = v.x; v.x = phase; phase = phase_step_fast(phase, s, cc);
+                    s = v.y; v.y = phase; phase = phase_step_fast(phase, s, cc);
+                    s = v.z; v.z = phase; phase = phase_step_fast(phase, s, cc);
+                    s = v.w; v.w = phase; phase = phase_step_fast(phase, s, cc);
                     *reinterpret_cast<float4 *>(r + c + 4 * g) = v;
                 }
             }
@@ -1024,6 +1029,7 @@ __global__ void __launch_bounds__((FP_WORKERS + 1) * 32) tx_fm_phase_kernel(cons
         }
     };
     // chain warp: PhaseAccumulator::run over chunk c of row `lane`, in place
+    const ChainConsts cc = {c_tabtx.k_sign, c_tabtx.k_m2pi_hi, c_tabtx.k_m2pi_lo};
     auto walk = [&](uint32_t c) {
         const int nb = (int)min((uint32_t)FP_CH, p.n8 - c * FP_CH);
         float *row = sm.t[c % 3][lane];
@@ -1047,7 +1053,7 @@ __global__ void __launch_bounds__((FP_WORKERS + 1) * 32) tx_fm_phase_kernel(cons
             for (int n = 0; n < FP_CH; n++) {
                 const float s = row[n];
                 row[n] = phase;
-                phase = phase_step_fast(phase, s);
+                phase = phase_step_fast(phase, s, cc);
             }
         } else {
             for (int n = 0; n < nb; n++) {
@@ -1161,11 +1167,9 @@ int launch_tx(int kind, const TxParams &p, cudaStream_t s)
         TxParams q = p;
         q.items_per_cta = balanced_items_per_cta(p.n_streams, p.sm_count, TW_ITEMS);
         const int grid = (p.n_streams + q.items_per_cta - 1) / q.items_per_cta;
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(tx_wbfm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTw));
-            attr_set = true;
-        }
+        static PerDeviceOnce optin;
+        const cudaError_t e = optin.run([] { return cudaFuncSetAttribute(tx_wbfm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTw)); });
+        if (e != cudaSuccess) return (int)e;
         tx_wbfm_kernel<<<grid, 1024, sizeof(SmemTw), s>>>(q); // always 32 warp slots (see WARP ROLES)
         return (int)cudaGetLastError();
     }
