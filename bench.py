@@ -4,14 +4,19 @@
     python bench.py --gpus N --steps K --warmup W            (ours: CUDA, sm_100a)
     python bench.py --impl reference --gpus N --steps K ...  (the reference's own CPU chain)
 
-Workload at every N (weak scaling, per GPU): BASELINE.json configs[1], "batched AM and SSB
-demod: 1024 independent synthetic IQ streams on 1 B200" -- 512 AM + 256 LSB + 256 USB streams,
-1 s of int8 IQ at 2.048 MS/s each (4.29 GB in, 16.8 MB of PCM out per step), entered at
-IqDataProcessor::acceptIqData.  A step is one pass over that batch; stream state carries from
-step to step exactly as consecutive reference calls would.  `value` is input IQ MS/s with the
-inputs resident in HBM; `e2e` is the same through hrd_rx_process with pinned HOST buffers
-(H2D of all IQ and D2H of all PCM inside the timed region).  Extra keys give every other
-mode (Rx and Tx, 4096 streams) with its own roofline fraction.
+Headline workload at every N (weak scaling, per GPU): BASELINE.json configs[4] at its 4k point, the MIXED-MODE
+batch -- 4096 streams per GPU, 1/4 AM, 1/4 NBFM, 1/4 WBFM, 1/8 LSB, 1/8 USB, 0.5 s of int8 IQ at 2.048 MS/s
+each (4.19 GB in, 16.4 MB of PCM out per step), entered at IqDataProcessor::acceptIqData, streams dealt to
+the ranks by hackrfdiags_b200.shard (contiguous ranges of one global plan, no collective).  A step is one
+pass over that batch; stream state carries from step to step exactly as consecutive reference calls would.
+`value` is input IQ MS/s with the inputs resident in HBM; `e2e` is the same through hrd_rx_process with pinned
+HOST buffers (H2D of all IQ and D2H of all PCM inside the timed region).  The same line carries, at every N:
+`modes` (each of the eight chains alone, 4096 streams per GPU, with its roofline fraction, the reference's CPU
+rate for that chain and a parity record against the reference), `min_mode_hbm_frac`, the 1k..64k mixed-mode
+stream sweep sharded over the N GPUs (strong scaling) and the WBFM-modulator stream-count sweep.
+
+oracle/ is used here as the CHECKER only (cpu_baseline / parity legs and --impl reference): the compiled
+reference oracle/_ref/libhrd_ref.so (unmodified sources), else the C port oracle/liboracle.so.
 """
 from __future__ import annotations
 
@@ -31,25 +36,27 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 FS = 2_048_000
 BYTES_PER_IN_SAMPLE_RX = 2.0 + 2.0 / 256.0
 BYTES_PER_OUT_SAMPLE_TX = 2.0 + 2.0 / 256.0
+MIX = {1: 0.25, 2: 0.25, 3: 0.25, 4: 0.125, 5: 0.125}  # config 5: AM, NBFM, WBFM, LSB, USB
+KIND_OF_MODE = {1: 1, 2: 2, 3: 3, 4: 1, 5: 1}          # kernel kind (AM and SSB share a launch)
+KIND_KERNEL = {1: "rx_kernel<AM+SSB, 2048k entry>", 2: "rx_kernel<FM, 2048k entry>", 3: "rx_wbfm_kernel<2048k entry>"}
+
+METRIC = ("aggregate input IQ MS/s (config 5: mixed-mode demod batch, 4096 streams/GPU = 1/4 AM + 1/4 NBFM + 1/4 WBFM "
+          "+ 1/8 LSB + 1/8 USB, 2.048 MS/s entry)")
+UNIT = "MS/s"
+MODE_NAMES = {1: "am", 2: "fm", 3: "wbfm", 4: "lsb", 5: "usb"}
+EDGE_CLASSES = ("full-range noise", "constant -128", "constant +127", "alternating +-127", "zero")
 
 
-def ncu_traffic_bytes(streams, n_samples):
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on this workload, from
-    the committed `ncu --set full` capture (profiles/ncu_traffic.json, written from the .ncu-rep by
-    tools/ncu_summary.py); None when no capture matches the workload."""
+def ncu_traffic_bytes(kernel, streams, n_samples):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of `kernel` on this workload, from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json, written from the .ncu-rep by tools/ncu_summary.py);
+    scaled by the unit count when the capture is of the same kernel at another size; None without a capture."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            t = json.load(f)["rx_kernel<AM+SSB,2048k>"]
-        if t["streams"] == streams and t["samples_per_stream"] == n_samples:
-            return t["dram_bytes_per_launch"]
+            t = json.load(f)[kernel]
+        return int(t["dram_bytes_per_launch"] * (streams * n_samples) / (t["streams"] * t["samples_per_stream"]))
     except Exception:
-        pass
-    return None
-
-METRIC = "aggregate input IQ MS/s (config 2: AM+SSB demod, 1024 streams/GPU, 2.048 MS/s entry)"
-UNIT = "MS/s"
-
-MODE_NAMES = {1: "am", 2: "fm", 3: "wbfm", 4: "lsb", 5: "usb"}
+        return None
 
 
 def measured_peak_gbs():
@@ -62,10 +69,12 @@ def measured_peak_gbs():
 
 
 # ----------------------------------------------------------------------------------------
-# synthetic inputs generated on the device (same signal classes as hackrfdiags_b200/synth.py)
+# synthetic inputs generated on the device (same signal classes as hackrfdiags_b200/synth.py);
+# every batch of >= 8 distinct streams ends with one stream of each EDGE class (SURVEY 8d)
 # ----------------------------------------------------------------------------------------
 def make_rx_iq_device(torch, mode, n_distinct, n_samples, device, seed):
-    """[n_distinct, 2*n_samples] int8: carrier at -64 kHz, signal of `mode`, amplitude / noise cycled."""
+    """[n_distinct, 2*n_samples] int8: carrier at -64 kHz, signal of `mode`, amplitude / noise cycled; the last
+    five rows are the edge classes (full-range noise, constant -128, constant +127, alternating +-127, zero)."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     t = torch.arange(n_samples, device=device, dtype=torch.float64) / FS
@@ -73,7 +82,8 @@ def make_rx_iq_device(torch, mode, n_distinct, n_samples, device, seed):
     out = torch.empty((n_distinct, 2 * n_samples), dtype=torch.int8, device=device)
     amps = (20.0, 60.0, 100.0, 127.0)
     sigmas = (1.0, 3.0, 10.0)
-    for s in range(n_distinct):
+    n_edge = 5 if n_distinct >= 8 else 0
+    for s in range(n_distinct - n_edge):
         amp, sigma = amps[s % 4], sigmas[(s // 4) % 3]
         if mode == 1:
             env = (1.0 + 0.8 * torch.sin(two_pi * 1000.0 * t)) / 1.8
@@ -95,22 +105,39 @@ def make_rx_iq_device(torch, mode, n_distinct, n_samples, device, seed):
         q = amp * env * torch.sin(ph) + sigma * torch.randn(n_samples, device=device, dtype=torch.float64, generator=g)
         out[s, 0::2] = torch.clamp(torch.round(i), -128, 127).to(torch.int8)
         out[s, 1::2] = torch.clamp(torch.round(q), -128, 127).to(torch.int8)
+    if n_edge:
+        e = n_distinct - n_edge
+        out[e] = torch.randint(-128, 128, (2 * n_samples,), device=device, generator=g).to(torch.int8)
+        out[e + 1] = -128
+        out[e + 2] = 127
+        alt = torch.full((n_samples,), 127, device=device, dtype=torch.int8)
+        alt[1::2] = -127
+        out[e + 3, 0::2] = alt
+        out[e + 3, 1::2] = alt
+        out[e + 4] = 0
     return out
 
 
 def make_tx_pcm_device(torch, n_distinct, n_samples, device, seed):
+    """[n_distinct, n_samples] int16 at 8 kS/s: full-scale sines 300..3400 Hz (reaching -32768), uniform noise,
+    amplitude-modulated tone, silence, +-32767 square wave -- cycled by stream index."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     t = torch.arange(n_samples, device=device, dtype=torch.float64) / 8000.0
+    two_pi = 2 * 3.141592653589793
     out = torch.empty((n_distinct, n_samples), dtype=torch.int16, device=device)
     for s in range(n_distinct):
-        k = s % 3
+        k = s % 5
         if k == 0:
-            x = -32768.0 * torch.cos(2 * 3.141592653589793 * (300.0 + 97.0 * s % 3100.0) * t)
+            x = -32768.0 * torch.cos(two_pi * (300.0 + 97.0 * s % 3100.0) * t)
         elif k == 1:
             x = torch.randint(-32768, 32768, (n_samples,), device=device, generator=g).to(torch.float64)
+        elif k == 2:
+            x = 12000.0 * torch.sin(two_pi * 440.0 * t) * (0.5 + 0.5 * torch.sin(two_pi * 3.0 * t))
+        elif k == 3:
+            x = torch.zeros_like(t)
         else:
-            x = 12000.0 * torch.sin(2 * 3.141592653589793 * 440.0 * t) * (0.5 + 0.5 * torch.sin(2 * 3.141592653589793 * 3.0 * t))
+            x = torch.where(torch.sin(two_pi * (150.0 + 10.0 * s) * t) >= 0, 32767.0, -32767.0).to(torch.float64)
         out[s] = torch.clamp(torch.round(x), -32768, 32767).to(torch.int16)
     return out
 
@@ -193,41 +220,70 @@ def time_calls(torch, calls, steps, warmup):
 
 
 def make_rx_batch(torch, capi, device, groups, n_samples, seed):
-    """ONE batch holding every group's streams: groups = [(mode, n_streams)]; returns (batch, iq, pcm)."""
+    """ONE batch holding every group's streams: groups = [(mode, n_streams)]; returns (batch, iq, pcm, distinct)
+    with distinct[mode] = the rows the group's streams repeat."""
     n = sum(g[1] for g in groups)
     iq = torch.empty((n, 2 * n_samples), dtype=torch.int8, device=device)
     b = capi.Batch(n, capi.RX, device.index or 0)
     at = 0
+    n_distinct = {}
     for mode, cnt in groups:
         distinct = make_rx_iq_device(torch, mode, min(cnt, 32), n_samples, device, seed + mode)
         iq[at:at + cnt] = tile_rows(torch, distinct, cnt)
+        n_distinct[mode] = (at, distinct.shape[0], cnt)
         del distinct
         for s in range(at, at + cnt):
             b.set_mode(mode, s)
         at += cnt
     pcm = torch.zeros((n, n_samples // 256), dtype=torch.int16, device=device)
-    return b, iq, pcm
+    return b, iq, pcm, n_distinct
 
 
-def bench_rx_modes(torch, capi, device, groups, n_samples, steps, warmup, seed):
-    """One batch, one hrd_rx_process call per step.  Returns (ms_per_step, kernel_ms, tail_ms, launches, keep):
-    kernel_ms = the tile kernel(s) alone, tail_ms = the AM/SSB IIR pass, both from CUDA events the
-    library records on the launching stream inside the timed steps (HRD_OPT_PROFILE)."""
+def repeats_identical(torch, out, layout):
+    """Rows that got identical input must give identical output: EVERY repeat of every distinct row, on the device."""
+    bad = 0
+    for at, nd, cnt in layout.values():
+        full = cnt // nd
+        if full >= 2:
+            v = out[at:at + full * nd].view(full, nd, -1)
+            bad += int((v != v[0:1]).any(dim=2).sum().item())
+        rest = cnt - full * nd
+        if rest and full:
+            bad += int((out[at + full * nd:at + cnt] != out[at:at + rest]).any(dim=1).sum().item())
+    return bad
+
+
+def bench_rx_modes(torch, capi, device, groups, n_samples, steps, warmup, seed, serial_pass=False):
+    """One batch, one hrd_rx_process call per step.  Returns a dict: ms (per step), kernel_ms (the tile kernels'
+    span), tail_ms (the AM/SSB IIR pass), both from CUDA events the library records on the launching stream
+    inside the timed steps (HRD_OPT_PROFILE); launches per step; repeat_mismatches (all row repeats compared on the
+    device); and, with serial_pass, kind_ms: each kernel kind's own duration from three extra steps with the
+    kinds run one after the other (HRD_OPT_RX_SERIAL) -- side by side their spans overlap and cannot be told apart."""
     stream = torch.cuda.current_stream().cuda_stream
-    b, iq, pcm = make_rx_batch(torch, capi, device, groups, n_samples, seed)
+    b, iq, pcm, layout = make_rx_batch(torch, capi, device, groups, n_samples, seed)
     b.set_option(capi.OPT_PROFILE, 1)
     call = lambda: b.rx_device(iq.data_ptr(), iq.shape[1], iq.stride(0), pcm.data_ptr(), pcm.stride(0),
                                capi.ENTRY_2048K, stream)
     l0 = b.launch_count()
     ms_step, _ = time_calls(torch, [call], steps, warmup)
-    launches = (b.launch_count() - l0) * steps // (steps + warmup)
+    launches = (b.launch_count() - l0) // (steps + warmup)
     k = min(steps, 32)
-    kernel_ms = sum(b.kernel_ms(0, a) for a in range(k)) / k
-    tail_ms = sum(b.kernel_ms(1, a) for a in range(k)) / k
-    return ms_step, kernel_ms, tail_ms, launches, (b, iq, pcm)
+    res = {"ms": ms_step, "kernel_ms": sum(b.kernel_ms(0, a) for a in range(k)) / k,
+           "tail_ms": sum(b.kernel_ms(1, a) for a in range(k)) / k, "launches": launches,
+           "repeat_mismatches": repeats_identical(torch, pcm, layout),
+           "wbfm_fallbacks": b.wbfm_fallback_count()}
+    if serial_pass:
+        b.set_option(capi.OPT_RX_SERIAL, 1)
+        for _ in range(4):
+            call()
+        torch.cuda.synchronize()
+        kinds = sorted({KIND_OF_MODE[m] for m, _ in groups})
+        res["kind_ms"] = {kd: sum(b.kernel_ms(10 + kd, a) for a in range(3)) / 3 for kd in kinds}
+        b.set_option(capi.OPT_RX_SERIAL, 0)
+    return res, (b, iq, pcm, layout)
 
 
-def bench_tx_mode(torch, capi, device, mode, n, n_pcm, steps, warmup, seed):
+def bench_tx_mode(torch, capi, device, mode, n, n_pcm, steps, warmup, seed, want=False):
     stream = torch.cuda.current_stream().cuda_stream
     distinct = make_tx_pcm_device(torch, min(n, 32), n_pcm, device, seed)
     pcm = tile_rows(torch, distinct, n)
@@ -236,12 +292,24 @@ def bench_tx_mode(torch, capi, device, mode, n, n_pcm, steps, warmup, seed):
     b.set_mode(mode)
     call = lambda: b.tx_device(pcm.data_ptr(), n_pcm, pcm.stride(0), iq.data_ptr(), iq.stride(0), stream)
     ms_step, per_call = time_calls(torch, [call], steps, warmup)
+    if want:
+        bad = repeats_identical(torch, iq, {mode: (0, distinct.shape[0], n)})
+        return ms_step, bad, distinct
     return ms_step
+
+
+def reduce_max_ms(torch, dist, device, values):
+    """max over ranks of a list of per-rank times (identity on one rank)"""
+    if not dist:
+        return list(values)
+    t = torch.tensor(list(values), device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
 
 
 def run_ours(args):
     import torch
-    from hackrfdiags_b200 import capi
+    from hackrfdiags_b200 import capi, shard
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -271,60 +339,87 @@ def run_ours(args):
             os.close(saved_stdout)
     peak, peak_src = measured_peak_gbs()
 
+    # the rank's share of ONE global plan of world * streams mixed-mode streams (weak scaling: the plan grows with N)
     n_samples = int(args.seconds * FS) // 8192 * 8192
-    groups = [(1, args.streams // 2), (4, args.streams // 4), (5, args.streams - args.streams // 2 - args.streams // 4)]
-    in_samples_per_step = args.streams * n_samples
+    plan = shard.mixed_mode_plan(world * args.streams, MIX)
+    mine = shard.shard_modes(plan, world, rank)
+    groups = shard.mode_groups(mine)
+    my_streams = len(mine)
+    in_samples_per_step = my_streams * n_samples
 
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_step, kernel_ms, tail_ms, launches, keep = bench_rx_modes(torch, capi, device, groups, n_samples, args.steps,
-                                                                 args.warmup, seed=1234 + rank)
+    r, keep = bench_rx_modes(torch, capi, device, groups, n_samples, args.steps, args.warmup, seed=1234 + rank,
+                             serial_pass=True)
     torch.cuda.synchronize()
-    t_local = torch.tensor([ms_step], device=device, dtype=torch.float64)
     if dist:
         dist.barrier()
-        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
-    ms_max = float(t_local.item())
+    ms_max = reduce_max_ms(torch, dist, device, [r["ms"]])[0]
     clocks = sampler.stop() if sampler else None
     value = world * in_samples_per_step / (ms_max * 1e-3) / 1e6
 
-    # roofline of the dominant kernel: the AM+SSB tile kernel (one launch covers all 1024 streams)
-    dom_bytes = in_samples_per_step * BYTES_PER_IN_SAMPLE_RX
-    achieved = dom_bytes / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "rx_kernel<AM+SSB, 2048k entry>",
-                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": ncu_traffic_bytes(args.streams, n_samples), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": round(kernel_ms, 4),
-                "tail_kernel": {"name": "rx_dc_iir_kernel", "avg_launch_ms": round(tail_ms, 4)}}
+    # roofline of the dominant kernel: the kind that takes longest when the kinds run one after the other
+    per_kind_streams = {}
+    for m, c in groups:
+        per_kind_streams[KIND_OF_MODE[m]] = per_kind_streams.get(KIND_OF_MODE[m], 0) + c
+    dom = max(r["kind_ms"], key=lambda kd: r["kind_ms"][kd])
+    dom_bytes = per_kind_streams[dom] * n_samples * BYTES_PER_IN_SAMPLE_RX
+    achieved = dom_bytes / (r["kind_ms"][dom] * 1e-3) / 1e9
+    step_bytes = in_samples_per_step * BYTES_PER_IN_SAMPLE_RX
+    roofline = {"bound": "hbm", "kernel": KIND_KERNEL[dom], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4),
+                "traffic": ncu_traffic_bytes(KIND_KERNEL[dom], per_kind_streams[dom], n_samples), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": round(r["kind_ms"][dom], 4),
+                "how": "the three kernel kinds of the mixed batch run side by side in the timed steps; each kind's own "
+                       "launch time comes from three extra steps with the kinds serialised (HRD_OPT_RX_SERIAL), CUDA "
+                       "events on the launching stream",
+                "kinds": {KIND_KERNEL[kd]: {"streams": per_kind_streams[kd], "launch_ms": round(ms, 4),
+                                            "frac": round(per_kind_streams[kd] * n_samples * BYTES_PER_IN_SAMPLE_RX
+                                                          / (ms * 1e-3) / 1e9 / peak, 4)}
+                          for kd, ms in r["kind_ms"].items()},
+                "step": {"algorithmic_bytes": step_bytes, "ms": round(r["ms"], 4),
+                         "frac": round(step_bytes / (r["ms"] * 1e-3) / 1e9 / peak, 4)}}
 
     out = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_max, 4), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int32 (Q15 accumulate over int8/int16 samples) + f32 IIR tail", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: 1024 streams/GPU = 512 AM + 256 LSB + 256 USB, "
-                               f"{n_samples / FS:.3f} s of int8 IQ @2.048 MS/s each, IqDataProcessor entry",
+        "vs_baseline": None, "dtype": "int32 (Q15 accumulate over int8/int16 samples) + f32 detector / IIR sections",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE configs[4] (mixed-mode) at 4096 streams/GPU: 1/4 AM, 1/4 NBFM, 1/4 WBFM, 1/8 LSB, "
+                               f"1/8 USB, {n_samples / FS:.3f} s of int8 IQ @2.048 MS/s each, IqDataProcessor entry; every "
+                               "group of 32 distinct streams ends with the five edge classes",
                    "streams_per_gpu": args.streams, "input_bytes_per_step_per_gpu": 2 * in_samples_per_step,
                    "l2": "inputs per step exceed the 126 MB L2 many times over; no flush needed",
-                   "sharding": "disjoint stream sets per GPU, no collective"},
-        "roofline": roofline, "gpu_launches": launches * world,
-        "call_ms": {"tile_kernel": round(kernel_ms, 4), "iir_tail": round(tail_ms, 4)},
+                   "sharding": "one global plan, contiguous stream ranges per rank (hackrfdiags_b200.shard), no collective",
+                   "mode_groups_rank0": [[MODE_NAMES[m], c] for m, c in groups]},
+        "roofline": roofline, "gpu_launches": r["launches"] * args.steps * world,
+        "call_ms": {"tile_kernels": round(r["kernel_ms"], 4), "iir_tail": round(r["tail_ms"], 4)},
+        "repeat_mismatches": r["repeat_mismatches"], "wbfm_tile_fallback_streams": r["wbfm_fallbacks"],
     }
     if clocks:
         out["clocks"] = clocks
     del keep
     torch.cuda.empty_cache()
 
-    # end to end through the C ABI with host buffers: every rank drives its own GPU at the same time
-    # (their PCIe links are independent); whole-job value = all ranks' samples / slowest rank's time
+    # end to end through the C ABI with host buffers: every rank drives its own GPU at the same time;
+    # whole-job value = all ranks' samples / slowest rank's time
     e2e = run_e2e(torch, capi, device, args, groups, n_samples, dist)
     if rank == 0:
         out["e2e"] = e2e
-        if world == 1 and not args.quick:
-            out["modes"] = run_mode_sweep(torch, capi, device, args, peak)
-            out["mixed_mode_stream_sweep"] = run_stream_sweep(torch, capi, device, args, peak)
-            out["cpu_baseline"] = cpu_baseline(args, groups)
+    if not args.quick:
+        modes = run_mode_sweep(torch, capi, device, args, peak, dist, rank)
+        sweep = run_stream_sweep(torch, capi, shard, device, args, peak, dist, rank)
+        txsweep = run_tx_wbfm_sweep(torch, capi, device, args, peak) if rank == 0 else None
+        if rank == 0:
+            out["modes"] = modes
+            chains = [k for k in modes if k.split("_")[0] in ("rx", "tx") and k.count("_") == 1]
+            out["min_mode_hbm_frac"] = min((modes[k]["hbm_frac"], k) for k in chains)
+            out["mixed_mode_stream_sweep"] = sweep
+            out["tx_wbfm_stream_sweep"] = txsweep
+            out["parity"] = {k: v["parity"] for k, v in modes.items() if "parity" in v}
+            out["cpu_baseline"] = cpu_baseline(args)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -336,10 +431,11 @@ def run_e2e(torch, capi, device, args, groups, n_samples, dist):
     """Same workload through the C ABI with pinned HOST buffers: H2D + kernels + D2H per step, on every rank."""
     world = dist.get_world_size() if dist else 1
     steps = max(2, min(args.steps, 5))
-    b, iq, pcm = make_rx_batch(torch, capi, device, groups, n_samples, 99)
+    b, iq, pcm, _ = make_rx_batch(torch, capi, device, groups, n_samples, 99)
     host_iq = torch.empty(iq.shape, dtype=torch.int8, pin_memory=True)
     host_iq.copy_(iq)
     host_pcm = torch.empty(pcm.shape, dtype=torch.int16, pin_memory=True)
+    n_streams = iq.shape[0]
     del iq, pcm
     torch.cuda.synchronize()
 
@@ -353,51 +449,152 @@ def run_e2e(torch, capi, device, args, groups, n_samples, dist):
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    t = torch.tensor([dt], device=device, dtype=torch.float64)
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
-    value = world * args.streams * n_samples / dt / 1e6
+    dt = reduce_max_ms(torch, dist, device, [dt])[0]
+    value = world * n_streams * n_samples / dt / 1e6
     return {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": host_iq.numel() * world,
             "d2h_bytes_per_step": host_pcm.numel() * 2 * world, "ms_per_step": round(dt * 1e3, 3), "steps": steps,
+            "h2d_gbs_per_gpu": round(host_iq.numel() / dt / 1e9, 2),
             "note": "hrd_rx_process(HRD_MEM_HOST) on pinned host buffers, one call per step per GPU, copies inside "
                     "the call; whole job = all ranks, slowest rank's wall time; bound by PCIe H2D (2 B per IQ sample)"}
 
 
-def run_mode_sweep(torch, capi, device, args, peak):
-    """Every other chain at 4096 streams: MS/s and fraction of the HBM roofline."""
+# ----------------------------------------------------------------------------------------
+# checkers (test infrastructure): the compiled reference when it travelled, else the C port
+# ----------------------------------------------------------------------------------------
+_checker = None
+
+
+def checker():
+    global _checker
+    if _checker is None:
+        import cpu_checkers
+        if cpu_checkers.have_ref():
+            _checker = ("reference", cpu_checkers.Ref())
+        else:
+            _checker = ("port", cpu_checkers.Oracle())
+    return _checker
+
+
+def cpu_rx(mode, iq, cores):
+    """(seconds, pcm[n, n_pcm]) of the checker's Rx chain over iq[n, bytes] on `cores` threads (1 for the port)."""
+    import numpy as np
+    kind, c = checker()
+    if kind == "reference":
+        return c.bench_rx(mode, iq, cores, want_pcm=True)
+    t0 = time.perf_counter()
+    pcm = np.stack([c.run_rx(mode, row) for row in iq])
+    return time.perf_counter() - t0, pcm
+
+
+def cpu_tx(mode, pcm, cores):
+    import numpy as np
+    kind, c = checker()
+    if kind == "reference":
+        return c.bench_tx(mode, pcm, cores, want_iq=True)
+    t0 = time.perf_counter()
+    iq = np.stack([c.run_tx(mode, row) for row in pcm])
+    return time.perf_counter() - t0, iq
+
+
+def parity_record(got, want, tol, note=""):
+    import numpy as np
+    d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    return {"checker": checker()[0], "streams": int(got.shape[0]), "samples_per_stream": int(got.shape[1]),
+            "max_abs_err": int(d.max()) if d.size else 0, "mismatches": int((d > 0).sum()),
+            "tolerance": tol, "ok": bool((d.max() if d.size else 0) <= tol), "note": note}
+
+
+def rx_parity_and_cpu(torch, capi, device, mode, distinct_rows, cores):
+    """The distinct rows of a mode's batch (edge classes included), first 0.25 s: CUDA path from a fresh batch
+    through the C ABI (host buffers) against the checker; the checker's run is also the chain's CPU rate."""
+    import numpy as np
+    host = distinct_rows.cpu().numpy()
+    b = capi.Batch(host.shape[0], capi.RX, device.index or 0)
+    b.set_mode(mode)
+    got = b.rx(host)
+    b.close()
+    reps = max(1, (2 * cores + host.shape[0] - 1) // host.shape[0])
+    cpu_in = np.ascontiguousarray(np.tile(host, (reps, 1)))
+    cpu_rx(mode, cpu_in[:host.shape[0]], cores)  # warm
+    dt, want = cpu_rx(mode, cpu_in, cores)
+    cpu = {"MS/s": round(cpu_in.shape[0] * (cpu_in.shape[1] // 2) / dt / 1e6, 1), "cores": cores if checker()[0] == "reference" else 1,
+           "kind": checker()[0], "sample": f"{cpu_in.shape[0]} streams x {cpu_in.shape[1] / 2 / FS:.3f} s"}
+    return parity_record(got, want[:host.shape[0]], 0, "bit-exact required; rows end with: " + ", ".join(EDGE_CLASSES)), cpu
+
+
+def tx_parity_and_cpu(torch, capi, device, mode, distinct_rows, cores):
+    import numpy as np
+    host = distinct_rows.cpu().numpy()
+    b = capi.Batch(host.shape[0], capi.TX, device.index or 0)
+    b.set_mode(mode)
+    got = b.tx(host)
+    b.close()
+    reps = max(1, (2 * cores + host.shape[0] - 1) // host.shape[0])
+    cpu_in = np.ascontiguousarray(np.tile(host, (reps, 1)))
+    cpu_tx(mode, cpu_in[:host.shape[0]], cores)
+    dt, want = cpu_tx(mode, cpu_in, cores)
+    cpu = {"MS/s": round(cpu_in.shape[0] * cpu_in.shape[1] * 256 / dt / 1e6, 1), "cores": cores if checker()[0] == "reference" else 1,
+           "kind": checker()[0], "sample": f"{cpu_in.shape[0]} streams x {cpu_in.shape[1] / 8000:.3f} s"}
+    tol = 1 if mode == 2 else 0  # FM: libm sinf/cosf against CUDA's double sincos (DESIGN.md section 5)
+    return parity_record(got, want[:host.shape[0]], tol, "int8 I,Q; sines reaching -32768, noise, AM tone, silence, square wave"), cpu
+
+
+def run_mode_sweep(torch, capi, device, args, peak, dist, rank):
+    """Every chain alone, sweep_streams streams per GPU on every rank: MS/s (whole job, slowest rank's time), fraction
+    of the HBM roofline, and on rank 0 the chain's CPU rate and a parity record against the checker."""
+    world = dist.get_world_size() if dist else 1
+    cores = os.cpu_count() or 1
     res = {}
     n_streams = args.sweep_streams
     n_samples = int(args.sweep_seconds * FS) // 8192 * 8192
-    for mode in (1, 2, 3, 4):
-        ms, kms, tms, _, keep = bench_rx_modes(torch, capi, device, [(mode, n_streams)], n_samples, 5, 3, seed=7)
+    n_par = min(n_samples, int(0.25 * FS) // 131072 * 131072)
+    for mode in (1, 2, 3, 4, 5):
+        r, keep = bench_rx_modes(torch, capi, device, [(mode, n_streams)], n_samples, 5, 3, seed=7 + rank)
+        ms, kms, tms = reduce_max_ms(torch, dist, device, [r["ms"], r["kernel_ms"], r["tail_ms"]])
+        sps = world * n_streams * n_samples / (ms * 1e-3)
+        row = {"streams_per_gpu": n_streams, "MS/s": round(sps / 1e6, 1), "ms": round(ms, 3),
+               "hbm_frac": round(sps / world * BYTES_PER_IN_SAMPLE_RX / 1e9 / peak, 4),
+               "kernel_ms": round(kms, 3), "tail_ms": round(tms, 3), "repeat_mismatches": r["repeat_mismatches"]}
+        if rank == 0:
+            _, iq, _, layout = keep
+            at, nd, _ = layout[mode]
+            try:
+                row["parity"], row["cpu"] = rx_parity_and_cpu(torch, capi, device, mode, iq[at:at + nd, :2 * n_par], cores)
+            except Exception as e:  # the checker libraries are missing: say so, substitute nothing
+                row["parity"] = {"ok": None, "note": f"checker unavailable: {e}"}
+        res[f"rx_{MODE_NAMES[mode]}"] = row
         del keep
         torch.cuda.empty_cache()
-        sps = n_streams * n_samples / (ms * 1e-3)
-        res[f"rx_{MODE_NAMES[mode]}"] = {"streams": n_streams, "MS/s": round(sps / 1e6, 1), "ms": round(ms, 3),
-                                         "hbm_frac": round(sps * BYTES_PER_IN_SAMPLE_RX / 1e9 / peak, 4),
-                                         "kernel_ms": round(kms, 3), "tail_ms": round(tms, 3)}
     n_pcm = n_samples // 256
-    for mode in (1, 2, 3, 4):
-        ms = bench_tx_mode(torch, capi, device, mode, n_streams, n_pcm, 5, 3, seed=11)
+    for mode in (1, 2, 3, 4, 5):
+        ms, bad, distinct = bench_tx_mode(torch, capi, device, mode, n_streams, n_pcm, 5, 3, seed=11 + rank, want=True)
+        ms = reduce_max_ms(torch, dist, device, [ms])[0]
+        sps = world * n_streams * n_pcm * 256 / (ms * 1e-3)
+        row = {"streams_per_gpu": n_streams, "MS/s": round(sps / 1e6, 1), "ms": round(ms, 3),
+               "hbm_frac": round(sps / world * BYTES_PER_OUT_SAMPLE_TX / 1e9 / peak, 4), "repeat_mismatches": bad}
+        if rank == 0:
+            try:
+                row["parity"], row["cpu"] = tx_parity_and_cpu(torch, capi, device, mode, distinct[:, :n_par // 256], cores)
+            except Exception as e:
+                row["parity"] = {"ok": None, "note": f"checker unavailable: {e}"}
+        res[f"tx_{MODE_NAMES[mode]}"] = row
+        del distinct
         torch.cuda.empty_cache()
-        sps = n_streams * n_pcm * 256 / (ms * 1e-3)
-        res[f"tx_{MODE_NAMES[mode]}"] = {"streams": n_streams, "MS/s": round(sps / 1e6, 1), "ms": round(ms, 3),
-                                         "hbm_frac": round(sps * BYTES_PER_OUT_SAMPLE_TX / 1e9 / peak, 4)}
-    res.update(run_next_rows(torch, capi, device, args, peak))
+    if rank == 0:
+        res.update(run_next_rows(torch, capi, device, args, peak))
     return res
 
 
 def run_next_rows(torch, capi, device, args, peak):
-    """SURVEY 8f rows built so far, measured like the chains above (4096 streams x 0.5 s, device-resident):
-    the squelched receive call (AM streams whose level closes the gate on every other pair of 64 ms blocks:
-    front end for every block, demodulator for the open ones) and the signals/ tool chain on the transmit side."""
+    """SURVEY 8f rows, measured like the chains above (sweep_streams x sweep_seconds, device-resident, rank 0):
+    the squelched receive call (AM streams whose level closes the gate on every other pair of 64 ms blocks) and the
+    signals/ tool chain on the transmit side."""
     res = {}
     n_streams = args.sweep_streams
     n_samples = int(args.sweep_seconds * FS) // 131072 * 131072
     stream = torch.cuda.current_stream().cuda_stream
     # squelch: bursty level (loud, loud, quiet, quiet, ...) so that the tracker opens, holds its tail and closes
-    b, iq, pcm = make_rx_batch(torch, capi, device, [(1, n_streams)], n_samples, seed=17)
+    b, iq, pcm, _ = make_rx_batch(torch, capi, device, [(1, n_streams)], n_samples, seed=17)
     blocks = n_samples // 131072
     for k in range(blocks):
         if (k // 2) % 2 == 1:
@@ -409,9 +606,7 @@ def run_next_rows(torch, capi, device, args, peak):
     sps = n_streams * n_samples / (ms * 1e-3)
     res["rx_am_squelched"] = {"streams": n_streams, "MS/s": round(sps / 1e6, 1), "ms": round(ms, 3),
                               "hbm_frac": round(sps * BYTES_PER_IN_SAMPLE_RX / 1e9 / peak, 4),
-                              "blocks_per_call": int(blocks), "open_fraction": round(float(allowed.mean()), 3),
-                              "note": "gated path: front end + magnitudes for every block, one host read of the decisions, "
-                                      "demodulators over runs of like blocks for the open ones"}
+                              "blocks_per_call": int(blocks), "open_fraction": round(float(allowed.mean()), 3)}
     del b, iq, pcm
     torch.cuda.empty_cache()
     n_pcm = n_samples // 256
@@ -424,64 +619,87 @@ def run_next_rows(torch, capi, device, args, peak):
     return res
 
 
-def run_stream_sweep(torch, capi, device, args, peak):
-    """BASELINE configs[4] on one GPU: mixed-mode batches (1/4 each AM, NBFM, WBFM, SSB) from 1k to 64k streams,
-    the same total signal per point (so only the stream count changes)."""
-    from hackrfdiags_b200 import shard
+def run_stream_sweep(torch, capi, shard, device, args, peak, dist, rank):
+    """BASELINE configs[4]: mixed-mode jobs of 1k .. 64k streams IN TOTAL, dealt to the N ranks by shard.shard_modes
+    (strong scaling: the job is fixed, each GPU owns 1/N of the streams), the same total signal per point."""
+    world = dist.get_world_size() if dist else 1
     res = {}
     total_samples = 4096 * (int(0.5 * FS) // 8192 * 8192)
-    for n_streams in (1024, 4096, 16384, 65536):
-        n_samples = max(8192, total_samples // n_streams // 8192 * 8192)
-        modes = shard.mixed_mode_plan(n_streams, {1: 0.25, 2: 0.25, 3: 0.25, 4: 0.125, 5: 0.125})
-        groups = shard.mode_groups(sorted(enumerate(modes), key=lambda sm: sm[1]))
-        ms, kms, tms, launches, keep = bench_rx_modes(torch, capi, device, groups, n_samples, 5, 3, seed=13)
+    for n_total in (1024, 4096, 16384, 65536):
+        n_samples = max(8192, total_samples // n_total // 8192 * 8192)
+        plan = shard.mixed_mode_plan(n_total, MIX)
+        mine = shard.shard_modes(plan, world, rank)
+        groups = shard.mode_groups(mine)
+        r, keep = bench_rx_modes(torch, capi, device, groups, n_samples, 5, 3, seed=13 + rank)
         del keep
         torch.cuda.empty_cache()
-        sps = n_streams * n_samples / (ms * 1e-3)
-        res[str(n_streams)] = {"seconds_per_stream": round(n_samples / FS, 4), "MS/s": round(sps / 1e6, 1), "ms": round(ms, 3),
-                               "hbm_frac": round(sps * BYTES_PER_IN_SAMPLE_RX / 1e9 / peak, 4),
-                               "launches_per_step": launches // 5 if launches else None}
+        ms = reduce_max_ms(torch, dist, device, [r["ms"]])[0]
+        sps = n_total * n_samples / (ms * 1e-3)
+        res[str(n_total)] = {"streams_total": n_total, "streams_rank0": len(mine), "seconds_per_stream": round(n_samples / FS, 4),
+                             "MS/s": round(sps / 1e6, 1), "ms": round(ms, 3),
+                             "hbm_frac_per_gpu": round(sps / world * BYTES_PER_IN_SAMPLE_RX / 1e9 / peak, 4),
+                             "launches_per_step": r["launches"], "repeat_mismatches": r["repeat_mismatches"]}
+    return res
+
+
+def run_tx_wbfm_sweep(torch, capi, device, args, peak):
+    """The WBFM modulator over the stream count (one GPU): its NCO phase chain is serial per stream (256 000 dependent
+    steps per stream-second), so below a few thousand streams that chain, not the bandwidth, sets the time."""
+    res = {}
+    n_pcm = (int(0.5 * FS) // 8192 * 8192) // 256
+    for n in (256, 1024, 4096, 16384):
+        ms = bench_tx_mode(torch, capi, device, 3, n, n_pcm, 5, 3, seed=23)
+        torch.cuda.empty_cache()
+        sps = n * n_pcm * 256 / (ms * 1e-3)
+        res[str(n)] = {"MS/s": round(sps / 1e6, 1), "ms": round(ms, 3),
+                       "hbm_frac": round(sps * BYTES_PER_OUT_SAMPLE_TX / 1e9 / peak, 4)}
     return res
 
 
 # ----------------------------------------------------------------------------------------
-# CPU arms (the compiled reference, oracle/_ref/libhrd_ref.so; falls back to nothing else)
+# CPU arms (the compiled reference, oracle/_ref/libhrd_ref.so; else the C port)
 # ----------------------------------------------------------------------------------------
-def cpu_sample(groups, n_streams_total, seconds):
-    """A bounded sample of the same workload: same mode mix, fewer streams."""
+def cpu_sample(n_streams_total, seconds):
+    """A bounded sample of the headline workload: the same mode mix, fewer streams."""
     import numpy as np
-    from hackrfdiags_b200 import synth
+    from hackrfdiags_b200 import shard, synth
     n_samples = int(seconds * FS) // 8192 * 8192
-    total = sum(n for _, n in groups)
+    plan = shard.mixed_mode_plan(n_streams_total, MIX)
     parts = []
-    for mode, n in groups:
-        k = max(1, round(n_streams_total * n / total))
+    for mode in sorted(set(plan)):
+        k = plan.count(mode)
         distinct = np.stack([synth.rx_stream(mode, n_samples, stream=s) for s in range(min(k, 4))])
         parts.append((mode, np.ascontiguousarray(np.tile(distinct, ((k + 3) // 4, 1))[:k])))
     return parts, n_samples
 
 
-def time_reference(parts, n_samples, cores):
-    from cpu_checkers import Ref
-    ref = Ref()
+def time_cpu(parts, n_samples, cores):
     t = 0.0
     for mode, iq in parts:
-        dt, _ = ref.bench_rx(mode, iq, cores)
+        dt, _ = cpu_rx(mode, iq, cores)
         t += dt
     n = sum(iq.shape[0] for _, iq in parts)
     return n * n_samples / t / 1e6, t
 
 
-def cpu_baseline(args, groups):
+def cpu_sample_size(cores):
+    return (16 * cores, 0.5) if checker()[0] == "reference" else (10, 0.125)
+
+
+def cpu_baseline(args):
     cores = os.cpu_count() or 1
     try:
-        parts, n_samples = cpu_sample(groups, 16 * cores, 1.0)
-        time_reference(parts, n_samples, cores)  # warm
-        value, t = time_reference(parts, n_samples, cores)
-        return {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "reference",
-                "sample": f"{sum(p[1].shape[0] for p in parts)} streams x {n_samples / FS:.3f} s, same AM/LSB/USB mix, "
-                          f"unmodified reference classes (oracle/_ref), one object graph per stream, "
-                          f"{cores} threads, {t:.2f} s wall"}
+        kind = checker()[0]
+        n, secs = cpu_sample_size(cores)
+        parts, n_samples = cpu_sample(n, secs)
+        time_cpu(parts, n_samples, cores)  # warm
+        value, t = time_cpu(parts, n_samples, cores)
+        used = cores if kind == "reference" else 1
+        return {"value": round(value, 1), "unit": UNIT, "cores": used, "kind": kind,
+                "sample": f"{sum(p[1].shape[0] for p in parts)} streams x {n_samples / FS:.3f} s, the headline's mode mix, "
+                          + ("unmodified reference classes (oracle/_ref), one object graph per stream, " if kind == "reference"
+                             else "the C port (oracle/liboracle.so), ")
+                          + f"{used} threads, {t:.2f} s wall"}
     except Exception as e:  # the checker library is missing: report, do not substitute anything
         return {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": f"unavailable: {e}"}
 
@@ -491,28 +709,31 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    groups = [(1, args.streams // 2), (4, args.streams // 4), (5, args.streams - args.streams // 2 - args.streams // 4)]
-    parts, n_samples = cpu_sample(groups, 16 * cores, 1.0)
+    kind = checker()[0]
+    used = cores if kind == "reference" else 1
+    n, secs = cpu_sample_size(cores)
+    parts, n_samples = cpu_sample(n, secs)
     for _ in range(max(1, min(args.warmup, 2))):
-        time_reference(parts, n_samples, cores)
+        time_cpu(parts, n_samples, cores)
     t_tot, n_tot = 0.0, 0
     for _ in range(args.steps):
-        v, t = time_reference(parts, n_samples, cores)
+        v, t = time_cpu(parts, n_samples, cores)
         t_tot += t
         n_tot += sum(p[1].shape[0] for p in parts) * n_samples
     value = n_tot / t_tot / 1e6
     sample = (f"each step: {sum(p[1].shape[0] for p in parts)} streams x {n_samples / FS:.3f} s of the same "
-              f"AM/LSB/USB mix through the unmodified reference classes (oracle/_ref/libhrd_ref.so), "
-              f"{cores} host threads")
+              f"AM/NBFM/WBFM/LSB/USB mix through "
+              + ("the unmodified reference classes (oracle/_ref/libhrd_ref.so), " if kind == "reference" else "the C port (oracle/liboracle.so), ")
+              + f"{used} host threads")
     out = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT,
            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": round(t_tot / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "int16 Q15 / f32 (reference CPU arithmetic)", "data": "synthetic",
            # the product arm's workload, named the same way; each step times a bounded sample of it
-           "config": {"workload": "BASELINE configs[1]: 1024 streams/GPU = 512 AM + 256 LSB + 256 USB, "
-                                  f"{n_samples / FS:.3f} s of int8 IQ @2.048 MS/s each, IqDataProcessor entry",
+           "config": {"workload": "BASELINE configs[4] (mixed-mode) at 4096 streams/GPU: 1/4 AM, 1/4 NBFM, 1/4 WBFM, 1/8 LSB, "
+                                  f"1/8 USB, int8 IQ @2.048 MS/s, IqDataProcessor entry",
                       "streams_per_gpu": args.streams, "bounded_sample": "see cpu_baseline.sample"},
-           "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "reference",
+           "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": used, "kind": kind,
                             "sample": sample},
            "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
@@ -524,11 +745,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=1024, help="streams per GPU (config 2)")
-    ap.add_argument("--seconds", type=float, default=1.0, help="signal seconds per stream per step")
+    ap.add_argument("--streams", type=int, default=4096, help="streams per GPU (headline: the mixed-mode batch)")
+    ap.add_argument("--seconds", type=float, default=0.5, help="signal seconds per stream per step")
     ap.add_argument("--sweep-streams", type=int, default=4096)
     ap.add_argument("--sweep-seconds", type=float, default=0.5)
-    ap.add_argument("--quick", action="store_true", help="skip the mode sweep and the CPU baseline")
+    ap.add_argument("--quick", action="store_true", help="skip the mode table, the sweeps, parity and the CPU baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

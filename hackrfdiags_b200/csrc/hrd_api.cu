@@ -138,6 +138,13 @@ int build_tables(hrd::ConstTables &t)
     for (int i = 0; i < 16; i++) t.delay[i] = quantise(k_delay16[i]);
     for (int i = 0; i < 8; i++) t.tx_hb8[i] = quantise(k_tx_hb8[i]);
     t.k_32768 = 32768;
+    // DbfsCalculator::DbfsCalculator (DbfsCalculator.cc:56-65): (int32_t)(20 * log10((float)i)), the float
+    // overload of log10 as the C++ reference resolves it; entry 0 repeats entry 1
+    for (int i = 1; i <= 256; i++) {
+        volatile float level = 20 * log10f((float)i);
+        t.db_table[i] = (int32_t)level;
+    }
+    t.db_table[0] = t.db_table[1];
     {
         const float hi = -6.28318548202514648438f, lo = 1.74845553146951715e-07f; // -fl32(2*pi), -(2*pi - fl32(2*pi))
         t.k_sign = 0x80000000u;
@@ -190,17 +197,6 @@ int ensure_tables(int device)
     if (rc) return rc;
     hrd::upload_tables(t);
     hrd::upload_tables_tx(t);
-    {
-        // DbfsCalculator::DbfsCalculator (DbfsCalculator.cc:56-65): (int32_t)(20 * log10((float)i)), the float
-        // overload of log10 as the C++ reference resolves it; entry 0 repeats entry 1
-        int32_t db[257];
-        for (int i = 1; i <= 256; i++) {
-            volatile float level = 20 * log10f((float)i);
-            db[i] = (int32_t)level;
-        }
-        db[0] = db[1];
-        hrd::upload_db_table(db);
-    }
     HRD_CUDA(cudaGetLastError());
     // atan2 table (FmDemodulator.cc:158-170): double atan2 narrowed to float, [q+128][i+128]
     std::vector<float> lut(65536);
@@ -300,10 +296,24 @@ int kernel_kind_of_mode(int mode)
 
 struct hrd_batch {
     int device = 0, n = 0, kind = HRD_RX;
+    // CONTROL STATE.  The reference's setters are plain member writes that the UI thread makes while the data
+    // thread runs (Radio.cc:1973, 2404-2633).  Here they write these host vectors under `ctl` and bump `gen`; the
+    // next process call snapshots them under the same lock and uploads the snapshot ON ITS STREAM (pinned
+    // staging, stream-ordered: no device-wide synchronisation, nothing blocks).  A setter that lands while a call
+    // is uploading simply leaves gen ahead of `uploaded`, and the call after picks it up.
+    std::mutex ctl;
     std::vector<int32_t> mode;
     std::vector<uint8_t> lsb;
     std::vector<float> param[HRD_PARAM_COUNT];
-    bool dirty = true;
+    uint64_t gen = 1, uploaded = 0;
+    void *h_stage[2] = {nullptr, nullptr}; // pinned: {kind[n], ids[n], lsb[n], mode[n], param[P][n]}
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+    int stage_at = 0;
+    bool armed = false;                    // some stream's squelch can close (snapshot of squelch_armed)
+    bool any_iq8k = false, any_fm_proto = false;
+    // calls on one batch are serialised by the caller, but they may name different CUDA streams: every call waits
+    // for the end of the one before it and marks its own end here
+    cudaEvent_t ev_last = nullptr;
     void *d_state[2] = {nullptr, nullptr}; // double-buffered, see hrd::RxParams / hrd::TxParams
     int cur = 0;                           // the half the next call reads
     int sm_count = 148;
@@ -329,13 +339,19 @@ struct hrd_batch {
     size_t d_in_cap = 0, d_out_cap = 0;
     // squelch gate (hrd_squelch.cu): the 256 kS/s stream of the call, per-(stream, block) magnitudes,
     // decisions and output offsets, one block of PCM, per-block stream lists, tracker state
-    void *d_sq256 = nullptr, *d_sq_mag = nullptr, *d_sq_open = nullptr, *d_sq_at = nullptr, *d_sq_pcm = nullptr, *d_sq_ids = nullptr;
-    size_t d_sq256_cap = 0, d_sq_mag_cap = 0, d_sq_open_cap = 0, d_sq_at_cap = 0, d_sq_pcm_cap = 0, d_sq_ids_cap = 0;
+    void *d_sq256 = nullptr, *d_sq_mag = nullptr, *d_sq_open = nullptr, *d_sq_n256 = nullptr;
+    size_t d_sq256_cap = 0, d_sq_mag_cap = 0, d_sq_open_cap = 0;
     uint8_t *d_sq_track = nullptr;
+    // what the gate decided, on its way to the host: pinned staging filled by stream-ordered copies, unpacked by a
+    // host function on the stream, ev_report behind it (hrd_rx_squelch_report waits for that, nothing else does)
+    void *h_sq = nullptr;
+    size_t h_sq_cap = 0;
+    cudaEvent_t ev_report = nullptr;
     std::vector<uint8_t> h_kind;           // kernel kind of every stream (host copy of d_kind)
     std::vector<uint32_t> sq_mag;          // latest squelched call: [n][sq_blocks]
     std::vector<uint8_t> sq_open;
     uint32_t sq_blocks = 0;
+    uint64_t gated_calls = 0;
     cudaStream_t own = nullptr;
     // mixed-mode batches: the tile kernels of the different modes run side by side (run_demods)
     cudaStream_t aux[4] = {};
@@ -344,6 +360,8 @@ struct hrd_batch {
     // HRD_OPT_PROFILE: events around the hot kernel(s) of the latest call and around its tail kernel
     // (a ring of the last HRD_PROFILE_RING calls, so back-to-back timed steps can all be read)
     cudaEvent_t ev[HRD_PROFILE_RING][3] = {};
+    cudaEvent_t ev_kind[HRD_PROFILE_RING][4][2] = {}; // HRD_OPT_RX_SERIAL: around each kind's kernels
+    bool ev_kind_set[HRD_PROFILE_RING][4] = {};
     uint64_t ev_calls = 0;
 };
 
@@ -351,31 +369,69 @@ namespace {
 
 size_t state_size(int kind) { return kind == HRD_RX ? sizeof(hrd::RxState) : sizeof(hrd::TxState); }
 
-int regroup(hrd_batch *b)
+size_t stage_bytes(int n) { return (size_t)n * (1 + 4 + 1 + 4 + 4 * HRD_PARAM_COUNT) + 64; }
+
+// Upload the control state if a setter ran since the last upload: snapshot under the lock, copy from pinned staging
+// on the call's stream.  Everything queued before on that stream (and, through ev_last, every earlier call) is
+// ordered in front of the copies, everything this call launches behind them.
+int regroup(hrd_batch *b, cudaStream_t s)
 {
-    if (!b->dirty) return HRD_OK;
-    HRD_CUDA(cudaDeviceSynchronize()); // earlier launches may still be reading the old tables
-    std::vector<int32_t> ids;
-    ids.reserve((size_t)b->n);
-    std::vector<uint8_t> kinds((size_t)b->n);
-    for (int s = 0; s < b->n; s++) kinds[(size_t)s] = (uint8_t)kernel_kind_of_mode(b->mode[(size_t)s]);
+    std::lock_guard<std::mutex> lock(b->ctl);
+    if (b->uploaded == b->gen) return HRD_OK;
+    const size_t n = (size_t)b->n;
+    const int at = b->stage_at;
+    HRD_CUDA(cudaEventSynchronize(b->ev_stage[at])); // the copies that last used this staging half are long done
+    char *st = (char *)b->h_stage[at];
+    uint8_t *kinds = (uint8_t *)st;
+    int32_t *ids = (int32_t *)(st + ((n + 15) & ~(size_t)15));
+    uint8_t *lsb = (uint8_t *)(ids + n);
+    int32_t *mode = (int32_t *)((char *)lsb + ((n + 15) & ~(size_t)15));
+    float *param = (float *)(mode + n);
+    b->armed = b->opt[HRD_OPT_RX_SQUELCH] != 0;
+    b->any_iq8k = b->any_fm_proto = false;
+    for (size_t i = 0; i < n; i++) {
+        kinds[i] = (uint8_t)kernel_kind_of_mode(b->mode[i]);
+        lsb[i] = b->lsb[i];
+        mode[i] = b->mode[i];
+        b->any_iq8k |= b->mode[i] == HRD_MODE_IQ8K;
+        b->any_fm_proto |= b->mode[i] == HRD_MODE_FM_PROTO;
+        // can the gate of this stream close?  dBFS >= dbTable[0] - 42 - gain (DbfsCalculator.cc, SignalDetector.cc:263)
+        if (b->kind == HRD_RX && (double)b->param[HRD_PARAM_SQUELCH_THRESHOLD][i] > -42.0 - (double)b->param[HRD_PARAM_RX_GAIN_DB][i])
+            b->armed = true;
+    }
+    for (int p = 0; p < HRD_PARAM_COUNT; p++) memcpy(param + (size_t)p * n, b->param[p].data(), n * sizeof(float));
     // AM and SSB streams sit next to each other: on Rx one launch runs both
     static const int order[hrd::K_COUNT] = {hrd::K_NONE, hrd::K_FM, hrd::K_WBFM, hrd::K_AM, hrd::K_SSB, hrd::K_IQ};
+    size_t fill = 0;
     for (int o = 0; o < hrd::K_COUNT; o++) {
         const int k = order[o];
-        b->group_off[k] = (int)ids.size();
-        for (int s = 0; s < b->n; s++)
-            if (kinds[(size_t)s] == k) ids.push_back(s);
-        b->group_cnt[k] = (int)ids.size() - b->group_off[k];
+        b->group_off[k] = (int)fill;
+        for (size_t i = 0; i < n; i++)
+            if (kinds[i] == k) ids[fill++] = (int32_t)i;
+        b->group_cnt[k] = (int)fill - b->group_off[k];
     }
-    b->h_kind = kinds;
-    HRD_CUDA(cudaMemcpy(b->d_kind, kinds.data(), (size_t)b->n, cudaMemcpyHostToDevice));
-    HRD_CUDA(cudaMemcpy(b->d_ids, ids.data(), (size_t)b->n * sizeof(int32_t), cudaMemcpyHostToDevice));
-    HRD_CUDA(cudaMemcpy(b->d_lsb, b->lsb.data(), (size_t)b->n, cudaMemcpyHostToDevice));
-    HRD_CUDA(cudaMemcpy(b->d_mode, b->mode.data(), (size_t)b->n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    b->h_kind.assign(kinds, kinds + n);
+    HRD_CUDA(cudaMemcpyAsync(b->d_kind, kinds, n, cudaMemcpyHostToDevice, s));
+    HRD_CUDA(cudaMemcpyAsync(b->d_ids, ids, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    HRD_CUDA(cudaMemcpyAsync(b->d_lsb, lsb, n, cudaMemcpyHostToDevice, s));
+    HRD_CUDA(cudaMemcpyAsync(b->d_mode, mode, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     for (int p = 0; p < HRD_PARAM_COUNT; p++)
-        HRD_CUDA(cudaMemcpy(b->d_param[p], b->param[p].data(), (size_t)b->n * sizeof(float), cudaMemcpyHostToDevice));
-    b->dirty = false;
+        HRD_CUDA(cudaMemcpyAsync(b->d_param[p], param + (size_t)p * n, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    HRD_CUDA(cudaEventRecord(b->ev_stage[at], s));
+    b->stage_at ^= 1;
+    b->uploaded = b->gen;
+    return HRD_OK;
+}
+
+// every call: behind the end of the call before it, whatever stream that one ran on
+int order_after_last(hrd_batch *b, cudaStream_t s)
+{
+    HRD_CUDA(cudaStreamWaitEvent(s, b->ev_last, 0));
+    return HRD_OK;
+}
+int mark_end(hrd_batch *b, cudaStream_t s)
+{
+    HRD_CUDA(cudaEventRecord(b->ev_last, s));
     return HRD_OK;
 }
 
@@ -568,6 +624,11 @@ int hrd_create(int device, int n_streams, int kind, hrd_batch_t **out)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_last, cudaEventDisableTiming);
+    for (int h = 0; h < 2 && e == cudaSuccess; h++) {
+        e = cudaHostAlloc(&b->h_stage[h], stage_bytes(n_streams), cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_stage[h], cudaEventDisableTiming);
+    }
     b->sm_count = prop.multiProcessorCount;
     for (int h = 0; h < 2; h++) {
         if (e == cudaSuccess) e = cudaMalloc(&b->d_state[h], ssz);
@@ -582,6 +643,8 @@ int hrd_create(int device, int n_streams, int kind, hrd_batch_t **out)
     if (e == cudaSuccess) e = cudaMalloc(&b->d_lsb, (size_t)n_streams);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_mode, (size_t)n_streams * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_kind, (size_t)n_streams);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_sq_n256, (size_t)n_streams * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_report, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_sq_track, (size_t)n_streams);
     if (e == cudaSuccess) e = cudaMemset(b->d_sq_track, 0, (size_t)n_streams); // SignalTracker: NoSignal
     for (int p = 0; p < HRD_PARAM_COUNT && e == cudaSuccess; p++)
@@ -603,7 +666,7 @@ int hrd_destroy(hrd_batch_t *b)
 {
     if (!b) return HRD_OK;
     DeviceGuard guard(b->device);
-    if (b->own) cudaStreamSynchronize(b->own);
+    cudaDeviceSynchronize(); // calls may have named other streams
     cudaFree(b->d_state[0]);
     cudaFree(b->d_state[1]);
     cudaFree(b->d_pre);
@@ -623,18 +686,27 @@ int hrd_destroy(hrd_batch_t *b)
     cudaFree(b->d_sq256);
     cudaFree(b->d_sq_mag);
     cudaFree(b->d_sq_open);
-    cudaFree(b->d_sq_at);
-    cudaFree(b->d_sq_pcm);
-    cudaFree(b->d_sq_ids);
+    cudaFree(b->d_sq_n256);
     cudaFree(b->d_sq_track);
-    for (int r = 0; r < HRD_PROFILE_RING; r++)
+    if (b->h_sq) cudaFreeHost(b->h_sq);
+    if (b->ev_report) cudaEventDestroy(b->ev_report);
+    for (int r = 0; r < HRD_PROFILE_RING; r++) {
         for (int i = 0; i < 3; i++)
             if (b->ev[r][i]) cudaEventDestroy(b->ev[r][i]);
+        for (int k = 0; k < 4; k++)
+            for (int i = 0; i < 2; i++)
+                if (b->ev_kind[r][k][i]) cudaEventDestroy(b->ev_kind[r][k][i]);
+    }
     for (int i = 0; i < 4; i++) {
         if (b->aux[i]) cudaStreamSynchronize(b->aux[i]), cudaStreamDestroy(b->aux[i]);
         if (b->ev_join[i]) cudaEventDestroy(b->ev_join[i]);
     }
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->ev_last) cudaEventDestroy(b->ev_last);
+    for (int h = 0; h < 2; h++) {
+        if (b->h_stage[h]) cudaFreeHost(b->h_stage[h]);
+        if (b->ev_stage[h]) cudaEventDestroy(b->ev_stage[h]);
+    }
     if (b->own) cudaStreamDestroy(b->own);
     delete b;
     return HRD_OK;
@@ -647,13 +719,14 @@ int hrd_set_mode(hrd_batch_t *b, int stream, int mode)
     if (mode < HRD_MODE_NONE || mode > (b->kind == HRD_TX ? HRD_MODE_FM_PROTO : HRD_MODE_USB))
         return fail(HRD_EINVAL, "bad mode %d", mode);
     const int lo = stream == HRD_ALL_STREAMS ? 0 : stream, hi = stream == HRD_ALL_STREAMS ? b->n : stream + 1;
+    std::lock_guard<std::mutex> lock(b->ctl);
     for (int s = lo; s < hi; s++) {
         b->mode[(size_t)s] = mode;
         // the sideband flag lives in the SSB object and survives mode changes
         if (mode == HRD_MODE_LSB) b->lsb[(size_t)s] = 1;
         if (mode == HRD_MODE_USB) b->lsb[(size_t)s] = 0;
     }
-    b->dirty = true;
+    b->gen++;
     return HRD_OK;
 }
 
@@ -662,6 +735,7 @@ int hrd_get_mode(hrd_batch_t *b, int stream, int *mode)
     int rc = check_stream_arg(b, stream);
     if (rc) return rc;
     if (stream == HRD_ALL_STREAMS || !mode) return fail(HRD_EINVAL, "hrd_get_mode needs one stream");
+    std::lock_guard<std::mutex> lock(b->ctl);
     *mode = b->mode[(size_t)stream];
     return HRD_OK;
 }
@@ -672,6 +746,7 @@ int hrd_set_param(hrd_batch_t *b, int stream, int param, float value)
     if (rc) return rc;
     if (param < 0 || param >= HRD_PARAM_COUNT) return fail(HRD_EINVAL, "bad param %d", param);
     const int lo = stream == HRD_ALL_STREAMS ? 0 : stream, hi = stream == HRD_ALL_STREAMS ? b->n : stream + 1;
+    std::lock_guard<std::mutex> lock(b->ctl);
     for (int s = lo; s < hi; s++) {
         float &cur = b->param[param][(size_t)s];
         switch (param) {
@@ -694,7 +769,7 @@ int hrd_set_param(hrd_batch_t *b, int stream, int param, float value)
             cur = value;
         }
     }
-    b->dirty = true;
+    b->gen++;
     return HRD_OK;
 }
 
@@ -704,6 +779,7 @@ int hrd_get_param(hrd_batch_t *b, int stream, int param, float *value)
     if (rc) return rc;
     if (stream == HRD_ALL_STREAMS || !value || param < 0 || param >= HRD_PARAM_COUNT)
         return fail(HRD_EINVAL, "hrd_get_param needs one stream and a valid param");
+    std::lock_guard<std::mutex> lock(b->ctl);
     *value = b->param[param][(size_t)stream];
     return HRD_OK;
 }
@@ -715,7 +791,9 @@ int hrd_set_option(hrd_batch_t *b, int option, int value)
     if (value < 0) return fail(HRD_EINVAL, "option values are non-negative");
     if (option == HRD_OPT_RX_SQUELCH_BLOCK && value % 512)
         return fail(HRD_EINVAL, "squelch block of %d bytes is not a whole number of PCM samples (512 bytes)", value);
+    std::lock_guard<std::mutex> lock(b->ctl);
     b->opt[option] = value;
+    if (option == HRD_OPT_RX_SQUELCH) b->gen++; // part of the "armed" snapshot
     return HRD_OK;
 }
 
@@ -732,7 +810,9 @@ int hrd_reset(hrd_batch_t *b, int stream, int unit)
     int rc = check_stream_arg(b, stream);
     if (rc) return rc;
     DeviceGuard guard(b->device);
-    HRD_CUDA(cudaDeviceSynchronize()); // calls on one batch are serialised; make that true on the device too
+    // stream-ordered like everything else: behind the call before, in front of the call after; nothing waits
+    rc = order_after_last(b, b->own);
+    if (rc) return rc;
     using hrd::RxState;
     using hrd::TxState;
 #define RANGE(T, first, next) offsetof(T, first), offsetof(T, next) - offsetof(T, first)
@@ -776,8 +856,7 @@ int hrd_reset(hrd_batch_t *b, int stream, int unit)
     }
 #undef RANGE
     if (rc) return rc;
-    HRD_CUDA(cudaStreamSynchronize(b->own));
-    return HRD_OK;
+    return mark_end(b, b->own);
 }
 
 int hrd_synchronize(hrd_batch_t *b)
@@ -809,12 +888,20 @@ int hrd_wbfm_fallback_count(hrd_batch_t *b, uint64_t *count)
 int hrd_kernel_ms(hrd_batch_t *b, int which, int age, float *ms)
 {
     if (!b || !ms) return fail(HRD_EINVAL, "null argument");
-    if (which < 0 || which > 1) return fail(HRD_EINVAL, "which must be 0 (main kernels) or 1 (tail kernel)");
+    if (!(which == 0 || which == 1 || (which >= 10 && which < 14)))
+        return fail(HRD_EINVAL, "which must be 0 (main kernels), 1 (tail kernel) or 10 + kind");
     if (age < 0 || age >= HRD_PROFILE_RING || (uint64_t)age >= b->ev_calls)
         return fail(HRD_EINVAL, "no profiled call of age %d: set HRD_OPT_PROFILE before the process calls", age);
     DeviceGuard guard(b->device);
-    cudaEvent_t *e = b->ev[(b->ev_calls - 1 - (uint64_t)age) % HRD_PROFILE_RING];
+    const size_t slot = (size_t)((b->ev_calls - 1 - (uint64_t)age) % HRD_PROFILE_RING);
+    cudaEvent_t *e = b->ev[slot];
     HRD_CUDA(cudaEventSynchronize(e[2]));
+    if (which >= 10) {
+        if (!b->ev_kind_set[slot][which - 10])
+            return fail(HRD_EINVAL, "kind %d was not timed in that call (HRD_OPT_RX_SERIAL + HRD_OPT_PROFILE, and the batch must hold it)", which - 10);
+        HRD_CUDA(cudaEventElapsedTime(ms, b->ev_kind[slot][which - 10][0], b->ev_kind[slot][which - 10][1]));
+        return HRD_OK;
+    }
     HRD_CUDA(cudaEventElapsedTime(ms, e[which], e[which + 1]));
     return HRD_OK;
 }
@@ -839,7 +926,7 @@ int hrd_get_table(hrd_batch_t *b, int which, float *out, size_t n)
 // other's last waves and the latency-bound recurrence pass of the AM/SSB streams runs beside the other
 // modes' tile kernels.  The kinds touch disjoint streams' records and disjoint scratch buffers.
 static int run_demods(hrd_batch_t *b, hrd::RxParams &p, int entry, uint32_t n_batches, const int32_t *const ids_of[4],
-                      const int cnt_of[4], cudaStream_t s, cudaEvent_t after_tiles)
+                      const int cnt_of[4], cudaStream_t s, cudaEvent_t after_tiles, int prof_slot = -1, bool one_tile = false)
 {
     static const int gain_of_kind[5] = {-1, HRD_PARAM_AM_GAIN, HRD_PARAM_FM_GAIN, HRD_PARAM_WBFM_GAIN, HRD_PARAM_SSB_GAIN};
     int rc;
@@ -847,10 +934,17 @@ static int run_demods(hrd_batch_t *b, hrd::RxParams &p, int entry, uint32_t n_ba
     bool iir = false;
     int kinds = 0;
     for (int k = 0; k < 4; k++) kinds += cnt_of[k] && !(k == hrd::K_NONE && entry == HRD_ENTRY_256K);
-    const bool fan = kinds >= 2;
+    const bool serial = b->opt[HRD_OPT_RX_SERIAL] != 0;
+    const bool fan = kinds >= 2 && !serial;
     if (fan) HRD_CUDA(cudaEventRecord(b->ev_fork, s));
+    if (prof_slot >= 0)
+        for (int k = 0; k < 4; k++) b->ev_kind_set[prof_slot][k] = false;
     int lane = 0;
-    for (int k = 0; k < 4; k++) {
+    // WBFM first: its launch is the longest and may end in a small exact re-run (a handful of CTAs walking whole calls
+    // serially); started first, that tail runs beside the other kinds' kernels instead of behind them
+    static const int launch_order[4] = {hrd::K_WBFM, hrd::K_FM, hrd::K_AM, hrd::K_NONE};
+    for (int o = 0; o < 4; o++) {
+        const int k = launch_order[o];
         const int cnt = cnt_of[k];
         if (!cnt) continue;
         if (k == hrd::K_NONE && entry == HRD_ENTRY_256K) continue;
@@ -859,10 +953,20 @@ static int run_demods(hrd_batch_t *b, hrd::RxParams &p, int entry, uint32_t n_ba
             ks = b->aux[lane];
             HRD_CUDA(cudaStreamWaitEvent(ks, b->ev_fork, 0));
         }
+        const bool time_kind = serial && prof_slot >= 0;
+        if (time_kind) {
+            for (int i = 0; i < 2; i++)
+                if (!b->ev_kind[prof_slot][k][i]) HRD_CUDA(cudaEventCreate(&b->ev_kind[prof_slot][k][i]));
+            HRD_CUDA(cudaEventRecord(b->ev_kind[prof_slot][k][0], ks));
+        }
         p.stream_ids = ids_of[k];
         p.n_streams = cnt;
         p.gain = k ? b->d_param[gain_of_kind[k]] : nullptr;
         choose_tiles(b, k, entry, p.n_streams, n_batches, &p.n_tiles, &p.tile_batches);
+        if (one_tile) { // ragged calls (the squelched path): one warp walks a stream's whole call
+            p.n_tiles = 1;
+            p.tile_batches = n_batches ? n_batches : 1;
+        }
         const bool speculate = k == hrd::K_WBFM && p.n_tiles > 1;
         if (speculate) { // verified speculation (hrd_rx.cu): pairs to compare, this call's flag
             rc = ensure_cap(&b->d_wbv, &b->d_wbv_cap, sizeof(float2) * (size_t)p.n_streams * (size_t)p.n_tiles);
@@ -898,6 +1002,10 @@ static int run_demods(hrd_batch_t *b, hrd::RxParams &p, int entry, uint32_t n_ba
                 iir = false;
             }
         }
+        if (time_kind) {
+            HRD_CUDA(cudaEventRecord(b->ev_kind[prof_slot][k][1], ks));
+            b->ev_kind_set[prof_slot][k] = true;
+        }
         if (fan) {
             HRD_CUDA(cudaEventRecord(b->ev_join[lane], ks));
             HRD_CUDA(cudaStreamWaitEvent(s, b->ev_join[lane], 0));
@@ -913,12 +1021,33 @@ static int run_demods(hrd_batch_t *b, hrd::RxParams &p, int entry, uint32_t n_ba
     return HRD_OK;
 }
 
-// The squelched receive call (include/hrd.h "Squelch"; hrd_squelch.cu): front end for every stream into a
-// 256 kS/s scratch, per-block magnitudes and tracker decisions, then block by block the demodulators of the
-// streams the gate lets through (256 kS/s entry kernels on the scratch, state carried for the others) and a
-// scatter of their PCM to the caller's rows.  p arrives with iq / state / tables set for the whole call.
-static int rx_squelched(hrd_batch_t *b, hrd::RxParams p, size_t n256, int16_t *d_pcm, size_t d_pcm_stride,
-                        uint32_t *pcm_counts, cudaStream_t s)
+// The squelched receive call (include/hrd.h "Squelch"; hrd_rx.cu rx_gate_kernel): ONE kernel runs the front end of
+// every stream, the per-block magnitudes, the tracker, and leaves each stream's open blocks packed in a 256 kS/s
+// scratch row; the demodulator kernels then take those rows as one ragged call at the 256 kS/s entry and write
+// their PCM packed into the caller's rows.  Nothing waits for the host: decisions, magnitudes and PCM counts
+// travel back through pinned staging and a host function on the stream.  p arrives with iq / tables set.
+struct GateReport {
+    hrd_batch *b;
+    size_t n, cells;
+    uint32_t n_blocks;
+    uint32_t *pcm_counts; // the caller's array (may be null)
+};
+static void CUDART_CB gate_report_landed(void *user)
+{
+    GateReport *r = (GateReport *)user;
+    hrd_batch *b = r->b;
+    const uint32_t *mag = (const uint32_t *)b->h_sq;
+    const uint32_t *n256 = mag + r->cells;
+    const uint8_t *open = (const uint8_t *)(n256 + r->n);
+    b->sq_mag.assign(mag, mag + r->cells);
+    b->sq_open.assign(open, open + r->cells);
+    b->sq_blocks = r->n_blocks;
+    if (r->pcm_counts)
+        for (size_t i = 0; i < r->n; i++) r->pcm_counts[i] = n256[i] / 32;
+    delete r;
+}
+
+static int rx_gated(hrd_batch_t *b, hrd::RxParams p, size_t n256, uint32_t *pcm_counts, cudaStream_t s)
 {
     // one reference call: 262144 bytes at 2.048 MS/s (hackRf/hackrf.c:101) = 16384 samples at 256 kS/s
     const size_t blk256 = b->opt[HRD_OPT_RX_SQUELCH_BLOCK] > 0 ? (size_t)b->opt[HRD_OPT_RX_SQUELCH_BLOCK] / 16 : 16384;
@@ -928,133 +1057,78 @@ static int rx_squelched(hrd_batch_t *b, hrd::RxParams p, size_t n256, int16_t *d
     int rc = ensure_cap(&b->d_sq256, &b->d_sq256_cap, row256 * n);
     if (!rc) rc = ensure_cap(&b->d_sq_mag, &b->d_sq_mag_cap, cells * sizeof(uint32_t));
     if (!rc) rc = ensure_cap(&b->d_sq_open, &b->d_sq_open_cap, cells);
-    if (!rc) rc = ensure_cap(&b->d_sq_at, &b->d_sq_at_cap, cells * sizeof(uint32_t));
-    if (!rc) rc = ensure_cap(&b->d_sq_ids, &b->d_sq_ids_cap, cells * sizeof(int32_t));
     if (rc) return rc;
+    const size_t report_bytes = cells * sizeof(uint32_t) + n * sizeof(uint32_t) + cells;
+    HRD_CUDA(cudaEventSynchronize(b->ev_report)); // the report of the call before has been unpacked
+    if (b->h_sq_cap < report_bytes) {
+        if (b->h_sq) cudaFreeHost(b->h_sq);
+        b->h_sq = nullptr, b->h_sq_cap = 0;
+        HRD_CUDA(cudaHostAlloc(&b->h_sq, report_bytes, cudaHostAllocDefault));
+        b->h_sq_cap = report_bytes;
+    }
 
-    // 1. IqDataProcessor::reduceSampleRate + upconvertByFsOver4 for every stream, gated or not (:937-946)
+    // 1. IqDataProcessor::reduceSampleRate + upconvertByFsOver4 (:937-946) and Squelch::run (:961) for every stream
+    hrd::GateParams g;
+    g.scratch = (int8_t *)b->d_sq256;
+    g.row256 = row256;
+    g.blk256 = (uint32_t)blk256;
+    g.n_blocks = n_blocks;
+    g.threshold = b->d_param[HRD_PARAM_SQUELCH_THRESHOLD];
+    g.gain_db = b->d_param[HRD_PARAM_RX_GAIN_DB];
+    g.tracking = b->d_sq_track;
+    g.magnitude = (uint32_t *)b->d_sq_mag;
+    g.allowed = (uint8_t *)b->d_sq_open;
+    g.n256_open = (uint32_t *)b->d_sq_n256;
     {
         hrd::RxParams fe = p;
-        fe.out256 = (int8_t *)b->d_sq256;
-        fe.out_stride = row256;
         fe.stream_ids = b->d_all;
         fe.n_streams = b->n;
-        choose_tiles(b, hrd::K_NONE, HRD_ENTRY_2048K, b->n, (uint32_t)((n256 + 1023) / 1024), &fe.n_tiles, &fe.tile_batches);
-        if (hrd::launch_rx(hrd::K_NONE, HRD_ENTRY_2048K, fe, s))
-            return fail(HRD_ECUDA, "front-end launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        fe.kind_of = b->d_kind;
+        fe.state_in = (const hrd::RxState *)b->d_state[b->cur];
+        fe.state_out = (hrd::RxState *)b->d_state[b->cur ^ 1];
+        if (hrd::launch_rx_gate(fe, g, s)) return fail(HRD_ECUDA, "gate launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         b->launches++;
         b->cur ^= 1;
     }
-    // 2. Squelch::run per block, in order (the tracker state lives across calls)
-    if (hrd::launch_squelch_magnitude((const int8_t *)b->d_sq256, row256, (uint32_t)(blk256 * 2), (uint32_t)(n256 * 2), b->n,
-                                      n_blocks, (uint32_t *)b->d_sq_mag, s) ||
-        hrd::launch_squelch_track((const uint32_t *)b->d_sq_mag, b->n, n_blocks, b->d_param[HRD_PARAM_SQUELCH_THRESHOLD],
-                                  b->d_param[HRD_PARAM_RX_GAIN_DB], b->d_sq_track, (uint8_t *)b->d_sq_open, s))
-        return fail(HRD_ECUDA, "squelch launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    b->launches += 2;
-    b->sq_mag.resize(cells);
-    b->sq_open.resize(cells);
-    b->sq_blocks = (uint32_t)n_blocks;
-    HRD_CUDA(cudaMemcpyAsync(b->sq_mag.data(), b->d_sq_mag, cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    HRD_CUDA(cudaMemcpyAsync(b->sq_open.data(), b->d_sq_open, cells, cudaMemcpyDeviceToHost, s));
-    HRD_CUDA(cudaStreamSynchronize(s)); // the decisions shape the launches below
-    // 3. where every open block's PCM goes, and who runs in which block
-    std::vector<uint32_t> at(cells);
-    std::vector<int32_t> ids(cells);
-    for (size_t st = 0; st < n; st++) {
-        uint32_t o = 0;
-        const bool demod = b->h_kind[st] != hrd::K_NONE;
-        for (int k = 0; k < n_blocks; k++) {
-            at[st * n_blocks + k] = o;
-            const size_t len = std::min(blk256, n256 - (size_t)k * blk256);
-            if (demod && b->sq_open[st * n_blocks + k]) o += (uint32_t)(len / 32);
-        }
-        if (pcm_counts) pcm_counts[st] = o;
+    // 2. what the gate decided, on its way to the host -- on a side stream, so that the demodulators below do not
+    // queue behind a host function; the caller's stream joins it at the end of the call
+    {
+        cudaStream_t rs = b->aux[3];
+        HRD_CUDA(cudaEventRecord(b->ev_fork, s));
+        HRD_CUDA(cudaStreamWaitEvent(rs, b->ev_fork, 0));
+        char *h = (char *)b->h_sq;
+        HRD_CUDA(cudaMemcpyAsync(h, b->d_sq_mag, cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, rs));
+        HRD_CUDA(cudaMemcpyAsync(h + cells * sizeof(uint32_t), b->d_sq_n256, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, rs));
+        HRD_CUDA(cudaMemcpyAsync(h + (cells + n) * sizeof(uint32_t), b->d_sq_open, cells, cudaMemcpyDeviceToHost, rs));
+        GateReport *r = new (std::nothrow) GateReport{b, n, cells, (uint32_t)n_blocks, pcm_counts};
+        if (!r) return fail(HRD_ENOMEM, "out of host memory");
+        HRD_CUDA(cudaLaunchHostFunc(rs, gate_report_landed, r));
+        HRD_CUDA(cudaEventRecord(b->ev_report, rs));
     }
-    static const int list_of_kind[5] = {hrd::K_NONE, hrd::K_AM, hrd::K_FM, hrd::K_WBFM, hrd::K_AM}; // SSB rides with AM
-    // Consecutive blocks that the gate treats alike (the same streams open) are demodulated as ONE call: the
-    // demodulators do not care where the reference cut its calls (block-size invariance, tests/), and a run of
-    // r blocks costs one set of launches instead of r.
-    std::vector<int> run_begin; // block index where each run starts, plus the end sentinel
-    for (int k = 0; k < n_blocks; k++) {
-        bool same = k > 0;
-        for (size_t st = 0; same && st < n; st++)
-            same = b->sq_open[st * n_blocks + k] == b->sq_open[st * n_blocks + k - 1];
-        if (!same) run_begin.push_back(k);
-    }
-    run_begin.push_back(n_blocks);
-    const int n_runs = (int)run_begin.size() - 1;
-    std::vector<int> cnt((size_t)n_runs * 4, 0), off((size_t)n_runs * 4, 0);
-    size_t fill = 0;
-    for (int r = 0; r < n_runs; r++)
-        for (int list = 1; list < 4; list++) {
-            const int k = run_begin[(size_t)r];
-            off[(size_t)r * 4 + list] = (int)fill;
-            for (size_t st = 0; st < n; st++)
-                if (list_of_kind[b->h_kind[st]] == list && b->sq_open[st * n_blocks + k]) ids[fill++] = (int32_t)st;
-            cnt[(size_t)r * 4 + list] = (int)fill - off[(size_t)r * 4 + list];
-        }
-    HRD_CUDA(cudaMemcpyAsync(b->d_sq_at, at.data(), cells * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    if (fill) HRD_CUDA(cudaMemcpyAsync(b->d_sq_ids, ids.data(), fill * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    HRD_CUDA(cudaStreamSynchronize(s)); // at / ids are stack-lived host vectors
-    // 4. the demodulators, one run of like blocks at a time
-    size_t longest = 0;
-    for (int r = 0; r < n_runs; r++)
-        longest = std::max(longest, std::min(n256, (size_t)run_begin[(size_t)r + 1] * blk256) - (size_t)run_begin[(size_t)r] * blk256);
-    const size_t run_pcm = longest / 32;
-    rc = ensure_cap(&b->d_sq_pcm, &b->d_sq_pcm_cap, n * run_pcm * sizeof(int16_t));
-    if (rc) return rc;
-    const size_t pre_need = (run_pcm + 7) & ~(size_t)7;
-    if (pre_need * n >= ((size_t)1 << 32)) return fail(HRD_EINVAL, "call too long for %d squelched AM/SSB streams", b->n);
-    if (b->pre_stride < pre_need) {
-        rc = ensure_cap((void **)&b->d_pre, &b->d_pre_cap, pre_need * sizeof(float) * n);
-        if (rc) return rc;
-        b->pre_stride = pre_need;
-    }
-    for (int r = 0; r < n_runs; r++) {
-        const int k = run_begin[(size_t)r];
-        const size_t begin = (size_t)k * blk256;
-        const size_t len = std::min(n256, (size_t)run_begin[(size_t)r + 1] * blk256) - begin;
-        if (!(cnt[(size_t)r * 4 + 1] + cnt[(size_t)r * 4 + 2] + cnt[(size_t)r * 4 + 3])) continue; // gate closed everywhere
-        hrd::RxParams q = p;
-        q.iq = (const int8_t *)b->d_sq256 + begin * 2;
-        q.iq_stride = row256;
-        q.n256 = (uint32_t)len;
-        q.pcm = (int16_t *)b->d_sq_pcm;
-        q.pcm_stride = run_pcm;
-        q.state_in = (const hrd::RxState *)b->d_state[b->cur];
-        q.state_out = (hrd::RxState *)b->d_state[b->cur ^ 1];
-        q.pre_iir = b->d_pre;
-        q.pre_stride = b->pre_stride;
-        q.kind_of = b->d_kind;
-        q.gain_ssb = b->d_param[HRD_PARAM_SSB_GAIN];
-        // streams that do not run in this run keep their record
+    // 3. the demodulators over every stream's open blocks: one ragged call at the 256 kS/s entry
+    hrd::RxParams q = p;
+    q.iq = (const int8_t *)b->d_sq256;
+    q.iq_stride = row256;
+    q.n256 = (uint32_t)n256;
+    q.n256_of = (const uint32_t *)b->d_sq_n256;
+    q.state_in = (const hrd::RxState *)b->d_state[b->cur];
+    q.state_out = (hrd::RxState *)b->d_state[b->cur ^ 1];
+    q.kind_of = b->d_kind;
+    q.gain_ssb = b->d_param[HRD_PARAM_SSB_GAIN];
+    if (b->group_cnt[hrd::K_NONE]) // no demodulator selected: nothing runs for those streams, their records carry over
         HRD_CUDA(cudaMemcpyAsync(b->d_state[b->cur ^ 1], b->d_state[b->cur], sizeof(hrd::RxState) * n, cudaMemcpyDeviceToDevice, s));
-        const int32_t *ids_of[4];
-        int cnt_of[4];
-        for (int list = 0; list < 4; list++) {
-            ids_of[list] = (const int32_t *)b->d_sq_ids + off[(size_t)r * 4 + list];
-            cnt_of[list] = list ? cnt[(size_t)r * 4 + list] : 0;
-        }
-        rc = run_demods(b, q, HRD_ENTRY_256K, (uint32_t)((len + 1023) / 1024), ids_of, cnt_of, s, nullptr);
-        if (rc) return rc;
-        if (hrd::launch_squelch_scatter((const int16_t *)b->d_sq_pcm, run_pcm, d_pcm, d_pcm_stride, (const uint32_t *)b->d_sq_at,
-                                        (const uint8_t *)b->d_sq_open, b->d_kind, b->n, n_blocks, k, (uint32_t)(len / 32), s))
-            return fail(HRD_ECUDA, "squelch scatter launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        b->launches++;
-        b->cur ^= 1;
+    const int32_t *ids_of[4];
+    int cnt_of[4];
+    for (int k = 0; k < 4; k++) {
+        ids_of[k] = b->d_ids + b->group_off[k];
+        cnt_of[k] = k ? b->group_cnt[k] + (k == hrd::K_AM ? b->group_cnt[hrd::K_SSB] : 0) : 0;
     }
+    rc = run_demods(b, q, HRD_ENTRY_256K, (uint32_t)((n256 + 1023) / 1024), ids_of, cnt_of, s, nullptr, -1, true);
+    if (rc) return rc;
+    HRD_CUDA(cudaStreamWaitEvent(s, b->ev_report, 0)); // "after synchronising cuda_stream" covers the report too
+    b->cur ^= 1;
+    b->gated_calls++;
     return HRD_OK;
-}
-
-// can the gate of any stream close?  dBFS >= dbTable[0] - 42 - gain = -42 - gain (DbfsCalculator.cc, SignalDetector.cc:263)
-static bool squelch_armed(const hrd_batch_t *b)
-{
-    if (b->opt[HRD_OPT_RX_SQUELCH]) return true;
-    for (int i = 0; i < b->n; i++)
-        if ((double)b->param[HRD_PARAM_SQUELCH_THRESHOLD][(size_t)i] > -42.0 - (double)b->param[HRD_PARAM_RX_GAIN_DB][(size_t)i])
-            return true;
-    return false;
 }
 
 static int rx_common(hrd_batch_t *b, const int8_t *iq, size_t bytes, size_t iq_stride, int entry, int16_t *pcm,
@@ -1069,17 +1143,18 @@ static int rx_common(hrd_batch_t *b, const int8_t *iq, size_t bytes, size_t iq_s
     if (mem != HRD_MEM_HOST && mem != HRD_MEM_DEVICE) return fail(HRD_EINVAL, "bad mem %d", mem);
     const size_t n256 = entry == HRD_ENTRY_2048K ? bytes / 16 : bytes / 2;
     const size_t npcm = n256 / 32;
-    if (n256 > 0xffffffffu) return fail(HRD_EINVAL, "call too long");
+    // the kernels address a stream's input with 32-bit byte offsets
+    if (bytes >= ((size_t)1 << 32)) return fail(HRD_EINVAL, "bytes_per_stream must be below 4 GiB per call");
     if (iq_stride < bytes) return fail(HRD_EINVAL, "iq_stride smaller than bytes_per_stream");
     if (!front_end_only && !pcm) return fail(HRD_EINVAL, "pcm is null");
     if (!front_end_only && pcm_stride < npcm) return fail(HRD_EINVAL, "pcm_stride too small");
     DeviceGuard guard(b->device);
-    int rc = regroup(b);
-    if (rc) return rc;
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : (mem == HRD_MEM_HOST ? b->own : (cudaStream_t) nullptr);
+    int rc = order_after_last(b, s);
+    if (!rc) rc = regroup(b, s);
+    if (rc) return rc;
     if (pcm_counts)
-        for (int i = 0; i < b->n; i++)
-            pcm_counts[i] = kernel_kind_of_mode(b->mode[(size_t)i]) == hrd::K_NONE ? 0u : (uint32_t)npcm;
+        for (int i = 0; i < b->n; i++) pcm_counts[i] = b->h_kind[(size_t)i] == hrd::K_NONE ? 0u : (uint32_t)npcm;
     if (bytes == 0) return HRD_OK;
 
     const int8_t *d_iq = iq;
@@ -1120,11 +1195,24 @@ static int rx_common(hrd_batch_t *b, const int8_t *iq, size_t bytes, size_t iq_s
     p.atan2_lut = g_dev_tables[b->device].atan2_lut;
     p.sm_count = b->sm_count;
     const uint32_t n_batches = (uint32_t)((n256 + 1023) / 1024);
-    b->sq_blocks = 0;
-    if (!front_end_only && entry == HRD_ENTRY_2048K && squelch_armed(b)) {
+    bool gated = false;
+    if (!front_end_only && entry == HRD_ENTRY_2048K && b->armed) {
         if (mem == HRD_MEM_HOST) HRD_CUDA(cudaMemsetAsync(b->d_out, 0, d_pcm_stride * sizeof(int16_t) * (size_t)b->n, s));
-        rc = rx_squelched(b, p, n256, d_pcm, d_pcm_stride, pcm_counts, s);
+        if (b->group_cnt[hrd::K_AM] || b->group_cnt[hrd::K_SSB]) {
+            const size_t stride = (npcm + 7) & ~(size_t)7;
+            if (stride * (size_t)b->n >= ((size_t)1 << 32))
+                return fail(HRD_EINVAL, "call too long for %d AM/SSB streams (IIR scratch is indexed with 32 bits)", b->n);
+            if (b->pre_stride < stride) {
+                rc = ensure_cap((void **)&b->d_pre, &b->d_pre_cap, stride * sizeof(float) * (size_t)b->n);
+                if (rc) return rc;
+                b->pre_stride = stride;
+            }
+            p.pre_iir = b->d_pre;
+            p.pre_stride = b->pre_stride;
+        }
+        rc = rx_gated(b, p, n256, pcm_counts, s);
         if (rc) return rc;
+        gated = true;
     } else if (front_end_only) {
         p.out256 = d_o256;
         p.out_stride = d_o_stride;
@@ -1153,6 +1241,11 @@ static int rx_common(hrd_batch_t *b, const int8_t *iq, size_t bytes, size_t iq_s
                                      cudaMemcpyDeviceToDevice, s));
         p.kind_of = b->d_kind;
         p.gain_ssb = b->d_param[HRD_PARAM_SSB_GAIN];
+        // Squelch::run still runs on every block of the reference (IqDataProcessor.cc:961); with no threshold able
+        // to close the gate every block counts as present, so the tracker of every stream sits in Tracking --
+        // which matters the moment a caller raises a threshold: the first quiet block is then the tail
+        // (ENDOFSIGNAL) and still passes
+        if (entry == HRD_ENTRY_2048K) HRD_CUDA(cudaMemsetAsync(b->d_sq_track, 1, (size_t)b->n, s));
         const bool prof = b->opt[HRD_OPT_PROFILE] != 0;
         cudaEvent_t *ev = b->ev[b->ev_calls % HRD_PROFILE_RING];
         if (prof) {
@@ -1166,14 +1259,22 @@ static int rx_common(hrd_batch_t *b, const int8_t *iq, size_t bytes, size_t iq_s
             ids_of[k] = b->d_ids + b->group_off[k];
             cnt_of[k] = b->group_cnt[k] + (k == hrd::K_AM ? b->group_cnt[hrd::K_SSB] : 0);
         }
-        rc = run_demods(b, p, entry, n_batches, ids_of, cnt_of, s, prof ? ev[1] : nullptr);
+        rc = run_demods(b, p, entry, n_batches, ids_of, cnt_of, s, prof ? ev[1] : nullptr,
+                        prof ? (int)(b->ev_calls % HRD_PROFILE_RING) : -1);
         if (rc) return rc;
         if (prof) {
             HRD_CUDA(cudaEventRecord(ev[2], s));
             b->ev_calls++;
         }
     }
-    if (!b->sq_blocks) b->cur ^= 1; // what this call wrote is what the next one reads (rx_squelched swaps per block)
+    if (!gated) { // what this call wrote is what the next one reads (rx_gated swaps twice itself)
+        b->cur ^= 1;
+        // a call that was not gated has no report: behind the last gated call's, so the two cannot cross
+        if (b->gated_calls) {
+            HRD_CUDA(cudaEventSynchronize(b->ev_report));
+            b->sq_blocks = 0;
+        }
+    }
     if (mem == HRD_MEM_HOST) {
         if (front_end_only)
             HRD_CUDA(cudaMemcpy2DAsync(out256, out_stride, b->d_out, d_o_stride, out_row, (size_t)b->n,
@@ -1183,7 +1284,7 @@ static int rx_common(hrd_batch_t *b, const int8_t *iq, size_t bytes, size_t iq_s
                                        out_row, (size_t)b->n, cudaMemcpyDeviceToHost, s));
         HRD_CUDA(cudaStreamSynchronize(s));
     }
-    return HRD_OK;
+    return mark_end(b, s);
 }
 
 int hrd_rx_process(hrd_batch_t *b, const int8_t *iq, size_t bytes_per_stream, size_t iq_stride, int entry,
@@ -1210,6 +1311,8 @@ int hrd_rx_fs4_rotate(hrd_batch_t *b, int8_t *iq, size_t bytes, int up, int mem,
     if (!bytes) return HRD_OK;
     DeviceGuard guard(b->device);
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : (mem == HRD_MEM_HOST ? b->own : (cudaStream_t) nullptr);
+    int orc = order_after_last(b, s);
+    if (orc) return orc;
     int8_t *d = iq;
     if (mem == HRD_MEM_HOST) {
         int rc = ensure_cap(&b->d_in, &b->d_in_cap, bytes);
@@ -1225,12 +1328,16 @@ int hrd_rx_fs4_rotate(hrd_batch_t *b, int8_t *iq, size_t bytes, int up, int mem,
         HRD_CUDA(cudaMemcpyAsync(iq, d, bytes, cudaMemcpyDeviceToHost, s));
         HRD_CUDA(cudaStreamSynchronize(s));
     }
-    return HRD_OK;
+    return mark_end(b, s);
 }
 
 int hrd_rx_squelch_report(hrd_batch_t *b, uint32_t *magnitudes, uint8_t *allowed, size_t blocks_cap, uint32_t *n_blocks)
 {
     if (!b || b->kind != HRD_RX) return fail(HRD_EINVAL, "not an Rx batch");
+    {
+        DeviceGuard guard(b->device);
+        HRD_CUDA(cudaEventSynchronize(b->ev_report)); // the latest gated call's report has been unpacked
+    }
     if (n_blocks) *n_blocks = b->sq_blocks;
     if (b->sq_blocks > blocks_cap && (magnitudes || allowed)) return fail(HRD_EINVAL, "blocks_cap %zu < %u blocks", blocks_cap, b->sq_blocks);
     for (size_t st = 0; st < (size_t)b->n; st++)
@@ -1249,18 +1356,18 @@ int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size
     if (mem != HRD_MEM_HOST && mem != HRD_MEM_DEVICE) return fail(HRD_EINVAL, "bad mem %d", mem);
     if (n_per_stream > 0x7fffffu) return fail(HRD_EINVAL, "call too long");
     if (pcm_stride < n_per_stream) return fail(HRD_EINVAL, "pcm_stride too small");
-    bool pairs = false; // a stream of int16 I,Q pairs (HRD_MODE_IQ8K) doubles the row
-    for (int i = 0; i < b->n; i++) pairs |= b->mode[(size_t)i] == HRD_MODE_IQ8K;
+    DeviceGuard guard(b->device);
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : (mem == HRD_MEM_HOST ? b->own : (cudaStream_t) nullptr);
+    int rc = order_after_last(b, s);
+    if (!rc) rc = regroup(b, s);
+    if (rc) return rc;
+    const bool pairs = b->any_iq8k; // a stream of int16 I,Q pairs (HRD_MODE_IQ8K) doubles the row
     const size_t in_elems = pairs ? 2 * n_per_stream : n_per_stream;
     if (pairs && (pcm_stride < in_elems || (pcm_stride & 1) || ((uintptr_t)pcm & 3)))
         return fail(HRD_EINVAL, "HRD_MODE_IQ8K rows hold %zu int16: pcm_stride must be even and at least that, pcm 4-byte aligned", in_elems);
     const size_t out_row = n_per_stream * 512;
     if (iq_stride < out_row) return fail(HRD_EINVAL, "iq_stride too small");
-    DeviceGuard guard(b->device);
-    int rc = regroup(b);
-    if (rc) return rc;
     if (n_per_stream == 0) return HRD_OK;
-    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : (mem == HRD_MEM_HOST ? b->own : (cudaStream_t) nullptr);
 
     const int16_t *d_pcm = pcm;
     int8_t *d_iq = iq;
@@ -1329,9 +1436,7 @@ int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size
             b->launches++;
         }
         if (k == hrd::K_IQ) { // signals/fm.cc streams: their theta recurrence first (own scratch: K_FM may run beside)
-            bool any = false;
-            for (int i = 0; i < b->n; i++) any |= b->mode[(size_t)i] == HRD_MODE_FM_PROTO;
-            if (any) {
+            if (b->any_fm_proto) {
                 rc = ensure_cap(&b->d_sigph, &b->d_sigph_cap, sizeof(float) * (size_t)p.n_streams * n_per_stream);
                 if (rc) return rc;
                 p.fm_phase = (float *)b->d_sigph;
@@ -1355,7 +1460,7 @@ int hrd_tx_process(hrd_batch_t *b, const int16_t *pcm, size_t n_per_stream, size
                                    cudaMemcpyDeviceToHost, s));
         HRD_CUDA(cudaStreamSynchronize(s));
     }
-    return HRD_OK;
+    return mark_end(b, s);
 }
 
 } // extern "C"

@@ -54,6 +54,8 @@ struct ConstTables {
     // the NCO chains (hrd_device.cuh phase_step_fast): sign mask, -2PI_HI and -2PI_LO as REGISTER operands, so that
     // "(step & mask) ^ constant" is one LOP3 (with immediates ptxas needs two)
     uint32_t k_sign, k_m2pi_hi, k_m2pi_lo;
+    // DbfsCalculator::DbfsCalculator (DbfsCalculator.cc:56-65): (int32_t)(20 * log10((float)i)), entry 0 = entry 1
+    int32_t db_table[257];
 };
 
 // ---------------------------------------------------------------- Rx per-stream state
@@ -161,6 +163,25 @@ struct RxParams {
     float2 *wb_verify;
     const uint32_t *run_if;    // [0] = number of streams to re-run
     const int32_t *rerun_ids;  // their stream ids (replaces stream_ids / n_streams in the re-run)
+    // Ragged calls (the squelched path: every stream demodulates only the blocks its gate let through): when
+    // non-null, stream sid has n256_of[sid] <= n256 samples in its row; such launches run with n_tiles == 1.
+    const uint32_t *n256_of;
+};
+
+// The squelch gate, fused into the front end (hrd_rx.cu rx_gate_kernel): per stream and per block of blk256
+// samples at 256 kS/s the average magnitude, the tracker's decision, and the 256 kS/s samples of the OPEN blocks
+// packed one behind the other in the stream's scratch row -- what the demodulators then read as one ragged call.
+struct GateParams {
+    int8_t *scratch;           // [n_streams][row256] int8 I,Q at 256 kS/s, open blocks only
+    size_t row256;             // bytes between rows
+    uint32_t blk256;           // samples per block (a multiple of 32); the last block of a call may be short
+    int32_t n_blocks;
+    const float *threshold;    // per stream: IqDataProcessor::setSignalDetectThreshold (an int32 in the reference)
+    const float *gain_db;      // per stream: radio_adjustableReceiveGainInDb (a uint32)
+    uint8_t *tracking;         // per stream: SignalTracker state (1 = Tracking), carried across calls
+    uint32_t *magnitude;       // [n_streams][n_blocks] Squelch::getSignalMagnitude()
+    uint8_t *allowed;          // [n_streams][n_blocks] Squelch::run()'s result
+    uint32_t *n256_open;       // [n_streams] samples written to the scratch row (0 for streams without a demodulator)
 };
 
 struct TxParams {
@@ -240,15 +261,7 @@ int launch_rx_wbfm_verify(const RxParams &p, uint32_t *count, int32_t *rerun_ids
                           cudaStream_t s);
 int rx_halo_batches(int kind);                            // batches a tile > 0 runs ahead
 int rx_resident_warps_per_sm(int kind, int entry);        // occupancy of that kernel (cached)
-// squelch gate (hrd_squelch.cu)
-void upload_db_table(const int32_t *table257);
-int launch_squelch_magnitude(const int8_t *iq256, size_t stride, uint32_t block_bytes, uint32_t total_bytes, int n_streams,
-                             int n_blocks, uint32_t *magnitude, cudaStream_t s);
-int launch_squelch_track(const uint32_t *magnitude, int n_streams, int n_blocks, const float *threshold, const float *gain_db,
-                         uint8_t *tracking, uint8_t *allowed, cudaStream_t s);
-int launch_squelch_scatter(const int16_t *scratch, size_t scratch_stride, int16_t *pcm, size_t pcm_stride, const uint32_t *out_at,
-                           const uint8_t *allowed, const uint8_t *kind_of, int n_streams, int n_blocks, int blk, uint32_t n,
-                           cudaStream_t s);
+int launch_rx_gate(const RxParams &p, const GateParams &g, cudaStream_t s); // hrd_rx.cu: front end + squelch gate, every stream
 int launch_fs4_rotate(int8_t *iq, size_t n_groups, int up, cudaStream_t s);
 int launch_tx(int kind, const TxParams &p, cudaStream_t s);
 int launch_tx_fm_phase(const TxParams &p, cudaStream_t s);   // FM streams, before their launch_tx

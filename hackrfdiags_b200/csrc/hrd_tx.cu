@@ -1096,12 +1096,12 @@ __global__ void __launch_bounds__((FP_WORKERS + 1) * 32) tx_fm_phase_kernel(cons
 // mode NONE: BasebandDataProcessor.cc:689-694 fills the block with 64
 __global__ void tx_idle_kernel(const TxParams p)
 {
-    const int slot = blockIdx.y;
+    const int slot = blockIdx.x;
     const int sid = p.stream_ids[slot];
     uint4 *dst = reinterpret_cast<uint4 *>(p.iq + (size_t)sid * p.iq_stride);
     const size_t n16 = (size_t)p.n8 * 32;
     const uint4 v = make_uint4(0x40404040u, 0x40404040u, 0x40404040u, 0x40404040u);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+    for (size_t i = (size_t)blockIdx.y * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.y * blockDim.x)
         dst[i] = v;
 }
 
@@ -1174,7 +1174,7 @@ int launch_tx(int kind, const TxParams &p, cudaStream_t s)
         return (int)cudaGetLastError();
     }
     case K_NONE: {
-        dim3 grid(8, p.n_streams);
+        dim3 grid(p.n_streams, 8); // streams on x: no 65535 ceiling
         tx_idle_kernel<<<grid, 256, 0, s>>>(p);
         return (int)cudaGetLastError();
     }

@@ -118,7 +118,11 @@ enum {
     /* Rx, 2.048 MS/s entry: input bytes per squelch decision, i.e. the size of the reference call being
      * modelled (a multiple of 512).  0 (default) = 262144, the HackRF transfer block. */
     HRD_OPT_RX_SQUELCH_BLOCK = 6,
-    HRD_OPT_COUNT = 7
+    /* Rx, measurement only: 1 = the kernels of a mixed-mode batch run one kind after the other on the caller's
+     * stream instead of side by side, and (with HRD_OPT_PROFILE) each kind's own span is timed: hrd_kernel_ms
+     * which = 10 + kind (1 AM+SSB, 2 FM, 3 WBFM).  Results are identical either way. */
+    HRD_OPT_RX_SERIAL = 7,
+    HRD_OPT_COUNT = 8
 };
 
 #define HRD_ALL_STREAMS (-1)
@@ -138,6 +142,9 @@ int hrd_destroy(hrd_batch_t *b);
 const char *hrd_last_error(void);
 
 /* ---- control (replaces the reference's unsynchronised member writes) - */
+/* Setters may be called from another thread than the one that makes the process calls (as Radio.cc:1973,
+ * 2404-2633 does from the UI thread): they take a per-batch lock, and the next process call uploads a consistent
+ * snapshot on its own stream.  Nothing here synchronises the device. */
 /* IqDataProcessor::setDemodulatorMode (IqDataProcessor.cc:346-372; LSB/USB
  * also flip the SSB demodulator's sideband) or, on a Tx batch,
  * BasebandDataProcessor::setModulatorMode (+ Ssb set{Lsb,Usb}ModulationMode). */
@@ -155,9 +162,9 @@ int hrd_get_option(hrd_batch_t *b, int option, int *value);
  *   entry 2048K: IqDataProcessor::acceptIqData(ts, iq, bytes_per_stream)
  *   entry 256K : <mode's demodulator>::acceptIqData(iq, bytes_per_stream)
  * iq        int8 interleaved I,Q; stream s starts at iq + s*iq_stride bytes
- *           (16-byte aligned starts)
+ *           (HRD_MEM_DEVICE: pointer and stride 32-byte aligned at the 2048K entry, 4-byte aligned at the 256K one)
  * bytes_per_stream  multiple of 512 (2048K) or 64 (256K): whole PCM samples.
- *           Unlike the reference there is no 262144 / 32768 byte ceiling.
+ *           Unlike the reference there is no 262144 / 32768 byte ceiling; one call takes less than 4 GiB per stream.
  * pcm       int16 out; stream s starts at pcm + s*pcm_stride samples; gets
  *           bytes_per_stream/512 (resp. /64) samples, 0 when the mode is NONE
  * pcm_counts  optional, host memory, n_streams entries
@@ -168,13 +175,18 @@ int hrd_get_option(hrd_batch_t *b, int option, int *value);
  * shorter last block counts as its own call); a block the gate closes is not demodulated: the
  * demodulator state does not move and the stream's PCM is shorter by that block (pcm_counts tells).
  * With every threshold at its default (-200 dBFS) the gate cannot close and the call runs fused as one
- * pass; otherwise it runs block by block and waits once for the decisions (the call synchronises
- * cuda_stream once even with HRD_MEM_DEVICE).
- * mem       HRD_MEM_HOST: pointers are host memory, copied through pinned
- *           staging inside the call (the call returns when pcm is ready);
+ * pass; otherwise one kernel runs the front end, the magnitudes and the tracker of every stream and packs each
+ * stream's open blocks, and the demodulators take those as one ragged call: still nothing waits for the host.
+ * With HRD_MEM_DEVICE pcm_counts (and hrd_rx_squelch_report) are then filled by a host function on cuda_stream:
+ * read them after synchronising that stream; the array must stay valid until then.
+ * mem       HRD_MEM_HOST: pointers are host memory; the copies are cudaMemcpy2DAsync on the batch's own
+ *           stream straight from / to the caller's buffers and the call returns when pcm is ready.  Pinned
+ *           buffers (cudaHostAlloc / cudaHostRegister) get the full PCIe rate; pageable ones work but are
+ *           staged by the driver and slower.
  *           HRD_MEM_DEVICE: device pointers, work is queued on cuda_stream
  *           and the call returns without synchronising
- * cuda_stream  a cudaStream_t (NULL = the legacy default stream)
+ * cuda_stream  a cudaStream_t (NULL = the legacy default stream).  Calls on one batch may name different
+ *           streams: each call is ordered behind the one before it by an event.
  */
 int hrd_rx_process(hrd_batch_t *b, const int8_t *iq, size_t bytes_per_stream, size_t iq_stride,
                    int entry, int16_t *pcm, size_t pcm_stride, uint32_t *pcm_counts, int mem,
@@ -250,7 +262,8 @@ int hrd_rx_from_queue(hrd_batch_t *b, hrd_iq_queue_t *q, int16_t *pcm, size_t pc
 int hrd_synchronize(hrd_batch_t *b);
 /* with HRD_OPT_PROFILE set: device time of a recent process call's kernels; age 0 = the latest
  * call, up to 31 calls back; which = 0 the main kernels (Rx tile kernels / Tx kernels), 1 the
- * tail kernel (Rx AM/SSB IIR pass).  Waits for that call to finish. */
+ * tail kernel (Rx AM/SSB IIR pass), 10 + kind = that kind's own kernels (HRD_OPT_RX_SERIAL).
+ * Waits for that call to finish. */
 int hrd_kernel_ms(hrd_batch_t *b, int which, int age, float *ms);
 /* kernels this batch has launched so far (bench.py's gpu_launches) */
 int hrd_launch_count(hrd_batch_t *b, uint64_t *count);

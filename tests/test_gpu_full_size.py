@@ -1,8 +1,11 @@
 """Parity at BASELINE.json's full sizes (configs 2, 3, 4), through the C ABI on device buffers.
 
 The oracle cannot chew through 4-17 GB in a test, so full size is covered by size-independent properties:
-  * a sample of streams, whole length, bit for bit against the CPU oracle (FM Tx: <= 1 LSB int8);
-  * streams fed identical inputs give identical outputs wherever they sit in the batch (independence);
+  * EVERY distinct stream of the batch (32 per mode, the last five of them the edge classes: full-range noise,
+    constant -128, constant +127, alternating +-127, zero), whole length, bit for bit against the CPU oracle
+    (FM Tx: <= 1 LSB int8);
+  * streams fed identical inputs give identical outputs wherever they sit in the batch (independence): every
+    repeat of every distinct row, compared on the device;
   * automatic time tiling == one tile per stream (the serial order);
   * one long call == the same signal in several calls (state carry-over);
 Inputs are generated on the device (bench.py's generators: 32 distinct rows per mode, tiled)."""
@@ -29,6 +32,11 @@ def _rx_call(capi, b, iq, pcm, lo=0, hi=None, stream=0):
     hi = iq.shape[1] if hi is None else hi
     b.rx_device(iq.data_ptr() + lo, hi - lo, iq.stride(0), pcm.data_ptr() + (lo // 512) * 2, pcm.stride(0),
                 capi.ENTRY_2048K, stream)
+
+
+def _distinct_rows(layout):
+    """the first occurrence of every distinct row of a batch built by bench.make_rx_batch"""
+    return [at + k for at, nd, _ in layout.values() for k in range(nd)]
 
 
 def _check_sample_vs_oracle(torch, oracle, iq, pcm, modes, picks):
@@ -63,15 +71,14 @@ def test_config2_am_ssb_1024_streams(env, oracle):
     torch, bench, capi, dev = env
     n_samples = FS  # 1 s per stream: 4.19 GB of IQ
     groups = [(capi.MODE_AM, 512), (capi.MODE_LSB, 256), (capi.MODE_USB, 256)]
-    b, iq, pcm = bench.make_rx_batch(torch, capi, dev, groups, n_samples, seed=21)
+    b, iq, pcm, layout = bench.make_rx_batch(torch, capi, dev, groups, n_samples, seed=21)
     modes = [m for m, c in groups for _ in range(c)]
     _rx_call(capi, b, iq, pcm)
     torch.cuda.synchronize()
-    # (1) a sample of streams against the oracle, whole second
-    _check_sample_vs_oracle(torch, oracle, iq, pcm, modes, [0, 3, 31, 511, 512, 530, 767, 768, 1000, 1023])
-    # (2) independence: rows repeat with period 32 inside each mode group
-    assert torch.equal(pcm[0:32], pcm[32:64]) and torch.equal(pcm[0:32], pcm[480:512])
-    assert torch.equal(pcm[512:544], pcm[736:768]) and torch.equal(pcm[768:800], pcm[992:1024])
+    # (1) every distinct stream (edge classes included) against the oracle, whole second; plus the last rows
+    _check_sample_vs_oracle(torch, oracle, iq, pcm, modes, _distinct_rows(layout) + [511, 767, 1023])
+    # (2) independence: every repeat of every distinct row
+    assert bench.repeats_identical(torch, pcm, layout) == 0
     assert not torch.equal(pcm[512:544], pcm[768:800])  # LSB vs USB of mirrored signals differ
     # (3) automatic tiling == a single tile per stream
     b2 = capi.Batch(1024, capi.RX, 0)
@@ -96,12 +103,12 @@ def test_config2_am_ssb_1024_streams(env, oracle):
 
 def test_config3_wbfm_4096_streams(env, oracle):
     torch, bench, capi, dev = env
-    n_samples = FS // 2 // 8192 * 8192  # 0.5 s per stream: 8.4 GB of IQ
-    b, iq, pcm = bench.make_rx_batch(torch, capi, dev, [(capi.MODE_WBFM, 4096)], n_samples, seed=22)
+    n_samples = FS  # 1 s per stream: 16.8 GB of IQ
+    b, iq, pcm, layout = bench.make_rx_batch(torch, capi, dev, [(capi.MODE_WBFM, 4096)], n_samples, seed=22)
     _rx_call(capi, b, iq, pcm)
     torch.cuda.synchronize()
-    _check_sample_vs_oracle(torch, oracle, iq, pcm, [capi.MODE_WBFM] * 4096, [0, 5, 30, 31, 2048, 4095])
-    assert torch.equal(pcm[0:32], pcm[32:64]) and torch.equal(pcm[0:32], pcm[4064:4096])
+    _check_sample_vs_oracle(torch, oracle, iq, pcm, [capi.MODE_WBFM] * 4096, _distinct_rows(layout) + [2048, 4095])
+    assert bench.repeats_identical(torch, pcm, layout) == 0
     # one call == three uneven calls (the de-emphasis recurrence and the FIR histories carry over)
     b2 = capi.Batch(4096, capi.RX, 0)
     b2.set_mode(capi.MODE_WBFM)
@@ -113,10 +120,26 @@ def test_config3_wbfm_4096_streams(env, oracle):
     assert torch.equal(pcm, pcm2)
 
 
+def test_config5_mixed_modes_4096_streams(env, oracle):
+    """BASELINE configs[4] at the bench's headline point: 4096 mixed-mode streams (1/4 AM, NBFM, WBFM, 1/8 LSB, USB)
+    in one batch, 0.5 s each; every distinct stream of every mode against the oracle, every repeat on the device."""
+    torch, bench, capi, dev = env
+    from hackrfdiags_b200 import shard
+    n_samples = FS // 2 // 8192 * 8192
+    plan = shard.mixed_mode_plan(4096, bench.MIX)
+    groups = shard.mode_groups(shard.shard_modes(plan, 1, 0))
+    b, iq, pcm, layout = bench.make_rx_batch(torch, capi, dev, groups, n_samples, seed=24)
+    modes = [m for m, c in groups for _ in range(c)]
+    _rx_call(capi, b, iq, pcm)
+    torch.cuda.synchronize()
+    _check_sample_vs_oracle(torch, oracle, iq, pcm, modes, _distinct_rows(layout))
+    assert bench.repeats_identical(torch, pcm, layout) == 0
+
+
 @pytest.mark.parametrize("mode", [1, 2, 3, 4, 5])
 def test_config4_tx_4096_streams(env, oracle, mode):
     torch, bench, capi, dev = env
-    n_pcm = 2000  # 0.25 s per stream -> 4.19 GB of IQ out
+    n_pcm = 8000  # 1 s per stream (SURVEY section 8) -> 16.8 GB of IQ out
     distinct = bench.make_tx_pcm_device(torch, 32, n_pcm, dev, seed=23)
     pcm = bench.tile_rows(torch, distinct, 4096)
     iq = torch.empty((4096, n_pcm * 512), dtype=torch.int8, device=dev)
@@ -125,12 +148,12 @@ def test_config4_tx_4096_streams(env, oracle, mode):
     b.tx_device(pcm.data_ptr(), n_pcm, pcm.stride(0), iq.data_ptr(), iq.stride(0), 0)
     torch.cuda.synchronize()
     tol = 1 if mode == capi.MODE_FM else 0
-    for s in (0, 1, 2, 31, 4095):
+    for s in list(range(32)) + [4095]:  # every distinct row (sines to -32768, noise, AM tone, silence, square wave)
         want = oracle.run_tx(mode, pcm[s].cpu().numpy())
         got = iq[s].cpu().numpy()
         err = np.abs(got.astype(np.int32) - want.astype(np.int32)).max()
         assert err <= tol, f"mode {mode} stream {s}: max abs err {err}"
-    assert torch.equal(iq[0:32], iq[32:64]) and torch.equal(iq[0:32], iq[4064:4096])
+    assert bench.repeats_identical(torch, iq, {mode: (0, 32, 4096)}) == 0
     # one call == two calls (interpolator histories and NCO phase carry over)
     b2 = capi.Batch(4096, capi.TX, 0)
     b2.set_mode(mode)
@@ -140,6 +163,8 @@ def test_config4_tx_4096_streams(env, oracle, mode):
     b2.tx_device(pcm.data_ptr() + 2 * cut, n_pcm - cut, pcm.stride(0), iq2.data_ptr() + cut * 512, iq2.stride(0), 0)
     torch.cuda.synchronize()
     assert torch.equal(iq, iq2)
+    del iq, iq2
+    torch.cuda.empty_cache()
 
 
 def test_squelched_batch_1024_streams(env, oracle):

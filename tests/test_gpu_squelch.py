@@ -75,6 +75,52 @@ def test_default_threshold_takes_the_fused_path_and_option_forces_the_report():
     assert np.array_equal(mags[1], want[1]) and np.array_equal(blockwise[1], want[0])
 
 
+def test_threshold_raised_after_fused_calls_keeps_the_tail():
+    """Squelch::run runs on every block of the reference, also while no threshold can close the gate: the tracker
+    sits in Tracking after loud blocks through the FUSED path, so when the threshold is raised the first quiet
+    block is the tail (ENDOFSIGNAL) and still passes; the ones after it are closed."""
+    oracle = Oracle()
+    mode = capi.MODE_AM
+    loud = synth.rx_stream(mode, 2 * 131072, stream=1)
+    quiet = (synth.rx_stream(mode, 3 * 131072, stream=2).astype(np.int16) // 32).astype(np.int8)
+    h = oracle.rx_new()
+    try:
+        oracle.rx_set_mode(h, mode)
+        want1 = oracle.rx_accept_2048k(h, loud)           # default threshold: every block present
+        oracle.lib.hro_rx_set_squelch_threshold(h, -40)
+        want2 = oracle.rx_accept_2048k(h, quiet)          # tail block passes, two closed
+    finally:
+        oracle.rx_free(h)
+    assert want1.size == 1024 and want2.size == 512
+    b = capi.Batch(1, capi.RX, 0)
+    b.set_mode(mode)
+    got1 = b.rx(loud[None].copy())
+    assert b.squelch_report()[0].shape[1] == 0            # the fused path ran
+    b.set_param(capi.PARAM_SQUELCH_THRESHOLD, -40)
+    got2 = b.rx(quiet[None].copy())
+    assert np.array_equal(got1[0], want1)
+    assert list(b.squelch_report()[1][0]) == [1, 0, 0]
+    assert b.last_counts[0] == 512 and np.array_equal(got2[0, :512], want2)
+
+
+def test_squelch_small_blocks_and_many_boundaries_per_iteration():
+    """Blocks of 512 bytes (32 samples at 256 kS/s): four block ends inside every warp iteration of the gate kernel."""
+    oracle = Oracle()
+    mode, thr = capi.MODE_FM, -38
+    iq = synth.rx_bursty_stream(mode, 2, stream=5)[: 40 * 512 * 16]
+    # a level that flips every few hundred samples, so that neighbouring tiny blocks decide differently
+    env = (np.arange(iq.size // 2) // 700) % 2
+    iq = (iq.astype(np.int16) // (1 + 31 * np.repeat(env, 2))).astype(np.int8)
+    want_pcm, want_mag, want_open = oracle.run_rx_squelch(mode, iq, thr, block=512)
+    b = _batch([mode], [thr], [16])
+    b.set_option(capi.OPT_RX_SQUELCH_BLOCK, 512)
+    got = b.rx(iq[None].copy())
+    mags, allowed = b.squelch_report()
+    assert np.array_equal(mags[0], want_mag) and np.array_equal(allowed[0], want_open)
+    assert 0 < want_open.sum() < want_open.size
+    assert b.last_counts[0] == want_pcm.size and np.array_equal(got[0, :want_pcm.size], want_pcm)
+
+
 def test_squelch_edge_inputs_device_memory():
     """Edge classes (full-range noise, constant -128 / +127, alternating, zero) with device pointers."""
     torch = pytest.importorskip("torch")

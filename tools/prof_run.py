@@ -13,17 +13,21 @@ from hackrfdiags_b200 import capi  # noqa: E402
 
 kind, mode_name, n, secs = sys.argv[1], sys.argv[2], int(sys.argv[3]), float(sys.argv[4])
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
-mode = {"am": 1, "fm": 2, "wbfm": 3, "lsb": 4, "usb": 5, "mix": 0}[mode_name]
+mode = {"am": 1, "fm": 2, "wbfm": 3, "lsb": 4, "usb": 5, "mix": 0, "mix5": 0}[mode_name]
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 n_samples = int(secs * bench.FS) // 8192 * 8192
 if kind == "rx":
-    if mode_name == "mix":  # the bench headline: half AM, quarter LSB, quarter USB
+    if mode_name == "mix":  # BASELINE config 2: half AM, quarter LSB, quarter USB
         groups = [(1, n // 2), (4, n // 4), (5, n - n // 2 - n // 4)]
+    elif mode_name == "mix5":  # the bench headline (config 5): AM, NBFM, WBFM, LSB, USB
+        from hackrfdiags_b200 import shard
+        groups = shard.mode_groups(shard.shard_modes(shard.mixed_mode_plan(n, bench.MIX), 1, 0))
     else:
         groups = [(mode, n)]
-    ms, kms, tms, launches, keep = bench.bench_rx_modes(torch, capi, dev, groups, n_samples, reps, 1, seed=5)
-    print(f"tile kernel {kms:.3f} ms, tail {tms:.3f} ms")
+    r, keep = bench.bench_rx_modes(torch, capi, dev, groups, n_samples, reps, 1, seed=5)
+    ms = r["ms"]
+    print(f"tile kernel {r['kernel_ms']:.3f} ms, tail {r['tail_ms']:.3f} ms")
 else:
     ms = bench.bench_tx_mode(torch, capi, dev, mode, n, n_samples // 256, reps, 1, seed=5)
 torch.cuda.synchronize()
