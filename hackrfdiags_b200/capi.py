@@ -34,6 +34,11 @@ EXPORTS = [
     "hrd_pcm_ring_create", "hrd_pcm_ring_destroy", "hrd_pcm_ring_start", "hrd_pcm_ring_write", "hrd_pcm_ring_read_all",
     "hrd_pcm_ring_stats", "hrd_tx_from_ring", "hrd_iq_queue_create", "hrd_iq_queue_destroy", "hrd_iq_queue_push",
     "hrd_iq_queue_pop_all", "hrd_iq_queue_stats", "hrd_rx_from_queue",
+    "hrd_rx_pipe_create", "hrd_rx_pipe_destroy", "hrd_rx_pipe_submit", "hrd_rx_pipe_collect", "hrd_rx_pipe_stats",
+    "hrd_tx_pipe_create", "hrd_tx_pipe_destroy", "hrd_tx_pipe_submit", "hrd_tx_pipe_collect",
+    "hrd_sharded_create", "hrd_sharded_destroy", "hrd_sharded_count", "hrd_sharded_shard", "hrd_sharded_last_error",
+    "hrd_sharded_set_mode", "hrd_sharded_set_param", "hrd_sharded_reset", "hrd_sharded_set_option",
+    "hrd_sharded_rx_process", "hrd_sharded_tx_process",
     "hrd_synchronize", "hrd_launch_count", "hrd_wbfm_fallback_count", "hrd_kernel_ms", "hrd_get_table", "hrd_get_taps", "hrd_state_bytes_per_stream",
 ]
 

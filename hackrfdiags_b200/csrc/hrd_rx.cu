@@ -858,9 +858,14 @@ struct SmemWbItem {                    // int16 samples, two per word {x[2w], x[
     uint32_t d64[4 + WB_STEP / 8];     // @64k: 8 samples of history + 64 new per step
     uint32_t a16[19 + WB_STEP / 32];   // @16k: 38 samples of history + 16 new per step
 };
-struct SmemWb {
-    float f[2][32][WB_PITCH];
-    SmemWbItem item[WB_ITEMS];
+// SMALL: the exact re-run after a failed verification (a handful of streams, four per CTA, each walked serially over
+// the whole call): eight rows and the atan2 table left in global memory -- 19 KB instead of 207 KB, so that its
+// CTAs fit beside the other modes' kernels of a mixed batch instead of waiting for whole SMs to drain (measured on
+// the mixed 4096-stream batch: the re-run used to run BEHIND the AM and FM kernels, 2.95 ms per step).
+constexpr int WB_RERUN_ITEMS = 4;
+template <bool SMALL> struct SmemWbT {
+    float f[2][SMALL ? 8 : 32][WB_PITCH];
+    SmemWbItem item[SMALL ? WB_RERUN_ITEMS : WB_ITEMS];
     // split taps of the 12-tap and the 40-tap decimator, by the lane's share of the taps (see consume)
     alignas(16) uint32_t t12[2][4];
     alignas(16) uint32_t t40[4][8];
@@ -870,15 +875,12 @@ struct SmemWb {
     // theta(q, i) = sign(q) * lut[|q|][i + 128].  132 KB: the whole table (256 KB) fits neither
     // shared memory nor L1, and at two scattered 4-byte gathers per lane per iteration the L1
     // tag stage, not HBM, was the limiter of this kernel (profiles/: L1 hit rate 52 %).
-#if HRD_EXP & 8
-    float lut[256];
-#else
-    float lut[129 * 256];
-#endif
+    float lut[SMALL ? 4 : 129 * 256];
 };
+typedef SmemWbT<false> SmemWb;
 
 // TILED: the call is cut into time tiles (n_tiles > 1); only that instance carries the verification stores
-template <int ENTRY, bool TILED>
+template <int ENTRY, bool TILED, bool SMALL = false>
 __global__ void __launch_bounds__(HRD_WB_THREADS, 1) rx_wbfm_kernel(const RxParams p)
 {
     typedef typename RawNarrowOf<ENTRY>::type Raw;
@@ -887,7 +889,7 @@ __global__ void __launch_bounds__(HRD_WB_THREADS, 1) rx_wbfm_kernel(const RxPara
     const int n_streams = p.run_if ? (int)*p.run_if : p.n_streams;
     const int32_t *stream_ids = p.run_if ? p.rerun_ids : p.stream_ids;
     if ((int)blockIdx.x * p.items_per_cta >= n_streams * p.n_tiles) return; // uniform over the CTA
-    SmemWb &sm = *reinterpret_cast<SmemWb *>(smem_raw);
+    SmemWbT<SMALL> &sm = *reinterpret_cast<SmemWbT<SMALL> *>(smem_raw);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     // WARP ROLES.  A warp's scheduler is warp id % 4.  tx_wbfm_kernel puts its chain on the scheduler with the fewest
@@ -1004,8 +1006,14 @@ __global__ void __launch_bounds__(HRD_WB_THREADS, 1) rx_wbfm_kernel(const RxPara
         asm("prmt.b32 %0, %1, 0, 0xaaa2;" : "=r"(q0) : "r"(word));
         asm("prmt.b32 %0, %1, 0, 0xbbb3;" : "=r"(q1) : "r"(word));
         const uint32_t x = word ^ 0x00008080u;
-        const float a0 = sm.lut[abs(q0) * 256 + (int)(x & 0xffu)];
-        const float a1 = sm.lut[abs(q1) * 256 + (int)__byte_perm(x, 0, 0x4441)];
+        // (the small instance reads the table where it lies in global memory: rows q >= 0 are rows 128 + q there,
+        //  and |q| = 128 is minus row 0)
+        auto lut_at = [&](int aq, int col) {
+            if constexpr (SMALL) return aq < 128 ? __ldg(p.atan2_lut + (128 + aq) * 256 + col) : -__ldg(p.atan2_lut + col);
+            else return sm.lut[aq * 256 + col];
+        };
+        const float a0 = lut_at(abs(q0), (int)(x & 0xffu));
+        const float a1 = lut_at(abs(q1), (int)__byte_perm(x, 0, 0x4441));
         const float th0 = __int_as_float(__float_as_int(a0) ^ (q0 & (int)0x80000000));
         const float th1 = __int_as_float(__float_as_int(a1) ^ (q1 & (int)0x80000000));
         // theta of the previous sample: previous lane's th1 (lane 0: kept from before)
@@ -1158,8 +1166,9 @@ __global__ void __launch_bounds__(HRD_WB_THREADS, 1) rx_wbfm_kernel(const RxPara
 
     if (threadIdx.x < 6) sm.t12[threadIdx.x / 3][threadIdx.x % 3] = c_tab.fm_post_sp[threadIdx.x];
     if (threadIdx.x < 20) sm.t40[threadIdx.x / 5][threadIdx.x % 5] = c_tab.audio40_sp[threadIdx.x];
-    for (int i = threadIdx.x; i < (int)(sizeof(sm.lut) / 4); i += blockDim.x) // table rows q = 0..127 are rows 128..255; row 128 = -row 0
-        sm.lut[i] = i < 128 * 256 ? __ldg(p.atan2_lut + 128 * 256 + i) : -__ldg(p.atan2_lut + (i - 128 * 256));
+    if constexpr (!SMALL)
+        for (int i = threadIdx.x; i < (int)(sizeof(sm.lut) / 4); i += blockDim.x) // table rows q = 0..127 are rows 128..255; row 128 = -row 0
+            sm.lut[i] = i < 128 * 256 ? __ldg(p.atan2_lut + 128 * 256 + i) : -__ldg(p.atan2_lut + (i - 128 * 256));
     __syncthreads(); // the tables are complete before any warp looks an angle up
     if (!member) return; // (a spare warp slot: exited warps do not count at later barriers)
     // Hand-over between the item warps and the chain warp: two pairs of named barriers (by step parity)
@@ -1457,13 +1466,13 @@ int rx_resident_warps_per_sm(int kind, int entry)
     return w;
 }
 
-template <int ENTRY, bool TILED>
+template <int ENTRY, bool TILED, bool SMALL>
 int launch_wbfm_as(const RxParams &q, int grid, cudaStream_t s)
 {
     static PerDeviceOnce optin; // per template instance
-    const cudaError_t e = optin.run([] { return cudaFuncSetAttribute(rx_wbfm_kernel<ENTRY, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemWb)); });
+    const cudaError_t e = optin.run([] { return cudaFuncSetAttribute(rx_wbfm_kernel<ENTRY, TILED, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemWbT<SMALL>)); });
     if (e != cudaSuccess) return (int)e;
-    rx_wbfm_kernel<ENTRY, TILED><<<grid, HRD_RX_WB_ROLES ? 1024 : (q.items_per_cta + 1) * 32, sizeof(SmemWb), s>>>(q);
+    rx_wbfm_kernel<ENTRY, TILED, SMALL><<<grid, HRD_RX_WB_ROLES ? 1024 : (q.items_per_cta + 1) * 32, sizeof(SmemWbT<SMALL>), s>>>(q);
     return (int)cudaGetLastError();
 }
 
@@ -1473,9 +1482,10 @@ int launch_wbfm(const RxParams &p, cudaStream_t s)
     const long long items = (long long)p.n_streams * p.n_tiles;
     RxParams q = p;
     // (the re-run's stream count is only known on the device: small CTAs, surplus ones exit at once)
-    q.items_per_cta = p.run_if ? 4 : balanced_items_per_cta(items, p.sm_count, WB_ITEMS);
+    q.items_per_cta = p.run_if ? WB_RERUN_ITEMS : balanced_items_per_cta(items, p.sm_count, WB_ITEMS);
     const int grid = (int)((items + q.items_per_cta - 1) / q.items_per_cta);
-    return p.n_tiles > 1 ? launch_wbfm_as<ENTRY, true>(q, grid, s) : launch_wbfm_as<ENTRY, false>(q, grid, s);
+    if (p.run_if) return launch_wbfm_as<ENTRY, false, true>(q, grid, s);
+    return p.n_tiles > 1 ? launch_wbfm_as<ENTRY, true, false>(q, grid, s) : launch_wbfm_as<ENTRY, false, false>(q, grid, s);
 }
 
 // kind: K_NONE, K_AM (AM and SSB streams together), K_FM or K_WBFM

@@ -214,7 +214,8 @@ __device__ __forceinline__ uint32_t pack_b2(int a, int b) { return __byte_perm((
 __device__ __forceinline__ uint32_t merge16(uint32_t lo, uint32_t hi) { return __byte_perm(lo, hi, 0x5410); }
 
 // ---- stages 6..8 only (WBFM: the NCO sits between stage 5 and stage 6) ----------------------
-__device__ __forceinline__ void tail3(int x0, int xm1, int (&out)[8])
+// (the integer form per rail: the reference arithmetic as written; the kernel runs tail3_h2 below unless HRD_TW_H2 == 0)
+[[maybe_unused]] __device__ __forceinline__ void tail3(int x0, int xm1, int (&out)[8])
 {
     const int c6 = c_tabtx.tx_c3, c7 = c_tabtx.tx_c7, c8d = 2 * c_tabtx.tx_c8;
     const int k15 = c_tabtx.k_32768;

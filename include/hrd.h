@@ -258,6 +258,54 @@ int hrd_iq_queue_stats(hrd_iq_queue_t *q, int stream, uint32_t out[3]);
  * (host pcm buffers); 1 = a round was processed, 0 = nothing to do */
 int hrd_rx_from_queue(hrd_batch_t *b, hrd_iq_queue_t *q, int16_t *pcm, size_t pcm_stride, uint32_t *pcm_counts);
 
+/* Pipelined rounds (the adapters at rate).  The block pool of hrd_iq_queue_* is page-locked and laid out
+ * [slot][stream][262144], so a round whose streams sit at the same slot (producers in step) is ONE asynchronous
+ * host-to-device copy straight from the pool.  A pipe keeps up to `depth` rounds in flight, each on a CUDA stream of
+ * its own: the copy of round k+1 runs beside the kernels of round k and the PCM copy of round k-1.  One consumer
+ * thread drives a pipe (submit / collect), producers keep pushing concurrently; depth <= 8 (half the pool: a slot
+ * is not reused while its copy may still be reading it, provided the consumer keeps up as the reference requires). */
+typedef struct hrd_rx_pipe hrd_rx_pipe_t;
+typedef struct hrd_tx_pipe hrd_tx_pipe_t;
+int hrd_rx_pipe_create(hrd_batch_t *b, hrd_iq_queue_t *q, int depth, hrd_rx_pipe_t **out);
+int hrd_rx_pipe_destroy(hrd_rx_pipe_t *p);
+/* 1 = a round was started (every stream had a block queued and the pipe had room), 0 = not now; HRD_EINVAL when the
+ * blocks at the heads of the queues differ in size or are not whole PCM samples (nothing is dequeued then) */
+int hrd_rx_pipe_submit(hrd_rx_pipe_t *p);
+/* waits for the OLDEST round in flight: 1 and its PCM (pinned rows of 512 samples, valid until depth - 1 more
+ * rounds have been submitted) and per-stream sample counts; 0 = no round in flight */
+int hrd_rx_pipe_collect(hrd_rx_pipe_t *p, const int16_t **pcm, size_t *pcm_stride, const uint32_t **pcm_counts);
+/* rounds started, host-to-device copies issued for them */
+int hrd_rx_pipe_stats(hrd_rx_pipe_t *p, uint64_t out[2]);
+/* the transmit side: one getIqData of every stream per round (ring policy, modulators, 262144 bytes per stream
+ * back into pinned rows) */
+int hrd_tx_pipe_create(hrd_batch_t *b, hrd_pcm_ring_t *r, int depth, hrd_tx_pipe_t **out);
+int hrd_tx_pipe_destroy(hrd_tx_pipe_t *p);
+int hrd_tx_pipe_submit(hrd_tx_pipe_t *p);
+int hrd_tx_pipe_collect(hrd_tx_pipe_t *p, const int8_t **iq, size_t *iq_stride);
+
+/* ---- one job on several GPUs (host side; hrd_shard.cc) ----------------- */
+/*
+ * Streams are independent, so N streams on G GPUs are G disjoint batches: shard g owns streams [g*N/G, (g+1)*N/G)
+ * on devices[g] (a device may be listed twice: two shards on it).  One worker thread per shard; the process calls
+ * take HOST rows of the whole job, hand every shard its rows at the same time and return when all are done.  Nothing
+ * crosses GPUs.  Stream numbers are the job's.  hrd_sharded_shard gives a shard's device, range and batch handle
+ * for anything else (device-memory calls on that GPU, options, introspection).
+ */
+typedef struct hrd_sharded hrd_sharded_t;
+int hrd_sharded_create(const int *devices, int n_devices, int n_streams, int kind, hrd_sharded_t **out);
+int hrd_sharded_destroy(hrd_sharded_t *s);
+int hrd_sharded_count(hrd_sharded_t *s);
+int hrd_sharded_shard(hrd_sharded_t *s, int shard, int *device, int *lo, int *hi, hrd_batch_t **batch);
+const char *hrd_sharded_last_error(hrd_sharded_t *s); /* the failing shard's message (the workers' are thread-local) */
+int hrd_sharded_set_mode(hrd_sharded_t *s, int stream, int mode);
+int hrd_sharded_set_param(hrd_sharded_t *s, int stream, int param, float value);
+int hrd_sharded_reset(hrd_sharded_t *s, int stream, int unit);
+int hrd_sharded_set_option(hrd_sharded_t *s, int option, int value);
+int hrd_sharded_rx_process(hrd_sharded_t *s, const int8_t *iq, size_t bytes_per_stream, size_t iq_stride, int entry,
+                           int16_t *pcm, size_t pcm_stride, uint32_t *pcm_counts);
+int hrd_sharded_tx_process(hrd_sharded_t *s, const int16_t *pcm, size_t n_per_stream, size_t pcm_stride, int8_t *iq,
+                           size_t iq_stride);
+
 /* ---- introspection (tests, bench) ------------------------------------ */
 int hrd_synchronize(hrd_batch_t *b);
 /* with HRD_OPT_PROFILE set: device time of a recent process call's kernels; age 0 = the latest
