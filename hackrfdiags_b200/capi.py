@@ -39,7 +39,7 @@ EXPORTS = [
     "hrd_sharded_create", "hrd_sharded_destroy", "hrd_sharded_count", "hrd_sharded_shard", "hrd_sharded_last_error",
     "hrd_sharded_set_mode", "hrd_sharded_set_param", "hrd_sharded_reset", "hrd_sharded_set_option",
     "hrd_sharded_rx_process", "hrd_sharded_tx_process",
-    "hrd_synchronize", "hrd_launch_count", "hrd_wbfm_fallback_count", "hrd_kernel_ms", "hrd_get_table", "hrd_get_taps", "hrd_state_bytes_per_stream",
+    "hrd_synchronize", "hrd_launch_count", "hrd_wbfm_fallback_count", "hrd_wbfm_serial_count", "hrd_kernel_ms", "hrd_get_table", "hrd_get_taps", "hrd_state_bytes_per_stream",
 ]
 
 
@@ -79,6 +79,7 @@ def load():
     lib.hrd_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.hrd_kernel_ms.argtypes = [vp, i, i, C.POINTER(C.c_float)]
     lib.hrd_wbfm_fallback_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+    lib.hrd_wbfm_serial_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.hrd_get_table.argtypes = [vp, i, vp, sz]
     lib.hrd_get_taps.argtypes = [i, vp, i]
     lib.hrd_state_bytes_per_stream.argtypes = [i]
@@ -160,6 +161,11 @@ class Batch:
     def wbfm_fallback_count(self) -> int:
         c = C.c_uint64()
         _check(self.lib.hrd_wbfm_fallback_count(self.h, C.byref(c)))
+        return c.value
+
+    def wbfm_serial_count(self) -> int:
+        c = C.c_uint64()
+        _check(self.lib.hrd_wbfm_serial_count(self.h, C.byref(c)))
         return c.value
 
     def kernel_ms(self, which: int = 0, age: int = 0) -> float:

@@ -881,12 +881,13 @@ typedef SmemWbT<false> SmemWb;
 
 // TILED: the call is cut into time tiles (n_tiles > 1); only that instance carries the verification stores
 template <int ENTRY, bool TILED, bool SMALL = false>
-__global__ void __launch_bounds__(HRD_WB_THREADS, 1) rx_wbfm_kernel(const RxParams p)
+__global__ void __launch_bounds__(SMALL ? (WB_RERUN_ITEMS + 1) * 32 : HRD_WB_THREADS, 1) rx_wbfm_kernel(const RxParams p)
 {
     typedef typename RawNarrowOf<ENTRY>::type Raw;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // the exact re-run after a failed verification: only the streams the verifier listed
-    const int n_streams = p.run_if ? (int)*p.run_if : p.n_streams;
+    // (p.n_streams bounds it: the tiled retry is sized for a part of the batch, what does not fit goes on to the serial run)
+    const int n_streams = p.run_if ? min((int)*p.run_if, p.n_streams) : p.n_streams;
     const int32_t *stream_ids = p.run_if ? p.rerun_ids : p.stream_ids;
     if ((int)blockIdx.x * p.items_per_cta >= n_streams * p.n_tiles) return; // uniform over the CTA
     SmemWbT<SMALL> &sm = *reinterpret_cast<SmemWbT<SMALL> *>(smem_raw);
@@ -968,7 +969,7 @@ __global__ void __launch_bounds__(HRD_WB_THREADS, 1) rx_wbfm_kernel(const RxPara
         // |y| <= max(|y[-1]|, pi * scale * (1 + 1e-6)): the de-emphasis filter has unit DC gain and a
         // positive impulse response, and |x| <= pi * scale.  Below 2^31 the (int16_t) narrowing needs no
         // out-of-range patch (f32_to_i16).  NaN gains fail the test and take the patched path.
-        narrow_fast = scale < 0x1p27f && fabsf(first ? st.wb_y1 : 0.f) < 0x1p30f;
+        narrow_fast = scale < 0x1p27f && fabsf(first ? st.wb_y1 : (TILED && p.wb_guess) ? p.wb_guess[slot] : 0.f) < 0x1p30f;
         pf = (start + 2 * lane) * BPS;
         pf_last = end >= 2 ? (end - 2) * BPS : 0u;
 #pragma unroll
@@ -1159,7 +1160,10 @@ __global__ void __launch_bounds__(HRD_WB_THREADS, 1) rx_wbfm_kernel(const RxPara
         // verified speculation: y at the two check points of this tile (see the kernel's header)
         if constexpr (TILED) {
             const uint32_t pos = done + nb;
-            if (tile >= 1 && pos == start + BATCH256) p.wb_verify[(size_t)slot * p.n_tiles + tile].x = y1;
+            if (tile >= 1 && pos == start + BATCH256) {
+                if (p.wb_guess) y1 = p.wb_guess[slot]; // the retry: a given value instead of the warmed-up one
+                p.wb_verify[(size_t)slot * p.n_tiles + tile].x = y1;
+            }
             if (tile + 1 < p.n_tiles && pos == end - BATCH256) p.wb_verify[(size_t)slot * p.n_tiles + tile + 1].y = y1;
         }
     };
@@ -1239,10 +1243,16 @@ __global__ void __launch_bounds__(HRD_WB_THREADS, 1) rx_wbfm_kernel(const RxPara
 // it, and from there on the two recurrences are identical.  Without this rule every silent stream took the
 // untiled re-run (measured: 32 of 1024 streams, the launch 4 x slower).
 __global__ void rx_wbfm_verify_kernel(const float2 *pairs, const int32_t *stream_ids, const float *gain, int n_streams, int n_tiles,
-                                      uint32_t *count, int32_t *rerun_ids, unsigned long long *fallbacks, int force)
+                                      const uint32_t *n_if, uint32_t *count, int32_t *rerun_ids, float *guess_out,
+                                      unsigned long long *fallbacks, unsigned long long *fallbacks2, int force)
 {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= n_streams) return;
+    if (slot >= (n_if ? (int)*n_if : n_streams)) return;
+    if (slot >= n_streams) { // listed, but the retry had no room for it
+        rerun_ids[atomicAdd(count, 1u)] = stream_ids[slot];
+        atomicAdd(fallbacks, 1ull);
+        return;
+    }
     bool bad = force != 0;
     const bool tiny_ok = fabsf(gain[stream_ids[slot]]) >= 1e-3f; // scale = gain / 75000 * 32767 >= 2^-20 with room (NaN: false)
     for (int t = 1; t < n_tiles; t++) {
@@ -1251,8 +1261,11 @@ __global__ void rx_wbfm_verify_kernel(const float2 *pairs, const int32_t *stream
         bad |= __float_as_uint(v.x) != __float_as_uint(v.y) && !vanishing;
     }
     if (bad) {
-        rerun_ids[atomicAdd(count, 1u)] = stream_ids[slot];
+        const uint32_t at = atomicAdd(count, 1u);
+        rerun_ids[at] = stream_ids[slot];
+        if (guess_out) guess_out[at] = pairs[(size_t)slot * n_tiles + 1].y; // tile 0's value: true by construction
         atomicAdd(fallbacks, 1ull);
+        if (fallbacks2) atomicAdd(fallbacks2, 1ull);
     }
 }
 
@@ -1484,7 +1497,7 @@ int launch_wbfm(const RxParams &p, cudaStream_t s)
     // (the re-run's stream count is only known on the device: small CTAs, surplus ones exit at once)
     q.items_per_cta = p.run_if ? WB_RERUN_ITEMS : balanced_items_per_cta(items, p.sm_count, WB_ITEMS);
     const int grid = (int)((items + q.items_per_cta - 1) / q.items_per_cta);
-    if (p.run_if) return launch_wbfm_as<ENTRY, false, true>(q, grid, s);
+    if (p.run_if) return p.n_tiles > 1 ? launch_wbfm_as<ENTRY, true, true>(q, grid, s) : launch_wbfm_as<ENTRY, false, true>(q, grid, s);
     return p.n_tiles > 1 ? launch_wbfm_as<ENTRY, true, false>(q, grid, s) : launch_wbfm_as<ENTRY, false, false>(q, grid, s);
 }
 
@@ -1506,11 +1519,13 @@ int launch_rx(int kind, int entry, const RxParams &p, cudaStream_t s)
     return (int)cudaErrorInvalidValue;
 }
 
-int launch_rx_wbfm_verify(const RxParams &p, uint32_t *count, int32_t *rerun_ids, unsigned long long *fallbacks, int force,
-                          cudaStream_t s)
+int launch_rx_wbfm_verify(const RxParams &p, const uint32_t *n_if, int most, uint32_t *count, int32_t *rerun_ids, float *guess_out,
+                          unsigned long long *fallbacks, unsigned long long *fallbacks2, int force, cudaStream_t s)
 {
-    rx_wbfm_verify_kernel<<<(p.n_streams + 127) / 128, 128, 0, s>>>(p.wb_verify, p.stream_ids, p.gain, p.n_streams, p.n_tiles, count,
-                                                                     rerun_ids, fallbacks, force);
+    // (the retry's verification: the list is the first pass's, p.rerun_ids, *n_if <= most long; p.n_streams of them were run)
+    const int32_t *ids = n_if ? p.rerun_ids : p.stream_ids;
+    rx_wbfm_verify_kernel<<<((n_if ? most : p.n_streams) + 127) / 128, 128, 0, s>>>(p.wb_verify, ids, p.gain, p.n_streams, p.n_tiles, n_if,
+                                                                                   count, rerun_ids, guess_out, fallbacks, fallbacks2, force);
     return (int)cudaGetLastError();
 }
 

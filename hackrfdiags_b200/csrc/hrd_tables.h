@@ -163,6 +163,9 @@ struct RxParams {
     float2 *wb_verify;
     const uint32_t *run_if;    // [0] = number of streams to re-run
     const int32_t *rerun_ids;  // their stream ids (replaces stream_ids / n_streams in the re-run)
+    // the TILED retry of those streams (hrd_rx.cu "second pass"): per listed stream the value every tile >= 1 puts
+    // into the recurrence at its check point instead of the warmed-up one; null otherwise
+    const float *wb_guess;
     // Ragged calls (the squelched path: every stream demodulates only the blocks its gate let through): when
     // non-null, stream sid has n256_of[sid] <= n256 samples in its row; such launches run with n_tiles == 1.
     const uint32_t *n256_of;
@@ -257,8 +260,12 @@ int launch_rx(int kind, int entry, const RxParams &p, cudaStream_t s);
 int launch_rx_dc_iir(const RxParams &p, cudaStream_t s);  // AM + SSB streams, after their launch_rx
 // WBFM, tiled call: compare every tile's speculated recurrence value with the true one; streams with any
 // difference are appended to rerun_ids (*count of them) and added to *fallbacks (or always, when force is set: test hook)
-int launch_rx_wbfm_verify(const RxParams &p, uint32_t *count, int32_t *rerun_ids, unsigned long long *fallbacks, int force,
-                          cudaStream_t s);
+// n_if: when non-null this is the verification of the tiled RETRY: the streams are the first pass's list p.rerun_ids,
+// *n_if of them (at most `most`), of which the retry ran the first p.n_streams -- the others fail without a look.
+// guess_out: when non-null, receives per failing stream the TRUE value at the first check point (the retry's wb_guess).
+// fallbacks2: a second counter to add the failures to, or null.
+int launch_rx_wbfm_verify(const RxParams &p, const uint32_t *n_if, int most, uint32_t *count, int32_t *rerun_ids, float *guess_out,
+                          unsigned long long *fallbacks, unsigned long long *fallbacks2, int force, cudaStream_t s);
 int rx_halo_batches(int kind);                            // batches a tile > 0 runs ahead
 int rx_resident_warps_per_sm(int kind, int entry);        // occupancy of that kernel (cached)
 int launch_rx_gate(const RxParams &p, const GateParams &g, cudaStream_t s); // hrd_rx.cu: front end + squelch gate, every stream

@@ -100,8 +100,8 @@ enum {
     HRD_OPT_RX_TILE_BATCHES = 0,
     /* Rx WBFM: time tiling by verified speculation.  1 (default): tiles after the first warm the
      * 256 kS/s de-emphasis recurrence up from zero, every tile's warmed-up value is compared bit
-     * for bit with the true one, and streams where any differs are re-run untiled -- the result is
-     * bit-exact either way (hrd_wbfm_fallback_count tells how often the re-run was needed).
+     * for bit with the true one, and streams where any differs are run again (hrd_wbfm_fallback_count)
+     * -- the result is bit-exact either way.
      * 0: never tile WBFM calls. */
     HRD_OPT_RX_WBFM_TILING = 1,
     /* Tx: PCM samples per time tile (multiple of 32).  0 = choose automatically. */
@@ -109,7 +109,8 @@ enum {
     /* record CUDA events around the kernels of every process call (bench.py's roofline):
      * hrd_kernel_ms() then reports the main and tail kernel times of the latest calls */
     HRD_OPT_PROFILE = 3,
-    /* test hook: make the WBFM verification fail, so that the exact re-run path is exercised */
+    /* test hook: 1 = make the WBFM verification fail, so that the retry (and, where its guess is wrong, the serial
+     * re-run) is exercised; 2 = make the retry's verification fail as well */
     HRD_OPT_DEBUG_WBFM_FORCE_RERUN = 4,
     /* Rx, 2.048 MS/s entry: 1 = take the squelched path (per-block magnitudes and decisions, see
      * hrd_rx_squelch_report) even when no stream's threshold can close the gate.  The path is taken
@@ -315,9 +316,11 @@ int hrd_synchronize(hrd_batch_t *b);
 int hrd_kernel_ms(hrd_batch_t *b, int which, int age, float *ms);
 /* kernels this batch has launched so far (bench.py's gpu_launches) */
 int hrd_launch_count(hrd_batch_t *b, uint64_t *count);
-/* Rx WBFM: how many stream-calls failed the tile verification and were re-run untiled so far
- * (HRD_OPT_RX_WBFM_TILING); waits for the batch's queued work */
+/* Rx WBFM (HRD_OPT_RX_WBFM_TILING): how many stream-calls failed the tile verification so far and were run again --
+ * tiled once more from the true value at the first check point (constant inputs pass that), and serially from the
+ * saved state when that fails too (hrd_wbfm_serial_count); both wait for the batch's queued work */
 int hrd_wbfm_fallback_count(hrd_batch_t *b, uint64_t *count);
+int hrd_wbfm_serial_count(hrd_batch_t *b, uint64_t *count);
 /* copy a device table back: 0 = atan2 LUT (65536 floats), 1 = NCO sin,
  * 2 = NCO cos (16384 floats each) */
 int hrd_get_table(hrd_batch_t *b, int which, float *out, size_t n);

@@ -220,15 +220,17 @@ def test_rx_wbfm_time_tiles_bit_exact(oracle, tile_batches):
     assert b.wbfm_fallback_count() <= 4 * len(sizes)
 
 
-def test_rx_wbfm_failed_verification_reruns_exactly(oracle):
-    """Force the verification to fail: the untiled re-run from the untouched state must give the same bits,
-    call after call (state carry-over through the re-run path)."""
+@pytest.mark.parametrize("force", [1, 2])
+def test_rx_wbfm_failed_verification_reruns_exactly(oracle, force):
+    """Force the verification to fail: the tiled retry (whose guess is wrong for a signal that is not constant, so
+    its own verification sends the stream on; force = 2 fails that verification outright) and the serial re-run
+    from the untouched state must give the same bits, call after call (state carry-over through the re-run path)."""
     n_streams, sizes = 5, [8192 * 9, 8192 * 6]
-    iq = synth.rx_batch(capi.MODE_WBFM, n_streams, sum(sizes), config=9)
+    iq = synth.rx_batch(capi.MODE_WBFM, n_streams, sum(sizes), config=9, with_edges=False)
     b = capi.Batch(n_streams, capi.RX)
     b.set_mode(capi.MODE_WBFM)
     b.set_option(capi.OPT_RX_TILE_BATCHES, 2)
-    b.set_option(capi.OPT_DEBUG_WBFM_FORCE_RERUN, 1)
+    b.set_option(capi.OPT_DEBUG_WBFM_FORCE_RERUN, force)
     parts, off = [], 0
     for sz in sizes:
         parts.append(b.rx(np.ascontiguousarray(iq[:, 2 * off:2 * (off + sz)])))
@@ -237,9 +239,41 @@ def test_rx_wbfm_failed_verification_reruns_exactly(oracle):
     for s in range(n_streams):
         assert np.array_equal(got[s], oracle.run_rx(capi.MODE_WBFM, iq[s])), f"stream {s}"
     assert b.wbfm_fallback_count() == 2 * n_streams
+    assert b.wbfm_serial_count() == 2 * n_streams  # retried in tiles, failed again (a wrong guess, or force = 2), walked serially
     b.set_option(capi.OPT_RX_WBFM_TILING, 0)  # never tile: nothing to verify, nothing to re-run
     b.rx(np.ascontiguousarray(iq[:, :2 * 8192 * 4]))
     assert b.wbfm_fallback_count() == 2 * n_streams
+
+
+def test_rx_wbfm_constant_inputs_pass_the_tiled_retry(oracle):
+    """Constant inputs leave the de-emphasis recurrence on one of several neighbouring fixed points of its rounded
+    map; the warm-up from zero reaches another, so the first verification fails for good.  The retry starts every
+    tile from the value tile 0 saw, which is the value everywhere: bit-exact, and nothing is walked serially.  A
+    stream that is constant only in its first half fails the retry too and is walked serially: also bit-exact."""
+    n = 8192 * 24
+    rows = [synth.rx_stream(capi.MODE_WBFM, n, stream=0, config=31),
+            synth.rx_stream(capi.MODE_WBFM, n, stream=1, config=31, edge="min"),
+            synth.rx_stream(capi.MODE_WBFM, n, stream=2, config=31, edge="max"),
+            synth.rx_stream(capi.MODE_WBFM, n, stream=3, config=31, edge="zero"),
+            synth.rx_stream(capi.MODE_WBFM, n, stream=4, config=31, edge="alt")]
+    half = synth.rx_stream(capi.MODE_WBFM, n, stream=5, config=31, edge="max").copy()
+    half[n:] = rows[0][n:]  # constant, then a signal
+    iq = np.stack(rows + [half])
+    b = capi.Batch(len(iq), capi.RX)
+    b.set_mode(capi.MODE_WBFM)
+    for s in range(len(iq)):
+        b.set_param(capi.PARAM_WBFM_GAIN, 300.0 + 77.0 * s, s)
+    b.set_option(capi.OPT_RX_TILE_BATCHES, 3)
+    sizes = [8192 * 10, 8192 * 14]
+    parts, off = [], 0
+    for sz in sizes:
+        parts.append(b.rx(np.ascontiguousarray(iq[:, 2 * off:2 * (off + sz)])))
+        off += sz
+    got = np.concatenate(parts, axis=1)
+    for s in range(len(iq)):
+        assert np.array_equal(got[s], oracle.run_rx(capi.MODE_WBFM, iq[s], gain=300.0 + 77.0 * s)), f"stream {s}"
+    assert b.wbfm_fallback_count() >= 2       # the two rails at least, in some call
+    assert b.wbfm_serial_count() <= 1         # at most the half-constant stream, in the call where it changes
 
 
 def test_rx_mixed_modes_one_batch(oracle):
