@@ -532,6 +532,53 @@ void choose_tiles(hrd_batch *b, int kind, int entry, int n_streams, uint32_t n_b
     if (*n_tiles < 1) *n_tiles = 1;
 }
 
+// WBFM launches run one CTA per SM, so a stream count just above a whole number of waves (4096 streams on
+// 148 x 27 slots) would leave the last wave nearly empty, or force every stream into tiles.  Instead the list is
+// cut in two: the streams that fill whole waves run untiled, the rest are tiled finely enough to share one more
+// (short) wave.  Cost model, in batch-times of a full CTA: waves x (batches per tile + halo) x the step time of
+// the CTA size the launcher will pick (flat below 16 items: measured, 7 items per CTA run at 0.45 of the rate of 28).
+struct WbPart {
+    int first, count;
+    int32_t n_tiles;
+    uint32_t tile_batches;
+};
+static double wbfm_uniform_cost(hrd_batch *b, int entry, int n_streams, uint32_t n_batches, int32_t *n_tiles, uint32_t *tile_batches)
+{
+    choose_tiles(b, hrd::K_WBFM, entry, n_streams, n_batches, n_tiles, tile_batches);
+    const int cap = hrd::rx_resident_warps_per_sm(hrd::K_WBFM, entry);
+    const double items = (double)*n_tiles * n_streams;
+    const double waves = ceil(items / ((double)b->sm_count * cap));
+    const int ipc = hrd::balanced_items_per_cta((long long)items, b->sm_count, cap);
+    const uint32_t halo = *n_tiles > 1 ? (uint32_t)hrd::rx_halo_batches(hrd::K_WBFM) : 0u;
+    return waves * (double)(*tile_batches + halo) * (double)std::max(ipc, 16) / (double)cap;
+}
+static int plan_wbfm(hrd_batch *b, int entry, int n_streams, uint32_t n_batches, bool one_tile, WbPart parts[2])
+{
+    parts[0].first = 0;
+    parts[0].count = n_streams;
+    if (one_tile) { // ragged calls (the squelched path): one warp walks a stream's whole call
+        parts[0].n_tiles = 1;
+        parts[0].tile_batches = n_batches ? n_batches : 1;
+        return 1;
+    }
+    const double whole = wbfm_uniform_cost(b, entry, n_streams, n_batches, &parts[0].n_tiles, &parts[0].tile_batches);
+    const int slots = b->sm_count * hrd::rx_resident_warps_per_sm(hrd::K_WBFM, entry);
+    const int n_main = n_streams / slots * slots;
+    if (n_main == 0 || n_main == n_streams || b->opt[HRD_OPT_RX_TILE_BATCHES] > 0 || !b->opt[HRD_OPT_RX_WBFM_TILING] || n_batches < 2)
+        return 1;
+    WbPart rest;
+    rest.first = n_main;
+    rest.count = n_streams - n_main;
+    const double split = (double)(n_main / slots) * (double)n_batches
+                         + wbfm_uniform_cost(b, entry, rest.count, n_batches, &rest.n_tiles, &rest.tile_batches);
+    if (split >= whole) return 1;
+    parts[0].count = n_main;
+    parts[0].n_tiles = 1;
+    parts[0].tile_batches = n_batches;
+    parts[1] = rest;
+    return 2;
+}
+
 // Tx: tiles of whole 32-sample batches; same trade-off as choose_tiles (fill of the last wave of
 // resident warps against the halo every tile after the first recomputes)
 void choose_tx_tiles(hrd_batch *b, int kind, int n_streams, uint32_t n8, int32_t *n_tiles, uint32_t *tile_len8)
@@ -978,73 +1025,87 @@ static int run_demods(hrd_batch_t *b, hrd::RxParams &p, int entry, uint32_t n_ba
                 if (!b->ev_kind[prof_slot][k][i]) HRD_CUDA(cudaEventCreate(&b->ev_kind[prof_slot][k][i]));
             HRD_CUDA(cudaEventRecord(b->ev_kind[prof_slot][k][0], ks));
         }
+        WbPart parts[2];
+        int n_parts = 1;
+        parts[0].first = 0;
+        parts[0].count = cnt;
+        if (k == hrd::K_WBFM) n_parts = plan_wbfm(b, entry, cnt, n_batches, one_tile, parts);
+        for (int part = 0; part < n_parts; part++) {
+            p.stream_ids = ids_of[k] + parts[part].first;
+            p.n_streams = parts[part].count;
+            p.gain = k ? b->d_param[gain_of_kind[k]] : nullptr;
+            if (k == hrd::K_WBFM) {
+                p.n_tiles = parts[part].n_tiles;
+                p.tile_batches = parts[part].tile_batches;
+            } else {
+                choose_tiles(b, k, entry, p.n_streams, n_batches, &p.n_tiles, &p.tile_batches);
+                if (one_tile) { // ragged calls (the squelched path): one warp walks a stream's whole call
+                    p.n_tiles = 1;
+                    p.tile_batches = n_batches ? n_batches : 1;
+                }
+            }
+            const bool speculate = k == hrd::K_WBFM && p.n_tiles > 1;
+            if (speculate) { // verified speculation (hrd_rx.cu): pairs to compare, this call's flag
+                rc = ensure_cap(&b->d_wbv, &b->d_wbv_cap, sizeof(float2) * (size_t)p.n_streams * (size_t)p.n_tiles);
+                if (rc) return rc;
+                p.wb_verify = (float2 *)b->d_wbv;
+                HRD_CUDA(cudaMemsetAsync(b->d_wbflag, 0, 2 * sizeof(uint32_t), ks));
+            }
+            int e = hrd::launch_rx(k, entry, p, ks);
+            if (e) return fail(HRD_ECUDA, "rx launch (kind %d) failed: %s", k, cudaGetErrorString((cudaError_t)e));
+            b->launches++;
+            if (speculate) {
+                const int force = b->opt[HRD_OPT_DEBUG_WBFM_FORCE_RERUN];
+                const uint32_t tb2 = std::max<uint32_t>(4u, (n_batches + 15) / 16);
+                const int nt2 = (int)((n_batches + tb2 - 1) / tb2);
+                e = hrd::launch_rx_wbfm_verify(p, nullptr, 0, b->d_wbflag, b->d_wbrerun, b->d_wbguess, (unsigned long long *)(b->d_wbflag + 2),
+                                               nt2 >= 2 ? nullptr : (unsigned long long *)(b->d_wbflag + 4), force, ks);
+                if (e) return fail(HRD_ECUDA, "wbfm verify launch failed: %s", cudaGetErrorString((cudaError_t)e));
+                // SECOND PASS for the streams that failed: tiled again (finer, they are few), every tile >= 1 taking the
+                // TRUE value at the first check point as its recurrence value.  What fails in practice is a constant
+                // input: the recurrence then sits on one of several neighbouring fixed points of its rounded map and
+                // stays there, the warm-up from zero reaches another one, and no amount of warm-up brings them
+                // together -- but the value tile 0 saw is the value at every later check point as well.  The retry is
+                // verified like the first pass (each tile's value against the one the tile before it arrives at), so a
+                // wrong guess costs time only: what fails again is walked serially by the third launch.
+                hrd::RxParams again = p;
+                again.wb_verify = nullptr;
+                again.run_if = b->d_wbflag;
+                again.rerun_ids = b->d_wbrerun;
+                if (nt2 >= 2) { // (too short a call for two tiles: straight to the serial run)
+                    hrd::RxParams retry = again;
+                    retry.n_streams = std::min(p.n_streams, 512); // the part of the list it is sized for
+                    retry.n_tiles = nt2;
+                    retry.tile_batches = tb2;
+                    rc = ensure_cap(&b->d_wbv2, &b->d_wbv2_cap, sizeof(float2) * (size_t)retry.n_streams * (size_t)nt2);
+                    if (rc) return rc;
+                    retry.wb_verify = (float2 *)b->d_wbv2;
+                    retry.wb_guess = b->d_wbguess;
+                    e = hrd::launch_rx(k, entry, retry, ks);
+                    if (e) return fail(HRD_ECUDA, "wbfm retry launch failed: %s", cudaGetErrorString((cudaError_t)e));
+                    e = hrd::launch_rx_wbfm_verify(retry, b->d_wbflag, p.n_streams, b->d_wbflag + 1, b->d_wbrerun + b->n, nullptr,
+                                                   (unsigned long long *)(b->d_wbflag + 4), nullptr, force >= 2, ks);
+                    if (e) return fail(HRD_ECUDA, "wbfm retry verify launch failed: %s", cudaGetErrorString((cudaError_t)e));
+                    b->launches += 2;
+                    again.run_if = b->d_wbflag + 1;
+                    again.rerun_ids = b->d_wbrerun + b->n;
+                }
+                // the exact untiled run, from the untouched state_in; runs only for the streams still listed
+                again.n_tiles = 1;
+                again.tile_batches = n_batches;
+                e = hrd::launch_rx(k, entry, again, ks);
+                if (e) return fail(HRD_ECUDA, "wbfm re-run launch failed: %s", cudaGetErrorString((cudaError_t)e));
+                b->launches += 2;
+                p.wb_verify = nullptr;
+            }
+        }
         p.stream_ids = ids_of[k];
         p.n_streams = cnt;
-        p.gain = k ? b->d_param[gain_of_kind[k]] : nullptr;
-        choose_tiles(b, k, entry, p.n_streams, n_batches, &p.n_tiles, &p.tile_batches);
-        if (one_tile) { // ragged calls (the squelched path): one warp walks a stream's whole call
-            p.n_tiles = 1;
-            p.tile_batches = n_batches ? n_batches : 1;
-        }
-        const bool speculate = k == hrd::K_WBFM && p.n_tiles > 1;
-        if (speculate) { // verified speculation (hrd_rx.cu): pairs to compare, this call's flag
-            rc = ensure_cap(&b->d_wbv, &b->d_wbv_cap, sizeof(float2) * (size_t)p.n_streams * (size_t)p.n_tiles);
-            if (rc) return rc;
-            p.wb_verify = (float2 *)b->d_wbv;
-            HRD_CUDA(cudaMemsetAsync(b->d_wbflag, 0, 2 * sizeof(uint32_t), ks));
-        }
-        int e = hrd::launch_rx(k, entry, p, ks);
-        if (e) return fail(HRD_ECUDA, "rx launch (kind %d) failed: %s", k, cudaGetErrorString((cudaError_t)e));
-        b->launches++;
-        if (speculate) {
-            const int force = b->opt[HRD_OPT_DEBUG_WBFM_FORCE_RERUN];
-            const uint32_t tb2 = std::max<uint32_t>(4u, (n_batches + 15) / 16);
-            const int nt2 = (int)((n_batches + tb2 - 1) / tb2);
-            e = hrd::launch_rx_wbfm_verify(p, nullptr, 0, b->d_wbflag, b->d_wbrerun, b->d_wbguess, (unsigned long long *)(b->d_wbflag + 2),
-                                           nt2 >= 2 ? nullptr : (unsigned long long *)(b->d_wbflag + 4), force, ks);
-            if (e) return fail(HRD_ECUDA, "wbfm verify launch failed: %s", cudaGetErrorString((cudaError_t)e));
-            // SECOND PASS for the streams that failed: tiled again (finer, they are few), every tile >= 1 taking the
-            // TRUE value at the first check point as its recurrence value.  What fails in practice is a constant
-            // input: the recurrence then sits on one of several neighbouring fixed points of its rounded map and
-            // stays there, the warm-up from zero reaches another one, and no amount of warm-up brings them
-            // together -- but the value tile 0 saw is the value at every later check point as well.  The retry is
-            // verified like the first pass (each tile's value against the one the tile before it arrives at), so a
-            // wrong guess costs time only: what fails again is walked serially by the third launch.
-            hrd::RxParams again = p;
-            again.wb_verify = nullptr;
-            again.run_if = b->d_wbflag;
-            again.rerun_ids = b->d_wbrerun;
-            if (nt2 >= 2) { // (too short a call for two tiles: straight to the serial run)
-                hrd::RxParams retry = again;
-                retry.n_streams = std::min(p.n_streams, 512); // the part of the list it is sized for
-                retry.n_tiles = nt2;
-                retry.tile_batches = tb2;
-                rc = ensure_cap(&b->d_wbv2, &b->d_wbv2_cap, sizeof(float2) * (size_t)retry.n_streams * (size_t)nt2);
-                if (rc) return rc;
-                retry.wb_verify = (float2 *)b->d_wbv2;
-                retry.wb_guess = b->d_wbguess;
-                e = hrd::launch_rx(k, entry, retry, ks);
-                if (e) return fail(HRD_ECUDA, "wbfm retry launch failed: %s", cudaGetErrorString((cudaError_t)e));
-                e = hrd::launch_rx_wbfm_verify(retry, b->d_wbflag, p.n_streams, b->d_wbflag + 1, b->d_wbrerun + b->n, nullptr,
-                                               (unsigned long long *)(b->d_wbflag + 4), nullptr, force >= 2, ks);
-                if (e) return fail(HRD_ECUDA, "wbfm retry verify launch failed: %s", cudaGetErrorString((cudaError_t)e));
-                b->launches += 2;
-                again.run_if = b->d_wbflag + 1;
-                again.rerun_ids = b->d_wbrerun + b->n;
-            }
-            // the exact untiled run, from the untouched state_in; runs only for the streams still listed
-            again.n_tiles = 1;
-            again.tile_batches = n_batches;
-            e = hrd::launch_rx(k, entry, again, ks);
-            if (e) return fail(HRD_ECUDA, "wbfm re-run launch failed: %s", cudaGetErrorString((cudaError_t)e));
-            b->launches += 2;
-            p.wb_verify = nullptr;
-        }
         if (k == hrd::K_AM) {
             iir_p = p;
             iir = true;
             if (fan) { // the recurrence pass follows its tile kernel on the same stream, beside the other kinds
-                e = hrd::launch_rx_dc_iir(iir_p, ks);
+                int e = hrd::launch_rx_dc_iir(iir_p, ks);
                 if (e) return fail(HRD_ECUDA, "rx IIR launch failed: %s", cudaGetErrorString((cudaError_t)e));
                 b->launches++;
                 iir = false;

@@ -135,6 +135,28 @@ __device__ __forceinline__ void named_bar_arrive(int base, uint32_t parity, int 
         asm volatile("bar.arrive %0, %1;" ::"r"(base), "r"(threads) : "memory");
 }
 
+// the same with three ids per direction (rx_wbfm_kernel with three row buffers: ids base .. base + 2 by step mod 3)
+#define HRD_BAR3_PRODUCED 1
+#define HRD_BAR3_CHAINED 4
+__device__ __forceinline__ void named_bar_sync3(int base, uint32_t phase, int threads)
+{
+    if (phase == 0)
+        asm volatile("bar.sync %0, %1;" ::"r"(base), "r"(threads) : "memory");
+    else if (phase == 1)
+        asm volatile("bar.sync %0, %1;" ::"r"(base + 1), "r"(threads) : "memory");
+    else
+        asm volatile("bar.sync %0, %1;" ::"r"(base + 2), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive3(int base, uint32_t phase, int threads)
+{
+    if (phase == 0)
+        asm volatile("bar.arrive %0, %1;" ::"r"(base), "r"(threads) : "memory");
+    else if (phase == 1)
+        asm volatile("bar.arrive %0, %1;" ::"r"(base + 1), "r"(threads) : "memory");
+    else
+        asm volatile("bar.arrive %0, %1;" ::"r"(base + 2), "r"(threads) : "memory");
+}
+
 // ------------------------------------------------------------------------------------
 // the reference's C++ casts, restated for the GPU
 // ------------------------------------------------------------------------------------

@@ -34,6 +34,8 @@
 // Integer sections are bit-exact by construction (same Q15 arithmetic, same wrap-around);
 // float sections use the reference's operation order with FMA contraction disabled
 // (-fmad=false) and IEEE division.
+#include <type_traits>
+
 #include "hrd_device.cuh"
 
 #ifndef HRD_EXP
@@ -43,7 +45,10 @@
 #define HRD_RX_WB_ROLES 0 // rx_wbfm_kernel: 1 = chain on warp 31 / scheduler 3 with the fewest items (as tx_wbfm_kernel), 0 = behind the items
 #endif
 #ifndef HRD_RX_WB_DEP
-#define HRD_RX_WB_DEP 0 // rx_wbfm_kernel: transpose_after's scheduling dependency on (1) or off (0)
+#define HRD_RX_WB_DEP 1 // rx_wbfm_kernel: transpose_after's scheduling dependency on (1) or off (0)
+#endif
+#ifndef HRD_RX_WB_LDDEP
+#define HRD_RX_WB_LDDEP 1 // rx_wbfm_kernel: the refill load waits for the first transposition (offset_after)
 #endif
 
 namespace hrd {
@@ -122,6 +127,18 @@ __device__ __forceinline__ uint32_t transpose_after(uint32_t raw, uint32_t after
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, 0x3120;" : "=r"(d) : "r"(raw), "r"(after));
     return d;
+}
+
+// The same kind of dependency for the NEXT load's offset: selector 0x3210 returns `off` unchanged, but the load that
+// uses the result cannot be issued before `after` (a transposed word of the buffer being consumed) exists.  ptxas
+// renames the in-place refill to another register block and, left alone, hoists that LDG above the transpositions
+// of the old block -- onto the SAME counting scoreboard, so the first transposition then waits for the load that
+// was issued a few instructions earlier: a full memory latency, once per step (ncu: 12 % of rx_wbfm_kernel's warp
+// samples sat on that one PRMT).
+__device__ __forceinline__ uint32_t offset_after(uint32_t off, uint32_t after)
+{
+    asm("prmt.b32 %0, %0, %1, 0x3210;" : "+r"(off) : "r"(after));
+    return off;
 }
 
 // byte 2 of a and byte 2 of b into bytes 0,1 (the >>16 of the doubled-tap accumulators)
@@ -848,9 +865,26 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, HRD_RX_MIN_CTAS) rx_ga
 // step is HBM- or issue-bound on them).  Results are bit-identical to the serial evaluation:
 // same operations, same order, per stream.
 #ifndef HRD_WB_THREADS
-#define HRD_WB_THREADS 1024 // threads per CTA the kernel is compiled for: 1024 -> 64 registers, 800 -> 80
+#define HRD_WB_THREADS 896 // threads per CTA the kernel is compiled for: 896 -> 72 registers, 27 item warps + the chain warp = 7 warps on each of the four schedulers (1024 -> 64 registers; 28 items put 8 warps on one scheduler and ran 8 % slower per item)
 #endif
-constexpr int WB_ITEMS = HRD_WB_THREADS / 32 - 1;
+// Row buffers of the item-warp / chain-warp pipeline.  Two: an item warp can be one step ahead of the chain warp.
+// Three: two steps (28 rows each then, so that they still fit beside the atan2 table).
+#ifndef HRD_RX_WB_NBUF
+#define HRD_RX_WB_NBUF 2
+#endif
+constexpr int WB_NBUF = HRD_RX_WB_NBUF;
+// The item warps' front half: 1 = the wide form (four 256 kS/s samples per lane and iteration: 64-byte loads, one
+// neighbour shuffle per stage and per detector quantity for twice the samples; needs ~80 registers), 0 = the narrow
+// one (two samples per lane; fits 64 registers).
+#ifndef HRD_RX_WB_WIDE
+#define HRD_RX_WB_WIDE 0
+#endif
+constexpr bool WB_WIDE = HRD_RX_WB_WIDE != 0;
+constexpr int WB_IT = WB_WIDE ? IT_SAMPLES : IT_NARROW; // 256 kS/s samples per warp iteration
+constexpr int WB_SPL = WB_IT / 32;                        // ... per lane
+constexpr int WB_ROWS = WB_NBUF == 3 ? 28 : 32;
+constexpr int WB_ITEMS = WB_NBUF == 3 ? (HRD_WB_THREADS / 32 - 1 < WB_ROWS ? HRD_WB_THREADS / 32 - 1 : WB_ROWS) : HRD_WB_THREADS / 32 - 1;
+__device__ __forceinline__ uint32_t wb_buf(uint32_t t) { return WB_NBUF == 3 ? t % 3u : t & 1u; }
 constexpr int WB_STEP = 256;            // 256 kS/s samples per pipeline step (4 warp iterations)
 constexpr int WB_PITCH = WB_STEP + 4;   // floats per row
 
@@ -864,7 +898,7 @@ struct SmemWbItem {                    // int16 samples, two per word {x[2w], x[
 // the mixed 4096-stream batch: the re-run used to run BEHIND the AM and FM kernels, 2.95 ms per step).
 constexpr int WB_RERUN_ITEMS = 4;
 template <bool SMALL> struct SmemWbT {
-    float f[2][SMALL ? 8 : 32][WB_PITCH];
+    float f[WB_NBUF][SMALL ? 8 : WB_ROWS][WB_PITCH];
     SmemWbItem item[SMALL ? WB_RERUN_ITEMS : WB_ITEMS];
     // split taps of the 12-tap and the 40-tap decimator, by the lane's share of the taps (see consume)
     alignas(16) uint32_t t12[2][4];
@@ -883,7 +917,7 @@ typedef SmemWbT<false> SmemWb;
 template <int ENTRY, bool TILED, bool SMALL = false>
 __global__ void __launch_bounds__(SMALL ? (WB_RERUN_ITEMS + 1) * 32 : HRD_WB_THREADS, 1) rx_wbfm_kernel(const RxParams p)
 {
-    typedef typename RawNarrowOf<ENTRY>::type Raw;
+    typedef typename std::conditional<WB_WIDE, typename RawOf<ENTRY>::type, typename RawNarrowOf<ENTRY>::type>::type Raw;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // the exact re-run after a failed verification: only the streams the verifier listed
     // (p.n_streams bounds it: the tiled retry is sized for a part of the batch, what does not fit goes on to the serial run)
@@ -970,24 +1004,29 @@ __global__ void __launch_bounds__(SMALL ? (WB_RERUN_ITEMS + 1) * 32 : HRD_WB_THR
         // positive impulse response, and |x| <= pi * scale.  Below 2^31 the (int16_t) narrowing needs no
         // out-of-range patch (f32_to_i16).  NaN gains fail the test and take the patched path.
         narrow_fast = scale < 0x1p27f && fabsf(first ? st.wb_y1 : (TILED && p.wb_guess) ? p.wb_guess[slot] : 0.f) < 0x1p30f;
-        pf = (start + 2 * lane) * BPS;
-        pf_last = end >= 2 ? (end - 2) * BPS : 0u;
+        pf = (start + WB_SPL * lane) * BPS;
+        pf_last = end >= WB_SPL ? (end - WB_SPL) * BPS : 0u;
 #pragma unroll
         for (int d = 0; d < WB_DEPTH; d++) {
-            buf[d] = load_raw_narrow<ENTRY>(src, pf, pf_last);
-            pf += IT_NARROW * BPS;
+            if constexpr (WB_WIDE && ENTRY >= 0) buf[d] = load_raw<ENTRY>(src, pf, pf_last);
+            else buf[d] = load_raw_narrow<ENTRY>(src, pf, pf_last);
+            pf += WB_IT * BPS;
         }
     }
     __syncwarp();
 
     // one warp iteration: 64 samples at 256 kS/s -> 64 floats of the row (FIR half done)
-    auto iter = [&](Raw &b, float *dst) {
+    auto iter_narrow = [&](auto &b, float *dst) {
         uint32_t word;
         if constexpr (ENTRY == 0) {
             uint32_t t[8];
 #pragma unroll
             for (int r = 0; r < 8; r++) t[r] = transpose_after(b.v[r], sched_dep);
+#if HRD_RX_WB_LDDEP
+            b = load_raw_narrow<ENTRY>(src, offset_after(pf, t[0]), pf_last);
+#else
             b = load_raw_narrow<ENTRY>(src, pf, pf_last);
+#endif
             word = front_end_iter_narrow(t, fc, fk, lane);
 #if HRD_RX_WB_DEP
             sched_dep = word;
@@ -1038,20 +1077,88 @@ __global__ void __launch_bounds__(SMALL ? (WB_RERUN_ITEMS + 1) * 32 : HRD_WB_THR
         *reinterpret_cast<float2 *>(dst + 2 * lane) = o;
     };
 
+    // the same for four samples per lane: 128 samples at 256 kS/s -> 128 floats of the row
+    auto iter_wide = [&](auto &b, float *dst) {
+        uint2 words;
+        if constexpr (ENTRY == 0) {
+            uint32_t t[16];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                t[r] = transpose_after(b.a.v[r], sched_dep);
+                t[8 + r] = transpose_after(b.b.v[r], sched_dep);
+            }
+            b = load_raw<ENTRY>(src, pf, pf_last);
+            words = front_end_iter(t, fc, fk, lane);
+#if HRD_RX_WB_DEP
+            sched_dep = words.y;
+#endif
+        } else {
+            words = make_uint2(__byte_perm(b.x, 0, 0x3120), __byte_perm(b.y, 0, 0x3120));
+            b = load_raw<ENTRY>(src, pf, pf_last);
+        }
+        pf += IT_SAMPLES * BPS;
+        // theta = atan2LookupTable[(uint8_t)Q + 128][(uint8_t)I + 128]  (WbFmDemodulator.cc:403-406), as in iter_narrow
+        auto lut_at = [&](int aq, int col) {
+            if constexpr (SMALL) return aq < 128 ? __ldg(p.atan2_lut + (128 + aq) * 256 + col) : -__ldg(p.atan2_lut + col);
+            else return sm.lut[aq * 256 + col];
+        };
+        float th[4];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t word = h ? words.y : words.x;
+            int q0, q1;
+            asm("prmt.b32 %0, %1, 0, 0xaaa2;" : "=r"(q0) : "r"(word));
+            asm("prmt.b32 %0, %1, 0, 0xbbb3;" : "=r"(q1) : "r"(word));
+            const uint32_t x = word ^ 0x00008080u;
+            const float a0 = lut_at(abs(q0), (int)(x & 0xffu));
+            const float a1 = lut_at(abs(q1), (int)__byte_perm(x, 0, 0x4441));
+            th[2 * h] = __int_as_float(__float_as_int(a0) ^ (q0 & (int)0x80000000));
+            th[2 * h + 1] = __int_as_float(__float_as_int(a1) ^ (q1 & (int)0x80000000));
+        }
+        const float sel = (lane == 31) ? th_keep : th[3];
+        const float thp = __shfl_sync(HRD_FULL_MASK, sel, (lane + 31) & 31);
+        float m[4], v3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float d = wrap_pi_select(__fsub_rn(th[i], i ? th[i - 1] : thp));
+            const float v = __fmul_rn(scale, d);
+            m[i] = __fmul_rn(0.0253863f, v); // FirFilter::filterData, b0 == b1: see iter_narrow
+            if (i == 3) v3 = v;
+        }
+        const float selm = (lane == 31) ? m_keep : m[3];
+        const float mp = __shfl_sync(HRD_FULL_MASK, selm, (lane + 31) & 31);
+        th_keep = th[3];
+        v_keep = v3;
+        m_keep = m[3];
+        float4 o;
+        o.x = __fadd_rn(m[0], mp);
+        o.y = __fadd_rn(m[1], m[0]);
+        o.z = __fadd_rn(m[2], m[1]);
+        o.w = __fadd_rn(m[3], m[2]);
+        *reinterpret_cast<float4 *>(dst + 4 * lane) = o;
+    };
+    auto iter = [&](Raw &b, float *dst) {
+        if constexpr (WB_WIDE && ENTRY >= 0) iter_wide(b, dst); // (a dependent condition: the other form is not instantiated)
+        else iter_narrow(b, dst);
+    };
+
     // step t of this item: samples [start + t*WB_STEP, ...) -> row of buffer t&1
     auto produce = [&](uint32_t t) {
         const uint32_t done = start + t * WB_STEP;
         if (done >= end) return;
         const uint32_t nb = min((uint32_t)WB_STEP, end - done);
-        const uint32_t n_it = (nb + IT_NARROW - 1) / IT_NARROW;
-        last_active = min(32u, (nb - (n_it - 1) * IT_NARROW) / 2);
-        if constexpr (ENTRY == 0) prefetch_chunk_narrow(src, pf, pf_last, lane); // a step is four iterations = 4 KiB
-        float *dst = sm.f[t & 1][row];
-        if (n_it == WB_STEP / IT_NARROW) { // a full step, unrolled: the in-place refill of buf needs no register moves
+        const uint32_t n_it = (nb + WB_IT - 1) / WB_IT;
+        last_active = min(32u, (nb - (n_it - 1) * WB_IT) / WB_SPL);
+        if constexpr (ENTRY == 0) { // a step is 4 KiB: lane l pulls its line l, one step ahead (pf = the lane's own next offset)
+            if constexpr (WB_WIDE) prefetch_l2(src + min(pf + 64u * (uint32_t)lane + RX_L2_AHEAD * 1024u, pf_last));
+            else prefetch_chunk_narrow(src, pf, pf_last, lane);
+        }
+        float *dst = sm.f[wb_buf(t)][row];
+        if (n_it == WB_STEP / WB_IT) { // a full step, unrolled: the in-place refill of buf needs no register moves
 #pragma unroll
-            for (uint32_t i = 0; i < WB_STEP / IT_NARROW; i++) iter(buf[i % WB_DEPTH], dst + i * IT_NARROW);
+            for (uint32_t i = 0; i < WB_STEP / WB_IT; i++) iter(buf[i % WB_DEPTH], dst + i * WB_IT);
         } else {
-            for (uint32_t i = 0; i < n_it; i++) iter(buf[i % WB_DEPTH], dst + i * IT_NARROW);
+            for (uint32_t i = 0; i < n_it; i++) iter(buf[i % WB_DEPTH], dst + i * WB_IT);
         }
         __syncwarp();
     };
@@ -1065,7 +1172,7 @@ __global__ void __launch_bounds__(SMALL ? (WB_RERUN_ITEMS + 1) * 32 : HRD_WB_THR
         const int nb = (int)min((uint32_t)WB_STEP, end - done); // multiple of 32
         const int nl = nb >> 3;                                   // live lanes, a multiple of 4
         last_nl = nl;
-        const float *y = sm.f[t & 1][row] + 8 * lane;             // lanes >= nl read stale floats and store nothing
+        const float *y = sm.f[wb_buf(t)][row] + 8 * lane;         // lanes >= nl read stale floats and store nothing
         const float4 ya = *reinterpret_cast<const float4 *>(y), yb = *reinterpret_cast<const float4 *>(y + 4);
         const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
         int v[8];
@@ -1139,7 +1246,7 @@ __global__ void __launch_bounds__(SMALL ? (WB_RERUN_ITEMS + 1) * 32 : HRD_WB_THR
         const uint32_t done = start + t * WB_STEP;
         if (done >= end) return;
         const uint32_t nb = min((uint32_t)WB_STEP, end - done); // multiple of 32
-        float *r = sm.f[t & 1][lane];
+        float *r = sm.f[wb_buf(t)][lane];
         // (All eight loads of a 32-sample round first.  Reading the row a few groups AHEAD of its use instead was
         // measured and lost: ptxas puts every shared-memory load of the loop on one counting scoreboard, so the
         // consumer of an old load also waits for the one just issued -- a full load latency per group of four
@@ -1181,7 +1288,34 @@ __global__ void __launch_bounds__(SMALL ? (WB_RERUN_ITEMS + 1) * 32 : HRD_WB_THR
     // they narrow that step.  No item warp ever waits for another item warp's consume, so a slow warp
     // costs the CTA nothing as long as it keeps within a step of the others.
     const int bar_threads = (p.items_per_cta + 1) * 32;
-    if (chain_warp) {
+    if constexpr (WB_NBUF == 3) { // three row buffers: the item warps run up to two steps ahead of the chain warp
+        if (chain_warp) {
+            for (uint32_t t = 0; t < n_steps; t++) {
+                named_bar_sync3(HRD_BAR3_PRODUCED, t % 3u, bar_threads);
+#if !(HRD_EXP & 1)
+                if (live) chain(t);
+#endif
+                named_bar_arrive3(HRD_BAR3_CHAINED, t % 3u, bar_threads);
+            }
+        } else {
+            if (live) produce(0);
+            named_bar_arrive3(HRD_BAR3_PRODUCED, 0, bar_threads);
+            if (n_steps > 1) {
+                if (live) produce(1);
+                named_bar_arrive3(HRD_BAR3_PRODUCED, 1, bar_threads);
+            }
+            for (uint32_t t = 0; t < n_steps; t++) {
+                if (t + 2 < n_steps) {
+                    if (live) produce(t + 2); // into the buffer this warp drained in consume(t - 1)
+                    named_bar_arrive3(HRD_BAR3_PRODUCED, (t + 2) % 3u, bar_threads);
+                }
+                named_bar_sync3(HRD_BAR3_CHAINED, t % 3u, bar_threads);
+#if !(HRD_EXP & 2)
+                if (live) consume(t);
+#endif
+            }
+        }
+    } else if (chain_warp) {
         for (uint32_t t = 0; t < n_steps; t++) {
             named_bar_sync(HRD_BAR_PRODUCED, t, bar_threads);
 #if !(HRD_EXP & 1)
