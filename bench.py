@@ -271,7 +271,7 @@ def bench_rx_modes(torch, capi, device, groups, n_samples, steps, warmup, seed, 
     res = {"ms": ms_step, "kernel_ms": sum(b.kernel_ms(0, a) for a in range(k)) / k,
            "tail_ms": sum(b.kernel_ms(1, a) for a in range(k)) / k, "launches": launches,
            "repeat_mismatches": repeats_identical(torch, pcm, layout),
-           "wbfm_fallbacks": b.wbfm_fallback_count()}
+           "wbfm_fallbacks": b.wbfm_fallback_count(), "wbfm_serial": b.wbfm_serial_count()}
     if serial_pass:
         b.set_option(capi.OPT_RX_SERIAL, 1)
         for _ in range(4):
@@ -397,6 +397,7 @@ def run_ours(args):
         "roofline": roofline, "gpu_launches": r["launches"] * args.steps * world,
         "call_ms": {"tile_kernels": round(r["kernel_ms"], 4), "iir_tail": round(r["tail_ms"], 4)},
         "repeat_mismatches": r["repeat_mismatches"], "wbfm_tile_fallback_streams": r["wbfm_fallbacks"],
+        "wbfm_serial_rerun_streams": r["wbfm_serial"],
     }
     if clocks:
         out["clocks"] = clocks

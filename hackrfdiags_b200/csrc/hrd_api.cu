@@ -1044,7 +1044,7 @@ static int run_demods(hrd_batch_t *b, hrd::RxParams &p, int entry, uint32_t n_ba
                     p.tile_batches = n_batches ? n_batches : 1;
                 }
             }
-            const bool speculate = k == hrd::K_WBFM && p.n_tiles > 1;
+        const bool speculate = k == hrd::K_WBFM && p.n_tiles > 1;
             if (speculate) { // verified speculation (hrd_rx.cu): pairs to compare, this call's flag
                 rc = ensure_cap(&b->d_wbv, &b->d_wbv_cap, sizeof(float2) * (size_t)p.n_streams * (size_t)p.n_tiles);
                 if (rc) return rc;
@@ -1056,7 +1056,8 @@ static int run_demods(hrd_batch_t *b, hrd::RxParams &p, int entry, uint32_t n_ba
             b->launches++;
             if (speculate) {
                 const int force = b->opt[HRD_OPT_DEBUG_WBFM_FORCE_RERUN];
-                const uint32_t tb2 = std::max<uint32_t>(4u, (n_batches + 15) / 16);
+                // (short tiles: the retry is a handful of streams, its time is the LENGTH of a tile)
+            const uint32_t tb2 = std::max<uint32_t>(3u, (n_batches + 31) / 32);
                 const int nt2 = (int)((n_batches + tb2 - 1) / tb2);
                 e = hrd::launch_rx_wbfm_verify(p, nullptr, 0, b->d_wbflag, b->d_wbrerun, b->d_wbguess, (unsigned long long *)(b->d_wbflag + 2),
                                                nt2 >= 2 ? nullptr : (unsigned long long *)(b->d_wbflag + 4), force, ks);

@@ -966,6 +966,13 @@ __global__ void __launch_bounds__(SMALL ? (WB_RERUN_ITEMS + 1) * 32 : HRD_WB_THR
     // ---- chain warp state ----------------------------------------------------------------
     float y1 = 0.f;
     if (chain_warp && live && first) y1 = st.wb_y1;
+    // A later tile's HINT: the value the call started from.  A stream that has been silent (discriminator output
+    // exactly zero) since before the call sits on a vanishing value -- a denormal the rounded recurrence no longer
+    // shrinks, or zero; a tile's warm-up from zero histories begins with a start transient and is still on that
+    // transient's tail (~1e-22) at the check point: different bits in every call, although both are nothing.
+    // When the hint vanishes and the warmed-up value is that small, the tile takes the hint.  (Any value may be
+    // tried at the check point: the verification decides, so this costs time at worst.)
+    const float y_hint = (TILED && chain_warp && live && !first) ? st.wb_y1 : 1.f;
 
     // ---- item warp state -----------------------------------------------------------------
     SmemWbItem &it = sm.item[chain_warp || !member ? 0 : item_of_warp];
@@ -1269,6 +1276,7 @@ __global__ void __launch_bounds__(SMALL ? (WB_RERUN_ITEMS + 1) * 32 : HRD_WB_THR
             const uint32_t pos = done + nb;
             if (tile >= 1 && pos == start + BATCH256) {
                 if (p.wb_guess) y1 = p.wb_guess[slot]; // the retry: a given value instead of the warmed-up one
+                else if (fabsf(y_hint) < 0x1p-100f && fabsf(y1) < 0x1p-60f) y1 = y_hint;
                 p.wb_verify[(size_t)slot * p.n_tiles + tile].x = y1;
             }
             if (tile + 1 < p.n_tiles && pos == end - BATCH256) p.wb_verify[(size_t)slot * p.n_tiles + tile + 1].y = y1;

@@ -27,7 +27,7 @@ if kind == "rx":
         groups = [(mode, n)]
     r, keep = bench.bench_rx_modes(torch, capi, dev, groups, n_samples, reps, 1, seed=5)
     ms = r["ms"]
-    print(f"tile kernel {r['kernel_ms']:.3f} ms, tail {r['tail_ms']:.3f} ms")
+    print(f"tile kernel {r['kernel_ms']:.3f} ms, tail {r['tail_ms']:.3f} ms, wbfm fallbacks {r['wbfm_fallbacks']} serial {r['wbfm_serial']} in {reps + 1} calls")
 else:
     ms = bench.bench_tx_mode(torch, capi, dev, mode, n, n_samples // 256, reps, 1, seed=5)
 torch.cuda.synchronize()

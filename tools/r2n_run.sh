@@ -1,2 +1,2 @@
 #!/bin/bash
-timeout 300 python tools/rem_probe.py 2>&1 | tail -25
+timeout 900 python -m pytest tests/test_gpu_parity_small.py tests/test_gpu_full_size.py tests/test_gpu_squelch.py -x -q 2>&1 | tail -12
