@@ -454,11 +454,30 @@ def run_e2e(torch, capi, device, args, groups, n_samples, dist):
     dt = (time.perf_counter() - t0) / steps
     dt = reduce_max_ms(torch, dist, device, [dt])[0]
     value = world * n_streams * n_samples / dt / 1e6
+    # the platform's ceiling for this step: the same pinned buffer copied to the device by a plain cudaMemcpyAsync
+    # and nothing else, every rank at the same time (the host side -- root complexes, memory channels -- is shared)
+    del b
+    dev_iq = torch.empty(host_iq.shape, dtype=torch.int8, device=device)
+    dev_iq.copy_(host_iq, non_blocking=True)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        dev_iq.copy_(host_iq, non_blocking=True)
+    torch.cuda.synchronize()
+    dt_copy = (time.perf_counter() - t0) / steps
+    dt_copy = reduce_max_ms(torch, dist, device, [dt_copy])[0]
+    del dev_iq
     return {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": host_iq.numel() * world,
             "d2h_bytes_per_step": host_pcm.numel() * 2 * world, "ms_per_step": round(dt * 1e3, 3), "steps": steps,
             "h2d_gbs_per_gpu": round(host_iq.numel() / dt / 1e9, 2),
+            "platform_h2d_gbs_per_gpu": round(host_iq.numel() / dt_copy / 1e9, 2),
+            "of_platform_ceiling": round(dt_copy / dt, 4),
             "note": "hrd_rx_process(HRD_MEM_HOST) on pinned host buffers, one call per step per GPU, copies inside "
-                    "the call; whole job = all ranks, slowest rank's wall time; bound by PCIe H2D (2 B per IQ sample)"}
+                    "the call; whole job = all ranks, slowest rank's wall time; bound by PCIe H2D (2 B per IQ sample). "
+                    "platform_h2d_gbs_per_gpu = the same buffers through a bare cudaMemcpyAsync on all ranks at once: "
+                    "what this box's host side delivers per GPU at this N"}
 
 
 # ----------------------------------------------------------------------------------------

@@ -18,6 +18,10 @@
 //   hrd_replay rx <am|fm|wbfm|lsb|usb> [-s squelch_dBFS] [-g demod_gain] <out_dir> <file.iq>...   -> <out_dir>/<name>.pcm
 //   hrd_replay fe <out_dir> <file.iq>...                                                           -> <out_dir>/<name>.iq256k
 //   hrd_replay tx <am|fm|wbfm|lsb|usb|dsb|pm|amproto|fmproto> [-p index_or_deviation] <out_dir> <file.pcm>...      -> <out_dir>/<name>.iq
+// -l <blocks> (rx, fe): LOOP replay, DataProvider's way (src_diags/DataProvider.cc:230-286 loadIqFile, :163-212
+// retrieveIqDataFromBuffer): every file is read whole into a ring and handed out 262144 bytes at a time modulo its
+// length -- a block may straddle the end of the file, files of any (even odd) length keep their own phase -- for
+// exactly <blocks> rounds.
 // There is no CPU fallback: without a B200 hrd_create fails and so does this program.
 #include <stdint.h>
 #include <stdio.h>
@@ -60,6 +64,8 @@ static std::string out_name(const std::string &dir, const char *path, const char
 
 struct Stream {
     FILE *in = nullptr, *out = nullptr;
+    std::vector<char> ring; // -l: the whole file (iqSampleBufferPtr)
+    size_t ring_at = 0;     //     iqSampleBufferIndex
     long left = 0; // input units (bytes for rx/fe, PCM samples for tx) still to read
     bool live = true;
 };
@@ -77,16 +83,19 @@ int main(int argc, char **argv)
     const int mode = fe ? HRD_MODE_NONE : mode_of(argv[a++], tx);
     float squelch = -200.f, gain = 0.f, param = 0.f;
     bool have_gain = false, have_param = false;
+    long loop_blocks = 0;
     while (a + 1 < argc && argv[a][0] == '-' && argv[a][1] && !argv[a][2]) {
         const char opt = argv[a][1];
         const float v = (float)atof(argv[a + 1]);
         if (opt == 's') squelch = v;
         else if (opt == 'g') gain = v, have_gain = true;
         else if (opt == 'p') param = v, have_param = true;
+        else if (opt == 'l') loop_blocks = atol(argv[a + 1]);
         else return fprintf(stderr, "hrd_replay: unknown option -%c\n", opt), 2;
         a += 2;
     }
     if (argc - a < 2) return fprintf(stderr, "hrd_replay: need an output directory and at least one file\n"), 2;
+    if (loop_blocks < 0 || (loop_blocks && tx)) return fprintf(stderr, "hrd_replay: -l takes a block count, with rx or fe\n"), 2;
     const std::string dir = argv[a++];
     const int n = argc - a;
     const long unit = tx ? 1 : 512;              // a whole PCM sample
@@ -100,6 +109,15 @@ int main(int argc, char **argv)
         fseek(st[(size_t)i].in, 0, SEEK_END);
         st[(size_t)i].left = ftell(st[(size_t)i].in) / (long)in_elem / unit * unit;
         fseek(st[(size_t)i].in, 0, SEEK_SET);
+        if (loop_blocks) { // DataProvider::loadIqFile: the whole file, every byte of it
+            Stream &s = st[(size_t)i];
+            fseek(s.in, 0, SEEK_END);
+            s.ring.resize((size_t)ftell(s.in));
+            fseek(s.in, 0, SEEK_SET);
+            if (s.ring.empty() || fread(s.ring.data(), 1, s.ring.size(), s.in) != s.ring.size())
+                return fprintf(stderr, "hrd_replay: cannot load %s\n", argv[a + i]), 1;
+            s.left = block; // never runs out
+        }
         const std::string o = out_name(dir, argv[a + i], tx ? ".iq" : (fe ? ".iq256k" : ".pcm"));
         st[(size_t)i].out = fopen(o.c_str(), "wb");
         if (!st[(size_t)i].out) return perror(o.c_str()), 1;
@@ -133,11 +151,19 @@ int main(int argc, char **argv)
                 if (s.left < unit) s.live = false;
                 else len = std::min(len, s.left), running++;
             }
-        if (!running) break;
+        if (!running || (loop_blocks && (long)rounds >= loop_blocks)) break;
         for (int i = 0; i < n; i++) {
             Stream &s = st[(size_t)i];
             char *row = in.data() + (size_t)i * in_stride;
-            if (s.live) {
+            if (loop_blocks) { // DataProvider::retrieveIqDataFromBuffer
+                size_t todo = (size_t)len;
+                while (todo) {
+                    const size_t part = std::min(todo, s.ring.size() - s.ring_at);
+                    memcpy(row + ((size_t)len - todo), s.ring.data() + s.ring_at, part);
+                    todo -= part;
+                    s.ring_at = (s.ring_at + part) % s.ring.size();
+                }
+            } else if (s.live) {
                 if (fread(row, in_elem, (size_t)len, s.in) != (size_t)len) return fprintf(stderr, "hrd_replay: short read on %s\n", argv[a + i]), 1;
                 s.left -= len;
             } else {

@@ -70,3 +70,23 @@ def test_tx_files(tmp_path, mode, name):
     for i, p in enumerate(paths):
         pcm = np.fromfile(p, dtype=np.int16)
         assert np.array_equal(np.fromfile(out / f"voice{i}.iq", dtype=np.int8), oracle.run_tx(mode, pcm)), f"file {i}"
+
+
+def test_rx_loop_replay_the_data_providers_way(tmp_path):
+    """-l: every file is a ring handed out 262144 bytes at a time modulo its length (DataProvider.cc:163-212,
+    230-286): blocks straddle the end of the file, an odd-length file swaps I and Q on every lap."""
+    oracle = Oracle()
+    sizes = [BLOCK + 1000, 70001, 3 * BLOCK]
+    paths = []
+    for i, size in enumerate(sizes):
+        p = tmp_path / f"loop{i}.iq"
+        synth.rx_stream(capi.MODE_AM, (size + 1) // 2, stream=i, config=14)[:size].tofile(p)
+        paths.append(p)
+    out = tmp_path / "out"
+    out.mkdir()
+    blocks = 5
+    _run("rx", "am", "-l", blocks, out, *paths)
+    for i, p in enumerate(paths):
+        looped = np.resize(np.fromfile(p, dtype=np.int8), blocks * BLOCK)  # cyclic repetition
+        got = np.fromfile(out / f"loop{i}.pcm", dtype=np.int16)
+        assert np.array_equal(got, oracle.run_rx(capi.MODE_AM, looped)), f"file {i}"

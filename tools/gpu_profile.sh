@@ -22,7 +22,7 @@ for chain in ${CHAINS:-rx_mix rx_iir rx_fm rx_wbfm tx_am tx_fm tx_lsb tx_wbfm}; 
     rx_mix)  cap rx_mix  'rx_kernel'  2 rx mix 1024 1.0 3 ;;
     rx_iir)  cap rx_iir  'rx_dc_iir'  2 rx mix 1024 1.0 3 ;;
     rx_fm)   cap rx_fm   'rx_kernel'  2 rx fm 4096 0.5 3 ;;
-    rx_wbfm) cap rx_wbfm 'rx_kernel|rx_wbfm'  2 rx wbfm 4096 0.25 3 ;;
+    rx_wbfm) cap rx_wbfm 'rx_wbfm_kernel'  2 rx wbfm 3996 0.25 3 ;; # 27 x 148 streams: one untiled launch per call
     tx_am)   cap tx_am   'tx_kernel'  2 tx am 4096 0.25 3 ;;
     tx_fm)   cap tx_fm   'tx_kernel'  2 tx fm 4096 0.25 3 ;;
     tx_lsb)  cap tx_lsb  'tx_kernel'  2 tx lsb 4096 0.25 3 ;;
