@@ -78,26 +78,32 @@ if os.path.exists(bpath):
     bench = json.load(open(bpath))
     json.dump(bench, open(os.path.join(P, f"{TAG}_bench.json"), "w"), indent=1)
 
-# traffic of the dominant kernel ----------------------------------------------------------
-mix = os.path.join(G, f"{TAG}_rx_mix.ncu-rep")
-if os.path.exists(mix):
-    row, units = raw(mix)
+# traffic of the three Rx kernel kinds (bench.py picks the dominant one's entry) ----------------
+traffic = {}
+for chain, key, streams, sps, what in (
+        ("rx_mix", "rx_kernel<AM+SSB, 2048k entry>", 1024, FS, "1024 streams (512 AM + 256 LSB + 256 USB) x 1.000 s"),
+        ("rx_fm", "rx_kernel<FM, 2048k entry>", 4096, FS // 2 // 8192 * 8192, "4096 NBFM streams x 0.5 s"),
+        ("rx_wbfm", "rx_wbfm_kernel<2048k entry>", 3996, FS // 4 // 8192 * 8192, "3996 WBFM streams x 0.25 s (27 per SM, one untiled launch)")):
+    path = os.path.join(G, f"{TAG}_{chain}.ncu-rep")
+    if not os.path.exists(path):
+        continue
+    row, units = raw(path)
     rd, wr = num(row, units, "dram__bytes_read.sum"), num(row, units, "dram__bytes_write.sum")
-    json.dump({"rx_kernel<AM+SSB,2048k>": {
-        "workload": "bench.py default: 1024 streams (512 AM + 256 LSB + 256 USB) x 1.000 s, 2.048 MS/s entry",
-        "streams": 1024, "samples_per_stream": FS, "dram_bytes_per_launch": int(rd + wr),
-        "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
-        "algorithmic_bytes_per_launch": int(1024 * FS * 2.0078125),
-        "source": f"profiles/{TAG}_ncu_summary.txt (ncu --set full --clock-control none, gpurun_out/{TAG}_rx_mix.ncu-rep): "
-                  "dram__bytes_read.sum + dram__bytes_write.sum",
+    traffic[key] = {
+        "workload": what + ", 2.048 MS/s entry", "streams": streams, "samples_per_stream": sps,
+        "dram_bytes_per_launch": int(rd + wr), "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
+        "algorithmic_bytes_per_launch": int(streams * sps * 2.0078125),
+        "source": f"profiles/{TAG}_ncu_summary.txt (ncu --set full --clock-control none, gpurun_out/{TAG}_{chain}.ncu-rep): "
+                  "dram__bytes_read.sum + dram__bytes_write.sum; bench.py scales it by the unit count of its own launch",
         "note": "above the algorithmic bytes by the halo batches time tiles after the first re-read, the float scratch of "
-                "the DC-removal IIR (4 B per PCM sample each way) and the state records"}},
-        open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
+                "the DC-removal IIR (AM/SSB: 4 B per PCM sample each way) and the state records"}
+if traffic:
+    json.dump(traffic, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
 
 # README ----------------------------------------------------------------------------------
 work = {"rx_mix": ("rx_kernel<AM+SSB,2048k>", 1024 * FS), "rx_iir": ("rx_dc_iir_kernel", 1024 * FS),
         "rx_fm": ("rx_kernel<FM,2048k>", 4096 * (FS // 2 // 8192 * 8192)),
-        "rx_wbfm": ("rx_wbfm_kernel<2048k>", 4096 * (FS // 4 // 8192 * 8192)),
+        "rx_wbfm": ("rx_wbfm_kernel<2048k>", 3996 * (FS // 4 // 8192 * 8192)),
         "tx_am": ("tx_kernel<AM>", 4096 * (FS // 4 // 8192 * 8192)), "tx_fm": ("tx_kernel<FM>", 4096 * (FS // 4 // 8192 * 8192)),
         "tx_lsb": ("tx_kernel<SSB>", 4096 * (FS // 4 // 8192 * 8192)), "tx_wbfm": ("tx_wbfm_kernel", 4096 * (FS // 4 // 8192 * 8192))}
 peak = 6549.8
@@ -105,7 +111,7 @@ try:
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     pass
-md = [f"# profiles/ — ncu evidence, round 1 (session `{TAG}`)", "",
+md = [f"# profiles/ — ncu evidence, round 2 (session `{TAG}`; round 1's files `r1w_*` are kept beside it)", "",
       "B200 (148 SMs, 1965 MHz, no throttle reasons), `ncu --set full --clock-control none --import-source on`, one capture",
       "per chain of the launch after warm-up (`tools/gpu_profile.sh`, `tools/prof_run.py`); summaries made here with",
       "`tools/make_profiles.py` from the `.ncu-rep` files (which stay in `gpurun_out/`). Durations under ncu are",
@@ -142,20 +148,26 @@ for r in reps:
               f"{float(g('sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active')):.0f} / "
               f"{float(g('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active')):.0f} | "
               f"{inst * 32 / samples:.1f} | " + ", ".join(f"{n} {v:.2f}" for v, n in stalls[:3]) + " |")
-md += ["", "Reading: every chain issues 6–13 lane-operations per IQ sample against a ceiling of 11.4 at the HBM roofline, so the",
-       "kernels are instruction-issue-bound (issue slots 70–85 % busy, `math_pipe_throttle`/`not_selected` the top stalls, DRAM",
-       "28–65 %); DRAM traffic is within a few percent of the algorithmic bytes, i.e. nothing is re-read except tile halos.", ""]
+md += ["", "Reading: every chain issues 8–15 lane-operations per IQ sample against a ceiling of 11.4 at the HBM roofline, so the",
+       "kernels are instruction-issue-bound (issue slots 70–90 % busy, `math_pipe_throttle`/`not_selected` the top stalls, DRAM",
+       "45–77 %); DRAM traffic is within a few percent of the algorithmic bytes, i.e. nothing is re-read except tile halos.",
+       "What changed against round 1 and the experiments behind it: `r2_experiments.md`.", ""]
 if launch_txt:
     md += ["## Launch list (`" + f"{TAG}_launches.txt" + "`)", "", "```", launch_txt.rstrip(), "```", ""]
 if bench:
+    rf = bench["roofline"]
     md += ["## Bench of the same build (`" + f"{TAG}_bench.json" + "`, CUDA events, not under ncu)", "",
-           f"* headline (config 2, 1024 streams × 1 s): **{bench['value'] / 1e6:.3f} T samples/s**, {bench['ms_per_step']} ms/step; dominant kernel "
-           f"{bench['roofline']['achieved']} GB/s algorithmic = **{bench['roofline']['frac']:.3f} of measured HBM peak**; tile kernel "
-           f"{bench['call_ms']['tile_kernel']} ms + IIR tail {bench['call_ms']['iir_tail']} ms per step (share "
-           f"{100 * bench['call_ms']['tile_kernel'] / (bench['call_ms']['tile_kernel'] + bench['call_ms']['iir_tail']):.1f} % / "
-           f"{100 * bench['call_ms']['iir_tail'] / (bench['call_ms']['tile_kernel'] + bench['call_ms']['iir_tail']):.1f} %, compare the launch list)",
-           f"* end to end through the C ABI from pinned host memory: {bench['e2e']['value']:.0f} MS/s (PCIe-bound: 2 B per sample in)",
-           f"* CPU reference in the same run: {bench.get('cpu_baseline', {}).get('value')} MS/s on {bench.get('cpu_baseline', {}).get('cores')} host threads", "",
+           f"* headline (config 5: the mixed-mode batch, 4096 streams × 0.5 s: 1/4 AM, 1/4 NBFM, 1/4 WBFM, 1/8 LSB, 1/8 USB): "
+           f"**{bench['value'] / 1e6:.3f} T samples/s**, {bench['ms_per_step']} ms/step = **{rf['step']['frac']:.3f} of the measured HBM peak for the whole step**; "
+           f"the kinds run side by side; each kind's own launch (serialised pass): "
+           + "; ".join(f"`{k}` {v['streams']} streams {v['launch_ms']} ms = {v['frac']:.3f}" for k, v in rf["kinds"].items()),
+           f"* dominant kernel `{rf['kernel']}`: {rf['achieved']} GB/s algorithmic = **{rf['frac']:.3f}**; DRAM traffic {rf.get('traffic')} B per launch "
+           f"against {int(rf['algorithmic_bytes_per_launch'])} algorithmic",
+           f"* end to end through the C ABI from pinned host memory: {bench['e2e']['value']:.0f} MS/s = {bench['e2e'].get('of_platform_ceiling')} of the box's own "
+           f"H2D ceiling ({bench['e2e'].get('platform_h2d_gbs_per_gpu')} GB/s; 2 B per sample in)",
+           f"* CPU reference in the same run: {bench.get('cpu_baseline', {}).get('value')} MS/s on {bench.get('cpu_baseline', {}).get('cores')} host threads",
+           f"* mixed-mode stream sweep (fraction of the HBM roofline): " + ", ".join(f"{k}: {v['hbm_frac_per_gpu']}" for k, v in bench.get("mixed_mode_stream_sweep", {}).items()),
+           f"* WBFM verification: {bench.get('wbfm_tile_fallback_streams')} stream-calls retried, {bench.get('wbfm_serial_rerun_streams')} walked serially in the timed run", "",
            "| chain (4096 streams × 0.5 s) | MS/s | ms | fraction of HBM roofline (of measured) |", "|---|---|---|---|"]
     for k, v in bench.get("modes", {}).items():
         md.append(f"| {k} | {v['MS/s']:.0f} | {v['ms']} | {v['hbm_frac']:.3f} |")
