@@ -32,7 +32,7 @@ EXPORTS = [
     "hrd_abi_version", "hrd_create", "hrd_destroy", "hrd_last_error", "hrd_set_mode", "hrd_get_mode",
     "hrd_set_param", "hrd_get_param", "hrd_reset", "hrd_set_option", "hrd_get_option", "hrd_rx_process", "hrd_rx_front_end", "hrd_rx_squelch_report", "hrd_rx_fs4_rotate", "hrd_tx_process",
     "hrd_pcm_ring_create", "hrd_pcm_ring_destroy", "hrd_pcm_ring_start", "hrd_pcm_ring_write", "hrd_pcm_ring_read_all",
-    "hrd_pcm_ring_stats", "hrd_tx_from_ring", "hrd_iq_queue_create", "hrd_iq_queue_destroy", "hrd_iq_queue_push",
+    "hrd_pcm_ring_stats", "hrd_tx_from_ring", "hrd_iq_queue_create", "hrd_iq_queue_destroy", "hrd_iq_queue_push", "hrd_iq_queue_push_rows",
     "hrd_iq_queue_pop_all", "hrd_iq_queue_stats", "hrd_rx_from_queue",
     "hrd_rx_pipe_create", "hrd_rx_pipe_destroy", "hrd_rx_pipe_submit", "hrd_rx_pipe_collect", "hrd_rx_pipe_stats",
     "hrd_tx_pipe_create", "hrd_tx_pipe_destroy", "hrd_tx_pipe_submit", "hrd_tx_pipe_collect",

@@ -269,6 +269,18 @@ int hrd_iq_queue_push(hrd_iq_queue_t *q, int stream, uint32_t time_stamp, const 
     return HRD_OK;
 }
 
+// One transfer of each of `count` consecutive streams (a receive thread that serves several radios): row i is the
+// block of stream first + i.  The same as `count` hrd_iq_queue_push calls.
+int hrd_iq_queue_push_rows(hrd_iq_queue_t *q, int first, int count, uint32_t time_stamp, const void *rows, size_t row_stride, uint32_t bytes)
+{
+    if (!q || first < 0 || count < 0 || first + count > q->n || !rows) return HRD_EINVAL;
+    for (int i = 0; i < count; i++) {
+        const int rc = hrd_iq_queue_push(q, first + i, time_stamp, (const char *)rows + (size_t)i * row_stride, bytes);
+        if (rc) return rc;
+    }
+    return HRD_OK;
+}
+
 // the consumer thread's dequeue (:319-351) for a whole round: returns 1 and one block per stream when every
 // stream has one queued, 0 (and takes nothing) otherwise
 int hrd_iq_queue_pop_all(hrd_iq_queue_t *q, int8_t *rows, size_t row_stride, uint32_t *bytes, uint32_t *time_stamps)

@@ -251,6 +251,9 @@ int hrd_iq_queue_create(int n_streams, hrd_iq_queue_t **out);
 int hrd_iq_queue_destroy(hrd_iq_queue_t *q);
 /* DataConsumer::acceptData (:219-261): at most 262144 bytes into the stream's next pool slot, queued */
 int hrd_iq_queue_push(hrd_iq_queue_t *q, int stream, uint32_t time_stamp, const void *data, uint32_t bytes);
+/* the same for `count` consecutive streams in one call: row i (rows + i * row_stride) is the block of stream first + i */
+int hrd_iq_queue_push_rows(hrd_iq_queue_t *q, int first, int count, uint32_t time_stamp, const void *rows, size_t row_stride,
+                           uint32_t bytes);
 /* one round: returns 1 with one block of every stream in rows (bytes / time_stamps optional), 0 if a stream has none */
 int hrd_iq_queue_pop_all(hrd_iq_queue_t *q, int8_t *rows, size_t row_stride, uint32_t *bytes, uint32_t *time_stamps);
 /* blocks queued, shortBlockCount, lastTimeStamp */

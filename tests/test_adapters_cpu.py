@@ -152,9 +152,29 @@ def test_iq_queue_follows_dataconsumer_rules():
     lib.hrd_iq_queue_destroy(q)
 
 
+def test_iq_queue_push_rows_is_a_push_per_stream():
+    lib = _lib()
+    lib.hrd_iq_queue_push_rows.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_size_t, C.c_uint32]
+    q = C.c_void_p()
+    assert lib.hrd_iq_queue_create(5, C.byref(q)) == 0
+    blocks = (np.arange(3 * 4096, dtype=np.int64) % 251).astype(np.int8).reshape(3, 4096)
+    assert lib.hrd_iq_queue_push_rows(q, 1, 3, 77, blocks.ctypes.data, blocks.strides[0], 4096) == 0   # streams 1..3
+    assert lib.hrd_iq_queue_push_rows(q, 3, 3, 78, blocks.ctypes.data, blocks.strides[0], 4096) == -1  # HRD_EINVAL: past the end
+    one = np.full(4096, 9, dtype=np.int8)
+    for s in (0, 4):
+        assert lib.hrd_iq_queue_push(q, s, 77, one.ctypes.data, 4096) == 0
+    rows = np.zeros((5, 262144), dtype=np.int8)
+    nbytes = np.zeros(5, dtype=np.uint32)
+    assert lib.hrd_iq_queue_pop_all(q, rows.ctypes.data, 262144, nbytes.ctypes.data, None) == 1
+    assert list(nbytes) == [4096] * 5
+    for i in range(3):
+        assert np.array_equal(rows[1 + i, :4096], blocks[i])
+    lib.hrd_iq_queue_destroy(q)
+
+
 def test_library_exports_the_adapter_symbols():
     lib = capi.load()
     for name in ("hrd_pcm_ring_create", "hrd_pcm_ring_destroy", "hrd_pcm_ring_start", "hrd_pcm_ring_write", "hrd_pcm_ring_read_all",
-                 "hrd_pcm_ring_stats", "hrd_tx_from_ring", "hrd_iq_queue_create", "hrd_iq_queue_destroy", "hrd_iq_queue_push",
+                 "hrd_pcm_ring_stats", "hrd_tx_from_ring", "hrd_iq_queue_create", "hrd_iq_queue_destroy", "hrd_iq_queue_push", "hrd_iq_queue_push_rows",
                  "hrd_iq_queue_pop_all", "hrd_iq_queue_stats", "hrd_rx_from_queue"):
         assert hasattr(lib, name), name
