@@ -1044,6 +1044,7 @@ static int run_demods(hrd_batch_t *b, hrd::RxParams &p, int entry, uint32_t n_ba
                     p.tile_batches = n_batches ? n_batches : 1;
                 }
             }
+        p.wb_pack = fan ? 1 : 0; // beside other kinds: full WBFM CTAs on fewer SMs (hrd_tables.h)
         const bool speculate = k == hrd::K_WBFM && p.n_tiles > 1;
             if (speculate) { // verified speculation (hrd_rx.cu): pairs to compare, this call's flag
                 rc = ensure_cap(&b->d_wbv, &b->d_wbv_cap, sizeof(float2) * (size_t)p.n_streams * (size_t)p.n_tiles);

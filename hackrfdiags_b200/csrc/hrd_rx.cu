@@ -1637,7 +1637,7 @@ int launch_wbfm(const RxParams &p, cudaStream_t s)
     const long long items = (long long)p.n_streams * p.n_tiles;
     RxParams q = p;
     // (the re-run's stream count is only known on the device: small CTAs, surplus ones exit at once)
-    q.items_per_cta = p.run_if ? WB_RERUN_ITEMS : balanced_items_per_cta(items, p.sm_count, WB_ITEMS);
+    q.items_per_cta = p.run_if ? WB_RERUN_ITEMS : p.wb_pack ? WB_ITEMS : balanced_items_per_cta(items, p.sm_count, WB_ITEMS);
     const int grid = (int)((items + q.items_per_cta - 1) / q.items_per_cta);
     if (p.run_if) return p.n_tiles > 1 ? launch_wbfm_as<ENTRY, true, true>(q, grid, s) : launch_wbfm_as<ENTRY, false, true>(q, grid, s);
     return p.n_tiles > 1 ? launch_wbfm_as<ENTRY, true, false>(q, grid, s) : launch_wbfm_as<ENTRY, false, false>(q, grid, s);

@@ -166,6 +166,10 @@ struct RxParams {
     // the TILED retry of those streams (hrd_rx.cu "second pass"): per listed stream the value every tile >= 1 puts
     // into the recurrence at its check point instead of the warmed-up one; null otherwise
     const float *wb_guess;
+    // rx_wbfm_kernel beside other kinds' kernels (a mixed batch fanned out over streams): 1 = full CTAs on as many SMs
+    // as that takes instead of every SM with a partly filled one -- a CTA's step time falls more slowly than its item
+    // count (21 items: 3.53 us, 27: 3.92 us), and the SMs left over are not idle, the other kinds run there
+    int32_t wb_pack;
     // Ragged calls (the squelched path: every stream demodulates only the blocks its gate let through): when
     // non-null, stream sid has n256_of[sid] <= n256 samples in its row; such launches run with n_tiles == 1.
     const uint32_t *n256_of;
