@@ -225,6 +225,8 @@ def make_rx_batch(torch, capi, device, groups, n_samples, seed):
     n = sum(g[1] for g in groups)
     iq = torch.empty((n, 2 * n_samples), dtype=torch.int8, device=device)
     b = capi.Batch(n, capi.RX, device.index or 0)
+    if os.environ.get("HRD_BENCH_TILE_BATCHES"):  # experiments (tools/prof_run.py): force the time-tile size
+        b.set_option(capi.OPT_RX_TILE_BATCHES, int(os.environ["HRD_BENCH_TILE_BATCHES"]))
     at = 0
     n_distinct = {}
     for mode, cnt in groups:
