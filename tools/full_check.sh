@@ -1,10 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-bash tools/final_run.sh r2z
+bash tools/final_run.sh ${TAG:-final}
 python - <<'PY'
 import json
-d=json.load(open('gpurun_out/r2z_bench.json'))
+d=json.load(open('gpurun_out/${TAG:-final}_bench.json'))
 print('value',d['value'],'ms',d['ms_per_step'],'roofline',d['roofline']['kernel'],d['roofline']['frac'],'step',d['roofline']['step']['frac'])
 print('kinds',d['roofline']['kinds'])
 for k,v in d['modes'].items(): print(k, v.get('MS/s'), v.get('ms'), v.get('hbm_frac'))
