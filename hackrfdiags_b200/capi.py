@@ -39,7 +39,7 @@ EXPORTS = [
     "hrd_sharded_create", "hrd_sharded_destroy", "hrd_sharded_count", "hrd_sharded_shard", "hrd_sharded_last_error",
     "hrd_sharded_set_mode", "hrd_sharded_set_param", "hrd_sharded_reset", "hrd_sharded_set_option",
     "hrd_sharded_rx_process", "hrd_sharded_tx_process",
-    "hrd_synchronize", "hrd_launch_count", "hrd_wbfm_fallback_count", "hrd_wbfm_serial_count", "hrd_kernel_ms", "hrd_get_table", "hrd_get_taps", "hrd_state_bytes_per_stream",
+    "hrd_synchronize", "hrd_get_device", "hrd_launch_count", "hrd_wbfm_fallback_count", "hrd_wbfm_serial_count", "hrd_kernel_ms", "hrd_get_table", "hrd_get_taps", "hrd_state_bytes_per_stream",
 ]
 
 

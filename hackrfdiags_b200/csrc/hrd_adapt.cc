@@ -354,6 +354,26 @@ int hrd_rx_from_queue(hrd_batch_t *b, hrd_iq_queue_t *q, int16_t *pcm, size_t pc
 } // extern "C"
 
 namespace {
+// the pipes' CUDA objects live on the batch's device, whatever the caller's current device is
+struct OnDevice {
+    int prev = -1;
+    explicit OnDevice(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~OnDevice()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+int device_of(hrd_batch_t *b)
+{
+    int d = 0;
+    hrd_get_device(b, &d);
+    return d;
+}
 struct RxRound {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
@@ -387,7 +407,7 @@ struct hrd_rx_pipe {
 struct hrd_tx_pipe {
     hrd_batch_t *b = nullptr;
     hrd_pcm_ring_t *ring = nullptr;
-    int depth = 0, head = 0, tail = 0, in_flight = 0;
+    int depth = 0, head = 0, tail = 0, in_flight = 0, device = 0;
     std::vector<TxRound> r;
 };
 
@@ -396,6 +416,7 @@ extern "C" {
 int hrd_rx_pipe_destroy(hrd_rx_pipe_t *p)
 {
     if (!p) return HRD_OK;
+    OnDevice guard(p->device);
     for (RxRound &k : p->r) {
         if (k.stream) cudaStreamSynchronize(k.stream);
         if (k.done) cudaEventDestroy(k.done);
@@ -414,7 +435,8 @@ int hrd_rx_pipe_create(hrd_batch_t *b, hrd_iq_queue_t *q, int depth, hrd_rx_pipe
     if (!b || !q || !out || depth < 1 || depth > IQ_SLOTS / 2) return HRD_EINVAL;
     hrd_rx_pipe *p = new (std::nothrow) hrd_rx_pipe;
     if (!p) return HRD_ENOMEM;
-    p->b = b, p->q = q, p->depth = depth;
+    p->b = b, p->q = q, p->depth = depth, p->device = device_of(b);
+    OnDevice guard(p->device);
     p->r.resize((size_t)depth);
     p->bytes.resize((size_t)q->n);
     p->slots.resize((size_t)q->n);
@@ -443,6 +465,7 @@ int hrd_rx_pipe_submit(hrd_rx_pipe_t *p)
 {
     if (!p) return HRD_EINVAL;
     if (p->in_flight == p->depth) return 0;
+    OnDevice guard(p->device);
     hrd_iq_queue_t *q = p->q;
     bool uniform = true;
     const int ready = peek_round(q, p->bytes.data(), &uniform, p->slots.data());
@@ -485,6 +508,7 @@ int hrd_rx_pipe_collect(hrd_rx_pipe_t *p, const int16_t **pcm, size_t *pcm_strid
 {
     if (!p) return HRD_EINVAL;
     if (!p->in_flight) return 0;
+    OnDevice guard(p->device);
     RxRound &k = p->r[(size_t)p->tail];
     if (cudaEventSynchronize(k.done) != cudaSuccess) return HRD_ECUDA;
     if (pcm) *pcm = k.h_pcm;
@@ -507,6 +531,7 @@ int hrd_rx_pipe_stats(hrd_rx_pipe_t *p, uint64_t out[2])
 int hrd_tx_pipe_destroy(hrd_tx_pipe_t *p)
 {
     if (!p) return HRD_OK;
+    OnDevice guard(p->device);
     for (TxRound &k : p->r) {
         if (k.stream) cudaStreamSynchronize(k.stream);
         if (k.done) cudaEventDestroy(k.done);
@@ -525,7 +550,8 @@ int hrd_tx_pipe_create(hrd_batch_t *b, hrd_pcm_ring_t *r, int depth, hrd_tx_pipe
     if (!b || !r || !out || depth < 1 || depth > 8) return HRD_EINVAL;
     hrd_tx_pipe *p = new (std::nothrow) hrd_tx_pipe;
     if (!p) return HRD_ENOMEM;
-    p->b = b, p->ring = r, p->depth = depth;
+    p->b = b, p->ring = r, p->depth = depth, p->device = device_of(b);
+    OnDevice guard(p->device);
     p->r.resize((size_t)depth);
     const size_t n = (size_t)r->n;
     cudaError_t e = cudaSuccess;
@@ -551,6 +577,7 @@ int hrd_tx_pipe_submit(hrd_tx_pipe_t *p)
 {
     if (!p) return HRD_EINVAL;
     if (p->in_flight == p->depth) return 0;
+    OnDevice guard(p->device);
     TxRound &k = p->r[(size_t)p->head];
     const size_t n = (size_t)p->ring->n;
     int rc = hrd_pcm_ring_read_all(p->ring, k.h_rows, BLOCK, nullptr);
@@ -571,6 +598,7 @@ int hrd_tx_pipe_collect(hrd_tx_pipe_t *p, const int8_t **iq, size_t *iq_stride)
 {
     if (!p) return HRD_EINVAL;
     if (!p->in_flight) return 0;
+    OnDevice guard(p->device);
     TxRound &k = p->r[(size_t)p->tail];
     if (cudaEventSynchronize(k.done) != cudaSuccess) return HRD_ECUDA;
     if (iq) *iq = k.h_iq;

@@ -940,6 +940,13 @@ int hrd_wbfm_fallback_count(hrd_batch_t *b, uint64_t *count)
     return HRD_OK;
 }
 
+int hrd_get_device(hrd_batch_t *b, int *device)
+{
+    if (!b || !device) return fail(HRD_EINVAL, "null argument");
+    *device = b->device;
+    return HRD_OK;
+}
+
 int hrd_wbfm_serial_count(hrd_batch_t *b, uint64_t *count)
 {
     if (!b || !count) return fail(HRD_EINVAL, "null argument");

@@ -312,6 +312,8 @@ int hrd_sharded_tx_process(hrd_sharded_t *s, const int16_t *pcm, size_t n_per_st
 
 /* ---- introspection (tests, bench) ------------------------------------ */
 int hrd_synchronize(hrd_batch_t *b);
+/* the CUDA device the batch lives on (hrd_create's argument) */
+int hrd_get_device(hrd_batch_t *b, int *device);
 /* with HRD_OPT_PROFILE set: device time of a recent process call's kernels; age 0 = the latest
  * call, up to 31 calls back; which = 0 the main kernels (Rx tile kernels / Tx kernels), 1 the
  * tail kernel (Rx AM/SSB IIR pass), 10 + kind = that kind's own kernels (HRD_OPT_RX_SERIAL).

@@ -120,3 +120,47 @@ def test_two_devices_from_one_process_wbfm():
         for s in range(3):
             assert np.array_equal(got[s], oracle.run_rx(capi.MODE_WBFM, iq[s])), f"rx device {device} stream {s}"
             assert np.array_equal(out[s], oracle.run_tx(capi.MODE_WBFM, pcm[s])), f"tx device {device} stream {s}"
+
+
+def test_pipe_on_the_second_device():
+    """A pipelined ingest on device 1 driven from a thread whose current device is 0: the pipe's streams, buffers
+    and events must live where the batch lives."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    torch.cuda.set_device(0)
+    lib, oracle = capi.load(), Oracle()
+    vp = C.c_void_p
+    lib.hrd_rx_pipe_create.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
+    lib.hrd_rx_pipe_destroy.argtypes = [vp]
+    lib.hrd_rx_pipe_submit.argtypes = [vp]
+    lib.hrd_rx_pipe_collect.argtypes = [vp, C.POINTER(C.POINTER(C.c_int16)), C.POINTER(C.c_size_t), C.POINTER(C.POINTER(C.c_uint32))]
+    lib.hrd_iq_queue_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.hrd_iq_queue_push.argtypes = [vp, C.c_int, C.c_uint32, vp, C.c_uint32]
+    lib.hrd_iq_queue_destroy.argtypes = [vp]
+    lib.hrd_get_device.argtypes = [vp, C.POINTER(C.c_int)]
+    n, rounds = 5, 3
+    rows = [synth.rx_stream(RX_MODES[s], rounds * 131072, stream=s, config=22) for s in range(n)]
+    b = capi.Batch(n, capi.RX, 1)
+    d = C.c_int(-1)
+    assert lib.hrd_get_device(b.h, C.byref(d)) == 0 and d.value == 1
+    for s in range(n):
+        b.set_mode(RX_MODES[s], s)
+    q, pipe = vp(), vp()
+    assert lib.hrd_iq_queue_create(n, C.byref(q)) == 0
+    assert lib.hrd_rx_pipe_create(b.h, q, 2, C.byref(pipe)) == 0
+    got = [[] for _ in range(n)]
+    pcm_p, stride, cnt_p = C.POINTER(C.c_int16)(), C.c_size_t(), C.POINTER(C.c_uint32)()
+    for k in range(rounds):
+        for s in range(n):
+            blk = rows[s][k * 262144:(k + 1) * 262144]
+            assert lib.hrd_iq_queue_push(q, s, k, blk.ctypes.data, blk.size) == 0
+        assert lib.hrd_rx_pipe_submit(pipe) == 1
+        assert lib.hrd_rx_pipe_collect(pipe, C.byref(pcm_p), C.byref(stride), C.byref(cnt_p)) == 1
+        pcm = np.ctypeslib.as_array(pcm_p, shape=(n, stride.value))
+        for s in range(n):
+            got[s].append(pcm[s, :512].copy())
+    lib.hrd_rx_pipe_destroy(pipe)
+    lib.hrd_iq_queue_destroy(q)
+    for s in range(n):
+        assert np.array_equal(np.concatenate(got[s]), oracle.run_rx(RX_MODES[s], rows[s])), f"stream {s}"
