@@ -227,6 +227,8 @@ def make_rx_batch(torch, capi, device, groups, n_samples, seed):
     b = capi.Batch(n, capi.RX, device.index or 0)
     if os.environ.get("HRD_BENCH_TILE_BATCHES"):  # experiments (tools/prof_run.py): force the time-tile size
         b.set_option(capi.OPT_RX_TILE_BATCHES, int(os.environ["HRD_BENCH_TILE_BATCHES"]))
+    if os.environ.get("HRD_BENCH_WBFM_PACK"):
+        b.set_option(capi.OPT_RX_WBFM_PACK, int(os.environ["HRD_BENCH_WBFM_PACK"]))
     at = 0
     n_distinct = {}
     for mode, cnt in groups:

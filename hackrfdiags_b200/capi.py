@@ -25,7 +25,7 @@ ENTRY_2048K, ENTRY_256K = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 ALL_STREAMS = -1
 (OPT_RX_TILE_BATCHES, OPT_RX_WBFM_TILING, OPT_TX_TILE_SAMPLES, OPT_PROFILE, OPT_DEBUG_WBFM_FORCE_RERUN, OPT_RX_SQUELCH,
- OPT_RX_SQUELCH_BLOCK, OPT_RX_SERIAL) = range(8)
+ OPT_RX_SQUELCH_BLOCK, OPT_RX_SERIAL, OPT_RX_WBFM_PACK) = range(9)
 
 # every symbol include/hrd.h declares (tests check that the library exports all of them)
 EXPORTS = [

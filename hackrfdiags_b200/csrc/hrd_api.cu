@@ -691,6 +691,7 @@ int hrd_create(int device, int n_streams, int kind, hrd_batch_t **out)
     if (e == cudaSuccess) e = cudaMalloc(&b->d_wbrerun, 2 * (size_t)n_streams * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_wbguess, (size_t)n_streams * sizeof(float));
     b->opt[HRD_OPT_RX_WBFM_TILING] = 1;
+    b->opt[HRD_OPT_RX_WBFM_PACK] = 1;
     if (e == cudaSuccess) e = cudaMalloc(&b->d_ids, (size_t)n_streams * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_all, (size_t)n_streams * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_lsb, (size_t)n_streams);
@@ -1051,7 +1052,7 @@ static int run_demods(hrd_batch_t *b, hrd::RxParams &p, int entry, uint32_t n_ba
                     p.tile_batches = n_batches ? n_batches : 1;
                 }
             }
-        p.wb_pack = fan ? 1 : 0; // beside other kinds: full WBFM CTAs on fewer SMs (hrd_tables.h)
+        p.wb_pack = fan && b->opt[HRD_OPT_RX_WBFM_PACK] ? 1 : 0; // beside other kinds: full WBFM CTAs on fewer SMs (hrd_tables.h)
         const bool speculate = k == hrd::K_WBFM && p.n_tiles > 1;
             if (speculate) { // verified speculation (hrd_rx.cu): pairs to compare, this call's flag
                 rc = ensure_cap(&b->d_wbv, &b->d_wbv_cap, sizeof(float2) * (size_t)p.n_streams * (size_t)p.n_tiles);

@@ -123,7 +123,11 @@ enum {
      * stream instead of side by side, and (with HRD_OPT_PROFILE) each kind's own span is timed: hrd_kernel_ms
      * which = 10 + kind (1 AM+SSB, 2 FM, 3 WBFM).  Results are identical either way. */
     HRD_OPT_RX_SERIAL = 7,
-    HRD_OPT_COUNT = 8
+    /* Rx, mixed-mode batches: 1 (default) = the WBFM launch fills whole CTAs (one per SM, 27 streams each) on as many
+     * SMs as that takes, leaving the others to the AM / NBFM kernels running beside it; 0 = it spreads over all SMs
+     * as it does when it runs alone.  Results are identical either way. */
+    HRD_OPT_RX_WBFM_PACK = 8,
+    HRD_OPT_COUNT = 9
 };
 
 #define HRD_ALL_STREAMS (-1)
