@@ -120,6 +120,26 @@ def test_config3_wbfm_4096_streams(env, oracle):
     assert torch.equal(pcm, pcm2)
 
 
+def test_wbfm_whole_waves_plus_a_small_remainder(env, oracle):
+    """WBFM launches are planned in two parts (hrd_api.cu plan_wbfm): the streams that fill whole waves of CTAs run
+    untiled, the rest finely tiled in one more wave.  One wave plus 5 streams, and two waves plus 1, three calls in a
+    row (state carried through both parts): every distinct row against the oracle, all repeats identical."""
+    torch, bench, capi, dev = env
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    for n in (sms * 27 + 5, 2 * sms * 27 + 1):
+        n_samples = 8192 * 12  # 12 batches per stream: 0.8 / 1.6 GB of IQ
+        b, iq, pcm, layout = bench.make_rx_batch(torch, capi, dev, [(capi.MODE_WBFM, n)], n_samples, seed=29)
+        cuts = [0, 8192 * 2 * 5, 8192 * 2 * 9, iq.shape[1]]
+        for lo, hi in zip(cuts, cuts[1:]):
+            _rx_call(capi, b, iq, pcm, lo, hi)
+        torch.cuda.synchronize()
+        _check_sample_vs_oracle(torch, oracle, iq, pcm, [capi.MODE_WBFM] * n, _distinct_rows(layout) + [sms * 27 - 1, sms * 27, n - 1])
+        assert bench.repeats_identical(torch, pcm, layout) == 0
+        assert b.wbfm_serial_count() == 0
+        del b, iq, pcm
+        torch.cuda.empty_cache()
+
+
 def test_config5_mixed_modes_4096_streams(env, oracle):
     """BASELINE configs[4] at the bench's headline point: 4096 mixed-mode streams (1/4 AM, NBFM, WBFM, 1/8 LSB, USB)
     in one batch, 0.5 s each; every distinct stream of every mode against the oracle, every repeat on the device."""
