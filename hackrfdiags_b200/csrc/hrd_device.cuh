@@ -229,6 +229,50 @@ __device__ __forceinline__ float wrap_pi_select(float d)
     return (s >= HRD_PI_UP) ? w : d;
 }
 
+// cosf / sinf as the reference's libm computes them (Nco::run, Nco/Nco.cc:186-199: cos(phase), sin(phase) of a float;
+// signals/pm.cc:39-55, fm.cc:41-62).  glibc's routines (sysdeps/ieee754/flt-32/s_sinf.c, s_cosf.c, sincosf.h, unchanged
+// since 2.28: Szabolcs Nagy's double-precision polynomials) are not always correctly rounded, so "sin in double,
+// rounded to float" -- what this library did in round 1 -- differs from them in the last bit now and then, and a last
+// bit times 16000, truncated and interpolated, is the occasional 1 LSB of int8 IQ that FM transmit used to be allowed.
+// This is that algorithm restated: range reduction x - n * (pi/2) with n = round(x * 2/pi) taken from the integer part
+// of x * (2/pi * 2^24), then the odd / even polynomial of the quadrant, all in double, one rounding to float at the
+// end.  tools/verify_sincosf.c evaluates the same restatement on the host for EVERY float with |x| < 8 (2.18e9 of
+// them) against libm's sinf and cosf: 0 mismatches, with and without contraction of the a + b * c forms.  The phases
+// that reach it are wrapped to +-pi (the prototype FM head: +-2 pi); beyond 8 (never) the double sincos is used.
+__device__ __forceinline__ void glibc_sincosf(float y, float &sin_out, float &cos_out)
+{
+    const uint32_t top = (__float_as_uint(y) >> 20) & 0x7ffu; // abstop12
+    if (!(top < 0x410u)) { // |y| >= 8, NaN: outside the verified range
+        double sd, cd;
+        sincos((double)y, &sd, &cd);
+        sin_out = (float)sd, cos_out = (float)cd;
+        return;
+    }
+    double x = (double)y;
+    int n = 0;
+    if (top >= 0x3f4u) { // abstop12(pi/4): reduce_fast
+        const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
+        n = (__double2int_rz(r) + 0x800000) >> 24;
+        x = __fma_rn(-(double)n, 0x1.921FB54442D18p0, x);
+    } else if (top < 0x398u) { // |y| < 2^-12
+        sin_out = y, cos_out = 1.0f;
+        return;
+    }
+    const double x2 = __dmul_rn(x, x);
+    // quadrant: sign[n & 3] = {1, -1, -1, 1} on the odd polynomial's argument; table 1 (n & 2) negates the even one
+    const double xs = ((n + 1) & 2) ? -x : x;
+    const double neg = (n & 2) ? -1.0 : 1.0;
+    const double x3 = __dmul_rn(xs, x2), s1 = __fma_rn(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7), x5 = __dmul_rn(x3, x2),
+                 s = __fma_rn(x3, -0x1.555545995a603p-3, xs);
+    const float odd = (float)__fma_rn(x5, s1, s);
+    const double x4 = __dmul_rn(x2, x2), c2 = __fma_rn(x2, neg * 0x1.99343027bf8c3p-16, neg * -0x1.6c087e89a359dp-10),
+                 c1 = __fma_rn(x2, neg * -0x1.ffffffd0c621cp-2, neg), x6 = __dmul_rn(x4, x2), c = __fma_rn(x4, neg * 0x1.55553e1068f19p-5, c1);
+    const float even = (float)__fma_rn(x6, c2, c);
+    // sinf uses the odd polynomial in even quadrants, cosf the other way round
+    sin_out = (n & 1) ? even : odd;
+    cos_out = (n & 1) ? odd : even;
+}
+
 // One step of PhaseAccumulator::run (Nco/PhaseAccumulator.cc:157-181) on the serial NCO chains of hrd_tx.cu, for
 // |phase| < pi and |step| < 3 (so |phase + step| < 6.2 and at most one wrap, in the direction of the step):
 // acc += step; then (float)((double)acc -+ 2*M_PI) when |acc| passed pi.

@@ -371,9 +371,9 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxPara
                 a = (float)((double)a * 3.14159265358979323846);
                 // fm.cc:41-62: theta comes from the serial pre-pass (tx_fm_phase_kernel<true>)
                 if (sub == SIG_MODE_FM_PROTO) a = (lane < nb) ? p.fm_phase[(size_t)slot * p.n8 + done + lane] : 0.f;
-                double sd, cd;
-                sincos((double)a, &sd, &cd); // evaluated in double and rounded (DESIGN.md "the one tolerance")
-                head = pack16(f32_to_i16(__fmul_rn((float)cd, 16000.f)), f32_to_i16(__fmul_rn((float)sd, 16000.f)));
+                float sf, cf;
+                glibc_sincosf(a, sf, cf); // libm's cosf / sinf, bit for bit (hrd_device.cuh)
+                head = pack16(f32_to_i16(__fmul_rn(cf, 16000.f)), f32_to_i16(__fmul_rn(sf, 16000.f)));
             }
         }
         if constexpr (KIND == K_AM) {
@@ -389,13 +389,13 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32) tx_kernel(const TxPara
             // FmModulator.cc:596-617: the NCO phase before this sample's step (tx_fm_phase_kernel walked
             // PhaseAccumulator::run for the whole call already)
             const float my_phase = (lane < nb) ? fm_phase[done + lane] : 0.f;
-            // Nco::run (Nco.cc:186-199): cosf/sinf of the float phase.  Evaluated in double
-            // and rounded to float (see DESIGN.md "float tolerance").  (Measured: moving the sincos into
+            // Nco::run (Nco.cc:186-199): cosf/sinf of the float phase, as libm computes them (hrd_device.cuh
+            // glibc_sincosf: bit for bit).  (Measured in round 1 with the heavier double sincos: moving it into
             // tx_fm_phase_kernel makes that kernel FP64-pipe-bound and the pair slower, 2.28 -> 2.36 ms.)
-            double sd, cd;
-            sincos((double)my_phase, &sd, &cd);
-            int ci = f32_to_i16(__fmul_rn((float)cd, 16000.f));
-            int si = f32_to_i16(__fmul_rn((float)sd, 16000.f));
+            float sf, cf;
+            glibc_sincosf(my_phase, sf, cf);
+            int ci = f32_to_i16(__fmul_rn(cf, 16000.f));
+            int si = f32_to_i16(__fmul_rn(sf, 16000.f));
             head = pack16(ci, si);
         }
         if constexpr (KIND == K_SSB) {

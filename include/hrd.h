@@ -53,7 +53,7 @@ enum {
      * i.e. signals/interpolateSignal.cc's eight-stage interpolator with ITS stage-1 taps (:30-72) behind ... */
     HRD_MODE_IQ8K = 6,     /* nothing: the input rows are int16 I,Q PAIRS at 8 kS/s (interpolateSignal.cc:266-340) */
     HRD_MODE_DSB = 7,      /* signals/dsb.cc:38-47  x/4 on both rails                                            */
-    HRD_MODE_PM = 8,       /* signals/pm.cc:39-55   (cos, sin)(x/60000*pi) * 16000 (libm: <= 1 LSB, like FM Tx)  */
+    HRD_MODE_PM = 8,       /* signals/pm.cc:39-55   (cos, sin)(x/60000*pi) * 16000 (libm's cosf / sinf, bit for bit) */
     HRD_MODE_AM_PROTO = 9, /* signals/am.cc:38-50   (x*0.8 + 65536)/4 on both rails                              */
     HRD_MODE_FM_PROTO = 10 /* signals/fm.cc:41-62   theta += x/65536*3.5 wrapped at +-2*pi, (cos, sin)*16000 (libm)   */
 };

@@ -2,7 +2,7 @@
 dev container through oracle/_ref/libhrd_ref.so).  They travel with the repo, so they pin
 
   * the CPU oracle  (not gpu): every vector bit for bit;
-  * the CUDA path   (gpu)    : every vector bit for bit (FM Tx: <= 1 LSB int8, Nco::run uses libm),
+  * the CUDA path   (gpu)    : every vector bit for bit (FM Tx included),
                                called through the C ABI exactly as the reference calls were made.
 """
 import hashlib

@@ -3,7 +3,7 @@
 The oracle cannot chew through 4-17 GB in a test, so full size is covered by size-independent properties:
   * EVERY distinct stream of the batch (32 per mode, the last five of them the edge classes: full-range noise,
     constant -128, constant +127, alternating +-127, zero), whole length, bit for bit against the CPU oracle
-    (FM Tx: <= 1 LSB int8);
+    (FM Tx included);
   * streams fed identical inputs give identical outputs wherever they sit in the batch (independence): every
     repeat of every distinct row, compared on the device;
   * automatic time tiling == one tile per stream (the serial order);
@@ -167,7 +167,7 @@ def test_config4_tx_4096_streams(env, oracle, mode):
     b.set_mode(mode)
     b.tx_device(pcm.data_ptr(), n_pcm, pcm.stride(0), iq.data_ptr(), iq.stride(0), 0)
     torch.cuda.synchronize()
-    tol = 1 if mode == capi.MODE_FM else 0
+    tol = 0  # FM too: the Nco::run head computes libm's cosf / sinf bit for bit (hrd_device.cuh glibc_sincosf)
     for s in list(range(32)) + [4095]:  # every distinct row (sines to -32768, noise, AM tone, silence, square wave)
         want = oracle.run_tx(mode, pcm[s].cpu().numpy())
         got = iq[s].cpu().numpy()

@@ -92,7 +92,7 @@ def test_tx(oracle, mode):
     b = capi.Batch(n_streams, capi.TX)
     b.set_mode(mode)
     got = b.tx(pcm)
-    tol = 1 if mode == capi.MODE_FM else 0  # Nco::run calls libm sinf/cosf: <= 1 LSB allowed
+    tol = 0  # FM included: Nco::run's libm cosf / sinf are restated bit for bit (hrd_device.cuh glibc_sincosf)
     for s in range(n_streams):
         want = oracle.run_tx(mode, pcm[s])
         mx, cnt = _diff(got[s], want)
@@ -111,7 +111,7 @@ def test_tx_streaming_state(oracle, mode):
         parts.append(b.tx(np.ascontiguousarray(pcm[:, off:off + sz])))
         off += sz
     got = np.concatenate(parts, axis=1)
-    tol = 1 if mode == capi.MODE_FM else 0
+    tol = 0
     for s in range(n_streams):
         want = oracle.run_tx(mode, pcm[s])
         mx, cnt = _diff(got[s], want)
@@ -122,7 +122,7 @@ def test_tx_streaming_state(oracle, mode):
 @pytest.mark.parametrize("tile_samples", [32, 64, 96, 160])
 def test_tx_time_tiles(oracle, mode, tile_samples):
     """Tx tiles of 1..5 batches (halo 32 or 64 PCM samples), ragged last tile, three calls in a row; FM reads the
-    NCO phases of the serial pre-pass.  Same bits as one tile (FM: <= 1 LSB, libm sinf/cosf in the reference)."""
+    NCO phases of the serial pre-pass.  Same bits as one tile."""
     n_streams = 7
     sizes = [32 * 11 + 5, 32 * 4, 77]
     pcm = synth.tx_batch(n_streams, sum(sizes), config=12)
@@ -134,7 +134,7 @@ def test_tx_time_tiles(oracle, mode, tile_samples):
         parts.append(b.tx(np.ascontiguousarray(pcm[:, off:off + sz])))
         off += sz
     got = np.concatenate(parts, axis=1)
-    tol = 1 if mode == capi.MODE_FM else 0
+    tol = 0
     for s in range(n_streams):
         want = oracle.run_tx(mode, pcm[s])
         mx, cnt = _diff(got[s], want)
@@ -156,7 +156,7 @@ def test_tx_mixed_modes_one_batch(oracle):
             continue
         want = oracle.run_tx(m, pcm[i])
         err = np.abs(got[i].astype(np.int32) - want.astype(np.int32)).max()
-        assert err <= (1 if m == capi.MODE_FM else 0), f"stream {i} mode {m}: max abs err {err}"
+        assert err == 0, f"stream {i} mode {m}: max abs err {err}"
 
 
 # ---- time tiling: every tile size must give what one tile (= the serial order) gives -----

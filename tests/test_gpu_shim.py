@@ -3,7 +3,7 @@
 The SAME driver source (shim/shim_test.cc) is built twice: against the shim headers + libhrd_b200.so
 (shim_test) and against the reference's own headers and sources (oracle/_ref/shim_test_ref, built by
 oracle/Makefile where /root/reference exists).  Both run on the same input files; outputs must be
-byte-identical (FM Tx: <= 1 LSB, Nco::run calls libm) and so must the text the classes print through
+byte-identical (FM Tx included) and so must the text the classes print through
 nprintf.  When the compiled reference driver is absent the CPU oracle stands in for it."""
 import os
 import stat
@@ -99,7 +99,7 @@ def test_modulator_classes_drop_in(ours, oracle, tmp_path, mode):
         want = np.concatenate(parts)
     assert got.size == want.size == pcm.size * 512
     err = np.abs(got.astype(np.int32) - want.astype(np.int32))
-    tol = 1 if mode == "fm" else 0  # Nco::run -> libm sinf/cosf vs CUDA double sincos
+    tol = 0  # FM too: Nco::run's libm sinf / cosf are restated bit for bit
     assert err.max() <= tol, f"{mode}: max abs err {err.max()}, {(err != 0).sum()} of {want.size} bytes differ"
 
 
