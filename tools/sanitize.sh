@@ -11,7 +11,7 @@ run() { # tool seconds pytest-args...
         python -m pytest "$@" -m gpu -q > $OUT/san_$tool.log 2>&1
     echo "$tool rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' $OUT/san_$tool.log | tr '\n' ' ')"
 }
-run memcheck 240 tests/test_gpu_parity_small.py tests/test_gpu_squelch.py tests/test_gpu_adapters.py tests/test_gpu_sharded.py
+run memcheck 300 tests/test_gpu_parity_small.py tests/test_gpu_squelch.py tests/test_gpu_signals.py tests/test_gpu_adapters.py tests/test_gpu_sharded.py
 run racecheck 300 tests/test_gpu_parity_small.py tests/test_gpu_squelch.py -k "wbfm or mixed or squelch or tile"
 run synccheck 120 tests/test_gpu_parity_small.py -k "wbfm or mixed"
 run initcheck 200 tests/test_gpu_parity_small.py tests/test_gpu_squelch.py
