@@ -254,7 +254,7 @@ __device__ __forceinline__ uint32_t merge16(uint32_t lo, uint32_t hi) { return _
 //          rounding, and the low 16 bits of the result are the B+ bits
 //   even8 = fma(s, 1/4 + 2^-12, 1536)               c8 = 8206 only breaks the ties of s/4
 //   stage-8 odd outputs: integer shifts on the B-form bits, (bits + 1) >> 1 resp. (0xe801 - bits) >> 1 per half
-// tools/verify_tx_tail_h2.c proves the whole block equal to tail3 for every (x, xm) in [-900, 900]^2.
+// tools/verify_tx_tail_h2.c proves the whole block equal to tail3 for every (x, xm) in [-995, 995]^2 (the largest square that passes).
 struct TailCarry {
     __half2 xm;  // U:  the sample before
     __half2 bm;  // B-: its stage-6 odd output

@@ -53,3 +53,18 @@ def test_sincosf_restatement_is_libm(tmp_path):
     subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), os.path.join(root, "tools", "verify_sincosf.c"), "-lm"], check=True)
     out = subprocess.run([str(exe), "61"], check=True, capture_output=True, text=True).stdout
     assert "sinf 0 mismatches, cosf 0" in out.splitlines()[1] and "sinf 0 mismatches, cosf 0" in out.splitlines()[2], out
+
+
+def test_packed_half_tx_tail_is_the_integer_tail(tmp_path):
+    """Stages 6-8 of the transmit interpolator run on both rails at once as fp16 pairs (hrd_tx.cu tail3_h2) wherever
+    the stage-6 inputs stay within +-995 (checked per warp iteration, integer form otherwise).
+    tools/verify_tx_tail_h2.c emulates the fp16 arithmetic exactly and compares all 3 964 081 input pairs of that
+    range with the reference's integer arithmetic."""
+    import os
+    import subprocess
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    exe = tmp_path / "verify_tx_tail_h2"
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), os.path.join(root, "tools", "verify_tx_tail_h2.c"), "-lm"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert "3964081 (x, xm) pairs, 0 mismatches" in out, out
+    assert subprocess.run([str(exe), "1000"], capture_output=True, text=True).returncode != 0  # the range is tight

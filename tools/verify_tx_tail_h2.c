@@ -1,5 +1,5 @@
 /* tools/verify_tx_tail_h2.c -- exhaustive CPU proof of the packed-half (both rails per instruction) form of Tx
- * interpolator stages 6, 7, 8 that tx_wbfm_kernel uses (hackrfdiags_b200/csrc/hrd_tx.cu, tail3_h2).
+ * interpolator stages 6, 7, 8 that tx_wbfm_kernel and the two-rail tx_kernel instances use (hackrfdiags_b200/csrc/hrd_tx.cu, tail3_h2).
  *
  *   gcc -O2 -ffp-contract=off -fopenmp -o /tmp/verify_tx_tail_h2 tools/verify_tx_tail_h2.c -lm && /tmp/verify_tx_tail_h2
  *
@@ -14,11 +14,14 @@
  *   even7 in fp32 per rail: fma(s, 8249/32768, 1.5*2^23 + 0x6600): exact product, one rounding, low 16 bits = B+ bits
  *   a B+ half plus a B- half is their exact integer sum; stage-8 odd outputs are integer shifts on the B-form bits.
  * fp16 operations are emulated exactly (every operand is a double, every result is rounded once to binary16, RNE).
- * Every (x, xm) in [-900, 900]^2 is checked for both halves of the packed word (cross-field effects included).
+ * Every (x, xm) in [-995, 995]^2 is checked for both halves of the packed word (cross-field effects included): the
+ * WBFM modulator's NCO samples stay within +-900; tx_kernel<FM|SSB|IQ> checks its stage-5 outputs against 995 and
+ * falls back to the integer form beyond (at +-1000 the packed form has 13 mismatching pairs).
  */
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 static double rh(double x) /* round an exact double to binary16, ties to even */
@@ -85,14 +88,15 @@ static rail_t tail3_h2_rail(int x, int xm)
     return r;
 }
 
-int main(void)
+int main(int argc, char **argv)
 {
     long bad = 0, n = 0;
+    const int R = argc > 1 ? atoi(argv[1]) : 995; /* 995 is the largest range that passes (1000: 13 mismatches) */
     /* constants must be halves */
     if (rh(1053.0 / 4096.0) != 1053.0 / 4096.0 || rh(0.25 + 1.0 / 4096.0) != 0.25 + 1.0 / 4096.0) { printf("constants are not binary16\n"); return 1; }
 #pragma omp parallel for reduction(+ : bad, n) schedule(dynamic, 16)
-    for (int x = -900; x <= 900; x++)
-        for (int xm = -900; xm <= 900; xm++) {
+    for (int x = -R; x <= R; x++)
+        for (int xm = -R; xm <= R; xm++) {
             int8_t wi[8], wq[8];
             /* rail I = (x, xm); rail Q = (xm, x) (any other valid pair: exercises the cross-field terms) */
             tail3_ref(x, xm, wi);
