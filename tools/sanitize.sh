@@ -13,5 +13,5 @@ run() { # tool seconds pytest-args...
 }
 run memcheck 300 tests/test_gpu_parity_small.py tests/test_gpu_squelch.py tests/test_gpu_signals.py tests/test_gpu_adapters.py tests/test_gpu_sharded.py
 run racecheck 300 tests/test_gpu_parity_small.py tests/test_gpu_squelch.py -k "wbfm or mixed or squelch or tile"
-run synccheck 120 tests/test_gpu_parity_small.py -k "wbfm or mixed"
+run synccheck 150 tests/test_gpu_parity_small.py tests/test_gpu_signals.py -k "wbfm or mixed or tx or signals"
 run initcheck 200 tests/test_gpu_parity_small.py tests/test_gpu_squelch.py
