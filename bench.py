@@ -142,6 +142,18 @@ def make_tx_pcm_device(torch, n_distinct, n_samples, device, seed):
     return out
 
 
+def wbfm_pack():
+    """HRD_OPT_RX_WBFM_PACK for the bench's batches.  Packing the WBFM launch of a mixed batch onto fewer SMs wins
+    2.7 % in a process of its own (1.73 against 1.78 ms per step, the same under torchrun with one rank or with a gloo
+    process group) and LOSES 3.3 % once a multi-rank NCCL communicator is alive in the process (1.83 against 1.77 ms,
+    both ranks alike; profiles/r2_experiments.md section 5): the kernels of different streams are co-scheduled
+    differently then.  So: on, unless this process is one of several NCCL ranks; HRD_BENCH_WBFM_PACK overrides."""
+    if os.environ.get("HRD_BENCH_WBFM_PACK"):
+        return int(os.environ["HRD_BENCH_WBFM_PACK"])
+    nccl_ranks = int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("HRD_BENCH_BACKEND", "nccl") == "nccl"
+    return 0 if nccl_ranks else 1
+
+
 def tile_rows(torch, distinct, n_rows):
     reps = (n_rows + distinct.shape[0] - 1) // distinct.shape[0]
     return distinct.repeat(reps, 1)[:n_rows].contiguous()
@@ -227,8 +239,7 @@ def make_rx_batch(torch, capi, device, groups, n_samples, seed):
     b = capi.Batch(n, capi.RX, device.index or 0)
     if os.environ.get("HRD_BENCH_TILE_BATCHES"):  # experiments (tools/prof_run.py): force the time-tile size
         b.set_option(capi.OPT_RX_TILE_BATCHES, int(os.environ["HRD_BENCH_TILE_BATCHES"]))
-    if os.environ.get("HRD_BENCH_WBFM_PACK"):
-        b.set_option(capi.OPT_RX_WBFM_PACK, int(os.environ["HRD_BENCH_WBFM_PACK"]))
+    b.set_option(capi.OPT_RX_WBFM_PACK, wbfm_pack())
     at = 0
     n_distinct = {}
     for mode, cnt in groups:
@@ -306,7 +317,7 @@ def reduce_max_ms(torch, dist, device, values):
     """max over ranks of a list of per-rank times (identity on one rank)"""
     if not dist:
         return list(values)
-    t = torch.tensor(list(values), device=device, dtype=torch.float64)
+    t = torch.tensor(list(values), device=device if dist.get_backend() == "nccl" else "cpu", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return [float(x) for x in t.tolist()]
 
@@ -334,7 +345,10 @@ def run_ours(args):
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=device)
+            if os.environ.get("HRD_BENCH_BACKEND", "nccl") == "nccl":
+                dist.init_process_group("nccl", device_id=device)
+            else:  # experiments only: the control plane over another backend (the reductions then go through the host)
+                dist.init_process_group(os.environ["HRD_BENCH_BACKEND"])
             dist.barrier()  # the communicator (and its banner) is created here at the latest
             torch.cuda.synchronize()
         finally:
@@ -360,6 +374,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
+    if os.environ.get("HRD_BENCH_RANK_MS"):  # experiments: every rank's own step time
+        print(f"rank {rank}: {r['ms']:.4f} ms per step, tile kernels {r['kernel_ms']:.4f}", file=sys.stderr, flush=True)
     ms_max = reduce_max_ms(torch, dist, device, [r["ms"]])[0]
     clocks = sampler.stop() if sampler else None
     value = world * in_samples_per_step / (ms_max * 1e-3) / 1e6
@@ -397,6 +413,7 @@ def run_ours(args):
                    "streams_per_gpu": args.streams, "input_bytes_per_step_per_gpu": 2 * in_samples_per_step,
                    "l2": "inputs per step exceed the 126 MB L2 many times over; no flush needed",
                    "sharding": "one global plan, contiguous stream ranges per rank (hackrfdiags_b200.shard), no collective",
+                   "wbfm_pack": wbfm_pack(),
                    "mode_groups_rank0": [[MODE_NAMES[m], c] for m, c in groups]},
         "roofline": roofline, "gpu_launches": r["launches"] * args.steps * world,
         "call_ms": {"tile_kernels": round(r["kernel_ms"], 4), "iir_tail": round(r["tail_ms"], 4)},
