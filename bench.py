@@ -483,12 +483,16 @@ def run_e2e(torch, capi, device, args, groups, n_samples, dist):
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        dev_iq.copy_(host_iq, non_blocking=True)
-    torch.cuda.synchronize()
-    dt_copy = (time.perf_counter() - t0) / steps
-    dt_copy = reduce_max_ms(torch, dist, device, [dt_copy])[0]
+    dt_copy = None
+    for _ in range(2):  # the better of two passes: it is a ceiling
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            dev_iq.copy_(host_iq, non_blocking=True)
+        torch.cuda.synchronize()
+        dt_pass = reduce_max_ms(torch, dist, device, [(time.perf_counter() - t0) / steps])[0]
+        dt_copy = dt_pass if dt_copy is None else min(dt_copy, dt_pass)
     del dev_iq
     return {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": host_iq.numel() * world,
             "d2h_bytes_per_step": host_pcm.numel() * 2 * world, "ms_per_step": round(dt * 1e3, 3), "steps": steps,
