@@ -15,6 +15,10 @@ HOST buffers (H2D of all IQ and D2H of all PCM inside the timed region).  The sa
 rate for that chain and a parity record against the reference), `min_mode_hbm_frac`, the 1k..64k mixed-mode
 stream sweep sharded over the N GPUs (strong scaling) and the WBFM-modulator stream-count sweep.
 
+Experiment switches (environment; none is set in a driver run): HRD_BENCH_TILE_BATCHES (force the Rx time-tile size),
+HRD_BENCH_WBFM_PACK (0 / 1, see wbfm_pack), HRD_BENCH_BACKEND (process-group backend other than nccl),
+HRD_BENCH_RANK_MS (every rank prints its own step time to stderr).
+
 oracle/ is used here as the CHECKER only (cpu_baseline / parity legs and --impl reference): the compiled
 reference oracle/_ref/libhrd_ref.so (unmodified sources), else the C port oracle/liboracle.so.
 """
