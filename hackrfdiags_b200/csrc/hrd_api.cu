@@ -1046,11 +1046,8 @@ static int run_demods(hrd_batch_t *b, hrd::RxParams &p, int entry, uint32_t n_ba
                 p.n_tiles = parts[part].n_tiles;
                 p.tile_batches = parts[part].tile_batches;
             } else {
+                // (ragged calls too: tiled over the nominal length, hrd_rx.cu rx_kernel)
                 choose_tiles(b, k, entry, p.n_streams, n_batches, &p.n_tiles, &p.tile_batches);
-                if (one_tile) { // ragged calls (the squelched path): one warp walks a stream's whole call
-                    p.n_tiles = 1;
-                    p.tile_batches = n_batches ? n_batches : 1;
-                }
             }
         p.wb_pack = fan && b->opt[HRD_OPT_RX_WBFM_PACK] ? 1 : 0; // beside other kinds: full WBFM CTAs on fewer SMs (hrd_tables.h)
         const bool speculate = k == hrd::K_WBFM && p.n_tiles > 1;

@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, HRD_RX_MIN_CTAS) rx_ke
     const int tile = item / p.n_streams;
     const int slot = item - tile * p.n_streams;
     const int sid = p.stream_ids[slot];
-    const bool first = tile == 0, last = tile == p.n_tiles - 1;
+    const bool first = tile == 0;
     // the K_AM instance runs the AM and the SSB streams of a batch (same /32 decimator chain)
     const bool ssb = KIND == K_AM && p.kind_of[sid] == K_SSB;
     const uint32_t halo = (KIND == K_AM && ssb) ? 2u : (uint32_t)HaloOf<KIND>::value;
@@ -423,10 +423,14 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, HRD_RX_MIN_CTAS) rx_ke
     asm volatile("" : "+l"(src)); // keep the row pointer in registers (else it is recomputed per load)
 
     // ---- this tile's range, in 256 kS/s samples --------------------------------------
-    const uint32_t n256 = p.n256_of ? p.n256_of[sid] : p.n256; // (ragged calls run with one tile per stream)
+    // (ragged calls -- the squelched path, every stream demodulates only its open blocks -- are tiled over the
+    //  NOMINAL length: a stream's tiles past its own end have nothing to do, the tile that holds its end is its last)
+    const uint32_t n256 = p.n256_of ? p.n256_of[sid] : p.n256;
     const uint32_t tile_len = p.tile_batches * BATCH256;
     const uint32_t emit_from = (uint32_t)tile * tile_len; // outputs before this are the halo's
+    if (tile > 0 && emit_from >= n256) return;
     const uint32_t end256 = min(n256, emit_from + tile_len);
+    const bool last = end256 == n256; // leaves the stream's state for the next call
     uint32_t done256 = first ? 0u : emit_from - halo * BATCH256;
 
     // ---- start state: saved (tile 0) or all-zero (later tiles, rebuilt by the halo) -----
@@ -491,6 +495,11 @@ __global__ void __launch_bounds__(HRD_WARPS_PER_CTA * 32, HRD_RX_MIN_CTAS) rx_ke
         const bool emit = done256 >= emit_from;
         last_active = min(32u, (nb - (n_it - 1) * IT_SAMPLES) / 4);
 
+        // (256 kS/s entry: a lane's loads are 8 bytes, a warp's 256 -- far too little in flight to hide DRAM; the
+        //  batch after next is pulled into L2 here, 2 KiB = sixteen lines, so that the loads find it there)
+        if constexpr (ENTRY == 1) {
+            if (lane < 16) prefetch_l2(src + min((done256 + 2 * BATCH256) * BPS + 128u * (uint32_t)lane, pf_last));
+        }
         // ---- A. front end (or plain load at the 256 kS/s entry) ----------------------
         // one iteration: consume b (loaded RX_DEPTH iterations ago), refill it in place
         auto step = [&](Raw &b, const uint32_t it) {
@@ -1156,6 +1165,9 @@ __global__ void __launch_bounds__(SMALL ? (WB_RERUN_ITEMS + 1) * 32 : HRD_WB_THR
         const uint32_t nb = min((uint32_t)WB_STEP, end - done);
         const uint32_t n_it = (nb + WB_IT - 1) / WB_IT;
         last_active = min(32u, (nb - (n_it - 1) * WB_IT) / WB_SPL);
+        if constexpr (ENTRY == 1) { // 256 kS/s entry: a step is 512 bytes, four lines; pulled into L2 eight steps ahead
+            if (lane < 4) prefetch_l2(src + min((done + 8u * WB_STEP) * BPS + 128u * (uint32_t)lane, pf_last));
+        }
         if constexpr (ENTRY == 0) { // a step is 4 KiB: lane l pulls its line l, one step ahead (pf = the lane's own next offset)
             if constexpr (WB_WIDE) prefetch_l2(src + min(pf + 64u * (uint32_t)lane + RX_L2_AHEAD * 1024u, pf_last));
             else prefetch_chunk_narrow(src, pf, pf_last, lane);

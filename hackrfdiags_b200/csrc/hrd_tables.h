@@ -171,7 +171,7 @@ struct RxParams {
     // count (21 items: 3.53 us, 27: 3.92 us), and the SMs left over are not idle, the other kinds run there
     int32_t wb_pack;
     // Ragged calls (the squelched path: every stream demodulates only the blocks its gate let through): when
-    // non-null, stream sid has n256_of[sid] <= n256 samples in its row; such launches run with n_tiles == 1.
+    // non-null, stream sid has n256_of[sid] <= n256 samples in its row; rx_kernel tiles such calls over the nominal length, rx_wbfm_kernel runs them with n_tiles == 1.
     const uint32_t *n256_of;
 };
 
