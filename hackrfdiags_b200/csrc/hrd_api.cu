@@ -173,6 +173,10 @@ int build_tables(hrd::ConstTables &t)
         return fail(HRD_EINVAL, "Tx 4-tap half-band centre taps expected to be 16384");
     if (t.tx_c3 <= 0 || t.tx_c3 > 16384 || t.tx_c7 <= 0 || t.tx_c7 > 16384 || t.tx_c8 <= 0 || t.tx_c8 > 16384)
         return fail(HRD_EINVAL, "Tx 4-tap half-band outer taps out of the supported range");
+    // the fp16-pair form of stages 6..8 (hrd_tx.cu tail3_h2, proved by tools/verify_tx_tail_h2.c) has these three
+    // taps built into its constants
+    if (t.tx_c3 != 8424 || t.tx_c7 != 8249 || t.tx_c8 != 8206)
+        return fail(HRD_EINVAL, "Tx stage 6/7/8 taps are not 8424 / 8249 / 8206: the packed-half form does not apply");
     return HRD_OK;
 }
 
