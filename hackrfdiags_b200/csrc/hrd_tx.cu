@@ -51,6 +51,9 @@ __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)l
 // FM 1.931 ms (two, scalar LDS) / 1.924 (two, vector LDS) / 1.868 (four, LDS.128); SSB 1.895 / 1.917 / 1.845;
 // AM 1.308 / 1.296 / 1.326 (four costs it registers: 40 -> 48).  So: four for the two-rail modulators, two with
 // scalar loads for AM and for the signals/ kind (72 registers with four; not timed yet: -DHRD_TX_SPL_IQ=4 builds it).
+#ifndef HRD_TX_SPL_FM
+#define HRD_TX_SPL_FM 4
+#endif
 #ifndef HRD_TX_SPL_IQ
 #define HRD_TX_SPL_IQ 2
 #endif
@@ -59,7 +62,7 @@ __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)l
 #define HRD_TX_H2 1
 #endif
 template <int KIND> struct TxSplOf {
-    static constexpr int value = (KIND == K_FM || KIND == K_SSB) ? 4 : (KIND == K_IQ ? HRD_TX_SPL_IQ : 2);
+    static constexpr int value = (KIND == K_FM || KIND == K_SSB) ? HRD_TX_SPL_FM : (KIND == K_IQ ? HRD_TX_SPL_IQ : 2);
 };
 
 struct alignas(16) SmemTx {
