@@ -80,3 +80,30 @@ def test_reset_and_mode_validation():
     b.set_mode(capi.MODE_IQ8K)
     with pytest.raises(capi.HrdError):
         b.tx(np.zeros((1, 65), dtype=np.int16), n=64)  # 2n int16 do not fit the row
+
+
+def test_packed_half_tail_across_its_range_limit():
+    """Stages 6-8 run as fp16 pairs while the stage-6 inputs stay within +-995 and as integers beyond (a vote per
+    warp iteration, hrd_tx.cu).  Raw I,Q tones whose amplitude ramps through the level where that happens -- on one
+    rail only, on both, in phase and in quadrature, with a DC offset -- so that single iterations, single lanes and
+    whole streams sit on either side of the limit and switch back and forth: bit for bit against the oracle."""
+    oracle = Oracle()
+    n = 1536
+    t = np.arange(n)
+    ramp = np.linspace(27000.0, 32767.0, n)
+    rows, wants = [], []
+    cases = [(ramp, 0.0, 0.031, 0.0), (32767.0 - (ramp - 27000.0), 0.25, 0.013, 0.0), (ramp, 0.5, 0.047, 1500.0),
+             (np.full(n, 31200.0), 0.0, 0.002, 0.0), (np.full(n, 31900.0), 0.125, 0.11, -700.0), (ramp * 0.5, 0.0, 0.2, 0.0)]
+    for amp, quad, f, dc in cases:
+        i = np.clip(np.round(amp * np.cos(2 * np.pi * f * t) + dc), -32768, 32767).astype(np.int16)
+        q = np.clip(np.round(0.3 * amp * np.sin(2 * np.pi * (f * t + quad))), -32768, 32767).astype(np.int16)
+        data = np.empty(2 * n, dtype=np.int16)
+        data[0::2], data[1::2] = i, q
+        rows.append(data)
+        wants.append(oracle.run_tx_signals(HEAD_OF_MODE[capi.MODE_IQ8K], data))
+    b = capi.Batch(len(rows), capi.TX, 0)
+    b.set_mode(capi.MODE_IQ8K)
+    got = np.concatenate([b.tx(np.stack([r[:2 * 700] for r in rows]), n=700), b.tx(np.stack([r[2 * 700:] for r in rows]), n=n - 700)], axis=1)
+    for k, want in enumerate(wants):
+        d = np.abs(got[k].astype(np.int32) - want.astype(np.int32))
+        assert d.max() == 0, f"case {k}: max abs err {d.max()}, {(d != 0).sum()} of {d.size} differ"
