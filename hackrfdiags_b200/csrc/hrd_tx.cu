@@ -20,7 +20,9 @@
 //      5,6,7,8 in registers (the left-neighbour sample each half-band stage needs is an
 //      odd-phase output, which depends on a single input, so it is recomputed locally - no
 //      shuffles), narrows like (int8_t) does and writes 32 contiguous bytes with one
-//      STG.E.256: 1 KiB per warp instruction.
+//      STG.E.256: 1 KiB per warp instruction.  (Since round 2 a lane takes two or four consecutive samples, and
+//      the two-rail kinds -- FM, SSB, signals/ -- run stages 6,7,8 on both rails at once as fp16 pairs wherever
+//      the samples are small enough for that form to be exact: see the loop itself.)
 // All interpolation is the reference's Q15 arithmetic stage by stage (each stage rounds to
 // int16, so stages cannot be merged): y[nL+i] = (16384 + sum_k q[i+kL]*x[n-k]) >> 15
 // (Interpolator_int16.cc:398-418).
@@ -50,7 +52,8 @@ __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)l
 // the left-neighbour chain of the half-band stages is carried from one to the next.  Measured (4096 streams x 0.5 s):
 // FM 1.931 ms (two, scalar LDS) / 1.924 (two, vector LDS) / 1.868 (four, LDS.128); SSB 1.895 / 1.917 / 1.845;
 // AM 1.308 / 1.296 / 1.326 (four costs it registers: 40 -> 48).  So: four for the two-rail modulators, two with
-// scalar loads for AM and for the signals/ kind (72 registers with four; not timed yet: -DHRD_TX_SPL_IQ=4 builds it).
+// scalar loads for AM and for the signals/ kind (72 registers with four).  With the fp16-pair tail (HRD_TX_H2) the
+// choice was measured again: FM two 1.695 / four 1.639 ms, SSB 1.655 / 1.657, signals/ PM two 1.464 / four 1.463.
 #ifndef HRD_TX_SPL_FM
 #define HRD_TX_SPL_FM 4
 #endif
